@@ -1,0 +1,172 @@
+/*
+ * pfn_b200.h -- C ABI of libpfn_b200.so: the sm_100a implementation of PowerFlowNet's hot path
+ * (MaskEmbdMultiMPN forward + backward).
+ *
+ * The reference (StavrosOrf/PoweFlowNet) has no FFI/plugin API for this path: its only seam is the
+ * Python nn.Module surface (networks/MPN.py:456-559, constructed at train.py:109-117, called at
+ * utils/training.py:58,74).  The entry points below are therefore what a ctypes binding on the
+ * reference side would bind; each cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - plain C: raw DEVICE pointers, sizes and leading dimensions; no torch types; `stream` is a
+ *    `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *  - every function returns 0 on success, a `cudaError_t` value or a negative PFN_E_* code otherwise;
+ *    `pfn_last_error()` describes the most recent failure on the calling thread.  Nothing throws,
+ *    nothing allocates device memory: all workspaces are owned by the caller.
+ *  - nothing here synchronises the device (everything is stream-ordered) except `pfn_graph_meta`,
+ *    which copies three integers to the host.
+ *  - node-feature matrices are row-major fp32 with a leading dimension that is a multiple of 4 floats
+ *    (16-byte rows); base pointers are 16-byte aligned.  Weights are in the reference's state_dict
+ *    layout ([out, in] row-major) and are never repacked by the caller.
+ *  - efeature_dim must be 2 (the dataset's real edge width, datasets/PowerFlowData.py:112-113).
+ */
+#ifndef PFN_B200_H_
+#define PFN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PFN_API __attribute__((visibility("default")))
+#else
+#define PFN_API
+#endif
+
+#define PFN_E_INVALID (-1)   /* bad argument (null pointer, misaligned pointer, bad size) */
+#define PFN_E_UNSUPPORTED (-2) /* configuration outside the implemented path                */
+#define PFN_E_WORKSPACE (-3) /* caller-provided workspace too small                        */
+
+/* ---- library ------------------------------------------------------------------------------- */
+PFN_API const char* pfn_version(void);
+PFN_API const char* pfn_last_error(void);
+/* number of kernels this library has launched on the calling process since load (bench "gpu_launches") */
+PFN_API uint64_t pfn_launch_count(void);
+
+/* ---- graph preparation: networks/MPN.py:498-523 (is_directed / undirect_graph) + the CSR the
+ *      message passing needs (PyG MessagePassing.propagate gathers, `degree`, `gcn_norm`) ---------- */
+typedef struct pfn_graph_layout {
+  /* byte offsets of each array inside the caller-allocated graph workspace */
+  int64_t meta;      /* int32[8]: [0] reverse-of-first-edge found, [1] directed, [2] E (directed edges in
+                        use), [3] error flag (node id out of range), [4] e_raw, [5] n_nodes            */
+  int64_t rowptr_t;  /* int32[N+1]  CSR by TARGET node (edge_index[1])                                  */
+  int64_t nbr_t;     /* int32[Ecap] source node of each in-edge, CSR order                              */
+  int64_t eid_t;     /* int32[Ecap] directed-edge id of each slot (ascending inside a row => stable)    */
+  int64_t ea_t;      /* float[Ecap*2] edge_attr in CSR-by-target order                                  */
+  int64_t rowptr_s;  /* int32[N+1]  CSR by SOURCE node (edge_index[0]), for the transposed passes       */
+  int64_t nbr_s;     /* int32[Ecap] target node of each out-edge                                        */
+  int64_t eid_s;     /* int32[Ecap]                                                                     */
+  int64_t ea_s;      /* float[Ecap*2]                                                                   */
+  int64_t deg;       /* float[N]  in-degree (count of edges whose target is the node)                   */
+  int64_t dis;       /* float[N]  deg^-1/2, 0 where deg == 0  (gcn_norm)                                */
+  int64_t cursor;    /* int32[2N] scratch                                                               */
+  int64_t total_bytes;
+  int64_t e_cap;     /* 2*e_raw: capacity in directed edges                                             */
+} pfn_graph_layout;
+
+PFN_API int pfn_graph_layout_get(int64_t n_nodes, int64_t e_raw, pfn_graph_layout* out);
+
+/* undirect_mode 1: reference semantics -- look at the first edge only, append all reversed edges when
+ * its reverse is absent (networks/MPN.py:498-523); 0: take edge_index as it is (stand-alone layers).
+ * edge_index: int64 [2, e_raw] with row stride `ei_row_stride` elements; edge_attr: float [e_raw, 2]. */
+PFN_API int pfn_graph_prep(const int64_t* edge_index, int64_t ei_row_stride, const float* edge_attr,
+                   int64_t n_nodes, int64_t e_raw, int undirect_mode, void* graph_ws, void* stream);
+/* host_meta[0]=directed, [1]=E, [2]=error flag.  Synchronises `stream`. */
+PFN_API int pfn_graph_meta(const void* graph_ws, int32_t* host_meta, void* stream);
+/* materialise the undirected lists (what `undirect_graph` returns): ei_out int64 [2, E], ea_out float [E, 2] */
+PFN_API int pfn_graph_export(const int64_t* edge_index, int64_t ei_row_stride, const float* edge_attr,
+                     int64_t e_raw, int64_t e_out, int64_t* ei_out, float* ea_out, void* stream);
+
+/* ---- fused EdgeAggregation message + aggregate: networks/MPN.py:23-28 (message) + :53 (propagate,
+ *      aggr='add').  With W1 = [Wi | Wj | We] (columns of edge_aggr.0.weight), Hi = x Wi^T + b1,
+ *      Hj = x Wj^T:   S[i] = sum_{e: tgt(e)=i} ReLU(Hi[i] + Hj[src(e)] + We ea[e]);
+ *      the second Linear is applied after the sum by pfn_linear (sum aggregation is linear). ------- */
+PFN_API int pfn_ea_fwd(const float* Hi, const float* Hj, int64_t ldh, const void* graph_ws, int64_t n_nodes,
+               int64_t e_raw, const float* We, int64_t ldwe, float* S, int64_t lds, int64_t h, void* stream);
+/* backward of the above: dHi, dHj [N, ldd]; dWe [h, 2] written with row stride lddwe (it is a column
+ * block of the gradient of edge_aggr.0.weight).  scratch: at least pfn_ea_bwd_scratch_bytes(h). */
+PFN_API size_t pfn_ea_bwd_scratch_bytes(int64_t h);
+PFN_API int pfn_ea_bwd(const float* dS, int64_t ldds, const float* Hi, const float* Hj, int64_t ldh,
+               const void* graph_ws, int64_t n_nodes, int64_t e_raw, const float* We, int64_t ldwe,
+               float* dHi, float* dHj, int64_t ldd, float* dWe, int64_t lddwe, void* scratch,
+               int64_t h, void* stream);
+
+/* ---- TAGConv hop (PyG TAGConv.propagate with gcn_norm weights; call site networks/MPN.py:545):
+ *      Y[i] = dis[i] * sum_{e: tgt(e)=i} dis[src(e)] X[src(e)]   (+ addend[i]) ;
+ *      transpose != 0 walks the CSR by source instead (A_hat^T, used by the backward pass);
+ *      ymask != NULL multiplies the result by (ymask > 0 ? scale : 0) (ReLU/dropout backward). ------ */
+PFN_API int pfn_spmm_hop(const float* X, int64_t ldx, const void* graph_ws, int64_t n_nodes, int64_t e_raw,
+                 int transpose, const float* addend, int64_t ldadd, const float* ymask, int64_t ldym,
+                 float scale, float* Y, int64_t ldy, int64_t h, void* stream);
+
+/* ---- dense per-node Linear stacks (nn.Linear / PyG Linear; networks/MPN.py:17-21,491-495 and
+ *      TAGConv.lins).  W is [n_out, n_in] row-major with leading dimension ldw (state_dict layout). -- */
+#define PFN_ACT_NONE 0
+#define PFN_ACT_RELU 1
+#define PFN_ACT_DROPOUT_RELU 2 /* y = relu(keep ? v / (1-p) : 0): networks/MPN.py:546-547 */
+/* Y[M,n_out] = X[M,n_in] W^T + rowscale (.) bias + addend, then activation.
+ * rowscale NULL => 1.  dropout keep-mask: `inj_mask` (float 0/1, [M, ld_inj]) when non-NULL, else the
+ * library's counter-based generator keyed by `seed`. */
+PFN_API int pfn_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
+                   const float* rowscale, const float* addend, int64_t ldadd, float* Y, int64_t ldy,
+                   int64_t M, int64_t n_in, int64_t n_out, int act, float dropout_p, uint64_t seed,
+                   const float* inj_mask, int64_t ld_inj, void* stream);
+/* dX[M,n_in] = dY[M,n_out] W ; if ymask != NULL: dX *= (ymask > 0 ? scale : 0). */
+PFN_API int pfn_linear_dgrad(const float* dY, int64_t lddy, const float* W, int64_t ldw, const float* ymask,
+                     int64_t ldym, float scale, float* dX, int64_t lddx, int64_t M, int64_t n_in,
+                     int64_t n_out, void* stream);
+/* dW[n_out,n_in] = dY^T X (row stride lddw); dbias[n_out] = sum_m rowscale[m] dY[m,:] when dbias != NULL.
+ * scratch: at least pfn_linear_wgrad_scratch_bytes(M, n_in, n_out). */
+PFN_API size_t pfn_linear_wgrad_scratch_bytes(int64_t M, int64_t n_in, int64_t n_out);
+PFN_API int pfn_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* rowscale,
+                     float* dW, int64_t lddw, float* dbias, int64_t M, int64_t n_in, int64_t n_out,
+                     void* scratch, void* stream);
+
+/* ---- whole model: MaskEmbdMultiMPN.forward (networks/MPN.py:525-559) and its backward
+ *      (autograd of the same, utils/training.py:74) ------------------------------------------------ */
+typedef struct pfn_mpn_desc {
+  int32_t nfeature_dim; /* 4 */
+  int32_t efeature_dim; /* 2 */
+  int32_t output_dim;   /* 4 */
+  int32_t hidden_dim;
+  int32_t n_gnn_layers; /* >= 2 */
+  int32_t K;
+  float dropout_rate;
+  int32_t reserved;
+} pfn_mpn_desc;
+
+/* Number of parameter tensors and the order `params` / `grads` tables use:
+ * for each entry of `layers` in order: EdgeAggregation -> edge_aggr.0.weight, edge_aggr.0.bias,
+ * edge_aggr.2.weight, edge_aggr.2.bias; TAGConv -> lins.0.weight ... lins.K.weight, bias;
+ * then mask_embd.0.weight, mask_embd.0.bias, mask_embd.2.weight, mask_embd.2.bias. */
+PFN_API int pfn_mpn_num_params(const pfn_mpn_desc* desc);
+/* activation workspace (lives from forward to backward) and scratch (transient) sizes in bytes */
+PFN_API int pfn_mpn_workspace(const pfn_mpn_desc* desc, int64_t n_nodes, int64_t e_raw, size_t* act_bytes,
+                      size_t* scratch_bytes);
+/* x float [N,4]; pred_mask int64 [N,4]; graph_ws prepared by pfn_graph_prep(undirect_mode=1);
+ * training != 0 applies dropout (keep masks from `inj_masks[i]` [N, hidden] when inj_masks != NULL,
+ * else from the generator keyed by `seed`); out float [N, output_dim]. */
+PFN_API int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* params, const float* x,
+                    const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                    void* act_ws, void* scratch_ws, int training, uint64_t seed,
+                    const float* const* inj_masks, float* out, void* stream);
+/* dout float [N, output_dim]; grads[i] receives d loss / d params[i] (overwritten, same shapes) */
+PFN_API int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
+                     const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                     void* act_ws, void* scratch_ws, int training, void* stream);
+
+/* ---- loss head (utils/training.py:61-72 with torch.nn.MSELoss, train.py:103): fused forward +
+ *      gradient.  loss[0] = inv_count * sum (out-y)^2  (the mean when inv_count = 1/count; under data
+ *      parallelism inv_count = 1/global_count gives this rank's share), dout = 2 (out - y) * inv_count.
+ *      Deterministic two-pass reduction; scratch: at least pfn_mse_scratch_bytes(count). ------------ */
+PFN_API size_t pfn_mse_scratch_bytes(int64_t count);
+PFN_API int pfn_mse_fwd_bwd(const float* out, const float* y, int64_t count, float inv_count, float* loss,
+                    float* dout, void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFN_B200_H_ */

@@ -1,0 +1,333 @@
+// Segmented gather -> combine -> sum kernels over the stable CSR built by graph_prep.cu.
+//
+//   k_ea_fwd  : EdgeAggregation message + aggregate   (networks/MPN.py:23-28 message, :53 propagate, aggr='add')
+//   k_ea_bwd  : its backward (target-side pass: dHi + dWe ; source-side pass: dHj), ReLU mask recomputed
+//   k_hop     : one TAGConv propagation  x <- A_hat x     (PyG TAGConv.propagate, call site MPN.py:545)
+//
+// Work decomposition (all three): one thread owns one (node row, float4 column chunk); a CTA is
+// `cx` chunks wide and `rows` rows tall (cx*rows <= 256) and walks a CONTIGUOUS slab of rows, so
+//  - every row read/write is a run of consecutive 16-byte accesses (coalesced, vectorised),
+//  - a thread's column chunk is fixed => its slice of We / its dWe partial sums live in registers,
+//  - neighbour rows gathered by one CTA come from the same graph of the batch (block-diagonal
+//    adjacency) and hit L1/L2 instead of HBM,
+//  - a row is summed by exactly one thread in ascending edge id: no atomics, deterministic.
+// These kernels are HBM/L2-bandwidth work (a few flops per byte): no tensor cores by design.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pfn {
+namespace {
+
+struct RowTiling {
+  int c4, cx, rows, threads, nblocks, npb;
+};
+
+RowTiling make_tiling(int64_t n_nodes, int64_t h, int blocks_per_sm) {
+  RowTiling t;
+  t.c4 = static_cast<int>((h + 3) / 4);
+  t.cx = std::min(t.c4, 256);
+  t.rows = std::max(1, 256 / t.cx);
+  t.threads = t.cx * t.rows;
+  int64_t want = ceil_div64(std::max<int64_t>(n_nodes, 1), t.rows);
+  t.nblocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sm_count()) * blocks_per_sm)));
+  t.npb = static_cast<int>(ceil_div64(std::max<int64_t>(n_nodes, 1), t.nblocks));
+  return t;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ void load_we(const float* __restrict__ We, int64_t ldwe, int q, int h, float4& w0,
+                                        float4& w1) {
+  float a[4], b[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int ch = 4 * q + c;
+    a[c] = ch < h ? __ldg(We + ch * ldwe) : 0.f;
+    b[c] = ch < h ? __ldg(We + ch * ldwe + 1) : 0.f;
+  }
+  w0 = make_float4(a[0], a[1], a[2], a[3]);
+  w1 = make_float4(b[0], b[1], b[2], b[3]);
+}
+
+// pre-activation of one message:  Hi[tgt] + Hj[src] + ea0 * We[:,0] + ea1 * We[:,1]
+__device__ __forceinline__ float4 preact(float4 hi, float4 hj, float2 a, float4 w0, float4 w1) {
+  float4 p;
+  p.x = fmaf(a.y, w1.x, fmaf(a.x, w0.x, hi.x + hj.x));
+  p.y = fmaf(a.y, w1.y, fmaf(a.x, w0.y, hi.y + hj.y));
+  p.z = fmaf(a.y, w1.z, fmaf(a.x, w0.z, hi.z + hj.z));
+  p.w = fmaf(a.y, w1.w, fmaf(a.x, w0.w, hi.w + hj.w));
+  return p;
+}
+
+__device__ __forceinline__ void add_relu(float4& acc, float4 p) {
+  acc.x += fmaxf(p.x, 0.f);
+  acc.y += fmaxf(p.y, 0.f);
+  acc.z += fmaxf(p.z, 0.f);
+  acc.w += fmaxf(p.w, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh, const int* __restrict__ rowptr,
+         const int* __restrict__ nbr, const float2* __restrict__ ea, const float* __restrict__ We, int64_t ldwe,
+         float* __restrict__ S, int64_t lds, int n_nodes, int h, int c4, int cx, int rows, int npb) {
+  const int x = threadIdx.x % cx, y = threadIdx.x / cx;
+  const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
+  for (int q = x; q < c4; q += cx) {
+    float4 w0, w1;
+    load_we(We, ldwe, q, h, w0, w1);
+    for (int node = start + y; node < end; node += rows) {
+      const float4 hi = ld4(Hi + node * ldh + 4 * q);
+      const int beg = rowptr[node], fin = rowptr[node + 1];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int e = beg;
+      for (; e + 1 < fin; e += 2) {  // two gathers in flight per thread
+        const int s0 = nbr[e], s1 = nbr[e + 1];
+        const float2 a0 = ea[e], a1 = ea[e + 1];
+        const float4 h0 = ldg4(Hj + s0 * ldh + 4 * q);
+        const float4 h1 = ldg4(Hj + s1 * ldh + 4 * q);
+        add_relu(acc, preact(hi, h0, a0, w0, w1));
+        add_relu(acc, preact(hi, h1, a1, w0, w1));
+      }
+      if (e < fin) {
+        const int s0 = nbr[e];
+        const float2 a0 = ea[e];
+        add_relu(acc, preact(hi, ldg4(Hj + s0 * ldh + 4 * q), a0, w0, w1));
+      }
+      st4(S + node * lds + 4 * q, acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// blockIdx.y == 0: target-side pass over the CSR by target:  dHi[i] = sum_{e in in(i)} dS[i] * 1[p_e > 0]
+//                  and the per-CTA partial of dWe[c,k] = sum_e g_e[c] * ea_e[k]
+// blockIdx.y == 1: source-side pass over the CSR by source:  dHj[j] = sum_{e in out(j)} dS[tgt e] * 1[p_e > 0]
+__global__ void __launch_bounds__(256)
+k_ea_bwd(const float* __restrict__ dS, int64_t ldds, const float* __restrict__ Hi, const float* __restrict__ Hj,
+         int64_t ldh, const int* __restrict__ rowptr_t, const int* __restrict__ nbr_t,
+         const float2* __restrict__ ea_t, const int* __restrict__ rowptr_s, const int* __restrict__ nbr_s,
+         const float2* __restrict__ ea_s, const float* __restrict__ We, int64_t ldwe, float* __restrict__ dHi,
+         float* __restrict__ dHj, int64_t ldd, float* __restrict__ dwe_partial, int n_nodes, int h, int c4, int cx,
+         int rows, int npb) {
+  __shared__ float red[8][256];
+  const int x = threadIdx.x % cx, y = threadIdx.x / cx;
+  const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
+  const bool target_side = blockIdx.y == 0;
+  for (int q0 = 0; q0 < c4; q0 += cx) {  // trip count is CTA-uniform: the loop body holds barriers
+    const int q = q0 + x;
+    const bool active = q < c4;
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+    if (active) load_we(We, ldwe, q, h, w0, w1);
+    if (target_side) {
+      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;  // dWe[:,0], dWe[:,1] partial sums of this chunk
+      for (int node = start + y; active && node < end; node += rows) {
+        const float4 hi = ld4(Hi + node * ldh + 4 * q);
+        const float4 ds = ld4(dS + node * ldds + 4 * q);
+        const int beg = rowptr_t[node], fin = rowptr_t[node + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = beg; e < fin; ++e) {
+          const int s = nbr_t[e];
+          const float2 a = ea_t[e];
+          const float4 p = preact(hi, ldg4(Hj + s * ldh + 4 * q), a, w0, w1);
+          float4 g;
+          g.x = p.x > 0.f ? ds.x : 0.f;
+          g.y = p.y > 0.f ? ds.y : 0.f;
+          g.z = p.z > 0.f ? ds.z : 0.f;
+          g.w = p.w > 0.f ? ds.w : 0.f;
+          acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+          g0.x = fmaf(g.x, a.x, g0.x); g0.y = fmaf(g.y, a.x, g0.y); g0.z = fmaf(g.z, a.x, g0.z); g0.w = fmaf(g.w, a.x, g0.w);
+          g1.x = fmaf(g.x, a.y, g1.x); g1.y = fmaf(g.y, a.y, g1.y); g1.z = fmaf(g.z, a.y, g1.z); g1.w = fmaf(g.w, a.y, g1.w);
+        }
+        st4(dHi + node * ldd + 4 * q, acc);
+      }
+      // fixed-order reduction over the CTA's rows, then one partial row per CTA (no atomics)
+      red[0][threadIdx.x] = g0.x; red[1][threadIdx.x] = g0.y; red[2][threadIdx.x] = g0.z; red[3][threadIdx.x] = g0.w;
+      red[4][threadIdx.x] = g1.x; red[5][threadIdx.x] = g1.y; red[6][threadIdx.x] = g1.z; red[7][threadIdx.x] = g1.w;
+      __syncthreads();
+      if (y == 0 && active) {
+        float sum[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum[k] = 0.f;
+        for (int yy = 0; yy < rows; ++yy) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) sum[k] += red[k][yy * cx + x];
+        }
+        float* dst = dwe_partial + size_t(blockIdx.x) * (2 * 4 * c4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          dst[4 * q + c] = sum[c];
+          dst[4 * c4 + 4 * q + c] = sum[4 + c];
+        }
+      }
+      __syncthreads();
+    } else {
+      for (int node = start + y; active && node < end; node += rows) {
+        const float4 hj = ld4(Hj + node * ldh + 4 * q);
+        const int beg = rowptr_s[node], fin = rowptr_s[node + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = beg; e < fin; ++e) {
+          const int t = nbr_s[e];
+          const float2 a = ea_s[e];
+          const float4 p = preact(ldg4(Hi + t * ldh + 4 * q), hj, a, w0, w1);
+          const float4 ds = ldg4(dS + t * ldds + 4 * q);
+          acc.x += p.x > 0.f ? ds.x : 0.f;
+          acc.y += p.y > 0.f ? ds.y : 0.f;
+          acc.z += p.z > 0.f ? ds.z : 0.f;
+          acc.w += p.w > 0.f ? ds.w : 0.f;
+        }
+        st4(dHj + node * ldd + 4 * q, acc);
+      }
+    }
+  }
+}
+
+// dWe[c, k] = sum over CTAs of the partial rows, in CTA order (deterministic)
+__global__ void k_reduce_dwe(const float* __restrict__ partial, int nblocks, int c4, int h, float* __restrict__ dWe,
+                             int64_t lddwe) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 2 * h
+  if (idx >= 2 * h) return;
+  const int k = idx / h, c = idx - k * h;
+  float sum = 0.f;
+  for (int b = 0; b < nblocks; ++b) sum += partial[size_t(b) * (8 * c4) + k * 4 * c4 + c];
+  dWe[c * lddwe + k] = sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Y[i] = dis[i] * sum_{e in row i} dis[nbr e] * X[nbr e]  (+ addend[i])  (* (ymask[i] > 0 ? scale : 0))
+__global__ void __launch_bounds__(256)
+k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, const int* __restrict__ nbr,
+      const float* __restrict__ dis, const float* addend, int64_t ldadd, const float* __restrict__ ymask,
+      int64_t ldym, float scale, float* Y, int64_t ldy, int n_nodes, int c4, int cx, int rows, int npb) {
+  const int x = threadIdx.x % cx, y = threadIdx.x / cx;
+  const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
+  for (int q = x; q < c4; q += cx) {
+    for (int node = start + y; node < end; node += rows) {
+      const int beg = rowptr[node], fin = rowptr[node + 1];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int e = beg;
+      for (; e + 1 < fin; e += 2) {
+        const int s0 = nbr[e], s1 = nbr[e + 1];
+        const float d0 = __ldg(dis + s0), d1 = __ldg(dis + s1);
+        const float4 v0 = ldg4(X + s0 * ldx + 4 * q);
+        const float4 v1 = ldg4(X + s1 * ldx + 4 * q);
+        acc.x = fmaf(d0, v0.x, acc.x); acc.y = fmaf(d0, v0.y, acc.y); acc.z = fmaf(d0, v0.z, acc.z); acc.w = fmaf(d0, v0.w, acc.w);
+        acc.x = fmaf(d1, v1.x, acc.x); acc.y = fmaf(d1, v1.y, acc.y); acc.z = fmaf(d1, v1.z, acc.z); acc.w = fmaf(d1, v1.w, acc.w);
+      }
+      if (e < fin) {
+        const int s0 = nbr[e];
+        const float d0 = __ldg(dis + s0);
+        const float4 v0 = ldg4(X + s0 * ldx + 4 * q);
+        acc.x = fmaf(d0, v0.x, acc.x); acc.y = fmaf(d0, v0.y, acc.y); acc.z = fmaf(d0, v0.z, acc.z); acc.w = fmaf(d0, v0.w, acc.w);
+      }
+      const float di = dis[node];
+      float4 out = make_float4(di * acc.x, di * acc.y, di * acc.z, di * acc.w);
+      if (addend != nullptr) {
+        const float4 a = ld4(addend + node * ldadd + 4 * q);
+        out.x += a.x; out.y += a.y; out.z += a.z; out.w += a.w;
+      }
+      if (ymask != nullptr) {
+        const float4 m = ld4(ymask + node * ldym + 4 * q);
+        out.x = m.x > 0.f ? out.x * scale : 0.f;
+        out.y = m.y > 0.f ? out.y * scale : 0.f;
+        out.z = m.z > 0.f ? out.z * scale : 0.f;
+        out.w = m.w > 0.f ? out.w * scale : 0.f;
+      }
+      st4(Y + node * ldy + 4 * q, out);
+    }
+  }
+}
+
+constexpr int kBlocksPerSm = 8;
+
+bool rows_ok(const void* p, int64_t ld) { return p != nullptr && aligned16(p) && ld % 4 == 0; }
+
+}  // namespace
+
+int ea_fwd_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView& g, int64_t n_nodes, const float* We,
+                  int64_t ldwe, float* S, int64_t lds, int64_t h, cudaStream_t stream) {
+  PFN_REQUIRE(rows_ok(Hi, ldh) && rows_ok(Hj, ldh) && rows_ok(S, lds) && We != nullptr, PFN_E_INVALID,
+              "ea_fwd: node matrices must be 16-byte aligned with ld %% 4 == 0");
+  PFN_REQUIRE(h > 0 && ldh >= round_up64(h, 4) && lds >= round_up64(h, 4), PFN_E_INVALID, "ea_fwd: ld < round_up(h,4)");
+  if (n_nodes == 0) return 0;
+  const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
+  k_ea_fwd<<<t.nblocks, t.threads, 0, stream>>>(Hi, Hj, ldh, g.rowptr_t, g.nbr_t, reinterpret_cast<const float2*>(g.ea_t),
+                                               We, ldwe, S, lds, static_cast<int>(n_nodes), static_cast<int>(h), t.c4,
+                                               t.cx, t.rows, t.npb);
+  PFN_LAUNCHED();
+  return 0;
+}
+
+int ea_bwd_launch(const float* dS, int64_t ldds, const float* Hi, const float* Hj, int64_t ldh, const GraphView& g,
+                  int64_t n_nodes, const float* We, int64_t ldwe, float* dHi, float* dHj, int64_t ldd, float* dWe,
+                  int64_t lddwe, void* scratch, int64_t h, cudaStream_t stream) {
+  PFN_REQUIRE(rows_ok(dS, ldds) && rows_ok(Hi, ldh) && rows_ok(Hj, ldh) && rows_ok(dHi, ldd) && rows_ok(dHj, ldd),
+              PFN_E_INVALID, "ea_bwd: node matrices must be 16-byte aligned with ld %% 4 == 0");
+  PFN_REQUIRE(We && dWe && scratch, PFN_E_INVALID, "ea_bwd: null argument");
+  const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
+  float* partial = static_cast<float*>(scratch);
+  int nblocks = 0;
+  if (n_nodes > 0) {
+    nblocks = t.nblocks;
+    dim3 grid(t.nblocks, 2);
+    k_ea_bwd<<<grid, t.threads, 0, stream>>>(dS, ldds, Hi, Hj, ldh, g.rowptr_t, g.nbr_t,
+                                            reinterpret_cast<const float2*>(g.ea_t), g.rowptr_s, g.nbr_s,
+                                            reinterpret_cast<const float2*>(g.ea_s), We, ldwe, dHi, dHj, ldd, partial,
+                                            static_cast<int>(n_nodes), static_cast<int>(h), t.c4, t.cx, t.rows, t.npb);
+    PFN_LAUNCHED();
+  }
+  k_reduce_dwe<<<static_cast<int>(ceil_div64(2 * h, 128)), 128, 0, stream>>>(partial, nblocks, t.c4, static_cast<int>(h),
+                                                                           dWe, lddwe);
+  PFN_LAUNCHED();
+  return 0;
+}
+
+int hop_launch(const float* X, int64_t ldx, const GraphView& g, int64_t n_nodes, bool transpose, const float* addend,
+               int64_t ldadd, const float* ymask, int64_t ldym, float scale, float* Y, int64_t ldy, int64_t h,
+               cudaStream_t stream) {
+  PFN_REQUIRE(rows_ok(X, ldx) && rows_ok(Y, ldy), PFN_E_INVALID, "hop: node matrices must be 16-byte aligned with ld %% 4 == 0");
+  PFN_REQUIRE(addend == nullptr || rows_ok(addend, ldadd), PFN_E_INVALID, "hop: addend misaligned");
+  PFN_REQUIRE(ymask == nullptr || rows_ok(ymask, ldym), PFN_E_INVALID, "hop: ymask misaligned");
+  if (n_nodes == 0) return 0;
+  const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
+  k_hop<<<t.nblocks, t.threads, 0, stream>>>(X, ldx, transpose ? g.rowptr_s : g.rowptr_t, transpose ? g.nbr_s : g.nbr_t,
+                                            g.dis, addend, ldadd, ymask, ldym, scale, Y, ldy, static_cast<int>(n_nodes),
+                                            t.c4, t.cx, t.rows, t.npb);
+  PFN_LAUNCHED();
+  return 0;
+}
+
+}  // namespace pfn
+
+using namespace pfn;
+
+extern "C" int pfn_ea_fwd(const float* Hi, const float* Hj, int64_t ldh, const void* graph_ws, int64_t n_nodes,
+                          int64_t e_raw, const float* We, int64_t ldwe, float* S, int64_t lds, int64_t h, void* stream) {
+  PFN_REQUIRE(graph_ws != nullptr, PFN_E_INVALID, "pfn_ea_fwd: null graph workspace");
+  return ea_fwd_launch(Hi, Hj, ldh, graph_view(graph_ws, n_nodes, e_raw), n_nodes, We, ldwe, S, lds, h,
+                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t pfn_ea_bwd_scratch_bytes(int64_t h) {
+  return size_t(sm_count()) * kBlocksPerSm * 8 * size_t((h + 3) / 4) * sizeof(float);
+}
+
+extern "C" int pfn_ea_bwd(const float* dS, int64_t ldds, const float* Hi, const float* Hj, int64_t ldh,
+                          const void* graph_ws, int64_t n_nodes, int64_t e_raw, const float* We, int64_t ldwe,
+                          float* dHi, float* dHj, int64_t ldd, float* dWe, int64_t lddwe, void* scratch, int64_t h,
+                          void* stream) {
+  PFN_REQUIRE(graph_ws != nullptr, PFN_E_INVALID, "pfn_ea_bwd: null graph workspace");
+  return ea_bwd_launch(dS, ldds, Hi, Hj, ldh, graph_view(graph_ws, n_nodes, e_raw), n_nodes, We, ldwe, dHi, dHj, ldd,
+                       dWe, lddwe, scratch, h, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pfn_spmm_hop(const float* X, int64_t ldx, const void* graph_ws, int64_t n_nodes, int64_t e_raw,
+                            int transpose, const float* addend, int64_t ldadd, const float* ymask, int64_t ldym,
+                            float scale, float* Y, int64_t ldy, int64_t h, void* stream) {
+  PFN_REQUIRE(graph_ws != nullptr, PFN_E_INVALID, "pfn_spmm_hop: null graph workspace");
+  return hop_launch(X, ldx, graph_view(graph_ws, n_nodes, e_raw), n_nodes, transpose != 0, addend, ldadd, ymask, ldym,
+                    scale, Y, ldy, h, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,562 @@
+// Whole-model orchestration: MaskEmbdMultiMPN.forward (networks/MPN.py:525-559) and the backward
+// pass autograd would run for it (utils/training.py:74), as stream-ordered sequences of the kernels in
+// graph_prep.cu / edge_kernels.cu / gemm.cu.  No host synchronisation, no allocation, no atomics.
+//
+// Algebra used (identical to the reference up to fp32 rounding, checked against the oracle):
+//   EdgeAggregation (MPN.py:17-28,53)   W1 = [Wi | Wj | We]  (column blocks of edge_aggr.0.weight)
+//       Hi = x Wi^T + b1 ,  Hj = x Wj^T                       per-node GEMMs instead of per-edge
+//       S[i] = sum_{e in in(i)} ReLU(Hi[i] + Hj[src e] + We ea_e)           fused gather/sum kernel
+//       out  = S W2^T + deg (.) b2                            second Linear hoisted after the sum
+//   TAGConv (PyG; MPN.py:545)   x_k = A_hat x_{k-1} ;  out = sum_k x_k W_k^T + bias    one K-segmented GEMM
+//   dropout + ReLU (MPN.py:546-547) fused in the producing GEMM's epilogue; backward needs only the
+//   saved output: d pre = d post * (post > 0 ? 1/(1-p) : 0).
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pfn {
+
+// ---- library state -----------------------------------------------------------------------------
+static thread_local char g_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;  // B200
+  }
+  return cached;
+}
+
+namespace {
+
+// ---- small elementwise kernels -------------------------------------------------------------------
+__global__ void k_i64_to_f32(const int64_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    out[i] = static_cast<float>(in[i]);
+}
+
+constexpr int kMseBlock = 256;
+__global__ void __launch_bounds__(kMseBlock)
+k_mse_partial(const float* __restrict__ out, const float* __restrict__ y, int64_t count, float inv_count,
+              float* __restrict__ dout, float* __restrict__ partial) {
+  float local = 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    const float d = out[i] - y[i];
+    local = fmaf(d, d, local);
+    dout[i] = 2.f * d * inv_count;
+  }
+  __shared__ float red[kMseBlock];
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int s = kMseBlock / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(kMseBlock)
+k_mse_final(const float* __restrict__ partial, int n, float inv_count, float* __restrict__ loss) {
+  __shared__ float red[kMseBlock];
+  float local = 0.f;
+  for (int i = threadIdx.x; i < n; i += kMseBlock) local += partial[i];
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int s = kMseBlock / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = red[0] * inv_count;
+}
+int mse_blocks(int64_t count) {
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(count, kMseBlock * 4), 1024)));
+}
+
+// ---- model plan ------------------------------------------------------------------------------------
+struct LayerPlan {
+  bool is_ea;
+  int fin, fout;
+  int p0;       // index of the layer's first tensor in the params table
+  int slot;     // index among the EA layers (is_ea) or among the TAG layers
+  bool act;     // dropout+ReLU applied to the output (every layer but the last)
+};
+
+struct Plan {
+  pfn_mpn_desc d;
+  std::vector<LayerPlan> layers;
+  int n_ea = 0, n_tag = 0;
+  int p_mask = 0;  // index of mask_embd.0.weight
+  int n_params = 0;
+  int64_t N = 0, ldh = 0;
+  // activation workspace offsets (floats)
+  int64_t off_maskf = 0, off_t1 = 0, off_x0 = 0, off_ea = 0, off_tag = 0, act_floats = 0;
+  // scratch offsets (floats)
+  int64_t off_dz = 0, off_ds = 0, off_dhi = 0, off_dhj = 0, off_dxcat = 0, off_dx0 = 0, off_part = 0, scratch_floats = 0;
+  int64_t part_bytes = 0;
+
+  int64_t ea_stride() const { return 3 * N * ldh; }                       // Hi, Hj, S
+  int64_t xcat_ld() const { return int64_t(d.K + 1) * ldh; }
+  int64_t tag_stride() const { return N * xcat_ld() + N * ldh; }           // Xcat, Y
+};
+
+int make_plan(const pfn_mpn_desc* desc, int64_t n_nodes, Plan& p) {
+  PFN_REQUIRE(desc != nullptr, PFN_E_INVALID, "null model descriptor");
+  p.d = *desc;
+  const pfn_mpn_desc& d = p.d;
+  PFN_REQUIRE(d.efeature_dim == 2, PFN_E_UNSUPPORTED, "efeature_dim must be 2 (got %d)", d.efeature_dim);
+  PFN_REQUIRE(d.n_gnn_layers >= 2, PFN_E_UNSUPPORTED,
+              "n_gnn_layers must be >= 2 (the reference's single-layer constructor, MPN.py:475-477,489, is "
+              "shape-inconsistent)");
+  PFN_REQUIRE(d.nfeature_dim > 0 && d.output_dim > 0 && d.hidden_dim > 0 && d.K >= 0 && d.K + 1 <= kGemmMaxItems,
+              PFN_E_UNSUPPORTED, "unsupported dims (nfeat=%d out=%d hidden=%d K=%d)", d.nfeature_dim, d.output_dim,
+              d.hidden_dim, d.K);
+  PFN_REQUIRE(d.dropout_rate >= 0.f && d.dropout_rate < 1.f, PFN_E_INVALID, "dropout_rate out of [0,1)");
+  const int h = d.hidden_dim;
+  p.layers.clear();
+  int pi = 0;
+  auto add_ea = [&](int fin, int fout) {
+    p.layers.push_back(LayerPlan{true, fin, fout, pi, p.n_ea++, true});
+    pi += 4;
+  };
+  auto add_tag = [&](int fin, int fout) {
+    p.layers.push_back(LayerPlan{false, fin, fout, pi, p.n_tag++, true});
+    pi += d.K + 2;
+  };
+  add_ea(d.nfeature_dim, h);  // MPN.py:479-480
+  add_tag(h, h);
+  for (int l = 0; l < d.n_gnn_layers - 2; ++l) {  // MPN.py:482-484
+    add_ea(h, h);
+    add_tag(h, h);
+  }
+  add_ea(h, d.output_dim);  // MPN.py:489
+  p.layers.back().act = false;
+  p.p_mask = pi;
+  p.n_params = pi + 4;
+  p.N = n_nodes;
+  p.ldh = round_up64(h, 4);
+  // activation workspace
+  int64_t off = 0;
+  auto take = [&](int64_t floats) {
+    int64_t o = off;
+    off += round_up64(floats, 4);
+    return o;
+  };
+  p.off_maskf = take(n_nodes * d.nfeature_dim);
+  p.off_t1 = take(n_nodes * p.ldh);
+  p.off_x0 = take(n_nodes * d.nfeature_dim);
+  p.off_ea = take(p.n_ea * p.ea_stride());
+  p.off_tag = take(p.n_tag * p.tag_stride());
+  p.act_floats = off;
+  // scratch
+  off = 0;
+  p.off_dz = take(n_nodes * p.ldh);
+  p.off_ds = take(n_nodes * p.ldh);
+  p.off_dhi = take(n_nodes * p.ldh);
+  p.off_dhj = take(n_nodes * p.ldh);
+  p.off_dxcat = take(n_nodes * p.xcat_ld());
+  p.off_dx0 = take(n_nodes * d.nfeature_dim);
+  size_t part = pfn_ea_bwd_scratch_bytes(h);
+  // every split-K weight-gradient problem the backward launches: (rows of dW, cols of dW, problems per launch)
+  const int wg[][3] = {{h, h, 1}, {d.output_dim, h, 1},                   // EA  dW2 = G^T S
+                       {h, h, 2}, {h, d.nfeature_dim, 2},                 // EA  dWi | dWj
+                       {h, h, d.K + 1},                                   // TAG dW_k
+                       {d.nfeature_dim, h, 1}, {h, d.nfeature_dim, 1}};   // mask_embd
+  for (const auto& w : wg) part = std::max(part, gemm_splitk_scratch_bytes(w[0], w[1], n_nodes, w[2]));
+  p.part_bytes = static_cast<int64_t>(part);
+  p.off_part = take(static_cast<int64_t>((part + 3) / 4));
+  p.scratch_floats = off;
+  return 0;
+}
+
+struct Ctx {
+  const Plan& p;
+  const float* const* params;
+  GraphView g;
+  float* act;
+  float* scratch;
+  cudaStream_t stream;
+  bool training;
+  float scale;  // 1/(1-p) in training, 1 otherwise
+
+  float* hi(int slot) const { return act + p.off_ea + slot * p.ea_stride(); }
+  float* hj(int slot) const { return hi(slot) + p.N * p.ldh; }
+  float* s(int slot) const { return hi(slot) + 2 * p.N * p.ldh; }
+  float* xcat(int slot) const { return act + p.off_tag + slot * p.tag_stride(); }
+  float* ytag(int slot) const { return xcat(slot) + p.N * p.xcat_ld(); }
+};
+
+GemmArgs base_args(int M, int N) {
+  GemmArgs a{};
+  a.M = M;
+  a.N = N;
+  a.n_items = 1;
+  a.splitk = 1;
+  a.scale = 1.f;
+  return a;
+}
+
+// Y = X W^T view helpers -----------------------------------------------------------------------------
+inline GemmItem fwd_item(const float* X, int64_t ldx, const float* W, int64_t ldw, int K, float* C, int64_t ldc,
+                         const float* bias) {
+  return GemmItem{X, W, C, bias, nullptr, ldx, 1, 1, ldw, K, static_cast<int>(ldc)};
+}
+inline GemmItem dgrad_item(const float* dY, int64_t lddy, const float* W, int64_t ldw, int K, float* C, int64_t ldc) {
+  return GemmItem{dY, W, C, nullptr, nullptr, lddy, 1, ldw, 1, K, static_cast<int>(ldc)};
+}
+inline GemmItem wgrad_item(const float* dY, int64_t lddy, const float* X, int64_t ldx, int K, float* dW, int64_t lddw,
+                           float* dbias) {
+  return GemmItem{dY, X, dW, nullptr, dbias, 1, lddy, ldx, 1, K, static_cast<int>(lddw)};
+}
+
+void set_activation(GemmArgs& a, const Ctx& c, bool act, int layer_index, uint64_t seed, const float* inj, int64_t ld_inj) {
+  if (!act) {
+    a.act = PFN_ACT_NONE;
+    return;
+  }
+  if (c.training && c.p.d.dropout_rate > 0.f) {
+    a.act = PFN_ACT_DROPOUT_RELU;
+    a.scale = c.scale;
+    a.inj = inj;
+    a.ld_inj = static_cast<int>(ld_inj);
+    a.seed_lo = static_cast<uint32_t>(seed) ^ (0x9E3779B9u * static_cast<uint32_t>(layer_index + 1));
+    a.seed_hi = static_cast<uint32_t>(seed >> 32);
+    a.keep_thresh = keep_threshold(c.p.d.dropout_rate);
+  } else {
+    a.act = PFN_ACT_RELU;
+  }
+}
+
+// ---- forward ------------------------------------------------------------------------------------------
+int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_t seed, const float* const* inj_masks,
+                 float* out) {
+  const Plan& p = c.p;
+  const pfn_mpn_desc& d = p.d;
+  const int N = static_cast<int>(p.N), h = d.hidden_dim, nf = d.nfeature_dim;
+  const int64_t ldh = p.ldh;
+  if (N == 0) return 0;
+  float* maskf = c.act + p.off_maskf;
+  float* t1 = c.act + p.off_t1;
+  float* x0 = c.act + p.off_x0;
+  // mask_embd (MPN.py:533,537): x0 = Linear(ReLU(Linear(mask.float()))) + x
+  {
+    const int64_t n = int64_t(N) * nf;
+    k_i64_to_f32<<<static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 1184)), 256, 0, c.stream>>>(pred_mask, maskf, n);
+    PFN_LAUNCHED();
+    const float* const* mp = c.params + p.p_mask;
+    GemmArgs a = base_args(N, h);
+    a.it[0] = fwd_item(maskf, nf, mp[0], nf, nf, t1, ldh, mp[1]);
+    a.act = PFN_ACT_RELU;
+    PFN_TRY(gemm_launch(a, true, true, c.stream));
+    GemmArgs b = base_args(N, nf);
+    b.it[0] = fwd_item(t1, ldh, mp[2], h, h, x0, nf, mp[3]);
+    b.addend = x;
+    b.ld_add = nf;
+    PFN_TRY(gemm_launch(b, true, true, c.stream));
+  }
+  const float* cur = x0;
+  int64_t ldcur = nf;
+  const int n_layers = static_cast<int>(p.layers.size());
+  for (int li = 0; li < n_layers; ++li) {
+    const LayerPlan& L = p.layers[li];
+    const float* const* lp = c.params + L.p0;
+    const bool last = li == n_layers - 1;
+    const float* inj = (inj_masks != nullptr && L.act) ? inj_masks[li] : nullptr;
+    if (L.is_ea) {
+      const int ldw1 = 2 * L.fin + 2;
+      // Hi = cur Wi^T + b1 ; Hj = cur Wj^T   (one launch, two problems)
+      GemmArgs a = base_args(N, h);
+      a.n_items = 2;
+      a.batched = 1;
+      a.it[0] = fwd_item(cur, ldcur, lp[0], ldw1, L.fin, c.hi(L.slot), ldh, lp[1]);
+      a.it[1] = fwd_item(cur, ldcur, lp[0] + L.fin, ldw1, L.fin, c.hj(L.slot), ldh, nullptr);
+      PFN_TRY(gemm_launch(a, true, true, c.stream));
+      PFN_TRY(ea_fwd_launch(c.hi(L.slot), c.hj(L.slot), ldh, c.g, N, lp[0] + 2 * L.fin, ldw1, c.s(L.slot), ldh, h,
+                            c.stream));
+      // out = S W2^T + deg (.) b2, then dropout+ReLU unless this is the last layer
+      float* dest;
+      int64_t lddest;
+      if (last) {
+        dest = out;
+        lddest = L.fout;
+      } else {
+        dest = c.xcat(p.layers[li + 1].slot);  // block 0 of the next TAGConv's [x_0 | x_1 | ... | x_K]
+        lddest = p.xcat_ld();
+      }
+      GemmArgs b = base_args(N, L.fout);
+      b.it[0] = fwd_item(c.s(L.slot), ldh, lp[2], h, h, dest, lddest, lp[3]);
+      b.rowscale = c.g.deg;
+      set_activation(b, c, L.act, li, seed, inj, h);
+      PFN_TRY(gemm_launch(b, true, true, c.stream));
+      cur = dest;
+      ldcur = lddest;
+    } else {
+      float* xc = c.xcat(L.slot);
+      const int64_t ldx = p.xcat_ld();
+      for (int k = 1; k <= d.K; ++k)
+        PFN_TRY(hop_launch(xc + (k - 1) * ldh, ldx, c.g, N, false, nullptr, 0, nullptr, 0, 1.f, xc + k * ldh, ldx, L.fin,
+                           c.stream));
+      float* dest = last ? out : c.ytag(L.slot);
+      const int64_t lddest = last ? L.fout : ldh;
+      GemmArgs a = base_args(N, L.fout);
+      a.n_items = d.K + 1;
+      for (int k = 0; k <= d.K; ++k) a.it[k] = fwd_item(xc + k * ldh, ldx, lp[k], L.fin, L.fin, dest, lddest, lp[d.K + 1]);
+      set_activation(a, c, L.act, li, seed, inj, h);
+      PFN_TRY(gemm_launch(a, true, true, c.stream));
+      cur = dest;
+      ldcur = lddest;
+    }
+  }
+  return 0;
+}
+
+// ---- backward -----------------------------------------------------------------------------------------
+int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
+  const Plan& p = c.p;
+  const pfn_mpn_desc& d = p.d;
+  const int N = static_cast<int>(p.N), h = d.hidden_dim, nf = d.nfeature_dim;
+  const int64_t ldh = p.ldh;
+  if (N == 0) return 0;
+  float* dz = c.scratch + p.off_dz;
+  float* ds = c.scratch + p.off_ds;
+  float* dhi = c.scratch + p.off_dhi;
+  float* dhj = c.scratch + p.off_dhj;
+  float* dxcat = c.scratch + p.off_dxcat;
+  float* dx0 = c.scratch + p.off_dx0;
+  float* part = c.scratch + p.off_part;
+  const float* x0 = c.act + p.off_x0;
+  const float* G = dout;  // gradient w.r.t. the current layer's (pre-activation) output
+  int64_t ldG = d.output_dim;
+  const int n_layers = static_cast<int>(p.layers.size());
+  for (int li = n_layers - 1; li >= 0; --li) {
+    const LayerPlan& L = p.layers[li];
+    const float* const* lp = c.params + L.p0;
+    float* const* lg = grads + L.p0;
+    if (L.is_ea) {
+      const int ldw1 = 2 * L.fin + 2;
+      // input of this layer and whether it is the (post-activation) output of a previous layer
+      const float* cur;
+      int64_t ldcur;
+      bool cur_has_act;
+      if (li == 0) {
+        cur = x0;
+        ldcur = nf;
+        cur_has_act = false;
+      } else {
+        cur = c.ytag(p.layers[li - 1].slot);
+        ldcur = ldh;
+        cur_has_act = true;
+      }
+      // dW2 = G^T S ; db2 = sum_i deg_i G[i]
+      {
+        GemmArgs a = base_args(L.fout, h);
+        a.it[0] = wgrad_item(G, ldG, c.s(L.slot), ldh, N, lg[2], h, lg[3]);
+        a.extra_col = 2;
+        a.extra_vec = c.g.deg;
+        a.partial = part;
+        gemm_plan_splitk(a, N, 1);
+        PFN_TRY(gemm_launch(a, false, false, c.stream));
+      }
+      // dS = G W2
+      {
+        GemmArgs a = base_args(N, h);
+        a.it[0] = dgrad_item(G, ldG, lp[2], h, L.fout, ds, ldh);
+        PFN_TRY(gemm_launch(a, true, false, c.stream));
+      }
+      // dHi, dHj, dWe
+      PFN_TRY(ea_bwd_launch(ds, ldh, c.hi(L.slot), c.hj(L.slot), ldh, c.g, N, lp[0] + 2 * L.fin, ldw1, dhi, dhj, ldh,
+                            lg[0] + 2 * L.fin, ldw1, part, h, c.stream));
+      // dWi = dHi^T cur (+ db1 = colsum dHi) ; dWj = dHj^T cur
+      {
+        GemmArgs a = base_args(h, L.fin);
+        a.n_items = 2;
+        a.batched = 1;
+        a.it[0] = wgrad_item(dhi, ldh, cur, ldcur, N, lg[0], ldw1, lg[1]);
+        a.it[1] = wgrad_item(dhj, ldh, cur, ldcur, N, lg[0] + L.fin, ldw1, nullptr);
+        a.extra_col = 1;
+        a.partial = part;
+        gemm_plan_splitk(a, N, 2);
+        PFN_TRY(gemm_launch(a, false, false, c.stream));
+      }
+      // d cur = dHi Wi + dHj Wj, masked by the previous layer's activation
+      {
+        float* dest = li == 0 ? dx0 : dz;
+        const int64_t lddest = li == 0 ? nf : ldh;
+        GemmArgs a = base_args(N, L.fin);
+        a.n_items = 2;
+        a.it[0] = dgrad_item(dhi, ldh, lp[0], ldw1, h, dest, lddest);
+        a.it[1] = dgrad_item(dhj, ldh, lp[0] + L.fin, ldw1, h, dest, lddest);
+        if (cur_has_act) {
+          a.act = kActMaskByY;
+          a.ymask = cur;
+          a.ld_ym = static_cast<int>(ldcur);
+          a.scale = c.scale;
+        }
+        PFN_TRY(gemm_launch(a, true, false, c.stream));
+        G = dest;
+        ldG = lddest;
+      }
+    } else {
+      const float* xc = c.xcat(L.slot);
+      const int64_t ldx = p.xcat_ld();
+      // dW_k = G^T x_k (k = 0..K) ; dbias = colsum G
+      {
+        GemmArgs a = base_args(L.fout, L.fin);
+        a.n_items = d.K + 1;
+        a.batched = 1;
+        for (int k = 0; k <= d.K; ++k)
+          a.it[k] = wgrad_item(G, ldG, xc + k * ldh, ldx, N, lg[k], L.fin, k == 0 ? lg[d.K + 1] : nullptr);
+        a.extra_col = 1;
+        a.partial = part;
+        gemm_plan_splitk(a, N, d.K + 1);
+        PFN_TRY(gemm_launch(a, false, false, c.stream));
+      }
+      // d x_k = G W_k (k = 0..K), then the transposed hop chain d x_{k-1} += A_hat^T d x_k; the last hop
+      // also applies the activation mask of the layer input (which is block 0 of xcat itself)
+      {
+        GemmArgs a = base_args(N, L.fin);
+        a.n_items = d.K + 1;
+        a.batched = 1;
+        for (int k = 0; k <= d.K; ++k) a.it[k] = dgrad_item(G, ldG, lp[k], L.fin, L.fout, dxcat + k * ldh, ldx);
+        if (d.K == 0) {
+          a.act = kActMaskByY;
+          a.ymask = xc;
+          a.ld_ym = static_cast<int>(ldx);
+          a.scale = c.scale;
+        }
+        PFN_TRY(gemm_launch(a, true, false, c.stream));
+      }
+      for (int k = d.K; k >= 1; --k) {
+        const bool final_hop = k == 1;
+        PFN_TRY(hop_launch(dxcat + k * ldh, ldx, c.g, N, true, dxcat + (k - 1) * ldh, ldx, final_hop ? xc : nullptr, ldx,
+                           c.scale, dxcat + (k - 1) * ldh, ldx, L.fin, c.stream));
+      }
+      G = dxcat;
+      ldG = ldx;
+    }
+  }
+  // mask_embd backward: x0 = W2m relu(W1m mask + b1m) + b2m + x
+  {
+    const float* const* mp = c.params + p.p_mask;
+    float* const* mg = grads + p.p_mask;
+    const float* maskf = c.act + p.off_maskf;
+    const float* t1 = c.act + p.off_t1;
+    GemmArgs a = base_args(nf, h);
+    a.it[0] = wgrad_item(G, ldG, t1, ldh, N, mg[2], h, mg[3]);
+    a.extra_col = 1;
+    a.partial = part;
+    gemm_plan_splitk(a, N, 1);
+    PFN_TRY(gemm_launch(a, false, false, c.stream));
+    GemmArgs b = base_args(N, h);
+    b.it[0] = dgrad_item(G, ldG, mp[2], h, nf, ds, ldh);
+    b.act = kActMaskByY;
+    b.ymask = t1;
+    b.ld_ym = static_cast<int>(ldh);
+    b.scale = 1.f;
+    PFN_TRY(gemm_launch(b, true, false, c.stream));
+    GemmArgs w = base_args(h, nf);
+    w.it[0] = wgrad_item(ds, ldh, maskf, nf, N, mg[0], nf, mg[1]);
+    w.extra_col = 1;
+    w.partial = part;
+    gemm_plan_splitk(w, N, 1);
+    PFN_TRY(gemm_launch(w, false, false, c.stream));
+  }
+  return 0;
+}
+
+int check_tables(const Plan& p, const float* const* params, const char* what) {
+  PFN_REQUIRE(params != nullptr, PFN_E_INVALID, "%s: null pointer table", what);
+  for (int i = 0; i < p.n_params; ++i) PFN_REQUIRE(params[i] != nullptr, PFN_E_INVALID, "%s: entry %d is null", what, i);
+  return 0;
+}
+
+}  // namespace
+}  // namespace pfn
+
+using namespace pfn;
+
+extern "C" const char* pfn_version(void) { return "pfn_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* pfn_last_error(void) { return g_error; }
+extern "C" uint64_t pfn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int pfn_mpn_num_params(const pfn_mpn_desc* desc) {
+  Plan p;
+  if (make_plan(desc, 0, p) != 0) return -1;
+  return p.n_params;
+}
+
+extern "C" int pfn_mpn_workspace(const pfn_mpn_desc* desc, int64_t n_nodes, int64_t e_raw, size_t* act_bytes,
+                                 size_t* scratch_bytes) {
+  (void)e_raw;
+  PFN_REQUIRE(act_bytes && scratch_bytes && n_nodes >= 0, PFN_E_INVALID, "pfn_mpn_workspace: bad arguments");
+  Plan p;
+  PFN_TRY(make_plan(desc, n_nodes, p));
+  *act_bytes = size_t(p.act_floats) * sizeof(float) + 16;
+  *scratch_bytes = size_t(p.scratch_floats) * sizeof(float) + 16;
+  return 0;
+}
+
+extern "C" int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* params, const float* x,
+                               const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                               void* act_ws, void* scratch_ws, int training, uint64_t seed,
+                               const float* const* inj_masks, float* out, void* stream) {
+  Plan p;
+  PFN_TRY(make_plan(desc, n_nodes, p));
+  PFN_TRY(check_tables(p, params, "pfn_mpn_forward(params)"));
+  PFN_REQUIRE(n_nodes == 0 || (x && pred_mask && out), PFN_E_INVALID, "pfn_mpn_forward: null tensor");
+  PFN_REQUIRE(graph_ws && act_ws && aligned16(act_ws), PFN_E_INVALID, "pfn_mpn_forward: workspace null or misaligned");
+  (void)scratch_ws;
+  Ctx c{p, params, graph_view(graph_ws, n_nodes, e_raw), static_cast<float*>(act_ws), static_cast<float*>(scratch_ws),
+        static_cast<cudaStream_t>(stream), training != 0,
+        (training != 0 && desc->dropout_rate > 0.f) ? 1.f / (1.f - desc->dropout_rate) : 1.f};
+  return forward_impl(c, x, pred_mask, seed, inj_masks, out);
+}
+
+extern "C" int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
+                                const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws, void* act_ws,
+                                void* scratch_ws, int training, void* stream) {
+  Plan p;
+  PFN_TRY(make_plan(desc, n_nodes, p));
+  PFN_TRY(check_tables(p, params, "pfn_mpn_backward(params)"));
+  PFN_TRY(check_tables(p, const_cast<const float* const*>(grads), "pfn_mpn_backward(grads)"));
+  PFN_REQUIRE(n_nodes == 0 || dout, PFN_E_INVALID, "pfn_mpn_backward: null dout");
+  PFN_REQUIRE(graph_ws && act_ws && scratch_ws && aligned16(act_ws) && aligned16(scratch_ws), PFN_E_INVALID,
+              "pfn_mpn_backward: workspace null or misaligned");
+  Ctx c{p, params, graph_view(graph_ws, n_nodes, e_raw), static_cast<float*>(act_ws), static_cast<float*>(scratch_ws),
+        static_cast<cudaStream_t>(stream), training != 0,
+        (training != 0 && desc->dropout_rate > 0.f) ? 1.f / (1.f - desc->dropout_rate) : 1.f};
+  if (n_nodes == 0) {  // gradients of an empty batch are zero
+    return 0;
+  }
+  return backward_impl(c, grads, dout);
+}
+
+extern "C" size_t pfn_mse_scratch_bytes(int64_t count) { return size_t(mse_blocks(count)) * sizeof(float); }
+
+extern "C" int pfn_mse_fwd_bwd(const float* out, const float* y, int64_t count, float inv_count, float* loss,
+                               float* dout, void* scratch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PFN_REQUIRE(out && y && loss && dout && scratch && count > 0, PFN_E_INVALID, "pfn_mse_fwd_bwd: bad arguments");
+  const int blocks = mse_blocks(count);
+  k_mse_partial<<<blocks, kMseBlock, 0, stream>>>(out, y, count, inv_count, dout, static_cast<float*>(scratch));
+  PFN_LAUNCHED();
+  k_mse_final<<<1, kMseBlock, 0, stream>>>(static_cast<const float*>(scratch), blocks, inv_count, loss);
+  PFN_LAUNCHED();
+  return 0;
+}

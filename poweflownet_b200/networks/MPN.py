@@ -1,0 +1,236 @@
+"""Drop-in `nn.Module` surface of the reference hot path (reference: networks/MPN.py).
+
+Same class names, constructor signatures, attribute names (`layers`, `mask_embd`, `dropout`) and
+therefore the same `state_dict` keys/shapes as the reference (`layers.{i}.edge_aggr.{0,2}.{weight,bias}`,
+`layers.{i}.lins.{k}.weight`, `layers.{i}.bias`, `mask_embd.{0,2}.{weight,bias}`), so reference
+checkpoints load and `train.py` can construct and drive the model unchanged.
+The arithmetic runs in libpfn_b200.so (hand-written sm_100a kernels) -- CUDA tensors only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import MpnDesc, check, lib
+
+
+class EdgeAggregation(nn.Module):
+    """networks/MPN.py:6-56.  Parameters live in `edge_aggr` exactly as in the reference
+    (`nn.Sequential(Linear(2*nf+ef, hidden), ReLU, Linear(hidden, out))`, :17-21)."""
+
+    def __init__(self, nfeature_dim, efeature_dim, hidden_dim, output_dim):
+        super().__init__()
+        self.nfeature_dim, self.efeature_dim, self.output_dim = nfeature_dim, efeature_dim, output_dim
+        self.edge_aggr = nn.Sequential(
+            nn.Linear(nfeature_dim * 2 + efeature_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, output_dim))
+
+    def forward(self, x, edge_index, edge_attr):
+        """`out[i] = sum_{e: edge_index[1,e]=i} edge_aggr(cat[x_i, x_j, edge_attr_e])` (:23-28,:53).
+        The degree norm of :43-47 never reaches `message` in the reference and is not computed."""
+        if self.efeature_dim != 2:
+            raise NotImplementedError("the sm_100a path implements efeature_dim == 2 (the dataset's edge width)")
+        l0, l2 = self.edge_aggr[0], self.edge_aggr[2]
+        return ops.EdgeAggregationFn.apply(x, edge_index, edge_attr, l0.weight, l0.bias, l2.weight, l2.bias)
+
+
+class _Lin(nn.Module):
+    """Bias-free linear holder with PyG `Linear`'s state_dict key (`weight` [out, in]) and default init."""
+
+    def __init__(self, fin, fout):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(fout, fin))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.weight.size(1))
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound)
+
+
+class TAGConv(nn.Module):
+    """`torch_geometric.nn.TAGConv(in, out, K)` as the reference uses it (networks/MPN.py:477,480,484,545):
+    `out = sum_k lins[k](A_hat^k x) + bias`, `A_hat = D^-1/2 A D^-1/2`, degree over `edge_index[1]`."""
+
+    def __init__(self, in_channels, out_channels, K=3):
+        super().__init__()
+        self.in_channels, self.out_channels, self.K = in_channels, out_channels, K
+        self.lins = nn.ModuleList([_Lin(in_channels, out_channels) for _ in range(K + 1)])
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, x, edge_index):
+        return ops.TAGConvFn.apply(x, edge_index, self.bias, *[l.weight for l in self.lins])
+
+
+class _Workspace:
+    __slots__ = ("graph", "act", "scratch")
+
+    def __init__(self, graph, act, scratch):
+        self.graph, self.act, self.scratch = graph, act, scratch
+
+
+class _MPNFunction(torch.autograd.Function):
+    """Whole-model forward/backward through `pfn_mpn_forward` / `pfn_mpn_backward`."""
+
+    @staticmethod
+    def forward(ctx, model, x, pred_mask, edge_index, edge_attr, *params):
+        dev = ops.require_cuda(x, pred_mask, edge_index, edge_attr, *params)
+        n = int(x.size(0))
+        training = bool(model.training)
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x.requires_grad)
+        with torch.cuda.device(dev):
+            x = x.contiguous().float()
+            pred_mask = pred_mask.contiguous()
+            if pred_mask.dtype != torch.int64:
+                pred_mask = pred_mask.long()
+            ws = model._take_workspace(n, int(edge_index.size(1)), dev)
+            graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph)
+            ws.graph = graph.ws
+            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if training else 0
+            inj = model._inject_dropout_masks if training else None
+            inj_table = None
+            if inj is not None:
+                inj = [m.to(dev, torch.float32).contiguous() for m in inj]
+                inj_table = (C.c_void_p * len(model.layers))(*([m.data_ptr() for m in inj] + [None]))
+            out = torch.empty((n, model.output_dim), dtype=torch.float32, device=dev)
+            ptable = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+            desc = model._desc()
+            check(lib().pfn_mpn_forward(C.byref(desc), ptable, x.data_ptr(), pred_mask.data_ptr(), n, graph.e_raw,
+                                        ws.graph.data_ptr(), ws.act.data_ptr(), ws.scratch.data_ptr(), int(training),
+                                        seed, inj_table, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                  "pfn_mpn_forward")
+        if needs_grad:
+            ctx.model, ctx.ws, ctx.params, ctx.n, ctx.e_raw, ctx.training = model, ws, params, n, graph.e_raw, training
+            ctx.keep = (x, pred_mask, graph, inj)  # keep inputs alive until backward
+        else:
+            model._give_workspace(n, graph.e_raw, dev, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model, ws, params = ctx.model, ctx.ws, ctx.params
+        if ws is None:
+            raise RuntimeError("backward called twice on the same MaskEmbdMultiMPN forward: activations were released")
+        dev = dout.device
+        with torch.cuda.device(dev):
+            dout = dout.contiguous().float()
+            sizes = [p.numel() for p in params]
+            gflat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            views, off = [], 0
+            for p, s in zip(params, sizes):
+                views.append(gflat[off:off + s].view(p.shape))
+                off += s
+            ptable = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+            gtable = (C.c_void_p * len(params))(*[v.data_ptr() for v in views])
+            desc = model._desc()
+            check(lib().pfn_mpn_backward(C.byref(desc), ptable, gtable, dout.data_ptr(), ctx.n, ctx.e_raw,
+                                         ws.graph.data_ptr(), ws.act.data_ptr(), ws.scratch.data_ptr(),
+                                         int(ctx.training), torch.cuda.current_stream().cuda_stream), "pfn_mpn_backward")
+            dx = None
+            if ctx.needs_input_grad[1]:
+                # x enters as `mask_embd(mask) + x` (MPN.py:537): d loss / d x is the gradient w.r.t. that sum
+                dx = model._dx0_view(ws, ctx.n).clone()
+            if model._grad_reducer is not None:
+                model._grad_reducer(gflat)  # data parallel: ONE collective over the flat gradient buffer
+        model._give_workspace(ctx.n, ctx.e_raw, dev, ws)
+        ctx.ws = None
+        return (None, dx, None, None, None, *views)
+
+
+class MaskEmbdMultiMPN(nn.Module):
+    """networks/MPN.py:456-559 -- constructor mirrors :462-496 argument for argument."""
+
+    def __init__(self, nfeature_dim, efeature_dim, output_dim, hidden_dim, n_gnn_layers, K, dropout_rate):
+        super().__init__()
+        self.nfeature_dim, self.efeature_dim, self.output_dim = nfeature_dim, efeature_dim, output_dim
+        self.hidden_dim, self.n_gnn_layers, self.K, self.dropout_rate = hidden_dim, n_gnn_layers, K, dropout_rate
+        self.layers = nn.ModuleList()
+        self.layers.append(EdgeAggregation(nfeature_dim, efeature_dim, hidden_dim, hidden_dim))
+        # :475-480 -- with one GNN layer the TAGConv emits output_dim (kept for state_dict fidelity)
+        self.layers.append(TAGConv(hidden_dim, output_dim if n_gnn_layers == 1 else hidden_dim, K=K))
+        for _ in range(n_gnn_layers - 2):
+            self.layers.append(EdgeAggregation(hidden_dim, efeature_dim, hidden_dim, hidden_dim))
+            self.layers.append(TAGConv(hidden_dim, hidden_dim, K=K))
+        self.layers.append(EdgeAggregation(hidden_dim, efeature_dim, hidden_dim, output_dim))
+        self.mask_embd = nn.Sequential(
+            nn.Linear(nfeature_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, nfeature_dim))
+        self.dropout = nn.Dropout(self.dropout_rate, inplace=False)  # kept for attribute parity; p is read from it
+        self._pool = {}
+        self._inject_dropout_masks: Optional[Sequence[torch.Tensor]] = None  # test hook: replay given keep-masks
+        self._grad_reducer = None  # set by poweflownet_b200.parallel.attach_gradient_allreduce
+
+    # ---- reference helper methods (networks/MPN.py:498-523) -------------------------------------
+    def is_directed(self, edge_index):
+        """True iff the reverse of the FIRST edge is absent (the reference reads one edge only); False for
+        an empty edge list.  Evaluated on the device; returning a Python bool costs one sync, as in the reference."""
+        if edge_index.shape[1] == 0:
+            return False
+        dev = ops.require_cuda(edge_index)
+        with torch.cuda.device(dev):
+            n = int(edge_index.max().item()) + 1
+            dummy = torch.zeros((edge_index.size(1), 2), dtype=torch.float32, device=dev)
+            return ops.PreparedGraph(edge_index, dummy, n, mode=1).meta()[0]
+
+    def undirect_graph(self, edge_index, edge_attr):
+        dev = ops.require_cuda(edge_index, edge_attr)
+        if edge_index.shape[1] == 0:
+            return edge_index, edge_attr
+        with torch.cuda.device(dev):
+            n = int(edge_index.max().item()) + 1
+            return ops.PreparedGraph(edge_index, edge_attr.float(), n, mode=1).export()
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def _desc(self) -> MpnDesc:
+        return MpnDesc(self.nfeature_dim, self.efeature_dim, self.output_dim, self.hidden_dim, self.n_gnn_layers,
+                       self.K, float(self.dropout.p), 0)
+
+    def _engine_params(self) -> List[torch.Tensor]:
+        """Parameters in the order of pfn_mpn_num_params (include/pfn_b200.h)."""
+        out: List[torch.Tensor] = []
+        for layer in self.layers:
+            if isinstance(layer, EdgeAggregation):
+                l0, l2 = layer.edge_aggr[0], layer.edge_aggr[2]
+                out += [l0.weight, l0.bias, l2.weight, l2.bias]
+            else:
+                out += [l.weight for l in layer.lins] + [layer.bias]
+        out += [self.mask_embd[0].weight, self.mask_embd[0].bias, self.mask_embd[2].weight, self.mask_embd[2].bias]
+        return out
+
+    def _take_workspace(self, n, e_raw, dev) -> _Workspace:
+        free = self._pool.setdefault((n, e_raw, str(dev)), [])
+        if free:
+            return free.pop()
+        act, scratch = C.c_size_t(), C.c_size_t()
+        desc = self._desc()
+        check(lib().pfn_mpn_workspace(C.byref(desc), n, e_raw, C.byref(act), C.byref(scratch)), "pfn_mpn_workspace")
+        return _Workspace(None, torch.zeros(act.value, dtype=torch.uint8, device=dev),
+                          torch.zeros(scratch.value, dtype=torch.uint8, device=dev))
+
+    def _give_workspace(self, n, e_raw, dev, ws) -> None:
+        free = self._pool.setdefault((n, e_raw, str(dev)), [])
+        if len(free) < 2:
+            free.append(ws)
+
+    def _dx0_view(self, ws: _Workspace, n: int) -> torch.Tensor:
+        # scratch layout of engine.cu: dz, ds, dhi, dhj [n, ldh] ; dxcat [n, (K+1) ldh] ; dx0 [n, nfeat]
+        ldh = ops.round_up4(self.hidden_dim)
+        r4 = lambda v: (v + 3) // 4 * 4  # noqa: E731
+        off = 4 * r4(n * ldh) + r4(n * (self.K + 1) * ldh)
+        return ws.scratch.view(torch.float32)[off:off + n * self.nfeature_dim].view(n, self.nfeature_dim)
+
+    def forward(self, data):
+        """networks/MPN.py:525-559.  `data` is any object with the PyG `Batch` attributes the reference
+        reads: x [N,4], pred_mask [N,4], edge_index [2,E_raw], edge_attr [E_raw,2] (bus_type / batch are
+        read but unused by the reference, :531-532)."""
+        assert data.x.shape[-1] == 4  # :528
+        if self.n_gnn_layers < 2:
+            raise NotImplementedError(
+                "n_gnn_layers == 1 builds EA(4->h), TAG(h->out), EA(h->out) in the reference (MPN.py:475-477,489), "
+                "which cannot run unless hidden_dim == output_dim; the sm_100a path implements n_gnn_layers >= 2")
+        if self.efeature_dim != 2:
+            raise NotImplementedError("the sm_100a path implements efeature_dim == 2 (the dataset's edge width)")
+        return _MPNFunction.apply(self, data.x, data.pred_mask, data.edge_index, data.edge_attr, *self._engine_params())

@@ -1,0 +1,214 @@
+"""Whole-model parity on the B200: `poweflownet_b200.networks.MPN.MaskEmbdMultiMPN` (C ABI ->
+sm_100a kernels) against (a) the golden vectors produced by the reference's own networks/MPN.py and
+(b) the CPU oracle at BASELINE.json's full sizes.  Tolerance 1e-5 relative fp32 (north_star)."""
+import pytest
+import torch
+
+import common
+from oracle import pfn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda:0"
+ALL = list(common.CASES)
+
+
+def _model(kw, state=None):
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    m = MaskEmbdMultiMPN(**kw)
+    if state is None:
+        common.load_seeded(m)
+    else:
+        m.load_state_dict(state)
+    return m.to(DEV)
+
+
+def _close(got, want, what, tol=TOL):
+    e = common.rel_err(got.detach().cpu(), want)
+    assert max(e) < tol, (what, e)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_state_dict_keys_and_shapes_match_reference(name):
+    gold = torch.load(common.golden_path(name), weights_only=True)
+    m = _model(gold["meta"]["model_kwargs"])
+    ref = gold["grads"] if "grads" in gold else gold["grad_norm"]
+    assert list(m.state_dict().keys()) == list(ref.keys())
+    if "grads" in gold:
+        for k, v in m.state_dict().items():
+            assert tuple(v.shape) == tuple(gold["grads"][k].shape), k
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_eval_forward_matches_reference(name):
+    gold = torch.load(common.golden_path(name), weights_only=True)
+    m = _model(gold["meta"]["model_kwargs"]).eval()
+    batch = common.GraphBatch(**gold["inputs"]).to(DEV)
+    with torch.no_grad():
+        out = m(batch)
+    assert out.shape == gold["eval_out"].shape and out.dtype == torch.float32
+    _close(out, gold["eval_out"], "eval_out vs fp32 reference")
+    _close(out, gold["eval_out_fp64"].float(), "eval_out vs fp64 twin")
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_train_step_matches_reference(name):
+    gold = torch.load(common.golden_path(name), weights_only=True)
+    m = _model(gold["meta"]["model_kwargs"]).train()
+    batch = common.GraphBatch(**gold["inputs"]).to(DEV)
+    m._inject_dropout_masks = common.dropout_masks(name, batch.num_nodes)
+    out = m(batch)
+    loss = torch.nn.functional.mse_loss(out, batch.y)
+    loss.backward()
+    _close(out, gold["train_out"], "train_out")
+    assert abs(float(loss) - float(gold["train_loss"])) < TOL * abs(float(gold["train_loss"]))
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        if "grads" in gold:
+            _close(p.grad, gold["grads"][k], k)
+        else:
+            nrm = float(gold["grad_norm"][k])
+            assert abs(float(p.grad.double().norm()) - nrm) < TOL * nrm + 1e-12, k
+            flat = p.grad.reshape(-1).cpu()
+            step = max(1, flat.numel() // 257)
+            s = flat[::step][:257]
+            assert float((s - gold["grad_sample"][k]).abs().max()) < TOL * float(gold["grad_absmax"][k]) + 1e-12, k
+
+
+def test_fused_mse_step_equals_autograd_step():
+    from poweflownet_b200.training import fused_mse_step
+    name = "case118_h33"
+    gold = torch.load(common.golden_path(name), weights_only=True)
+    m = _model(gold["meta"]["model_kwargs"]).train()
+    batch = common.GraphBatch(**gold["inputs"]).to(DEV)
+    m._inject_dropout_masks = common.dropout_masks(name, batch.num_nodes)
+    loss = fused_mse_step(m, batch)
+    assert abs(float(loss) - float(gold["train_loss"])) < TOL * abs(float(gold["train_loss"]))
+    for k, p in m.named_parameters():
+        _close(p.grad, gold["grads"][k], k)
+
+
+@pytest.mark.parametrize("case,b,cfg", [("118v2", 128, dict(hidden_dim=129, n_gnn_layers=4, K=3, dropout_rate=0.2)),
+                                        ("6470rte", 2, dict(hidden_dim=64, n_gnn_layers=3, K=3, dropout_rate=0.2))])
+def test_full_size_against_oracle(case, b, cfg):
+    """BASELINE configs[1] (case118v2, batch 128, standard.json) forward+backward vs the CPU oracle, dropout off
+    (p=0 in train mode exercises the train path deterministically), plus a 6470-bus large-graph case."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS)
+    kw.update(cfg)
+    kw["dropout_rate"] = 0.0
+    batch = synthetic_batch(case, b)
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
+    loss_ref, out_ref = O.forward_loss_backward(oracle, batch, "mse")
+    m = _model(kw, oracle.state_dict()).train()
+    dbatch = batch.to(DEV)
+    out = m(dbatch)
+    loss = torch.nn.functional.mse_loss(out, dbatch.y)
+    loss.backward()
+    _close(out, out_ref, "out")
+    assert abs(float(loss) - float(loss_ref)) < TOL * float(loss_ref)
+    for (k, p), (_, q) in zip(m.named_parameters(), oracle.named_parameters()):
+        _close(p.grad, q.grad, k)
+
+
+def test_masked_l2_loss_through_autograd():
+    """Parser-default loss (utils/custom_loss_functions.py:10-46) composed in torch on top of the CUDA model."""
+    name = "mixed"
+    gold = torch.load(common.golden_path(name), weights_only=True)
+    kw = gold["meta"]["model_kwargs"]
+    batch = common.GraphBatch(**gold["inputs"])
+    masks = common.dropout_masks(name, batch.num_nodes)
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
+    O.forward_loss_backward(oracle, batch, "masked_l2", dropout_masks=masks)
+    m = _model(kw).train()
+    m._inject_dropout_masks = masks
+    db = batch.to(DEV)
+    O.masked_l2_loss(m(db), db.y, db.pred_mask).backward()
+    for (k, p), (_, q) in zip(m.named_parameters(), oracle.named_parameters()):
+        _close(p.grad, q.grad, k)
+
+
+def test_standalone_layers_match_oracle_layers():
+    from poweflownet_b200.networks.MPN import EdgeAggregation, TAGConv
+    batch = common.make_batch("mixed")
+    ei, ea = O.undirect_graph(batch.edge_index, batch.edge_attr)
+    n = batch.num_nodes
+    g = torch.Generator().manual_seed(0)
+    for fin, h, fout in ((4, 33, 33), (33, 33, 4), (129, 129, 129)):
+        x = torch.randn(n, fin, generator=g)
+        ref = O.EdgeAggregation(fin, 2, h, fout)
+        mine = EdgeAggregation(fin, 2, h, fout)
+        mine.load_state_dict(ref.state_dict())
+        mine = mine.to(DEV)
+        xr, xm = x.clone().requires_grad_(True), x.clone().to(DEV).requires_grad_(True)
+        yr, ym = ref(xr, ei, ea), mine(xm, ei.to(DEV), ea.to(DEV))
+        _close(ym, yr.detach(), f"EA {fin}->{fout}")
+        w = torch.randn(yr.shape, generator=g)
+        (yr * w).sum().backward()
+        (ym * w.to(DEV)).sum().backward()
+        _close(xm.grad, xr.grad, "EA dx")
+        for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+            _close(p.grad, q.grad, f"EA {k}")
+    for fin, fout, K in ((33, 33, 3), (16, 7, 2), (129, 129, 3)):
+        x = torch.randn(n, fin, generator=g)
+        ref = O.TAGConv(fin, fout, K)
+        with torch.no_grad():
+            ref.bias.uniform_(-0.5, 0.5)
+        mine = TAGConv(fin, fout, K)
+        mine.load_state_dict(ref.state_dict())
+        mine = mine.to(DEV)
+        xr, xm = x.clone().requires_grad_(True), x.clone().to(DEV).requires_grad_(True)
+        yr, ym = ref(xr, ei), mine(xm, ei.to(DEV))
+        _close(ym, yr.detach(), f"TAG {fin}->{fout}")
+        w = torch.randn(yr.shape, generator=g)
+        (yr * w).sum().backward()
+        (ym * w.to(DEV)).sum().backward()
+        _close(xm.grad, xr.grad, "TAG dx")
+        for (k, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
+            _close(p.grad, q.grad, f"TAG {k}")
+
+
+def test_train_mode_dropout_is_seeded_and_eval_is_deterministic():
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=129, n_gnn_layers=4, K=3, dropout_rate=0.2)
+    m = _model(kw)
+    batch = synthetic_batch("118v2", 8).to(DEV)
+    m.train()
+    torch.manual_seed(5)
+    a = m(batch).detach().clone()
+    torch.manual_seed(5)
+    b = m(batch).detach().clone()
+    c = m(batch).detach().clone()
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(batch).clone(), m(batch).clone()
+    assert torch.equal(e1, e2) and not torch.equal(e1, a)
+    # expectation of the dropout output stays near the eval output (inverted dropout): loose statistical check
+    m.train()
+    with torch.no_grad():
+        mean = torch.stack([m(batch) for _ in range(64)]).mean(0)
+    assert float((mean - e1).norm() / e1.norm()) < 0.5
+
+
+def test_backward_twice_is_rejected_and_input_grad_flows():
+    batch = common.make_batch("tiny").to(DEV)
+    m = _model(common.model_kwargs("tiny")).eval()
+    x = batch.x.clone().requires_grad_(True)
+    batch.x = x
+    out = m(batch)
+    out.sum().backward(retain_graph=True)
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**common.model_kwargs("tiny"))).eval()
+    cb = common.make_batch("tiny")
+    cb.x = cb.x.clone().requires_grad_(True)
+    oracle(cb).sum().backward()
+    _close(x.grad, cb.x.grad, "d out / d x")
+    with pytest.raises(RuntimeError):
+        out.sum().backward()
+
+
+def test_cpu_tensors_are_refused_loudly():
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    m = MaskEmbdMultiMPN(**common.model_kwargs("tiny"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(common.make_batch("tiny"))

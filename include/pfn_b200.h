@@ -46,6 +46,20 @@ PFN_API const char* pfn_last_error(void);
 /* number of kernels this library has launched on the calling process since load (bench "gpu_launches") */
 PFN_API uint64_t pfn_launch_count(void);
 
+/* ---- in-library kernel timing (bench.py's roofline figure): while enabled, every launch site brackets its
+ *      kernel(s) with CUDA events on the launching stream; pfn_profile_read synchronises on the recorded
+ *      events and returns the summed device time and the number of launches of one category. ----------- */
+#define PFN_PROF_EA_FWD 0     /* fused EdgeAggregation message+aggregate forward kernel */
+#define PFN_PROF_EA_BWD 1     /* its backward (both passes + the dWe reduction)          */
+#define PFN_PROF_HOP 2        /* TAGConv hop (forward and transposed)                    */
+#define PFN_PROF_GEMM_FWD 3   /* dense Linear forward                                    */
+#define PFN_PROF_GEMM_DGRAD 4 /* dense Linear data gradient                              */
+#define PFN_PROF_GEMM_WGRAD 5 /* dense Linear weight gradient (incl. split-K reduction)  */
+#define PFN_PROF_PREP 6       /* graph preparation (all passes)                          */
+#define PFN_PROF_CATEGORIES 7
+PFN_API int pfn_profile_enable(int on);
+PFN_API int pfn_profile_read(int category, double* total_ms, int64_t* launches);
+
 /* ---- graph preparation: networks/MPN.py:498-523 (is_directed / undirect_graph) + the CSR the
  *      message passing needs (PyG MessagePassing.propagate gathers, `degree`, `gcn_norm`) ---------- */
 typedef struct pfn_graph_layout {

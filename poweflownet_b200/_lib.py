@@ -35,6 +35,8 @@ SIGNATURES = {
     "pfn_version": (C.c_char_p, []),
     "pfn_last_error": (C.c_char_p, []),
     "pfn_launch_count": (c_u64, []),
+    "pfn_profile_enable": (C.c_int, [C.c_int]),
+    "pfn_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(c_i64)]),
     "pfn_graph_layout_get": (C.c_int, [c_i64, c_i64, C.POINTER(GraphLayout)]),
     "pfn_graph_prep": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p, C.c_void_p]),
     "pfn_graph_meta": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),

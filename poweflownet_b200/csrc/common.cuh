@@ -41,6 +41,14 @@ int sm_count();
     if (pfn_rc_ != 0) return pfn_rc_;    \
   } while (0)
 
+// RAII bracket used by the launch sites; a no-op unless pfn_profile_enable(1) was called.
+struct ProfScope {
+  int slot;
+  cudaStream_t stream;
+  ProfScope(int category, cudaStream_t s);
+  ~ProfScope();
+};
+
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up64(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -254,6 +254,7 @@ int ea_fwd_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView
   PFN_REQUIRE(h > 0 && ldh >= round_up64(h, 4) && lds >= round_up64(h, 4), PFN_E_INVALID, "ea_fwd: ld < round_up(h,4)");
   if (n_nodes == 0) return 0;
   const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
+  ProfScope prof(PFN_PROF_EA_FWD, stream);
   k_ea_fwd<<<t.nblocks, t.threads, 0, stream>>>(Hi, Hj, ldh, g.rowptr_t, g.nbr_t, reinterpret_cast<const float2*>(g.ea_t),
                                                We, ldwe, S, lds, static_cast<int>(n_nodes), static_cast<int>(h), t.c4,
                                                t.cx, t.rows, t.npb);
@@ -270,6 +271,7 @@ int ea_bwd_launch(const float* dS, int64_t ldds, const float* Hi, const float* H
   const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
   float* partial = static_cast<float*>(scratch);
   int nblocks = 0;
+  ProfScope prof(PFN_PROF_EA_BWD, stream);
   if (n_nodes > 0) {
     nblocks = t.nblocks;
     dim3 grid(t.nblocks, 2);
@@ -293,6 +295,7 @@ int hop_launch(const float* X, int64_t ldx, const GraphView& g, int64_t n_nodes,
   PFN_REQUIRE(ymask == nullptr || rows_ok(ymask, ldym), PFN_E_INVALID, "hop: ymask misaligned");
   if (n_nodes == 0) return 0;
   const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
+  ProfScope prof(PFN_PROF_HOP, stream);
   k_hop<<<t.nblocks, t.threads, 0, stream>>>(X, ldx, transpose ? g.rowptr_s : g.rowptr_t, transpose ? g.nbr_s : g.nbr_t,
                                             g.dis, addend, ldadd, ymask, ldym, scale, Y, ldy, static_cast<int>(n_nodes),
                                             t.c4, t.cx, t.rows, t.npb);

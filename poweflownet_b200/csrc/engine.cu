@@ -45,6 +45,37 @@ int sm_count() {
   return cached;
 }
 
+// ---- optional kernel timing ------------------------------------------------------------------------
+namespace {
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // 2 per slot
+  std::vector<int> cat;
+  size_t used = 0;
+};
+ProfState g_prof;
+constexpr size_t kProfMaxSlots = 1 << 16;
+}  // namespace
+
+ProfScope::ProfScope(int category, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_prof.on || g_prof.used >= kProfMaxSlots) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  if (g_prof.used * 2 >= g_prof.ev.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    g_prof.ev.push_back(a);
+    g_prof.ev.push_back(b);
+    g_prof.cat.push_back(category);
+  }
+  slot = static_cast<int>(g_prof.used++);
+  g_prof.cat[slot] = category;
+  cudaEventRecord(g_prof.ev[2 * slot], s);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
+}
+
 namespace {
 
 // ---- small elementwise kernels -------------------------------------------------------------------
@@ -494,6 +525,30 @@ using namespace pfn;
 extern "C" const char* pfn_version(void) { return "pfn_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* pfn_last_error(void) { return g_error; }
 extern "C" uint64_t pfn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int pfn_profile_enable(int on) {
+  g_prof.on = on != 0;
+  if (on) g_prof.used = 0;
+  return 0;
+}
+
+extern "C" int pfn_profile_read(int category, double* total_ms, int64_t* launches) {
+  PFN_REQUIRE(total_ms && launches && category >= 0 && category < PFN_PROF_CATEGORIES, PFN_E_INVALID,
+              "pfn_profile_read: bad arguments");
+  double total = 0.0;
+  int64_t n = 0;
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    if (g_prof.cat[i] != category) continue;
+    PFN_CUDA_OK(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+    float ms = 0.f;
+    PFN_CUDA_OK(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    total += ms;
+    ++n;
+  }
+  *total_ms = total;
+  *launches = n;
+  return 0;
+}
 
 extern "C" int pfn_mpn_num_params(const pfn_mpn_desc* desc) {
   Plan p;

@@ -246,6 +246,7 @@ int gemm_launch(const GemmArgs& args, bool a_kcontig, bool b_kcontig, cudaStream
   const int count = args.batched ? args.n_items : 1;
   dim3 grid(static_cast<unsigned>(ceil_div64(n_eff, 16 * tn)), static_cast<unsigned>(ceil_div64(args.M, 16 * tm)),
             static_cast<unsigned>(count * std::max(args.splitk, 1)));
+  ProfScope prof(a_kcontig ? (b_kcontig ? PFN_PROF_GEMM_FWD : PFN_PROF_GEMM_DGRAD) : PFN_PROF_GEMM_WGRAD, stream);
   int rc;
   if (a_kcontig && b_kcontig) {
     rc = launch_tn<8, true, true>(tn, args, grid, stream);

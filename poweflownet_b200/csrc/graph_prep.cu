@@ -218,6 +218,7 @@ extern "C" int pfn_graph_prep(const int64_t* edge_index, int64_t ei_row_stride, 
   PFN_TRY(pfn_graph_layout_get(n_nodes, e_raw, &lay));
   GraphView g = graph_view(graph_ws, n_nodes, e_raw);
   const int N = static_cast<int>(n_nodes), ER = static_cast<int>(e_raw);
+  ProfScope prof(PFN_PROF_PREP, stream);
   // meta + cursors start from zero
   PFN_CUDA_OK(cudaMemsetAsync(g.meta, 0, 8 * sizeof(int32_t), stream));
   if (N > 0) PFN_CUDA_OK(cudaMemsetAsync(g.cursor, 0, size_t(2) * N * sizeof(int32_t), stream));

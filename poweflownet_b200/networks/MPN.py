@@ -81,7 +81,7 @@ class _MPNFunction(torch.autograd.Function):
         dev = ops.require_cuda(x, pred_mask, edge_index, edge_attr, *params)
         n = int(x.size(0))
         training = bool(model.training)
-        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x.requires_grad)
+        needs_grad = any(ctx.needs_input_grad)  # (grad mode is off inside Function.forward; this is set by apply)
         with torch.cuda.device(dev):
             x = x.contiguous().float()
             pred_mask = pred_mask.contiguous()

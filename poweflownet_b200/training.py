@@ -10,14 +10,13 @@ Any other loss goes through `model(data)` + torch autograd as in the reference.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional, Tuple
 
 import torch
 
 from . import ops
 from ._lib import check, lib
-from .networks.MPN import MaskEmbdMultiMPN, _MPNFunction
+from .networks.MPN import MaskEmbdMultiMPN
 
 
 def mse_loss_and_grad(out: torch.Tensor, y: torch.Tensor, total_count: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:

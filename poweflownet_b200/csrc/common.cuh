@@ -127,8 +127,10 @@ struct GemmArgs {
   int splitk;
   int kchunk;
   float* partial;
+  size_t partial_bytes;    // capacity of `partial` (the tensor-core weight-gradient path picks its own split count)
   int extra_col;           // 0 none, 1 B gets a virtual extra column of ones, 2 extra column = extra_vec[k]
   const float* extra_vec;
+  int prof_cat;            // PFN_PROF_* + 1 to attribute the launch to, 0 = derive from the operand layout
 };
 
 constexpr int kActMaskByY = 3;
@@ -137,6 +139,19 @@ int gemm_launch(const GemmArgs& args, bool a_kcontig, bool b_kcontig, cudaStream
 size_t gemm_splitk_scratch_bytes(int64_t M, int64_t N, int64_t K, int count);
 // fills splitk/kchunk for a weight-gradient GEMM with reduction length K and `count` problems
 void gemm_plan_splitk(GemmArgs& args, int64_t K, int count);
+
+// ---- tensor-core path (gemm_tc.cu) ---------------------------------------------------------------
+// 0 = launched on tcgen05 ; 1 = shape/alignment outside that path, caller falls back to the FFMA kernel ; else error
+int gemm_tc_launch(const GemmArgs& args, cudaStream_t stream);
+int wgrad_tc_launch(GemmArgs& args, cudaStream_t stream);  // may rewrite args.splitk / args.kchunk
+bool tc_enabled();
+struct PackDesc {
+  const float* src;  // [rows, cols] with row pitch ld_src (a state_dict weight or a column block of one)
+  float* dst;        // [rows, ld_dst]   16-byte-pitched copy          (may be null)
+  float* dst_t;      // [cols, ld_dst_t] 16-byte-pitched transposed copy (may be null)
+  int ld_src, rows, cols, ld_dst, ld_dst_t;
+};
+int pack_weights_launch(const PackDesc* items, int n, cudaStream_t stream);
 
 // ---- hash-based dropout (shared by gemm.cu epilogue) ------------------------------------------
 __host__ __device__ inline uint32_t lowbias32(uint32_t x) {

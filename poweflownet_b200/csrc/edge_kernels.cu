@@ -185,15 +185,18 @@ k_ea_bwd(const float* __restrict__ dS, int64_t ldds, const float* __restrict__ H
   }
 }
 
-// dWe[c, k] = sum over CTAs of the partial rows, in CTA order (deterministic)
+// dWe[c, k] = sum over CTAs of the partial rows: one warp per output element, lanes stride over the CTAs and
+// combine with a fixed shuffle tree (deterministic; no atomics)
 __global__ void k_reduce_dwe(const float* __restrict__ partial, int nblocks, int c4, int h, float* __restrict__ dWe,
                              int64_t lddwe) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over 2 * h
-  if (idx >= 2 * h) return;
-  const int k = idx / h, c = idx - k * h;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= 2 * h) return;
+  const int k = warp / h, c = warp - k * h;
   float sum = 0.f;
-  for (int b = 0; b < nblocks; ++b) sum += partial[size_t(b) * (8 * c4) + k * 4 * c4 + c];
-  dWe[c * lddwe + k] = sum;
+  for (int b = lane; b < nblocks; b += 32) sum += partial[size_t(b) * (8 * c4) + k * 4 * c4 + c];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (lane == 0) dWe[c * lddwe + k] = sum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -281,7 +284,7 @@ int ea_bwd_launch(const float* dS, int64_t ldds, const float* Hi, const float* H
                                             static_cast<int>(n_nodes), static_cast<int>(h), t.c4, t.cx, t.rows, t.npb);
     PFN_LAUNCHED();
   }
-  k_reduce_dwe<<<static_cast<int>(ceil_div64(2 * h, 128)), 128, 0, stream>>>(partial, nblocks, t.c4, static_cast<int>(h),
+  k_reduce_dwe<<<static_cast<int>(ceil_div64(2 * h * 32, 256)), 256, 0, stream>>>(partial, nblocks, t.c4, static_cast<int>(h),
                                                                            dWe, lddwe);
   PFN_LAUNCHED();
   return 0;

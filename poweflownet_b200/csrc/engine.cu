@@ -141,6 +141,12 @@ struct Plan {
   // scratch offsets (floats)
   int64_t off_dz = 0, off_ds = 0, off_dhi = 0, off_dhj = 0, off_dxcat = 0, off_dx0 = 0, off_part = 0, scratch_floats = 0;
   int64_t part_bytes = 0;
+  // 16-byte-pitched (and transposed) weight copies for the TMA-fed tensor-core GEMMs; offsets in floats into act_ws
+  struct EaPack { int64_t wi, wj, w2, wiT, wjT, w2T; };
+  struct TagPack { int64_t w[kGemmMaxItems], wT[kGemmMaxItems]; };
+  std::vector<EaPack> ea_pack;
+  std::vector<TagPack> tag_pack;
+  int64_t mask_w1 = 0, mask_w2 = 0, mask_w2T = 0;
 
   int64_t ea_stride() const { return 3 * N * ldh; }                       // Hi, Hj, S
   int64_t xcat_ld() const { return int64_t(d.K + 1) * ldh; }
@@ -194,6 +200,31 @@ int make_plan(const pfn_mpn_desc* desc, int64_t n_nodes, Plan& p) {
   p.off_x0 = take(n_nodes * d.nfeature_dim);
   p.off_ea = take(p.n_ea * p.ea_stride());
   p.off_tag = take(p.n_tag * p.tag_stride());
+  auto ld4 = [](int v) { return round_up64(v, 4); };
+  p.ea_pack.clear();
+  p.tag_pack.clear();
+  for (const LayerPlan& L : p.layers) {
+    if (L.is_ea) {
+      Plan::EaPack e;
+      e.wi = take(h * ld4(L.fin));
+      e.wj = take(h * ld4(L.fin));
+      e.w2 = take(L.fout * ld4(h));
+      e.wiT = take(L.fin * ld4(h));
+      e.wjT = take(L.fin * ld4(h));
+      e.w2T = take(h * ld4(L.fout));
+      p.ea_pack.push_back(e);
+    } else {
+      Plan::TagPack t{};
+      for (int k = 0; k <= d.K; ++k) {
+        t.w[k] = take(L.fout * ld4(L.fin));
+        t.wT[k] = take(L.fin * ld4(L.fout));
+      }
+      p.tag_pack.push_back(t);
+    }
+  }
+  p.mask_w1 = take(h * ld4(d.nfeature_dim));
+  p.mask_w2 = take(d.nfeature_dim * ld4(h));
+  p.mask_w2T = take(h * ld4(d.nfeature_dim));
   p.act_floats = off;
   // scratch
   off = 0;
@@ -248,9 +279,6 @@ inline GemmItem fwd_item(const float* X, int64_t ldx, const float* W, int64_t ld
                          const float* bias) {
   return GemmItem{X, W, C, bias, nullptr, ldx, 1, 1, ldw, K, static_cast<int>(ldc)};
 }
-inline GemmItem dgrad_item(const float* dY, int64_t lddy, const float* W, int64_t ldw, int K, float* C, int64_t ldc) {
-  return GemmItem{dY, W, C, nullptr, nullptr, lddy, 1, ldw, 1, K, static_cast<int>(ldc)};
-}
 inline GemmItem wgrad_item(const float* dY, int64_t lddy, const float* X, int64_t ldx, int K, float* dW, int64_t lddw,
                            float* dbias) {
   return GemmItem{dY, X, dW, nullptr, dbias, 1, lddy, ldx, 1, K, static_cast<int>(lddw)};
@@ -285,6 +313,30 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
   float* maskf = c.act + p.off_maskf;
   float* t1 = c.act + p.off_t1;
   float* x0 = c.act + p.off_x0;
+  const int ld_h = static_cast<int>(ldh), ld_nf = static_cast<int>(round_up64(nf, 4));
+  // one launch: copy every weight into 16-byte-pitched K-major buffers (+ transposes for the data gradients)
+  {
+    std::vector<PackDesc> packs;
+    for (const LayerPlan& L : p.layers) {
+      const float* const* lp = c.params + L.p0;
+      const int ld_fin = static_cast<int>(round_up64(L.fin, 4)), ld_fout = static_cast<int>(round_up64(L.fout, 4));
+      if (L.is_ea) {
+        const Plan::EaPack& e = p.ea_pack[L.slot];
+        const int ldw1 = 2 * L.fin + 2;
+        packs.push_back(PackDesc{lp[0], c.act + e.wi, c.act + e.wiT, ldw1, h, L.fin, ld_fin, ld_h});
+        packs.push_back(PackDesc{lp[0] + L.fin, c.act + e.wj, c.act + e.wjT, ldw1, h, L.fin, ld_fin, ld_h});
+        packs.push_back(PackDesc{lp[2], c.act + e.w2, c.act + e.w2T, h, L.fout, h, ld_h, ld_fout});
+      } else {
+        const Plan::TagPack& t = p.tag_pack[L.slot];
+        for (int k = 0; k <= d.K; ++k)
+          packs.push_back(PackDesc{lp[k], c.act + t.w[k], c.act + t.wT[k], L.fin, L.fout, L.fin, ld_fin, ld_fout});
+      }
+    }
+    const float* const* mp = c.params + p.p_mask;
+    packs.push_back(PackDesc{mp[0], c.act + p.mask_w1, nullptr, nf, h, nf, ld_nf, 0});
+    packs.push_back(PackDesc{mp[2], c.act + p.mask_w2, c.act + p.mask_w2T, h, nf, h, ld_h, ld_nf});
+    PFN_TRY(pack_weights_launch(packs.data(), static_cast<int>(packs.size()), c.stream));
+  }
   // mask_embd (MPN.py:533,537): x0 = Linear(ReLU(Linear(mask.float()))) + x
   {
     const int64_t n = int64_t(N) * nf;
@@ -292,11 +344,11 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
     PFN_LAUNCHED();
     const float* const* mp = c.params + p.p_mask;
     GemmArgs a = base_args(N, h);
-    a.it[0] = fwd_item(maskf, nf, mp[0], nf, nf, t1, ldh, mp[1]);
+    a.it[0] = fwd_item(maskf, nf, c.act + p.mask_w1, ld_nf, nf, t1, ldh, mp[1]);
     a.act = PFN_ACT_RELU;
     PFN_TRY(gemm_launch(a, true, true, c.stream));
     GemmArgs b = base_args(N, nf);
-    b.it[0] = fwd_item(t1, ldh, mp[2], h, h, x0, nf, mp[3]);
+    b.it[0] = fwd_item(t1, ldh, c.act + p.mask_w2, ld_h, h, x0, nf, mp[3]);
     b.addend = x;
     b.ld_add = nf;
     PFN_TRY(gemm_launch(b, true, true, c.stream));
@@ -309,14 +361,16 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
     const float* const* lp = c.params + L.p0;
     const bool last = li == n_layers - 1;
     const float* inj = (inj_masks != nullptr && L.act) ? inj_masks[li] : nullptr;
+    const int ld_fin = static_cast<int>(round_up64(L.fin, 4));
     if (L.is_ea) {
       const int ldw1 = 2 * L.fin + 2;
+      const Plan::EaPack& pk = p.ea_pack[L.slot];
       // Hi = cur Wi^T + b1 ; Hj = cur Wj^T   (one launch, two problems)
       GemmArgs a = base_args(N, h);
       a.n_items = 2;
       a.batched = 1;
-      a.it[0] = fwd_item(cur, ldcur, lp[0], ldw1, L.fin, c.hi(L.slot), ldh, lp[1]);
-      a.it[1] = fwd_item(cur, ldcur, lp[0] + L.fin, ldw1, L.fin, c.hj(L.slot), ldh, nullptr);
+      a.it[0] = fwd_item(cur, ldcur, c.act + pk.wi, ld_fin, L.fin, c.hi(L.slot), ldh, lp[1]);
+      a.it[1] = fwd_item(cur, ldcur, c.act + pk.wj, ld_fin, L.fin, c.hj(L.slot), ldh, nullptr);
       PFN_TRY(gemm_launch(a, true, true, c.stream));
       PFN_TRY(ea_fwd_launch(c.hi(L.slot), c.hj(L.slot), ldh, c.g, N, lp[0] + 2 * L.fin, ldw1, c.s(L.slot), ldh, h,
                             c.stream));
@@ -331,7 +385,7 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
         lddest = p.xcat_ld();
       }
       GemmArgs b = base_args(N, L.fout);
-      b.it[0] = fwd_item(c.s(L.slot), ldh, lp[2], h, h, dest, lddest, lp[3]);
+      b.it[0] = fwd_item(c.s(L.slot), ldh, c.act + pk.w2, ld_h, h, dest, lddest, lp[3]);
       b.rowscale = c.g.deg;
       set_activation(b, c, L.act, li, seed, inj, h);
       PFN_TRY(gemm_launch(b, true, true, c.stream));
@@ -347,7 +401,9 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
       const int64_t lddest = last ? L.fout : ldh;
       GemmArgs a = base_args(N, L.fout);
       a.n_items = d.K + 1;
-      for (int k = 0; k <= d.K; ++k) a.it[k] = fwd_item(xc + k * ldh, ldx, lp[k], L.fin, L.fin, dest, lddest, lp[d.K + 1]);
+      const Plan::TagPack& tk = p.tag_pack[L.slot];
+      for (int k = 0; k <= d.K; ++k)
+        a.it[k] = fwd_item(xc + k * ldh, ldx, c.act + tk.w[k], ld_fin, L.fin, dest, lddest, lp[d.K + 1]);
       set_activation(a, c, L.act, li, seed, inj, h);
       PFN_TRY(gemm_launch(a, true, true, c.stream));
       cur = dest;
@@ -401,14 +457,17 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         a.extra_col = 2;
         a.extra_vec = c.g.deg;
         a.partial = part;
+        a.partial_bytes = static_cast<size_t>(p.part_bytes);
         gemm_plan_splitk(a, N, 1);
         PFN_TRY(gemm_launch(a, false, false, c.stream));
       }
-      // dS = G W2
+      // dS = G W2   (as G (W2^T)^T with the packed transpose: both operands K-major)
+      const Plan::EaPack& pk = p.ea_pack[L.slot];
       {
         GemmArgs a = base_args(N, h);
-        a.it[0] = dgrad_item(G, ldG, lp[2], h, L.fout, ds, ldh);
-        PFN_TRY(gemm_launch(a, true, false, c.stream));
+        a.it[0] = fwd_item(G, ldG, c.act + pk.w2T, round_up64(L.fout, 4), L.fout, ds, ldh, nullptr);
+        a.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
+        PFN_TRY(gemm_launch(a, true, true, c.stream));
       }
       // dHi, dHj, dWe
       PFN_TRY(ea_bwd_launch(ds, ldh, c.hi(L.slot), c.hj(L.slot), ldh, c.g, N, lp[0] + 2 * L.fin, ldw1, dhi, dhj, ldh,
@@ -422,6 +481,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         a.it[1] = wgrad_item(dhj, ldh, cur, ldcur, N, lg[0] + L.fin, ldw1, nullptr);
         a.extra_col = 1;
         a.partial = part;
+        a.partial_bytes = static_cast<size_t>(p.part_bytes);
         gemm_plan_splitk(a, N, 2);
         PFN_TRY(gemm_launch(a, false, false, c.stream));
       }
@@ -431,15 +491,16 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         const int64_t lddest = li == 0 ? nf : ldh;
         GemmArgs a = base_args(N, L.fin);
         a.n_items = 2;
-        a.it[0] = dgrad_item(dhi, ldh, lp[0], ldw1, h, dest, lddest);
-        a.it[1] = dgrad_item(dhj, ldh, lp[0] + L.fin, ldw1, h, dest, lddest);
+        a.it[0] = fwd_item(dhi, ldh, c.act + pk.wiT, ldh, h, dest, lddest, nullptr);
+        a.it[1] = fwd_item(dhj, ldh, c.act + pk.wjT, ldh, h, dest, lddest, nullptr);
+        a.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
         if (cur_has_act) {
           a.act = kActMaskByY;
           a.ymask = cur;
           a.ld_ym = static_cast<int>(ldcur);
           a.scale = c.scale;
         }
-        PFN_TRY(gemm_launch(a, true, false, c.stream));
+        PFN_TRY(gemm_launch(a, true, true, c.stream));
         G = dest;
         ldG = lddest;
       }
@@ -455,6 +516,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
           a.it[k] = wgrad_item(G, ldG, xc + k * ldh, ldx, N, lg[k], L.fin, k == 0 ? lg[d.K + 1] : nullptr);
         a.extra_col = 1;
         a.partial = part;
+        a.partial_bytes = static_cast<size_t>(p.part_bytes);
         gemm_plan_splitk(a, N, d.K + 1);
         PFN_TRY(gemm_launch(a, false, false, c.stream));
       }
@@ -464,14 +526,17 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         GemmArgs a = base_args(N, L.fin);
         a.n_items = d.K + 1;
         a.batched = 1;
-        for (int k = 0; k <= d.K; ++k) a.it[k] = dgrad_item(G, ldG, lp[k], L.fin, L.fout, dxcat + k * ldh, ldx);
+        const Plan::TagPack& tk = p.tag_pack[L.slot];
+        for (int k = 0; k <= d.K; ++k)
+          a.it[k] = fwd_item(G, ldG, c.act + tk.wT[k], round_up64(L.fout, 4), L.fout, dxcat + k * ldh, ldx, nullptr);
+        a.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
         if (d.K == 0) {
           a.act = kActMaskByY;
           a.ymask = xc;
           a.ld_ym = static_cast<int>(ldx);
           a.scale = c.scale;
         }
-        PFN_TRY(gemm_launch(a, true, false, c.stream));
+        PFN_TRY(gemm_launch(a, true, true, c.stream));
       }
       for (int k = d.K; k >= 1; --k) {
         const bool final_hop = k == 1;
@@ -484,7 +549,6 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
   }
   // mask_embd backward: x0 = W2m relu(W1m mask + b1m) + b2m + x
   {
-    const float* const* mp = c.params + p.p_mask;
     float* const* mg = grads + p.p_mask;
     const float* maskf = c.act + p.off_maskf;
     const float* t1 = c.act + p.off_t1;
@@ -492,19 +556,22 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
     a.it[0] = wgrad_item(G, ldG, t1, ldh, N, mg[2], h, mg[3]);
     a.extra_col = 1;
     a.partial = part;
+        a.partial_bytes = static_cast<size_t>(p.part_bytes);
     gemm_plan_splitk(a, N, 1);
     PFN_TRY(gemm_launch(a, false, false, c.stream));
     GemmArgs b = base_args(N, h);
-    b.it[0] = dgrad_item(G, ldG, mp[2], h, nf, ds, ldh);
+    b.it[0] = fwd_item(G, ldG, c.act + p.mask_w2T, round_up64(nf, 4), nf, ds, ldh, nullptr);
+    b.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
     b.act = kActMaskByY;
     b.ymask = t1;
     b.ld_ym = static_cast<int>(ldh);
     b.scale = 1.f;
-    PFN_TRY(gemm_launch(b, true, false, c.stream));
+    PFN_TRY(gemm_launch(b, true, true, c.stream));
     GemmArgs w = base_args(h, nf);
     w.it[0] = wgrad_item(ds, ldh, maskf, nf, N, mg[0], nf, mg[1]);
     w.extra_col = 1;
     w.partial = part;
+    w.partial_bytes = static_cast<size_t>(p.part_bytes);
     gemm_plan_splitk(w, N, 1);
     PFN_TRY(gemm_launch(w, false, false, c.stream));
   }

@@ -221,6 +221,8 @@ size_t gemm_splitk_scratch_bytes(int64_t M, int64_t N, int64_t K, int count) {
     gemm_plan_splitk(tmp, K, count);
     worst = std::max(worst, size_t(tmp.splitk) * count * size_t(M) * size_t(N + extra) * sizeof(float));
   }
+  // the tensor-core weight-gradient path splits so that (splits x problems) <= SM count
+  worst = std::max(worst, size_t(sm_count()) * size_t(M) * size_t(N + 1) * sizeof(float));
   return worst;
 }
 
@@ -234,7 +236,8 @@ void gemm_plan_splitk(GemmArgs& args, int64_t K, int count) {
   args.splitk = static_cast<int>(std::max<int64_t>(1, ceil_div64(std::max<int64_t>(K, 1), kchunk)));
 }
 
-int gemm_launch(const GemmArgs& args, bool a_kcontig, bool b_kcontig, cudaStream_t stream) {
+int gemm_launch(const GemmArgs& args_in, bool a_kcontig, bool b_kcontig, cudaStream_t stream) {
+  GemmArgs args = args_in;
   PFN_REQUIRE(args.n_items >= 1 && args.n_items <= kGemmMaxItems, PFN_E_INVALID, "gemm: bad item count %d", args.n_items);
   PFN_REQUIRE(!(args.splitk > 1) || args.partial != nullptr, PFN_E_INVALID, "gemm: split-K without scratch");
   PFN_REQUIRE(!(args.splitk > 1) || args.batched || args.n_items == 1, PFN_E_INVALID, "gemm: split-K with K-segments");
@@ -246,8 +249,25 @@ int gemm_launch(const GemmArgs& args, bool a_kcontig, bool b_kcontig, cudaStream
   const int count = args.batched ? args.n_items : 1;
   dim3 grid(static_cast<unsigned>(ceil_div64(n_eff, 16 * tn)), static_cast<unsigned>(ceil_div64(args.M, 16 * tm)),
             static_cast<unsigned>(count * std::max(args.splitk, 1)));
-  ProfScope prof(a_kcontig ? (b_kcontig ? PFN_PROF_GEMM_FWD : PFN_PROF_GEMM_DGRAD) : PFN_PROF_GEMM_WGRAD, stream);
+  ProfScope prof(args.prof_cat > 0 ? args.prof_cat - 1
+                                   : (a_kcontig ? (b_kcontig ? PFN_PROF_GEMM_FWD : PFN_PROF_GEMM_DGRAD) : PFN_PROF_GEMM_WGRAD),
+                 stream);
   int rc;
+  if (a_kcontig && b_kcontig) {  // both operands K-major: tcgen05 path when the operands are TMA-addressable
+    rc = gemm_tc_launch(args, stream);
+    if (rc != 1) return rc;
+  }
+  if (!a_kcontig && !b_kcontig && args.partial != nullptr) {  // weight gradient: tcgen05 with MN-major operands
+    rc = wgrad_tc_launch(args, stream);
+    if (rc == 0) {
+      const size_t total = size_t(args.M) * n_eff * count;
+      const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, size_t(sm_count()) * 8));
+      k_splitk_reduce<<<blocks, 256, 0, stream>>>(args);
+      PFN_LAUNCHED();
+      return 0;
+    }
+    if (rc != 1) return rc;
+  }
   if (a_kcontig && b_kcontig) {
     rc = launch_tn<8, true, true>(tn, args, grid, stream);
   } else if (a_kcontig && !b_kcontig) {
@@ -340,6 +360,7 @@ extern "C" int pfn_linear_wgrad(const float* dY, int64_t lddy, const float* X, i
   a.extra_col = dbias != nullptr ? (rowscale != nullptr ? 2 : 1) : 0;
   a.extra_vec = rowscale;
   a.partial = static_cast<float*>(scratch);
+  a.partial_bytes = pfn_linear_wgrad_scratch_bytes(M, n_in, n_out);
   gemm_plan_splitk(a, M, 1);
   return gemm_launch(a, false, false, static_cast<cudaStream_t>(stream));
 }

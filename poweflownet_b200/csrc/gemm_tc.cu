@@ -1,0 +1,825 @@
+// Tensor-core path for the dense per-node Linear stacks: tcgen05.mma (kind::tf32) with TMEM accumulators,
+// operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle), fp32-grade accuracy through a
+// 3-term split-precision scheme ("3xTF32"):
+//
+//     a = a_hi + a_lo (+ r),  a_hi = rn_tf32(a) (low 13 mantissa bits clear: exactly representable in TF32),
+//                             a_lo = rn_tf32(a - a_hi);  |r| <= 2^-24 |a|
+//     A B^T  ~=  A_lo B_hi^T + A_hi B_lo^T + A_hi B_hi^T            (accumulated in fp32 in TMEM)
+//
+// which keeps the result within ~1e-6 relative of an fp32 GEMM -- inside the path's 1e-5 contract -- at a third
+// of the TF32 tensor rate instead of the FFMA rate.  The split is done ON CHIP: converter warps rewrite each
+// TMA-landed tile in shared memory as (hi, lo) in place; because the transform is elementwise, the 128B swizzle
+// pattern written by TMA and read by the UMMA descriptors is untouched.
+//
+// Shape: Y[M, N] (+)= sum over segments  A_seg[M, K_seg] * B_seg[N, K_seg]^T, both operands K-major (row-major
+// activations x row-major [out, in] weights): forward Linear directly, data gradients through transposed weight
+// copies (k_pack_weights).  CTA tile 128 x BN (BN = N rounded up to 16, <= 256), K tile 32 floats (= one 128B
+// swizzle row), one CTA per output tile, 6 warps:
+//     warp 0      TMA producer (one elected lane)          warp 1   tcgen05.mma issuer (one lane) + TMEM alloc
+//     warps 2..9  hi/lo converters, then epilogue (tcgen05.ld -> shared-memory tile -> float4 rows with bias /
+//                 row-scaled bias / residual / dropout+ReLU / backward mask -> global)
+// Pipelines: full[s] (TMA -> converters), conv[s] (converters -> MMA), empty[s] (MMA commit -> TMA), accum (MMA -> epilogue).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace pfn {
+namespace {
+
+constexpr int kTcBM = 128;
+constexpr int kTcBK = 32;            // floats per K tile = 128 bytes = one swizzle row
+constexpr int kTcWorkers = 256;          // 8 converter / epilogue warps
+constexpr int kTcThreads = 64 + kTcWorkers;  // + TMA producer warp + MMA issuer warp
+constexpr int kTcMaxStages = 4;
+constexpr uint32_t kSmemLimit = 227 * 1024;
+
+struct TcItem {
+  CUtensorMap a;  // [rows = M, cols = K]   box {32, 128}
+  CUtensorMap b;  // [rows = N, cols = K]   box {32, BN}
+  int K;
+  int pad_[15];
+};
+static_assert(sizeof(TcItem) % 64 == 0, "tensor maps must stay 64-byte aligned inside the parameter block");
+
+struct TcArgs {
+  TcItem it[kGemmMaxItems];
+  float* C[kGemmMaxItems];
+  const float* bias[kGemmMaxItems];
+  int n_items, batched, M, N, BN, ldc, stages, tmem_cols, n_hi, pad0_;
+  const float* rowscale;
+  const float* addend;
+  const float* ymask;
+  const float* inj;
+  int ld_add, ld_ym, ld_inj, act;
+  float scale;
+  uint32_t seed_lo, seed_hi, keep_thresh;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address, LBO (unused for swizzled
+// K-major, canonical value 1), SBO = 1024 B between 8-row groups, descriptor version 1, layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+  return uint64_t((saddr >> 4) & 0x3FFFu) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+
+// round-to-nearest TF32 (result has its low 13 mantissa bits clear => exact whatever the tensor core does with them)
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// rewrite a TMA-landed tile as (hi in place, lo at +lo_off); n_vec float4 elements, kTcWorkers converter threads
+__device__ __forceinline__ void split_tile(uint32_t hi_addr, uint32_t lo_off, int n_vec, int tid_c) {
+  for (int i = tid_c; i < n_vec; i += kTcWorkers) {
+    const uint32_t a = hi_addr + 16u * i;
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+    float4 l = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + lo_off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+  }
+}
+
+struct EpiCtx {
+  uint32_t tile, tile_ld;
+  int row0, m0, n0, ncols, ncols_vec, lane;
+  float* C;
+  const float* bias;
+};
+
+__device__ __forceinline__ float epi_apply(float x, int act, float ym, bool keep, float scale) {
+  if (act == PFN_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == PFN_ACT_DROPOUT_RELU) return keep ? fmaxf(x * scale, 0.f) : 0.f;
+  if (act == kActMaskByY) return ym > 0.f ? x * scale : 0.f;
+  return x;
+}
+
+// 16 rows of the staged tile -> global.  Columns [0, ncols_vec) go out as float4 (lane = 4 columns, 8 rows per batch with
+// every load issued before the first use); the remaining columns (alignment tail, or everything when a pointer is not
+// 16-byte aligned / a test keep-mask is injected) take the scalar path with lanes across columns.
+template <int ACT, bool ADD>
+__device__ __forceinline__ void epilogue_rows(const TcArgs& args, const EpiCtx& e) {
+  const int M = args.M;
+  float* __restrict__ const C = e.C;
+  const float* __restrict__ const bias = e.bias;
+  const float* __restrict__ const addend = args.addend;
+  const float* __restrict__ const ymask = args.ymask;
+  const float* __restrict__ const rowscale = args.rowscale;
+  const float scale = args.scale;
+  for (int cb = 0; cb < e.ncols_vec; cb += 128) {
+    const int c = cb + 4 * e.lane;
+    const bool cok = c < e.ncols_vec;
+    const int n = e.n0 + c;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias != nullptr && cok) b4 = make_float4(bias[n], bias[n + 1], bias[n + 2], bias[n + 3]);
+#pragma unroll
+    for (int rb = 0; rb < 16; rb += 8) {
+      float4 v[8], ad[8], ym[8];
+      float rs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = e.row0 + rb + i, m = e.m0 + row;
+        const bool ok = cok && m < M;
+        v[i] = ad[i] = ym[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cok)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                       : "r"(e.tile + (uint32_t(row) * e.tile_ld + uint32_t(c)) * 4u));
+        rs[i] = (rowscale != nullptr && m < M) ? rowscale[m] : 1.f;
+        if (ADD && ok) ad[i] = *reinterpret_cast<const float4*>(addend + size_t(m) * args.ld_add + n);
+        if (ACT == kActMaskByY && ok) ym[i] = *reinterpret_cast<const float4*>(ymask + size_t(m) * args.ld_ym + n);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = e.m0 + e.row0 + rb + i;
+        if (!(cok && m < M)) continue;
+        float4 o;
+        bool k0 = true, k1 = true, k2 = true, k3 = true;
+        if (ACT == PFN_ACT_DROPOUT_RELU) {
+          k0 = dropout_hash(m, n, args.seed_lo, args.seed_hi) >= args.keep_thresh;
+          k1 = dropout_hash(m, n + 1, args.seed_lo, args.seed_hi) >= args.keep_thresh;
+          k2 = dropout_hash(m, n + 2, args.seed_lo, args.seed_hi) >= args.keep_thresh;
+          k3 = dropout_hash(m, n + 3, args.seed_lo, args.seed_hi) >= args.keep_thresh;
+        }
+        o.x = epi_apply(fmaf(rs[i], b4.x, v[i].x) + ad[i].x, ACT, ym[i].x, k0, scale);
+        o.y = epi_apply(fmaf(rs[i], b4.y, v[i].y) + ad[i].y, ACT, ym[i].y, k1, scale);
+        o.z = epi_apply(fmaf(rs[i], b4.z, v[i].z) + ad[i].z, ACT, ym[i].z, k2, scale);
+        o.w = epi_apply(fmaf(rs[i], b4.w, v[i].w) + ad[i].w, ACT, ym[i].w, k3, scale);
+        *reinterpret_cast<float4*>(C + size_t(m) * args.ldc + n) = o;
+      }
+    }
+  }
+  // scalar columns [ncols_vec, ncols): lanes across columns, rows in sequence
+  const float* __restrict__ const inj = args.inj;
+  for (int c = e.ncols_vec + e.lane; c < e.ncols; c += 32) {
+    const int n = e.n0 + c;
+    const float bn = bias != nullptr ? bias[n] : 0.f;
+#pragma unroll 4
+    for (int r = 0; r < 16; ++r) {
+      const int row = e.row0 + r, m = e.m0 + row;
+      if (m >= M) break;
+      float v;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(e.tile + (uint32_t(row) * e.tile_ld + uint32_t(c)) * 4u));
+      float x = fmaf(rowscale != nullptr ? rowscale[m] : 1.f, bn, v);
+      if (ADD) x += addend[size_t(m) * args.ld_add + n];
+      bool keep = true;
+      float ym = 0.f;
+      if (ACT == PFN_ACT_DROPOUT_RELU)
+        keep = inj != nullptr ? inj[size_t(m) * args.ld_inj + n] != 0.f : dropout_hash(m, n, args.seed_lo, args.seed_hi) >= args.keep_thresh;
+      if (ACT == kActMaskByY) ym = ymask[size_t(m) * args.ld_ym + n];
+      C[size_t(m) * args.ldc + n] = epi_apply(x, ACT, ym, keep, scale);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant__ TcArgs args) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  const int BN = args.BN, S = args.stages;
+  const uint32_t a_bytes = kTcBM * 128u, b_bytes = uint32_t(BN) * 128u;
+  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);  // A_hi | A_lo | B_hi | B_lo
+  const uint32_t bar_base = base + uint32_t(S) * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (kTcMaxStages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kTcMaxStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * kTcMaxStages);
+  const uint32_t tmem_slot = accum_bar + 8u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * BN;
+  const int prob = blockIdx.z;
+  const int seg_begin = args.batched ? prob : 0, seg_end = args.batched ? prob + 1 : args.n_items;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), kTcWorkers / 32);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(uint32_t(args.tmem_cols)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int seg = seg_begin; seg < seg_end; ++seg) {
+        const TcItem& item = args.it[seg];
+        for (int k0 = 0; k0 < item.K; k0 += kTcBK, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes);
+          const uint32_t st = base + uint32_t(s) * stage_bytes;
+          tma_load_2d(st, &item.a, k0, m0, full_bar(s));
+          tma_load_2d(st + 2u * a_bytes, &item.b, k0, n0, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(kTcBM >> 4) << 24);
+    // The tensor core adds into its fp32 accumulator with truncation, so the error grows with the number of
+    // accumulating instructions.  The hi*hi products therefore rotate over n_hi accumulators and the (2^-11 smaller)
+    // lo terms go to their own accumulator; the epilogue adds them in round-to-nearest fp32.
+    const int n_hi = args.n_hi;
+    const uint32_t d_lo = tmem_base + uint32_t(n_hi * BN);
+    int it = 0, kk = 0;
+    for (int seg = seg_begin; seg < seg_end; ++seg) {
+      const int K = args.it[seg].K;
+      for (int k0 = 0; k0 < K; k0 += kTcBK, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(conv_bar(s), ph);
+        tc_fence_after();
+        const int nk = min(kTcBK / 8, (K - k0 + 7) / 8);  // 8 TF32 elements (32 bytes) per UMMA K step
+        if (lane == 0) {
+          const uint32_t st = base + uint32_t(s) * stage_bytes;
+          const uint64_t a_hi = umma_desc_k128(st), a_lo = umma_desc_k128(st + a_bytes);
+          const uint64_t b_hi = umma_desc_k128(st + 2u * a_bytes), b_lo = umma_desc_k128(st + 2u * a_bytes + b_bytes);
+          for (int j = 0; j < nk; ++j) {
+            const uint64_t adv = uint64_t(j * 2);  // +32 bytes in the 16-byte-granular start-address field
+            const int k_idx = kk + j;
+            const uint32_t d_hi = tmem_base + uint32_t((k_idx % n_hi) * BN);
+            umma_tf32(d_lo, a_lo + adv, b_hi + adv, idesc, k_idx > 0 ? 1u : 0u);
+            umma_tf32(d_lo, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, k_idx >= n_hi ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
+        }
+        kk += nk;
+        __syncwarp();
+      }
+    }
+    if (lane == 0) umma_commit(accum_bar);
+    __syncwarp();
+  } else {
+    // ===== converters (hi/lo split in shared memory), then epilogue =====
+    const int tid_c = threadIdx.x - 64;
+    int it = 0;
+    for (int seg = seg_begin; seg < seg_end; ++seg) {
+      const int K = args.it[seg].K;
+      for (int k0 = 0; k0 < K; k0 += kTcBK, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full_bar(s), ph);
+        const uint32_t st = base + uint32_t(s) * stage_bytes;
+        split_tile(st, a_bytes, kTcBM * 8, tid_c);
+        split_tile(st + 2u * a_bytes, b_bytes, BN * 8, tid_c);
+        proxy_fence_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(s));
+      }
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    // Epilogue.  The pipeline stages are free now (every MMA has completed), so the accumulator tile is staged through
+    // shared memory: phase 1, each warp drains its TMEM lane quarter (two warps per quarter, alternating 16-column
+    // chunks) and adds the accumulators in fp32; phase 2, the eight warps take 16 rows each and stream them out as
+    // float4 with all global loads of a row batch in flight together.
+    const int wk = warp - 2;                 // 0..7
+    const int q = warp & 3, half = wk >> 2;  // TMEM lane quarter this warp may read / which 16-column chunks it drains
+    const uint32_t tile_ld = uint32_t(BN) + 4u;  // floats; +4 keeps the 16-byte row-chunk stores conflict-free
+    const int ncols = min(BN, args.N - n0);
+    {
+      int total_k = 0;
+      for (int seg = seg_begin; seg < seg_end; ++seg) total_k += (args.it[seg].K + 7) / 8;
+      const int n_act = min(args.n_hi, total_k);  // hi accumulators that were actually written
+      const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
+      const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
+      for (int c0 = 16 * half; c0 < ncols; c0 += 32) {
+        uint32_t r[16];
+        float acc[16];
+        tmem_ld16(lane_base + uint32_t(args.n_hi * BN + c0), r);  // the small (lo) terms first
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
+        for (int a = 0; a < n_act; ++a) {
+          tmem_ld16(lane_base + uint32_t(a * BN + c0), r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + 4u * (c0 + i)), "f"(acc[i]), "f"(acc[i + 1]),
+                       "f"(acc[i + 2]), "f"(acc[i + 3]) : "memory");
+      }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
+    EpiCtx e;
+    e.tile = base;
+    e.tile_ld = tile_ld;
+    e.row0 = 16 * wk;
+    e.m0 = m0;
+    e.n0 = n0;
+    e.ncols = ncols;
+    e.lane = lane;
+    e.C = args.C[args.batched ? prob : 0];
+    e.bias = args.bias[args.batched ? prob : 0];
+    const bool vec = args.inj == nullptr && (args.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(e.C) & 15u) == 0 &&
+                     (args.addend == nullptr || ((args.ld_add & 3) == 0 && (reinterpret_cast<uintptr_t>(args.addend) & 15u) == 0)) &&
+                     (args.ymask == nullptr || ((args.ld_ym & 3) == 0 && (reinterpret_cast<uintptr_t>(args.ymask) & 15u) == 0));
+    e.ncols_vec = vec ? (ncols & ~3) : 0;
+    const bool add = args.addend != nullptr;
+    switch (args.act) {
+      case PFN_ACT_NONE: add ? epilogue_rows<PFN_ACT_NONE, true>(args, e) : epilogue_rows<PFN_ACT_NONE, false>(args, e); break;
+      case PFN_ACT_RELU: add ? epilogue_rows<PFN_ACT_RELU, true>(args, e) : epilogue_rows<PFN_ACT_RELU, false>(args, e); break;
+      case PFN_ACT_DROPOUT_RELU: epilogue_rows<PFN_ACT_DROPOUT_RELU, false>(args, e); break;
+      default: epilogue_rows<kActMaskByY, false>(args, e); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(args.tmem_cols)) : "memory");
+  }
+}
+
+// ---- weight gradient on the tensor cores ---------------------------------------------------------------
+// dW[Mo, Ni] = dY^T X = sum over nodes m of dY[m, :Mo]^T X[m, :Ni]: the reduction runs over the node dimension, so both
+// operands are "MN-major" for the tensor core (the M/N index is the contiguous one).  For TF32 the only MN-major
+// shared-memory layout the tensor core accepts is SWIZZLE_128B_BASE32B (128-byte rows whose 32-byte chunks are XORed with
+// row mod 4), which is what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: boxes of 32 nodes x 32 floats land as
+// atoms of 4 K-rows x 128 B, K-groups 512 B apart (SBO), 32-float M/N blocks one box (4096 B) apart (LBO).  Split-K over node chunks fills the
+// GPU; every CTA writes a partial tile that k_splitk_reduce sums in fixed order.  A CTA can own two 128-row M tiles
+// sharing the X tile (hidden_dim 129 = 128 + 1), and the bias gradient rides along as one extra column of X that the
+// converter warps overwrite with ones (or the in-degree, for the deg (.) b2 term) before the hi/lo split.
+struct WgItem {
+  CUtensorMap a;  // dY  [rows = nodes, cols = Mo]   box {32, 32}
+  CUtensorMap b;  // X   [rows = nodes, cols = Ni]   box {32, 32}
+};
+struct WgArgs {
+  WgItem it[kGemmMaxItems];
+  int count, Mo, N, n_eff, BN, mt, nb, K, kchunk, splitk, stages, tmem_cols, extra_col;
+  const float* extra_vec;
+  float* partial;
+  uint32_t lbo, sbo, kstep_bytes;  // descriptor strides (bytes)
+  int mn_major, debug;
+  int acc_hi[2], acc_lo[2];        // TMEM column of each M tile's hi*hi / lo-term accumulator (equal = shared)
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  // layout type 1 = SWIZZLE_128B_BASE32B: the only shared-memory layout the tensor core accepts for MN-major TF32
+  return uint64_t((saddr >> 4) & 0x3FFFu) | (uint64_t((lbo >> 4) & 0x3FFFu) << 16) | (uint64_t((sbo >> 4) & 0x3FFFu) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constant__ WgArgs args) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const int BN = args.BN, S = args.stages, mt = args.mt, nb = args.nb;
+  const uint32_t a_bytes = uint32_t(mt) * 4u * 4096u, b_bytes = uint32_t(nb) * 4096u;
+  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);  // A_hi | A_lo | B_hi | B_lo
+  const uint32_t bar_base = base + uint32_t(S) * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (kTcMaxStages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kTcMaxStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * kTcMaxStages);
+  const uint32_t tmem_slot = accum_bar + 8u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, prob = blockIdx.y, mgrp = blockIdx.z;  // mgrp: group of `mt` M tiles
+  const int row0 = mgrp * mt * kTcBM;                                   // first dW row of this CTA
+  const int k_beg = split * args.kchunk, k_end = min(args.K, k_beg + args.kchunk);
+  const int n_tiles = (k_end > k_beg) ? (k_end - k_beg + kTcBK - 1) / kTcBK : 0;
+  const WgItem& item = args.it[prob];
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), kTcWorkers / 32);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(uint32_t(args.tmem_cols)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        const int k0 = k_beg + it * kTcBK;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes);
+        const uint32_t st = base + uint32_t(s) * stage_bytes;
+        for (int b = 0; b < mt * 4; ++b) tma_load_2d(st + uint32_t(b) * 4096u, &item.a, row0 + 32 * b, k0, full_bar(s));
+        for (int b = 0; b < nb; ++b) tma_load_2d(st + 2u * a_bytes + uint32_t(b) * 4096u, &item.b, 32 * b, k0, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    // D = F32, A = B = TF32, A and B MN-major (bits 15, 16), N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(args.mn_major) << 15) | (uint32_t(args.mn_major) << 16) |
+                           (uint32_t(BN >> 3) << 17) | (uint32_t(kTcBM >> 4) << 24);
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(conv_bar(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = base + uint32_t(s) * stage_bytes;
+        const uint32_t b_hi = st + 2u * a_bytes, b_lo = b_hi + b_bytes;
+        for (int j = 0; j < kTcBK / 8; ++j) {  // 8 nodes per UMMA K step = one 1024-byte K group
+          const uint32_t koff = uint32_t(j) * args.kstep_bytes;
+          const uint64_t dbh = umma_desc_mn128(b_hi + koff, args.lbo, args.sbo), dbl = umma_desc_mn128(b_lo + koff, args.lbo, args.sbo);
+          for (int t = 0; t < mt; ++t) {
+            const uint32_t a_hi = st + uint32_t(t) * 16384u, a_lo = a_hi + a_bytes;
+            const uint64_t dah = umma_desc_mn128(a_hi + koff, args.lbo, args.sbo), dal = umma_desc_mn128(a_lo + koff, args.lbo, args.sbo);
+            const uint32_t d_hi = tmem_base + uint32_t(args.acc_hi[t]), d_lo = tmem_base + uint32_t(args.acc_lo[t]);
+            const uint32_t first = (it > 0 || j > 0) ? 1u : 0u;
+            umma_tf32(d_lo, dal, dbh, idesc, first);
+            umma_tf32(d_lo, dah, dbl, idesc, 1u);
+            umma_tf32(d_hi, dah, dbh, idesc, (d_hi == d_lo) ? 1u : first);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(accum_bar);
+    __syncwarp();
+  } else {
+    const int tid_c = threadIdx.x - 64;
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      const int k0 = k_beg + it * kTcBK;
+      mbar_wait(full_bar(s), ph);
+      const uint32_t st = base + uint32_t(s) * stage_bytes;
+      if (args.extra_col != 0) {
+        // virtual column N of X := 1 (or extra_vec[node]) -> its dot products with dY are the bias gradient
+        if (tid_c < kTcBK) {
+          const int r = tid_c, cN = args.N, bb = cN >> 5, cc = cN & 31;
+          const int node = k0 + r;
+          float v = 0.f;
+          if (node < k_end) v = args.extra_col == 1 ? 1.f : args.extra_vec[node];
+          // 128B rows, 32-byte chunks XOR-swizzled with (row mod 4)  (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+          const uint32_t addr = st + 2u * a_bytes + uint32_t(bb) * 4096u + uint32_t(r) * 128u +
+                                (uint32_t((cc >> 3) ^ (r & 3)) << 5) + uint32_t(cc & 7) * 4u;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");
+      }
+      split_tile(st, a_bytes, int(a_bytes / 16u), tid_c);
+      split_tile(st + 2u * a_bytes, b_bytes, int(b_bytes / 16u), tid_c);
+      proxy_fence_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(conv_bar(s));
+    }
+    // epilogue: accumulators -> padded smem tile -> coalesced rows of the split-K partial buffer
+    const int wk = warp - 2, q = warp & 3, half = wk >> 2;
+    const int n_eff = args.n_eff, Mo = args.Mo;
+    float* __restrict__ const part = args.partial + size_t(split * args.count + prob) * size_t(Mo) * n_eff;
+    const uint32_t tile_ld = uint32_t(BN) + 4u;
+    if (n_tiles > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+    for (int t = 0; t < mt; ++t) {
+      if (row0 + t * kTcBM >= Mo) break;  // CTA-uniform
+      if (n_tiles > 0) {
+        const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
+        const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
+        for (int c0 = 16 * half; c0 < n_eff; c0 += 32) {
+          uint32_t r[16];
+          float acc[16];
+          tmem_ld16(lane_base + uint32_t(args.acc_lo[t] + c0), r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
+          if (args.acc_hi[t] != args.acc_lo[t]) {
+            tmem_ld16(lane_base + uint32_t(args.acc_hi[t] + c0), r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + 4u * (c0 + i)), "f"(acc[i]), "f"(acc[i + 1]),
+                         "f"(acc[i + 2]), "f"(acc[i + 3]) : "memory");
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
+      for (int rr = 0; rr < 16; ++rr) {
+        const int row = 16 * wk + rr, m = row0 + t * kTcBM + row;
+        if (m >= Mo) break;
+        const uint32_t row_addr = base + (uint32_t(row) * tile_ld) * 4u;
+        for (int c = lane; c < n_eff; c += 32) {
+          float v = 0.f;
+          if (n_tiles > 0) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(row_addr + 4u * c));
+          part[size_t(m) * n_eff + c] = v;
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(args.tmem_cols)) : "memory");
+  }
+}
+
+// ---- weight packing ------------------------------------------------------------------------------------
+// state_dict weights are [out, in] with arbitrary row pitch (129 floats = 516 B is not a legal TMA stride) and the
+// data-gradient GEMMs need them transposed: one small kernel per step copies every matrix into 16-byte-pitched
+// K-major buffers (dst = W, dstT = W^T).
+struct PackItem {
+  const float* src;
+  float* dst;
+  float* dst_t;
+  int ld_src, rows, cols, ld_dst, ld_dst_t, pad_;
+};
+constexpr int kPackMax = 64;
+struct PackArgs {
+  PackItem it[kPackMax];
+};
+static_assert(sizeof(PackArgs) <= 4000, "kernel parameter space");
+
+__global__ void k_pack_weights(const __grid_constant__ PackArgs args) {
+  const PackItem& p = args.it[blockIdx.y];
+  const int total = p.rows * p.cols;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / p.cols, c = idx - r * p.cols;
+    const float v = p.src[size_t(r) * p.ld_src + c];
+    if (p.dst != nullptr) p.dst[size_t(r) * p.ld_dst + c] = v;
+    if (p.dst_t != nullptr) p.dst_t[size_t(c) * p.ld_dst_t + r] = v;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr || rows <= 0 || cols <= 0) return false;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
+  cuuint32_t box[2] = {kTcBK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tma_ok(const float* p, int64_t ld) { return p != nullptr && aligned16(p) && ld % 4 == 0; }
+
+}  // namespace
+
+bool tc_enabled() {
+  static int state = -1;
+  if (state < 0) {
+    const char* e = std::getenv("PFN_GEMM");
+    state = (e != nullptr && std::strcmp(e, "ffma") == 0) ? 0 : 1;
+    if (state == 1 && encode_fn() == nullptr) state = 0;
+  }
+  return state == 1;
+}
+
+// Tensor-core launch of a GemmArgs problem whose operands are K-major (A row-major [M,K], B row-major [N,K]).
+// Returns 1 if the shapes/alignments do not fit this path (caller falls back to the FFMA kernel), 0 on success.
+int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
+  if (!tc_enabled() || g.splitk > 1 || g.extra_col != 0 || g.M <= 0 || g.N <= 0) return 1;
+  const int count = g.batched ? g.n_items : 1;
+  for (int i = 0; i < g.n_items; ++i) {
+    const GemmItem& it = g.it[i];
+    if (it.a_cs != 1 || it.b_rs != 1 || !tma_ok(it.A, it.a_rs) || !tma_ok(it.B, it.b_cs) || it.K <= 0) return 1;
+  }
+  TcArgs a;
+  std::memset(&a, 0, sizeof(a));
+  const int bn = static_cast<int>(std::min<int64_t>(256, round_up64(g.N, 16)));
+  a.BN = bn;
+  a.n_items = g.n_items;
+  a.batched = g.batched;
+  a.M = g.M;
+  a.N = g.N;
+  const uint32_t stage_bytes = 2u * (kTcBM + bn) * 128u;
+  a.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 2048u) / stage_bytes));
+  if (a.stages < 1) return 1;
+  a.n_hi = std::max(1, std::min(3, 512 / bn - 1));
+  int cols = 32;
+  while (cols < (a.n_hi + 1) * bn) cols <<= 1;
+  a.tmem_cols = cols;
+  for (int i = 0; i < g.n_items; ++i) {
+    const GemmItem& it = g.it[i];
+    if (!make_map(&a.it[i].a, it.A, g.M, it.K, it.a_rs, kTcBM) || !make_map(&a.it[i].b, it.B, g.N, it.K, it.b_cs, bn)) return 1;
+    a.it[i].K = it.K;
+    a.C[i] = it.C;
+    a.bias[i] = it.bias;
+  }
+  a.ldc = g.it[0].ldc;
+  for (int i = 1; i < count; ++i)
+    if (g.it[i].ldc != a.ldc) return 1;
+  a.rowscale = g.rowscale;
+  a.addend = g.addend;
+  a.ymask = g.ymask;
+  a.inj = g.inj;
+  a.ld_add = g.ld_add;
+  a.ld_ym = g.ld_ym;
+  a.ld_inj = g.ld_inj;
+  a.act = g.act;
+  a.scale = g.scale;
+  a.seed_lo = g.seed_lo;
+  a.seed_hi = g.seed_hi;
+  a.keep_thresh = g.keep_thresh;
+  const uint32_t smem = uint32_t(a.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFN_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
+    attr_set = true;
+  }
+  dim3 grid(static_cast<unsigned>(ceil_div64(g.M, kTcBM)), static_cast<unsigned>(ceil_div64(g.N, bn)), static_cast<unsigned>(count));
+  k_gemm_tc<<<grid, kTcThreads, smem, stream>>>(a);
+  PFN_LAUNCHED();
+  return 0;
+}
+
+// Tensor-core weight gradient for a split-K GemmArgs (A = dY viewed [Mo, nodes], B = X viewed [nodes, Ni], both with the
+// M/N index contiguous).  Fills the same partial buffer layout as the FFMA kernel; the caller runs k_splitk_reduce.
+// Returns 1 when the problem does not fit (caller falls back), 0 on success; *splitk_out receives the split count used.
+int wgrad_tc_launch(GemmArgs& g, cudaStream_t stream) {
+  if (!tc_enabled() || !g.batched && g.n_items != 1) return 1;
+  const int count = g.batched ? g.n_items : 1;
+  const int Mo = g.M, Ni = g.N, n_eff = Ni + (g.extra_col ? 1 : 0);
+  if (Mo <= 0 || Ni <= 0 || n_eff > 256 || g.partial == nullptr) return 1;
+  const int K = g.it[0].K;
+  for (int i = 0; i < count; ++i) {
+    const GemmItem& it = g.it[i];
+    if (it.a_rs != 1 || it.b_cs != 1 || it.K != K || !tma_ok(it.A, it.a_cs) || !tma_ok(it.B, it.b_rs)) return 1;
+  }
+  WgArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.count = count;
+  a.Mo = Mo;
+  a.N = Ni;
+  a.n_eff = n_eff;
+  a.BN = static_cast<int>(round_up64(n_eff, 16));
+  a.nb = (a.BN + 31) / 32;
+  const int m_tiles = static_cast<int>(ceil_div64(Mo, kTcBM));
+  a.mt = (m_tiles >= 2 && 2 * a.BN <= 512) ? 2 : 1;
+  const int m_groups = static_cast<int>(ceil_div64(m_tiles, a.mt));
+  a.K = K;
+  int used;
+  if (a.mt == 1) {
+    a.acc_hi[0] = 0; a.acc_lo[0] = a.BN; used = 2 * a.BN;
+  } else if (3 * a.BN <= 512) {
+    a.acc_hi[0] = 0; a.acc_lo[0] = a.BN; a.acc_hi[1] = a.acc_lo[1] = 2 * a.BN; used = 3 * a.BN;
+  } else {
+    a.acc_hi[0] = a.acc_lo[0] = 0; a.acc_hi[1] = a.acc_lo[1] = a.BN; used = 2 * a.BN;
+  }
+  int cols = 32;
+  while (cols < used) cols <<= 1;
+  a.tmem_cols = cols;
+  const uint32_t stage_bytes = 2u * (uint32_t(a.mt) * 16384u + uint32_t(a.nb) * 4096u);
+  a.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 2048u) / stage_bytes));
+  if (a.stages < 2) return 1;
+  // split the node dimension so that about one CTA per SM is in flight
+  int64_t want = std::max<int64_t>(1, int64_t(sm_count()) / std::max(1, count * m_groups));
+  int64_t kchunk = round_up64(std::max<int64_t>(ceil_div64(K, want), kTcBK), kTcBK);
+  a.kchunk = static_cast<int>(kchunk);
+  a.splitk = static_cast<int>(std::max<int64_t>(1, ceil_div64(K, kchunk)));
+  if (size_t(a.splitk) * count * size_t(Mo) * n_eff * sizeof(float) > g.partial_bytes) return 1;
+  for (int i = 0; i < count; ++i) {
+    const GemmItem& it = g.it[i];
+    if (!make_map(&a.it[i].a, it.A, K, Mo, it.a_cs, kTcBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map(&a.it[i].b, it.B, K, Ni, it.b_rs, kTcBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return 1;
+  }
+  a.extra_col = g.extra_col;
+  a.extra_vec = g.extra_vec;
+  a.partial = g.partial;
+  {
+    a.lbo = 4096u;        // one TMA box (32 floats of M/N x 32 nodes) to the next
+    a.sbo = 512u;         // 4 K-rows of 128 B: one SWIZZLE_128B_BASE32B atom to the next along K
+    a.kstep_bytes = 1024u;  // 8 nodes per UMMA K step
+    a.mn_major = 1;
+  }
+  g.splitk = a.splitk;  // the reduction pass must know how many partials were written
+  g.kchunk = a.kchunk;
+  const uint32_t smem = uint32_t(a.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
+    attr_set = true;
+  }
+  dim3 grid(static_cast<unsigned>(a.splitk), static_cast<unsigned>(count), static_cast<unsigned>(m_groups));
+  k_wgrad_tc<<<grid, kTcThreads, smem, stream>>>(a);
+  PFN_LAUNCHED();
+  return 0;
+}
+
+int pack_weights_launch(const PackDesc* items, int n, cudaStream_t stream) {
+  for (int base = 0; base < n; base += kPackMax) {
+    PackArgs args;
+    std::memset(&args, 0, sizeof(args));
+    const int cnt = std::min(kPackMax, n - base);
+    int max_elems = 1;
+    for (int i = 0; i < cnt; ++i) {
+      const PackDesc& d = items[base + i];
+      args.it[i] = PackItem{d.src, d.dst, d.dst_t, d.ld_src, d.rows, d.cols, d.ld_dst, d.ld_dst_t, 0};
+      max_elems = std::max(max_elems, d.rows * d.cols);
+    }
+    dim3 grid(static_cast<unsigned>(std::min<int64_t>(ceil_div64(max_elems, 256), 64)), static_cast<unsigned>(cnt));
+    k_pack_weights<<<grid, 256, 0, stream>>>(args);
+    PFN_LAUNCHED();
+  }
+  return 0;
+}
+
+}  // namespace pfn

@@ -100,6 +100,12 @@ def test_full_size_against_oracle(case, b, cfg):
     batch = synthetic_batch(case, b)
     oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
     loss_ref, out_ref = O.forward_loss_backward(oracle, batch, "mse")
+    # fp64 twin of the same oracle: at N = 15104 the fp32 reference's own rounding error reaches ~1e-5 on a few
+    # gradient tensors, so "within 1e-5 of the fp32 reference" is only meaningful down to that floor
+    twin = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).double().train()
+    b64 = common.GraphBatch(**{f: (getattr(batch, f).double() if getattr(batch, f).is_floating_point() else getattr(batch, f))
+                               for f in ("x", "y", "bus_type", "pred_mask", "edge_index", "edge_attr", "batch", "ptr")})
+    O.forward_loss_backward(twin, b64, "mse")
     m = _model(kw, oracle.state_dict()).train()
     dbatch = batch.to(DEV)
     out = m(dbatch)
@@ -107,8 +113,14 @@ def test_full_size_against_oracle(case, b, cfg):
     loss.backward()
     _close(out, out_ref, "out")
     assert abs(float(loss) - float(loss_ref)) < TOL * float(loss_ref)
-    for (k, p), (_, q) in zip(m.named_parameters(), oracle.named_parameters()):
-        _close(p.grad, q.grad, k)
+    for (k, p), (_, q), (_, r) in zip(m.named_parameters(), oracle.named_parameters(), twin.named_parameters()):
+        exact = r.grad
+        ours_vs_exact = max(common.rel_err(p.grad.cpu().double(), exact))
+        ref_vs_exact = max(common.rel_err(q.grad.double(), exact))
+        # within 1e-5 of the exact gradient and of the fp32 reference, each relaxed only by the reference's OWN distance
+        # from the exact value (its fp32 rounding floor, up to ~1.4e-5 on bias gradients summed over 15104 nodes)
+        assert ours_vs_exact < TOL + ref_vs_exact, (k, "vs fp64 twin", ours_vs_exact, ref_vs_exact)
+        assert max(common.rel_err(p.grad.cpu(), q.grad)) < TOL + ref_vs_exact, (k, "vs fp32 oracle", ref_vs_exact)
 
 
 def test_masked_l2_loss_through_autograd():

@@ -157,7 +157,7 @@ def run_ours(args):
     from poweflownet_b200 import _lib, parallel
     from poweflownet_b200.data import synthetic_batch
     from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
-    from poweflownet_b200.training import fused_mse_step, train_step
+    from poweflownet_b200.training import GraphedMSEStep, fused_mse_step
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -201,10 +201,17 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
-    step_resident = lambda i: fused_mse_step(model, dev_batches[i % N_ROTATE], total_count)  # noqa: E731
-    step_e2e = lambda i: train_step(model, host_batches[i % N_ROTATE], dev, "mse", total_count)  # noqa: E731
+    step_eager = lambda i: fused_mse_step(model, dev_batches[i % N_ROTATE], total_count)  # noqa: E731
+    graphed = None if args.no_graph else GraphedMSEStep(model, dev_batches[0], total_count)
+    if graphed is None:
+        step_resident = step_eager
+        step_e2e = lambda i: float(fused_mse_step(model, host_batches[i % N_ROTATE].to(dev, non_blocking=True), total_count).item())  # noqa: E731
+    else:
+        step_resident = lambda i: graphed(dev_batches[i % N_ROTATE])  # noqa: E731  (device->static copy + replay)
+        step_e2e = lambda i: float(graphed(host_batches[i % N_ROTATE]).item())  # noqa: E731  (pinned H2D + replay + D2H)
 
     for i in range(max(args.warmup, 3)):
+        step_eager(i)
         step_resident(i)
         step_e2e(i)
     sampler = ClockSampler(local_rank)
@@ -212,22 +219,22 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)
 
-    # ---- device-resident throughput, kernel timing hooks on (they bracket launches with events) ----
+    # ---- eager steps with the kernel timing hooks on (they bracket launches with events; not capturable) ----
     lib.pfn_profile_enable(1)
     launches0 = lib.pfn_launch_count()
-    ms_total, t0, t1 = timed(step_resident, args.steps)
+    ms_total, t0, t1 = timed(step_eager, args.steps)
     launches = int(lib.pfn_launch_count() - launches0)
     lib.pfn_profile_enable(0)
+    ms_eager, _, _ = timed(step_eager, args.steps)
     prof = {}
     names = ["ea_fwd", "ea_bwd", "hop", "gemm_fwd", "gemm_dgrad", "gemm_wgrad", "prep"]
     for cat, name in enumerate(names):
         tot, cnt = C.c_double(), C.c_int64()
         _lib.check(lib.pfn_profile_read(cat, C.byref(tot), C.byref(cnt)), "pfn_profile_read")
         prof[name] = (tot.value, cnt.value)
-    # same loop without the timing hooks: the headline number
-    launches0 = lib.pfn_launch_count()
+    # the headline number: the same step replayed as a CUDA graph (device-resident batches)
     ms_total_clean, t0b, t1b = timed(step_resident, args.steps)
-    launches_clean = int(lib.pfn_launch_count() - launches0)
+    launches_clean = launches  # a replay re-issues the captured launches: same kernels, same count per step
     clocks = sampler.stop(t0, t1b) if rank == 0 else None
     # ---- end to end from pinned host memory ----
     ms_e2e, _, _ = timed(step_e2e, args.steps)
@@ -262,10 +269,12 @@ def run_ours(args):
                    "global_batch": world * BATCH, "nodes_per_rank": n_nodes, "directed_edges_per_rank": n_edges,
                    "parallelism": f"dp{world}: graphs sharded per rank, one NCCL all-reduce of the flat fp32 gradient buffer per step" if world > 1 else "single GPU",
                    "l2": f"steps rotate over {N_ROTATE} resident batches; per-step activation+scratch working set ~305 MB > 126 MB L2 (no explicit flush)",
-                   "timed_region": "graph prep + forward + fused MSE + backward (+ all-reduce); optimizer.step excluded (stays in torch, SURVEY 8 f4)"},
+                   "timed_region": "graph prep + forward + fused MSE + backward (+ all-reduce); optimizer.step excluded (stays in torch, SURVEY 8 f4)",
+                   "launch": "eager (one launch per kernel)" if graphed is None else "CUDA graph replay of the captured step (poweflownet_b200.training.GraphedMSEStep)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": host_batches[0].nbytes(), "d2h_bytes_per_step": 4,
-                "api": "poweflownet_b200.training.train_step(model, pinned_host_batch, device)"},
+                "api": "poweflownet_b200.training.GraphedMSEStep(model, batch)(pinned_host_batch) + loss.item()" if graphed is not None
+                       else "poweflownet_b200.training.fused_mse_step(model, pinned_host_batch.to(device)) + loss.item()"},
         "gpu_launches": launches_clean,
         "clocks": clocks,
         "roofline": {"kernel": "k_ea_fwd (fused EdgeAggregation message+aggregate, forward)", "bound": "hbm",
@@ -276,6 +285,7 @@ def run_ours(args):
                             "(inputs are L2-warm from the producing GEMM, as in the real step)"},
         "kernel_time": kernel_share,
         "ms_per_step_with_timing_hooks": step_ms_hooks,
+        "ms_per_step_eager": ms_eager / args.steps,
         "gpu_launches_with_hooks": launches,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -296,6 +306,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU oracle timing (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -162,11 +162,13 @@ PFN_API int pfn_mpn_workspace(const pfn_mpn_desc* desc, int64_t n_nodes, int64_t
                       size_t* scratch_bytes);
 /* x float [N,4]; pred_mask int64 [N,4]; graph_ws prepared by pfn_graph_prep(undirect_mode=1);
  * training != 0 applies dropout (keep masks from `inj_masks[i]` [N, hidden] when inj_masks != NULL,
- * else from the generator keyed by `seed`); out float [N, output_dim]. */
+ * else from the generator keyed by `seed`, or -- when seed_device != NULL -- by the 64-bit value the
+ * kernels read from that DEVICE address at run time, so a captured CUDA graph draws fresh masks on every
+ * replay); out float [N, output_dim]. */
 PFN_API int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* params, const float* x,
                     const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
                     void* act_ws, void* scratch_ws, int training, uint64_t seed,
-                    const float* const* inj_masks, float* out, void* stream);
+                    const uint64_t* seed_device, const float* const* inj_masks, float* out, void* stream);
 /* dout float [N, output_dim]; grads[i] receives d loss / d params[i] (overwritten, same shapes) */
 PFN_API int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                      const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,

@@ -123,6 +123,7 @@ struct GemmArgs {
   const float* inj;
   int ld_inj;
   uint32_t seed_lo, seed_hi, keep_thresh;  // keep iff hash >= keep_thresh
+  const uint32_t* seed_dev;                 // optional device-resident 64-bit seed, XORed into (seed_lo, seed_hi)
   // split-K (weight gradients): partial[(split*count + z)][M][N + extra]
   int splitk;
   int kchunk;

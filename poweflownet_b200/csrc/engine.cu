@@ -256,6 +256,7 @@ struct Ctx {
   cudaStream_t stream;
   bool training;
   float scale;  // 1/(1-p) in training, 1 otherwise
+  const uint64_t* seed_device = nullptr;
 
   float* hi(int slot) const { return act + p.off_ea + slot * p.ea_stride(); }
   float* hj(int slot) const { return hi(slot) + p.N * p.ldh; }
@@ -294,8 +295,10 @@ void set_activation(GemmArgs& a, const Ctx& c, bool act, int layer_index, uint64
     a.scale = c.scale;
     a.inj = inj;
     a.ld_inj = static_cast<int>(ld_inj);
-    a.seed_lo = static_cast<uint32_t>(seed) ^ (0x9E3779B9u * static_cast<uint32_t>(layer_index + 1));
-    a.seed_hi = static_cast<uint32_t>(seed >> 32);
+    const uint64_t host_seed = c.seed_device != nullptr ? 0 : seed;  // the device seed is XORed in by the kernel
+    a.seed_lo = static_cast<uint32_t>(host_seed) ^ (0x9E3779B9u * static_cast<uint32_t>(layer_index + 1));
+    a.seed_hi = static_cast<uint32_t>(host_seed >> 32);
+    a.seed_dev = reinterpret_cast<const uint32_t*>(c.seed_device);
     a.keep_thresh = keep_threshold(c.p.d.dropout_rate);
   } else {
     a.act = PFN_ACT_RELU;
@@ -636,7 +639,7 @@ extern "C" int pfn_mpn_workspace(const pfn_mpn_desc* desc, int64_t n_nodes, int6
 
 extern "C" int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* params, const float* x,
                                const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
-                               void* act_ws, void* scratch_ws, int training, uint64_t seed,
+                               void* act_ws, void* scratch_ws, int training, uint64_t seed, const uint64_t* seed_device,
                                const float* const* inj_masks, float* out, void* stream) {
   Plan p;
   PFN_TRY(make_plan(desc, n_nodes, p));
@@ -647,6 +650,7 @@ extern "C" int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* par
   Ctx c{p, params, graph_view(graph_ws, n_nodes, e_raw), static_cast<float*>(act_ws), static_cast<float*>(scratch_ws),
         static_cast<cudaStream_t>(stream), training != 0,
         (training != 0 && desc->dropout_rate > 0.f) ? 1.f / (1.f - desc->dropout_rate) : 1.f};
+  c.seed_device = seed_device;
   return forward_impl(c, x, pred_mask, seed, inj_masks, out);
 }
 

@@ -129,6 +129,11 @@ __global__ void __launch_bounds__(256) k_gemm(const __grid_constant__ GemmArgs a
   // ---- epilogue -----------------------------------------------------------------------------
   const GemmItem& out = args.it[args.batched ? prob : 0];
   const int count = args.batched ? args.n_items : 1;
+  uint32_t seed_lo = args.seed_lo, seed_hi = args.seed_hi;
+  if (args.act == PFN_ACT_DROPOUT_RELU && args.seed_dev != nullptr) {
+    seed_lo ^= args.seed_dev[0];
+    seed_hi ^= args.seed_dev[1];
+  }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty + 16 * i;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(256) k_gemm(const __grid_constant__ GemmArgs a
         v = fmaxf(v, 0.f);
       } else if (args.act == PFN_ACT_DROPOUT_RELU) {
         const bool keep = args.inj != nullptr ? args.inj[size_t(m) * args.ld_inj + n] != 0.f
-                                              : dropout_hash(m, n, args.seed_lo, args.seed_hi) >= args.keep_thresh;
+                                              : dropout_hash(m, n, seed_lo, seed_hi) >= args.keep_thresh;
         v = keep ? fmaxf(v * args.scale, 0.f) : 0.f;
       } else if (args.act == kActMaskByY) {
         v = args.ymask[size_t(m) * args.ld_ym + n] > 0.f ? v * args.scale : 0.f;

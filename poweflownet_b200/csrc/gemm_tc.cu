@@ -22,6 +22,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -57,6 +58,8 @@ struct TcArgs {
   int ld_add, ld_ym, ld_inj, act;
   float scale;
   uint32_t seed_lo, seed_hi, keep_thresh;
+  const uint32_t* seed_dev;
+  long long* timing;  // debug: CTA 0 writes clock64() at phase boundaries when non-null
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -106,14 +109,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  tmem_ld16_issue(taddr, r);
+  tmem_ld_wait();
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address, LBO (unused for swizzled
@@ -158,8 +165,10 @@ __device__ __forceinline__ float epi_apply(float x, int act, float ym, bool keep
 }
 
 // 16 rows of the staged tile -> global.  Columns [0, ncols_vec) go out as float4 (lane = 4 columns, 8 rows per batch with
-// every load issued before the first use); the remaining columns (alignment tail, or everything when a pointer is not
-// 16-byte aligned / a test keep-mask is injected) take the scalar path with lanes across columns.
+// the batch's loads issued before the first use); the remaining columns (alignment tail, or everything when a pointer is
+// not 16-byte aligned / a test keep-mask is injected) take the scalar path with lanes across columns.
+// Deliberately NOT fully unrolled: a CTA executes its epilogue once, so straight-line code is instruction-fetch bound
+// (measured: 27k cycles unrolled vs the few thousand the data movement needs); small loop bodies stay in the I-cache.
 template <int ACT, bool ADD>
 __device__ __forceinline__ void epilogue_rows(const TcArgs& args, const EpiCtx& e) {
   const int M = args.M;
@@ -169,18 +178,32 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& args, const EpiCtx& 
   const float* __restrict__ const ymask = args.ymask;
   const float* __restrict__ const rowscale = args.rowscale;
   const float scale = args.scale;
+  uint32_t seed_lo = args.seed_lo, seed_hi = args.seed_hi;
+  if (ACT == PFN_ACT_DROPOUT_RELU && args.seed_dev != nullptr) {
+    seed_lo ^= args.seed_dev[0];
+    seed_hi ^= args.seed_dev[1];
+  }
+  constexpr int RB = 8;
+#define PFN_ESTAMP(slot)                                                                                        \
+  do {                                                                                                          \
+    if (args.timing != nullptr && threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)   \
+      args.timing[slot] = clock64();                                                                            \
+  } while (0)
+  PFN_ESTAMP(32);
+#pragma unroll 1
   for (int cb = 0; cb < e.ncols_vec; cb += 128) {
     const int c = cb + 4 * e.lane;
     const bool cok = c < e.ncols_vec;
     const int n = e.n0 + c;
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias != nullptr && cok) b4 = make_float4(bias[n], bias[n + 1], bias[n + 2], bias[n + 3]);
+    PFN_ESTAMP(33);
+#pragma unroll 1
+    for (int rb = 0; rb < 16; rb += RB) {
+      float4 v[RB], ad[RB], ym[RB];
+      float rs[RB];
 #pragma unroll
-    for (int rb = 0; rb < 16; rb += 8) {
-      float4 v[8], ad[8], ym[8];
-      float rs[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < RB; ++i) {
         const int row = e.row0 + rb + i, m = e.m0 + row;
         const bool ok = cok && m < M;
         v[i] = ad[i] = ym[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -192,50 +215,57 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& args, const EpiCtx& 
         if (ACT == kActMaskByY && ok) ym[i] = *reinterpret_cast<const float4*>(ymask + size_t(m) * args.ld_ym + n);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < RB; ++i) {
         const int m = e.m0 + e.row0 + rb + i;
         if (!(cok && m < M)) continue;
-        float4 o;
-        bool k0 = true, k1 = true, k2 = true, k3 = true;
-        if (ACT == PFN_ACT_DROPOUT_RELU) {
-          k0 = dropout_hash(m, n, args.seed_lo, args.seed_hi) >= args.keep_thresh;
-          k1 = dropout_hash(m, n + 1, args.seed_lo, args.seed_hi) >= args.keep_thresh;
-          k2 = dropout_hash(m, n + 2, args.seed_lo, args.seed_hi) >= args.keep_thresh;
-          k3 = dropout_hash(m, n + 3, args.seed_lo, args.seed_hi) >= args.keep_thresh;
+        float x[4] = {fmaf(rs[i], b4.x, v[i].x) + ad[i].x, fmaf(rs[i], b4.y, v[i].y) + ad[i].y,
+                      fmaf(rs[i], b4.z, v[i].z) + ad[i].z, fmaf(rs[i], b4.w, v[i].w) + ad[i].w};
+        const float y4[4] = {ym[i].x, ym[i].y, ym[i].z, ym[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bool keep = true;
+          if (ACT == PFN_ACT_DROPOUT_RELU) keep = dropout_hash(m, n + j, seed_lo, seed_hi) >= args.keep_thresh;
+          x[j] = epi_apply(x[j], ACT, y4[j], keep, scale);
         }
-        o.x = epi_apply(fmaf(rs[i], b4.x, v[i].x) + ad[i].x, ACT, ym[i].x, k0, scale);
-        o.y = epi_apply(fmaf(rs[i], b4.y, v[i].y) + ad[i].y, ACT, ym[i].y, k1, scale);
-        o.z = epi_apply(fmaf(rs[i], b4.z, v[i].z) + ad[i].z, ACT, ym[i].z, k2, scale);
-        o.w = epi_apply(fmaf(rs[i], b4.w, v[i].w) + ad[i].w, ACT, ym[i].w, k3, scale);
-        *reinterpret_cast<float4*>(C + size_t(m) * args.ldc + n) = o;
+        *reinterpret_cast<float4*>(C + size_t(m) * args.ldc + n) = make_float4(x[0], x[1], x[2], x[3]);
       }
+      PFN_ESTAMP(34 + rb / RB);
     }
   }
-  // scalar columns [ncols_vec, ncols): lanes across columns, rows in sequence
+  PFN_ESTAMP(38);
+  // scalar columns [ncols_vec, ncols): one (row, column) pair per lane and iteration, rows fastest, so the few tail
+  // columns of all 16 rows are in flight together (a lane walking 16 rows in sequence cost more than the float4 part)
   const float* __restrict__ const inj = args.inj;
-  for (int c = e.ncols_vec + e.lane; c < e.ncols; c += 32) {
-    const int n = e.n0 + c;
-    const float bn = bias != nullptr ? bias[n] : 0.f;
-#pragma unroll 4
-    for (int r = 0; r < 16; ++r) {
-      const int row = e.row0 + r, m = e.m0 + row;
-      if (m >= M) break;
-      float v;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(e.tile + (uint32_t(row) * e.tile_ld + uint32_t(c)) * 4u));
-      float x = fmaf(rowscale != nullptr ? rowscale[m] : 1.f, bn, v);
-      if (ADD) x += addend[size_t(m) * args.ld_add + n];
-      bool keep = true;
-      float ym = 0.f;
-      if (ACT == PFN_ACT_DROPOUT_RELU)
-        keep = inj != nullptr ? inj[size_t(m) * args.ld_inj + n] != 0.f : dropout_hash(m, n, args.seed_lo, args.seed_hi) >= args.keep_thresh;
-      if (ACT == kActMaskByY) ym = ymask[size_t(m) * args.ld_ym + n];
-      C[size_t(m) * args.ldc + n] = epi_apply(x, ACT, ym, keep, scale);
-    }
+  const int n_tail = e.ncols - e.ncols_vec;
+#pragma unroll 1
+  for (int idx = e.lane; idx < 16 * n_tail; idx += 32) {
+    const int r = idx & 15, c = e.ncols_vec + (idx >> 4);
+    const int row = e.row0 + r, m = e.m0 + row, n = e.n0 + c;
+    if (m >= M) continue;
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(e.tile + (uint32_t(row) * e.tile_ld + uint32_t(c)) * 4u));
+    float x = v;
+    if (bias != nullptr) x = fmaf(rowscale != nullptr ? rowscale[m] : 1.f, bias[n], v);
+    if (ADD) x += addend[size_t(m) * args.ld_add + n];
+    bool keep = true;
+    float ym = 0.f;
+    if (ACT == PFN_ACT_DROPOUT_RELU)
+      keep = inj != nullptr ? inj[size_t(m) * args.ld_inj + n] != 0.f : dropout_hash(m, n, seed_lo, seed_hi) >= args.keep_thresh;
+    if (ACT == kActMaskByY) ym = ymask[size_t(m) * args.ld_ym + n];
+    C[size_t(m) * args.ldc + n] = epi_apply(x, ACT, ym, keep, scale);
   }
+  PFN_ESTAMP(39);
 }
+
+#define PFN_TSTAMP(slot)                                                                   \
+  do {                                                                                     \
+    if (args.timing != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)   \
+      args.timing[slot] = clock64();                                                       \
+  } while (0)
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant__ TcArgs args) {
   extern __shared__ uint8_t smem_dyn[];
+  if (threadIdx.x == 0) PFN_TSTAMP(0);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
   const int BN = args.BN, S = args.stages;
   const uint32_t a_bytes = kTcBM * 128u, b_bytes = uint32_t(BN) * 128u;
@@ -252,7 +282,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
   const int prob = blockIdx.z;
   const int seg_begin = args.batched ? prob : 0, seg_end = args.batched ? prob + 1 : args.n_items;
 
+  // TMA producer state (warp 0, lane 0): the first S tiles are requested BEFORE the CTA-wide setup barrier so the
+  // first load's latency (~2 us: descriptor fetch + 272 row segments from L2/HBM) overlaps TMEM allocation
+  int p_it = 0, p_seg = seg_begin, p_k0 = 0;
+  auto produce = [&](int limit) {
+    while (p_seg < seg_end && p_it < limit) {
+      const TcItem& item = args.it[p_seg];
+      if (p_k0 >= item.K) {
+        ++p_seg;
+        p_k0 = 0;
+        continue;
+      }
+      const int s = p_it % S;
+      const uint32_t ph = (p_it / S) & 1;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes);
+      const uint32_t st = base + uint32_t(s) * stage_bytes;
+      tma_load_2d(st, &item.a, p_k0, m0, full_bar(s));
+      tma_load_2d(st + 2u * a_bytes, &item.b, p_k0, n0, full_bar(s));
+      p_k0 += kTcBK;
+      ++p_it;
+    }
+  };
   if (warp == 0 && lane == 0) {
+    for (int seg = seg_begin; seg < seg_end; ++seg) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.it[seg].a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.it[seg].b)) : "memory");
+    }
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(conv_bar(s), kTcWorkers / 32);
@@ -260,6 +316,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    produce(S);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(uint32_t(args.tmem_cols)) : "memory");
@@ -270,24 +327,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) PFN_TSTAMP(1);
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int it = 0;
-      for (int seg = seg_begin; seg < seg_end; ++seg) {
-        const TcItem& item = args.it[seg];
-        for (int k0 = 0; k0 < item.K; k0 += kTcBK, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes);
-          const uint32_t st = base + uint32_t(s) * stage_bytes;
-          tma_load_2d(st, &item.a, k0, m0, full_bar(s));
-          tma_load_2d(st + 2u * a_bytes, &item.b, k0, n0, full_bar(s));
-        }
-      }
-    }
+    // ===== TMA producer: remaining tiles =====
+    if (lane == 0) produce(1 << 30);
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
@@ -306,6 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         mbar_wait(conv_bar(s), ph);
         tc_fence_after();
         const int nk = min(kTcBK / 8, (K - k0 + 7) / 8);  // 8 TF32 elements (32 bytes) per UMMA K step
+        if (lane == 0 && it < 8) PFN_TSTAMP(18 + it);
         if (lane == 0) {
           const uint32_t st = base + uint32_t(s) * stage_bytes;
           const uint64_t a_hi = umma_desc_k128(st), a_lo = umma_desc_k128(st + a_bytes);
@@ -325,6 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       }
     }
     if (lane == 0) umma_commit(accum_bar);
+    if (lane == 0) PFN_TSTAMP(26);
     __syncwarp();
   } else {
     // ===== converters (hi/lo split in shared memory), then epilogue =====
@@ -336,16 +382,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(full_bar(s), ph);
+        if (tid_c == 0 && it < 8) PFN_TSTAMP(2 + it);
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         split_tile(st, a_bytes, kTcBM * 8, tid_c);
         split_tile(st + 2u * a_bytes, b_bytes, BN * 8, tid_c);
         proxy_fence_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        if (tid_c == 0 && it < 8) PFN_TSTAMP(10 + it);
         __syncwarp();
         if (lane == 0) mbar_arrive(conv_bar(s));
       }
     }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) PFN_TSTAMP(27);
     // Epilogue.  The pipeline stages are free now (every MMA has completed), so the accumulator tile is staged through
     // shared memory: phase 1, each warp drains its TMEM lane quarter (two warps per quarter, alternating 16-column
     // chunks) and adds the accumulators in fp32; phase 2, the eight warps take 16 rows each and stream them out as
@@ -361,15 +410,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
       const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
       for (int c0 = 16 * half; c0 < ncols; c0 += 32) {
-        uint32_t r[16];
+        uint32_t r[4][16];  // lo terms + up to three hi accumulators, all loads in flight before one wait
+        tmem_ld16_issue(lane_base + uint32_t(args.n_hi * BN + c0), r[0]);
+        if (n_act > 0) tmem_ld16_issue(lane_base + uint32_t(0 * BN + c0), r[1]);
+        if (n_act > 1) tmem_ld16_issue(lane_base + uint32_t(1 * BN + c0), r[2]);
+        if (n_act > 2) tmem_ld16_issue(lane_base + uint32_t(2 * BN + c0), r[3]);
+        tmem_ld_wait();
         float acc[16];
-        tmem_ld16(lane_base + uint32_t(args.n_hi * BN + c0), r);  // the small (lo) terms first
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
-        for (int a = 0; a < n_act; ++a) {
-          tmem_ld16(lane_base + uint32_t(a * BN + c0), r);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
+        for (int i = 0; i < 16; ++i) {
+          float a = __uint_as_float(r[0][i]);  // the small (lo) terms first
+          if (n_act > 0) a += __uint_as_float(r[1][i]);
+          if (n_act > 1) a += __uint_as_float(r[2][i]);
+          if (n_act > 2) a += __uint_as_float(r[3][i]);
+          acc[i] = a;
         }
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
@@ -377,7 +431,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
                        "f"(acc[i + 2]), "f"(acc[i + 3]) : "memory");
       }
     }
+    if (threadIdx.x == 64) PFN_TSTAMP(28);
     asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
+    if (threadIdx.x == 64) PFN_TSTAMP(29);
     EpiCtx e;
     e.tile = base;
     e.tile_ld = tile_ld;
@@ -399,6 +455,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       case PFN_ACT_DROPOUT_RELU: epilogue_rows<PFN_ACT_DROPOUT_RELU, false>(args, e); break;
       default: epilogue_rows<kActMaskByY, false>(args, e); break;
     }
+    if (threadIdx.x == 64) PFN_TSTAMP(30);
   }
   tc_fence_before();
   __syncthreads();
@@ -653,9 +710,18 @@ bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, in
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * sizeof(float)};
   cuuint32_t box[2] = {kTcBK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  auto encode = [&]() {
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = encode();
+  if (r == CUDA_ERROR_INVALID_CONTEXT) {
+    // a driver-API call on a thread that has not touched the runtime yet (autograd's backward thread): bind the
+    // primary context of the current device to this thread, then retry
+    cudaFree(nullptr);
+    r = encode();
+  }
+  return r == CUDA_SUCCESS;
 }
 
 bool tma_ok(const float* p, int64_t ld) { return p != nullptr && aligned16(p) && ld % 4 == 0; }
@@ -718,6 +784,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   a.seed_lo = g.seed_lo;
   a.seed_hi = g.seed_hi;
   a.keep_thresh = g.keep_thresh;
+  a.seed_dev = g.seed_dev;
   const uint32_t smem = uint32_t(a.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2);
   static bool attr_set = false;
   if (!attr_set) {
@@ -725,8 +792,27 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(static_cast<unsigned>(ceil_div64(g.M, kTcBM)), static_cast<unsigned>(ceil_div64(g.N, bn)), static_cast<unsigned>(count));
+  static const bool timing_on = std::getenv("PFN_TC_TIMING") != nullptr;  // debug aid: phase timestamps of CTA 0
+  static long long* timing_dev = nullptr;
+  if (timing_on) {
+    if (timing_dev == nullptr) cudaMalloc(&timing_dev, 64 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 64 * sizeof(long long), stream);
+    a.timing = timing_dev;
+  }
   k_gemm_tc<<<grid, kTcThreads, smem, stream>>>(a);
   PFN_LAUNCHED();
+  if (timing_on) {
+    long long t[64];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc-timing] M=%d N=%d K0=%d items=%d batched=%d act=%d | setup %lld |", g.M, g.N, g.it[0].K, g.n_items, g.batched,
+            g.act, t[1] - t[0]);
+    for (int i = 0; i < 8 && t[2 + i]; ++i)
+      fprintf(stderr, " tile%d: full@%lld conv@%lld mma@%lld |", i, t[2 + i] - t[0], t[10 + i] - t[0], t[18 + i] - t[0]);
+    fprintf(stderr, " mma_done@%lld accum@%lld epi1@%lld bar@%lld end@%lld || epi: entry@%lld bias@%lld b0@%lld b1@%lld b2@%lld b3@%lld vec@%lld tail@%lld\n",
+            t[26] - t[0], t[27] - t[0], t[28] - t[0], t[29] - t[0], t[30] - t[0], t[32] - t[0], t[33] - t[0], t[34] - t[0], t[35] - t[0],
+            t[36] - t[0], t[37] - t[0], t[38] - t[0], t[39] - t[0]);
+  }
   return 0;
 }
 

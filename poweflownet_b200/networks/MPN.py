@@ -90,7 +90,8 @@ class _MPNFunction(torch.autograd.Function):
             ws = model._take_workspace(n, int(edge_index.size(1)), dev)
             graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph)
             ws.graph = graph.ws
-            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if training else 0
+            seed_dev = model._seed_device if training else None  # device-resident seed (CUDA-graph replays)
+            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if (training and seed_dev is None) else 0
             inj = model._inject_dropout_masks if training else None
             inj_table = None
             if inj is not None:
@@ -101,7 +102,8 @@ class _MPNFunction(torch.autograd.Function):
             desc = model._desc()
             check(lib().pfn_mpn_forward(C.byref(desc), ptable, x.data_ptr(), pred_mask.data_ptr(), n, graph.e_raw,
                                         ws.graph.data_ptr(), ws.act.data_ptr(), ws.scratch.data_ptr(), int(training),
-                                        seed, inj_table, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                                        seed, None if seed_dev is None else seed_dev.data_ptr(), inj_table, out.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream),
                   "pfn_mpn_forward")
         if needs_grad:
             ctx.model, ctx.ws, ctx.params, ctx.n, ctx.e_raw, ctx.training = model, ws, params, n, graph.e_raw, training
@@ -162,6 +164,7 @@ class MaskEmbdMultiMPN(nn.Module):
         self._pool = {}
         self._inject_dropout_masks: Optional[Sequence[torch.Tensor]] = None  # test hook: replay given keep-masks
         self._grad_reducer = None  # set by poweflownet_b200.parallel.attach_gradient_allreduce
+        self._seed_device: Optional[torch.Tensor] = None  # int64[1] on the device: dropout seed read by the kernels
 
     # ---- reference helper methods (networks/MPN.py:498-523) -------------------------------------
     def is_directed(self, edge_index):

@@ -48,6 +48,76 @@ def fused_mse_step(model: MaskEmbdMultiMPN, data, total_count: Optional[int] = N
     return loss
 
 
+class GraphedMSEStep:
+    """forward + MSE + backward of one mini-batch SHAPE captured once as a CUDA graph and replayed per step.
+
+    The ~90 kernel launches of a step (and the host-side tensor-map encodes of the tensor-core GEMMs) cost more
+    CPU time than the kernels take on a B200, so the step is recorded once on static buffers; every call copies
+    the new batch into those buffers, refreshes the device-resident dropout seed and replays.  Parameter `.grad`s
+    are static tensors owned by the graph (as after `zero_grad(); loss.backward()`), so an optimizer step can
+    follow directly.  The data-parallel gradient all-reduce runs right after the replay, outside the graph.
+    Mini-batches of a different shape (other N / E_raw) need their own instance.
+    """
+
+    FIELDS = ("x", "y", "bus_type", "pred_mask", "edge_index", "edge_attr", "batch", "ptr")
+
+    def __init__(self, model: MaskEmbdMultiMPN, example_batch, total_count: Optional[int] = None, warmup: int = 3):
+        dev = ops.require_cuda(*[p for p in model.parameters()])
+        self.model, self.device, self.total_count = model, dev, total_count
+        self.static = example_batch.to(dev)
+        self.static = type(self.static)(*[getattr(self.static, f).clone() for f in self.FIELDS])
+        self.seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.reducer, model._grad_reducer = model._grad_reducer, None  # the collective stays outside the graph
+        model._seed_device = self.seed_dev
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(warmup, 1)):  # also runs every one-time cudaFuncSetAttribute / workspace allocation
+                    self._refresh_seed()
+                    fused_mse_step(model, self.static, total_count)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = fused_mse_step(model, self.static, total_count)
+            self.params = model._engine_params()
+            self.grads = [p.grad for p in self.params]
+        finally:
+            model._seed_device = None
+            model._grad_reducer = self.reducer
+
+    def _refresh_seed(self):
+        self.seed_host.random_()
+        self.seed_dev.copy_(self.seed_host, non_blocking=True)
+
+    def load(self, batch) -> None:
+        """Copy a batch of the captured shape (host pinned or device) into the static input buffers."""
+        for f in self.FIELDS:
+            dst, src = getattr(self.static, f), getattr(batch, f)
+            if dst.shape != src.shape:
+                raise ValueError(f"batch.{f} has shape {tuple(src.shape)}, the captured graph expects {tuple(dst.shape)}")
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+
+    def __call__(self, batch=None) -> torch.Tensor:
+        if batch is not None:
+            self.load(batch)
+        self._refresh_seed()
+        self.graph.replay()
+        for p, g in zip(self.params, self.grads):
+            p.grad = g
+        if self.reducer is not None:
+            flat = self.grads[0]._base if self.grads[0]._base is not None else None
+            if flat is not None and flat.numel() == sum(g.numel() for g in self.grads):
+                self.reducer(flat)
+            else:
+                for g in self.grads:
+                    self.reducer(g)
+        return self.loss
+
+
 def train_step(model: MaskEmbdMultiMPN, host_batch, device, loss: str = "mse", total_count: Optional[int] = None):
     """End-to-end step from HOST memory: H2D of the batch (pinned -> non_blocking), forward, loss, backward,
     and the device->host read of the loss (utils/training.py:56-77 minus optimizer.step)."""

@@ -13,6 +13,7 @@
 //  - a row is summed by exactly one thread in ascending edge id: no atomics, deterministic.
 // These kernels are HBM/L2-bandwidth work (a few flops per byte): no tensor cores by design.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -23,11 +24,19 @@ struct RowTiling {
   int c4, cx, rows, threads, nblocks, npb;
 };
 
+int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e != nullptr ? std::atoi(e) : dflt;
+}
+
 RowTiling make_tiling(int64_t n_nodes, int64_t h, int blocks_per_sm) {
+  static const int max_threads = std::min(1024, std::max(32, env_int("PFN_EDGE_THREADS", 256)));
+  static const int bps_override = env_int("PFN_EDGE_BPS", 0);
+  if (bps_override > 0) blocks_per_sm = bps_override;
   RowTiling t;
   t.c4 = static_cast<int>((h + 3) / 4);
-  t.cx = std::min(t.c4, 256);
-  t.rows = std::max(1, 256 / t.cx);
+  t.cx = std::min(t.c4, max_threads);
+  t.rows = std::max(1, max_threads / t.cx);
   t.threads = t.cx * t.rows;
   int64_t want = ceil_div64(std::max<int64_t>(n_nodes, 1), t.rows);
   t.nblocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sm_count()) * blocks_per_sm)));
@@ -69,36 +78,91 @@ __device__ __forceinline__ void add_relu(float4& acc, float4 p) {
   acc.w += fmaxf(p.w, 0.f);
 }
 
+// ---- CSR slab staging ---------------------------------------------------------------------------------
+// A CTA owns a contiguous slab of rows, so its CSR entries (rowptr slice, neighbour ids, edge_attr) are one contiguous
+// range: they are copied into shared memory once, cooperatively and coalesced.  Without this every thread walks a
+// chain of three dependent global loads per row (rowptr -> neighbour id -> neighbour row); with it the per-row work
+// is a single round of independent gathers.  Slabs larger than the staging buffers are walked in pieces; a piece
+// whose edge count exceeds the buffer (a hub bus) falls back to reading the CSR arrays from global memory.
+constexpr int kSlabRows = 64;
+constexpr int kSlabEdges = 768;
+
+struct SlabSmem {
+  int rowptr[kSlabRows + 1];
+  int nbr[kSlabEdges];
+  float2 ea[kSlabEdges];
+};
+
+struct SlabView {
+  const int* nbr;    // indexed by absolute edge id minus `e0` when staged, by absolute edge id otherwise
+  const float2* ea;
+  int e0;
+};
+
+__device__ __forceinline__ SlabView stage_slab(SlabSmem& sm, const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                               const float2* __restrict__ ea, int r0, int nr) {
+  for (int i = threadIdx.x; i <= nr; i += blockDim.x) sm.rowptr[i] = rowptr[r0 + i];
+  __syncthreads();
+  const int e0 = sm.rowptr[0], ne = sm.rowptr[nr] - e0;
+  SlabView v;
+  if (ne <= kSlabEdges) {
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+      sm.nbr[i] = nbr[e0 + i];
+      if (ea != nullptr) sm.ea[i] = ea[e0 + i];
+    }
+    v.nbr = sm.nbr;
+    v.ea = sm.ea;
+    v.e0 = e0;
+  } else {
+    v.nbr = nbr;
+    v.ea = ea;
+    v.e0 = 0;
+  }
+  __syncthreads();
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh, const int* __restrict__ rowptr,
          const int* __restrict__ nbr, const float2* __restrict__ ea, const float* __restrict__ We, int64_t ldwe,
          float* __restrict__ S, int64_t lds, int n_nodes, int h, int c4, int cx, int rows, int npb) {
+  __shared__ SlabSmem sm;
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
   const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
-  for (int q = x; q < c4; q += cx) {
-    float4 w0, w1;
-    load_we(We, ldwe, q, h, w0, w1);
-    for (int node = start + y; node < end; node += rows) {
-      const float4 hi = ld4(Hi + node * ldh + 4 * q);
-      const int beg = rowptr[node], fin = rowptr[node + 1];
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      int e = beg;
-      for (; e + 1 < fin; e += 2) {  // two gathers in flight per thread
-        const int s0 = nbr[e], s1 = nbr[e + 1];
-        const float2 a0 = ea[e], a1 = ea[e + 1];
-        const float4 h0 = ldg4(Hj + s0 * ldh + 4 * q);
-        const float4 h1 = ldg4(Hj + s1 * ldh + 4 * q);
-        add_relu(acc, preact(hi, h0, a0, w0, w1));
-        add_relu(acc, preact(hi, h1, a1, w0, w1));
+  for (int r0 = start; r0 < end; r0 += kSlabRows) {  // CTA-uniform
+    const int nr = min(kSlabRows, end - r0);
+    const SlabView sv = stage_slab(sm, rowptr, nbr, ea, r0, nr);
+    for (int q = x; q < c4; q += cx) {
+      float4 w0, w1;
+      load_we(We, ldwe, q, h, w0, w1);
+      for (int lr = y; lr < nr; lr += rows) {
+        const int node = r0 + lr;
+        const float4 hi = ld4(Hi + node * ldh + 4 * q);
+        const int beg = sm.rowptr[lr] - sv.e0, fin = sm.rowptr[lr + 1] - sv.e0;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = beg;
+        for (; e + 3 < fin; e += 4) {  // four gathers in flight per thread
+          const int s0 = sv.nbr[e], s1 = sv.nbr[e + 1], s2 = sv.nbr[e + 2], s3 = sv.nbr[e + 3];
+          const float4 h0 = ldg4(Hj + s0 * ldh + 4 * q), h1 = ldg4(Hj + s1 * ldh + 4 * q);
+          const float4 h2 = ldg4(Hj + s2 * ldh + 4 * q), h3 = ldg4(Hj + s3 * ldh + 4 * q);
+          add_relu(acc, preact(hi, h0, sv.ea[e], w0, w1));
+          add_relu(acc, preact(hi, h1, sv.ea[e + 1], w0, w1));
+          add_relu(acc, preact(hi, h2, sv.ea[e + 2], w0, w1));
+          add_relu(acc, preact(hi, h3, sv.ea[e + 3], w0, w1));
+        }
+        if (e + 1 < fin) {
+          const int s0 = sv.nbr[e], s1 = sv.nbr[e + 1];
+          const float4 h0 = ldg4(Hj + s0 * ldh + 4 * q), h1 = ldg4(Hj + s1 * ldh + 4 * q);
+          add_relu(acc, preact(hi, h0, sv.ea[e], w0, w1));
+          add_relu(acc, preact(hi, h1, sv.ea[e + 1], w0, w1));
+          e += 2;
+        }
+        if (e < fin) add_relu(acc, preact(hi, ldg4(Hj + sv.nbr[e] * ldh + 4 * q), sv.ea[e], w0, w1));
+        st4(S + node * lds + 4 * q, acc);
       }
-      if (e < fin) {
-        const int s0 = nbr[e];
-        const float2 a0 = ea[e];
-        add_relu(acc, preact(hi, ldg4(Hj + s0 * ldh + 4 * q), a0, w0, w1));
-      }
-      st4(S + node * lds + 4 * q, acc);
     }
+    __syncthreads();  // the staging buffers are rewritten by the next piece
   }
 }
 
@@ -106,47 +170,89 @@ k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh
 // blockIdx.y == 0: target-side pass over the CSR by target:  dHi[i] = sum_{e in in(i)} dS[i] * 1[p_e > 0]
 //                  and the per-CTA partial of dWe[c,k] = sum_e g_e[c] * ea_e[k]
 // blockIdx.y == 1: source-side pass over the CSR by source:  dHj[j] = sum_{e in out(j)} dS[tgt e] * 1[p_e > 0]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_ea_bwd(const float* __restrict__ dS, int64_t ldds, const float* __restrict__ Hi, const float* __restrict__ Hj,
          int64_t ldh, const int* __restrict__ rowptr_t, const int* __restrict__ nbr_t,
          const float2* __restrict__ ea_t, const int* __restrict__ rowptr_s, const int* __restrict__ nbr_s,
          const float2* __restrict__ ea_s, const float* __restrict__ We, int64_t ldwe, float* __restrict__ dHi,
          float* __restrict__ dHj, int64_t ldd, float* __restrict__ dwe_partial, int n_nodes, int h, int c4, int cx,
          int rows, int npb) {
-  __shared__ float red[8][256];
+  __shared__ SlabSmem sm;
+  __shared__ float red[8][1024];
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
   const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
   const bool target_side = blockIdx.y == 0;
-  for (int q0 = 0; q0 < c4; q0 += cx) {  // trip count is CTA-uniform: the loop body holds barriers
-    const int q = q0 + x;
+  const int nq = (c4 + cx - 1) / cx;  // column passes (1 unless hidden_dim > 1024)
+  float4 g0[1] = {make_float4(0.f, 0.f, 0.f, 0.f)}, g1[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
+  for (int qi = 0; qi < nq; ++qi) {  // CTA-uniform loops: the body holds barriers
+    const int q = qi * cx + x;
     const bool active = q < c4;
     float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
     if (active) load_we(We, ldwe, q, h, w0, w1);
-    if (target_side) {
-      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;  // dWe[:,0], dWe[:,1] partial sums of this chunk
-      for (int node = start + y; active && node < end; node += rows) {
-        const float4 hi = ld4(Hi + node * ldh + 4 * q);
-        const float4 ds = ld4(dS + node * ldds + 4 * q);
-        const int beg = rowptr_t[node], fin = rowptr_t[node + 1];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = beg; e < fin; ++e) {
-          const int s = nbr_t[e];
-          const float2 a = ea_t[e];
-          const float4 p = preact(hi, ldg4(Hj + s * ldh + 4 * q), a, w0, w1);
-          float4 g;
-          g.x = p.x > 0.f ? ds.x : 0.f;
-          g.y = p.y > 0.f ? ds.y : 0.f;
-          g.z = p.z > 0.f ? ds.z : 0.f;
-          g.w = p.w > 0.f ? ds.w : 0.f;
-          acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-          g0.x = fmaf(g.x, a.x, g0.x); g0.y = fmaf(g.y, a.x, g0.y); g0.z = fmaf(g.z, a.x, g0.z); g0.w = fmaf(g.w, a.x, g0.w);
-          g1.x = fmaf(g.x, a.y, g1.x); g1.y = fmaf(g.y, a.y, g1.y); g1.z = fmaf(g.z, a.y, g1.z); g1.w = fmaf(g.w, a.y, g1.w);
+    g0[0] = g1[0] = make_float4(0.f, 0.f, 0.f, 0.f);  // dWe[:,0], dWe[:,1] partial sums of this chunk
+    for (int r0 = start; r0 < end; r0 += kSlabRows) {
+      const int nr = min(kSlabRows, end - r0);
+      const SlabView sv = target_side ? stage_slab(sm, rowptr_t, nbr_t, ea_t, r0, nr) : stage_slab(sm, rowptr_s, nbr_s, ea_s, r0, nr);
+      if (active) {
+        for (int lr = y; lr < nr; lr += rows) {
+          const int node = r0 + lr;
+          const int beg = sm.rowptr[lr] - sv.e0, fin = sm.rowptr[lr + 1] - sv.e0;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (target_side) {
+            const float4 hi = ld4(Hi + node * ldh + 4 * q);
+            const float4 ds = ld4(dS + node * ldds + 4 * q);
+            int e = beg;
+            for (; e < fin; e += 2) {
+              const bool two = e + 1 < fin;
+              const int s0 = sv.nbr[e], s1 = two ? sv.nbr[e + 1] : s0;
+              const float4 h0 = ldg4(Hj + s0 * ldh + 4 * q), h1 = ldg4(Hj + s1 * ldh + 4 * q);
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                const float2 a = sv.ea[e + u];
+                const float4 p = preact(hi, u == 0 ? h0 : h1, a, w0, w1);
+                float4 g;
+                g.x = p.x > 0.f ? ds.x : 0.f;
+                g.y = p.y > 0.f ? ds.y : 0.f;
+                g.z = p.z > 0.f ? ds.z : 0.f;
+                g.w = p.w > 0.f ? ds.w : 0.f;
+                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+                g0[0].x = fmaf(g.x, a.x, g0[0].x); g0[0].y = fmaf(g.y, a.x, g0[0].y); g0[0].z = fmaf(g.z, a.x, g0[0].z); g0[0].w = fmaf(g.w, a.x, g0[0].w);
+                g1[0].x = fmaf(g.x, a.y, g1[0].x); g1[0].y = fmaf(g.y, a.y, g1[0].y); g1[0].z = fmaf(g.z, a.y, g1[0].z); g1[0].w = fmaf(g.w, a.y, g1[0].w);
+              }
+            }
+            st4(dHi + node * ldd + 4 * q, acc);
+          } else {
+            const float4 hj = ld4(Hj + node * ldh + 4 * q);
+            int e = beg;
+            for (; e < fin; e += 2) {
+              const bool two = e + 1 < fin;
+              const int t0 = sv.nbr[e], t1 = two ? sv.nbr[e + 1] : t0;
+              const float4 hi0 = ldg4(Hi + t0 * ldh + 4 * q), hi1 = ldg4(Hi + t1 * ldh + 4 * q);
+              const float4 ds0 = ldg4(dS + t0 * ldds + 4 * q), ds1 = ldg4(dS + t1 * ldds + 4 * q);
+              const float4 p0 = preact(hi0, hj, sv.ea[e], w0, w1);
+              acc.x += p0.x > 0.f ? ds0.x : 0.f;
+              acc.y += p0.y > 0.f ? ds0.y : 0.f;
+              acc.z += p0.z > 0.f ? ds0.z : 0.f;
+              acc.w += p0.w > 0.f ? ds0.w : 0.f;
+              if (two) {
+                const float4 p1 = preact(hi1, hj, sv.ea[e + 1], w0, w1);
+                acc.x += p1.x > 0.f ? ds1.x : 0.f;
+                acc.y += p1.y > 0.f ? ds1.y : 0.f;
+                acc.z += p1.z > 0.f ? ds1.z : 0.f;
+                acc.w += p1.w > 0.f ? ds1.w : 0.f;
+              }
+            }
+            st4(dHj + node * ldd + 4 * q, acc);
+          }
         }
-        st4(dHi + node * ldd + 4 * q, acc);
       }
+      __syncthreads();
+    }
+    if (target_side) {
       // fixed-order reduction over the CTA's rows, then one partial row per CTA (no atomics)
-      red[0][threadIdx.x] = g0.x; red[1][threadIdx.x] = g0.y; red[2][threadIdx.x] = g0.z; red[3][threadIdx.x] = g0.w;
-      red[4][threadIdx.x] = g1.x; red[5][threadIdx.x] = g1.y; red[6][threadIdx.x] = g1.z; red[7][threadIdx.x] = g1.w;
+      red[0][threadIdx.x] = g0[0].x; red[1][threadIdx.x] = g0[0].y; red[2][threadIdx.x] = g0[0].z; red[3][threadIdx.x] = g0[0].w;
+      red[4][threadIdx.x] = g1[0].x; red[5][threadIdx.x] = g1[0].y; red[6][threadIdx.x] = g1[0].z; red[7][threadIdx.x] = g1[0].w;
       __syncthreads();
       if (y == 0 && active) {
         float sum[8];
@@ -156,44 +262,29 @@ k_ea_bwd(const float* __restrict__ dS, int64_t ldds, const float* __restrict__ H
 #pragma unroll
           for (int k = 0; k < 8; ++k) sum[k] += red[k][yy * cx + x];
         }
-        float* dst = dwe_partial + size_t(blockIdx.x) * (2 * 4 * c4);
+        // partial layout [2][4*c4][nblocks]: the final reduction reads consecutive CTAs contiguously
+        const size_t nb = gridDim.x;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          dst[4 * q + c] = sum[c];
-          dst[4 * c4 + 4 * q + c] = sum[4 + c];
+          dwe_partial[(size_t(0) * 4 * c4 + 4 * q + c) * nb + blockIdx.x] = sum[c];
+          dwe_partial[(size_t(1) * 4 * c4 + 4 * q + c) * nb + blockIdx.x] = sum[4 + c];
         }
       }
       __syncthreads();
-    } else {
-      for (int node = start + y; active && node < end; node += rows) {
-        const float4 hj = ld4(Hj + node * ldh + 4 * q);
-        const int beg = rowptr_s[node], fin = rowptr_s[node + 1];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = beg; e < fin; ++e) {
-          const int t = nbr_s[e];
-          const float2 a = ea_s[e];
-          const float4 p = preact(ldg4(Hi + t * ldh + 4 * q), hj, a, w0, w1);
-          const float4 ds = ldg4(dS + t * ldds + 4 * q);
-          acc.x += p.x > 0.f ? ds.x : 0.f;
-          acc.y += p.y > 0.f ? ds.y : 0.f;
-          acc.z += p.z > 0.f ? ds.z : 0.f;
-          acc.w += p.w > 0.f ? ds.w : 0.f;
-        }
-        st4(dHj + node * ldd + 4 * q, acc);
-      }
     }
   }
 }
 
-// dWe[c, k] = sum over CTAs of the partial rows: one warp per output element, lanes stride over the CTAs and
-// combine with a fixed shuffle tree (deterministic; no atomics)
+// dWe[c, k] = sum over CTAs of the partial rows: one warp per output element, lanes stride over the CTAs (contiguous
+// in memory) and combine with a fixed shuffle tree (deterministic; no atomics)
 __global__ void k_reduce_dwe(const float* __restrict__ partial, int nblocks, int c4, int h, float* __restrict__ dWe,
                              int64_t lddwe) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= 2 * h) return;
   const int k = warp / h, c = warp - k * h;
+  const float* src = partial + (size_t(k) * 4 * c4 + c) * nblocks;
   float sum = 0.f;
-  for (int b = lane; b < nblocks; b += 32) sum += partial[size_t(b) * (8 * c4) + k * 4 * c4 + c];
+  for (int b = lane; b < nblocks; b += 32) sum += src[b];
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
   if (lane == 0) dWe[c * lddwe + k] = sum;
@@ -201,50 +292,57 @@ __global__ void k_reduce_dwe(const float* __restrict__ partial, int nblocks, int
 
 // ------------------------------------------------------------------------------------------------
 // Y[i] = dis[i] * sum_{e in row i} dis[nbr e] * X[nbr e]  (+ addend[i])  (* (ymask[i] > 0 ? scale : 0))
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, const int* __restrict__ nbr,
       const float* __restrict__ dis, const float* addend, int64_t ldadd, const float* __restrict__ ymask,
       int64_t ldym, float scale, float* Y, int64_t ldy, int n_nodes, int c4, int cx, int rows, int npb) {
+  __shared__ SlabSmem sm;
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
   const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
-  for (int q = x; q < c4; q += cx) {
-    for (int node = start + y; node < end; node += rows) {
-      const int beg = rowptr[node], fin = rowptr[node + 1];
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      int e = beg;
-      for (; e + 1 < fin; e += 2) {
-        const int s0 = nbr[e], s1 = nbr[e + 1];
-        const float d0 = __ldg(dis + s0), d1 = __ldg(dis + s1);
-        const float4 v0 = ldg4(X + s0 * ldx + 4 * q);
-        const float4 v1 = ldg4(X + s1 * ldx + 4 * q);
-        acc.x = fmaf(d0, v0.x, acc.x); acc.y = fmaf(d0, v0.y, acc.y); acc.z = fmaf(d0, v0.z, acc.z); acc.w = fmaf(d0, v0.w, acc.w);
-        acc.x = fmaf(d1, v1.x, acc.x); acc.y = fmaf(d1, v1.y, acc.y); acc.z = fmaf(d1, v1.z, acc.z); acc.w = fmaf(d1, v1.w, acc.w);
+  for (int r0 = start; r0 < end; r0 += kSlabRows) {
+    const int nr = min(kSlabRows, end - r0);
+    const SlabView sv = stage_slab(sm, rowptr, nbr, nullptr, r0, nr);
+    for (int q = x; q < c4; q += cx) {
+      for (int lr = y; lr < nr; lr += rows) {
+        const int node = r0 + lr;
+        const int beg = sm.rowptr[lr] - sv.e0, fin = sm.rowptr[lr + 1] - sv.e0;
+        const float di = dis[node];
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = a4;
+        if (addend != nullptr) a4 = ld4(addend + node * ldadd + 4 * q);
+        if (ymask != nullptr) m4 = ld4(ymask + node * ldym + 4 * q);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = beg;
+        for (; e + 3 < fin; e += 4) {
+          const int s0 = sv.nbr[e], s1 = sv.nbr[e + 1], s2 = sv.nbr[e + 2], s3 = sv.nbr[e + 3];
+          const float d0 = __ldg(dis + s0), d1 = __ldg(dis + s1), d2 = __ldg(dis + s2), d3 = __ldg(dis + s3);
+          const float4 v0 = ldg4(X + s0 * ldx + 4 * q), v1 = ldg4(X + s1 * ldx + 4 * q);
+          const float4 v2 = ldg4(X + s2 * ldx + 4 * q), v3 = ldg4(X + s3 * ldx + 4 * q);
+          acc.x = fmaf(d0, v0.x, acc.x); acc.y = fmaf(d0, v0.y, acc.y); acc.z = fmaf(d0, v0.z, acc.z); acc.w = fmaf(d0, v0.w, acc.w);
+          acc.x = fmaf(d1, v1.x, acc.x); acc.y = fmaf(d1, v1.y, acc.y); acc.z = fmaf(d1, v1.z, acc.z); acc.w = fmaf(d1, v1.w, acc.w);
+          acc.x = fmaf(d2, v2.x, acc.x); acc.y = fmaf(d2, v2.y, acc.y); acc.z = fmaf(d2, v2.z, acc.z); acc.w = fmaf(d2, v2.w, acc.w);
+          acc.x = fmaf(d3, v3.x, acc.x); acc.y = fmaf(d3, v3.y, acc.y); acc.z = fmaf(d3, v3.z, acc.z); acc.w = fmaf(d3, v3.w, acc.w);
+        }
+        for (; e < fin; ++e) {
+          const int s0 = sv.nbr[e];
+          const float d0 = __ldg(dis + s0);
+          const float4 v0 = ldg4(X + s0 * ldx + 4 * q);
+          acc.x = fmaf(d0, v0.x, acc.x); acc.y = fmaf(d0, v0.y, acc.y); acc.z = fmaf(d0, v0.z, acc.z); acc.w = fmaf(d0, v0.w, acc.w);
+        }
+        float4 out = make_float4(fmaf(di, acc.x, a4.x), fmaf(di, acc.y, a4.y), fmaf(di, acc.z, a4.z), fmaf(di, acc.w, a4.w));
+        if (ymask != nullptr) {
+          out.x = m4.x > 0.f ? out.x * scale : 0.f;
+          out.y = m4.y > 0.f ? out.y * scale : 0.f;
+          out.z = m4.z > 0.f ? out.z * scale : 0.f;
+          out.w = m4.w > 0.f ? out.w * scale : 0.f;
+        }
+        st4(Y + node * ldy + 4 * q, out);
       }
-      if (e < fin) {
-        const int s0 = nbr[e];
-        const float d0 = __ldg(dis + s0);
-        const float4 v0 = ldg4(X + s0 * ldx + 4 * q);
-        acc.x = fmaf(d0, v0.x, acc.x); acc.y = fmaf(d0, v0.y, acc.y); acc.z = fmaf(d0, v0.z, acc.z); acc.w = fmaf(d0, v0.w, acc.w);
-      }
-      const float di = dis[node];
-      float4 out = make_float4(di * acc.x, di * acc.y, di * acc.z, di * acc.w);
-      if (addend != nullptr) {
-        const float4 a = ld4(addend + node * ldadd + 4 * q);
-        out.x += a.x; out.y += a.y; out.z += a.z; out.w += a.w;
-      }
-      if (ymask != nullptr) {
-        const float4 m = ld4(ymask + node * ldym + 4 * q);
-        out.x = m.x > 0.f ? out.x * scale : 0.f;
-        out.y = m.y > 0.f ? out.y * scale : 0.f;
-        out.z = m.z > 0.f ? out.z * scale : 0.f;
-        out.w = m.w > 0.f ? out.w * scale : 0.f;
-      }
-      st4(Y + node * ldy + 4 * q, out);
     }
+    __syncthreads();
   }
 }
 
-constexpr int kBlocksPerSm = 8;
+constexpr int kBlocksPerSm = 4;  // measured: 4 x 231-thread CTAs per SM beat 8 (and 1 x 1024) at case118 sizes
 
 bool rows_ok(const void* p, int64_t ld) { return p != nullptr && aligned16(p) && ld % 4 == 0; }
 

@@ -167,18 +167,29 @@ __global__ void __launch_bounds__(256) k_gemm(const __grid_constant__ GemmArgs a
   }
 }
 
-// Second pass of the split-K weight gradient: sum the partial tiles in split order.
-__global__ void k_splitk_reduce(const __grid_constant__ GemmArgs args) {
+// Second pass of the split-K weight gradient: sum the partial tiles in a fixed order (deterministic).  Eight partials
+// are loaded before the first add so the pass is bandwidth- rather than latency-bound.
+__global__ void __launch_bounds__(256) k_splitk_reduce(const __grid_constant__ GemmArgs args) {
   const int M = args.M, N = args.N, n_eff = N + (args.extra_col ? 1 : 0);
   const int count = args.batched ? args.n_items : 1;
   const size_t per = size_t(M) * n_eff;
   const size_t total = per * count;
+  const int S = args.splitk;
   for (size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
     const int prob = static_cast<int>(idx / per);
     const size_t r = idx - size_t(prob) * per;
     const int m = static_cast<int>(r / n_eff), n = static_cast<int>(r - size_t(m) * n_eff);
+    const float* __restrict__ src = args.partial + size_t(prob) * per + r;
+    const size_t stride = size_t(count) * per;
     float sum = 0.f;
-    for (int s = 0; s < args.splitk; ++s) sum += args.partial[size_t(s * count + prob) * per + r];
+    int s = 0;
+    for (; s + 8 <= S; s += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + size_t(s + u) * stride);
+      sum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+    for (; s < S; ++s) sum += __ldg(src + size_t(s) * stride);
     const GemmItem& out = args.it[prob];
     if (n == N) {
       if (out.bias_out != nullptr) out.bias_out[m] = sum;

@@ -71,10 +71,35 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(int n_nodes, int32_t* cnt
                                                        float* dis) {
   int32_t* cnt = blockIdx.x == 0 ? cnt_t : cnt_s;
   int32_t* rowptr = blockIdx.x == 0 ? rowptr_t : rowptr_s;
-  const int per = (n_nodes + kScanThreads - 1) / kScanThreads;
+  // each thread owns a contiguous chunk whose length is a multiple of 4 so it can be read with 16-byte loads; chunks
+  // of up to kRegChunk counts stay in registers between the two passes (one memory round trip instead of two)
+  constexpr int kRegChunk = 16;
+  const int per = ((n_nodes + kScanThreads - 1) / kScanThreads + 3) & ~3;
   const int beg = min(n_nodes, (int)threadIdx.x * per), end = min(n_nodes, beg + per);
+  const bool vec = (reinterpret_cast<uintptr_t>(cnt) & 15u) == 0;
+  const bool in_regs = per <= kRegChunk;
+  int vals[kRegChunk];
   int local = 0;
-  for (int i = beg; i < end; ++i) local += cnt[i];
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kRegChunk; j += 4) {
+      int4 v = make_int4(0, 0, 0, 0);
+      if (j < per) {
+        if (vec && beg + j + 3 < end) {
+          v = *reinterpret_cast<const int4*>(cnt + beg + j);
+        } else {
+          if (beg + j + 0 < end) v.x = cnt[beg + j + 0];
+          if (beg + j + 1 < end) v.y = cnt[beg + j + 1];
+          if (beg + j + 2 < end) v.z = cnt[beg + j + 2];
+          if (beg + j + 3 < end) v.w = cnt[beg + j + 3];
+        }
+      }
+      vals[j] = v.x; vals[j + 1] = v.y; vals[j + 2] = v.z; vals[j + 3] = v.w;
+      local += v.x + v.y + v.z + v.w;
+    }
+  } else {
+    for (int i = beg; i < end; ++i) local += cnt[i];
+  }
   // block-wide exclusive scan of `local`
   __shared__ int warp_sums[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,14 +122,31 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(int n_nodes, int32_t* cnt
   }
   __syncthreads();
   int run = incl - local + (warp > 0 ? warp_sums[warp - 1] : 0);
-  for (int i = beg; i < end; ++i) {
-    const int c = cnt[i];
-    rowptr[i] = run;
-    run += c;
-    cnt[i] = 0;
-    if (blockIdx.x == 0) {
-      deg[i] = static_cast<float>(c);
-      dis[i] = c > 0 ? 1.0f / sqrtf(static_cast<float>(c)) : 0.0f;
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kRegChunk; ++j) {
+      const int i = beg + j;
+      if (j < per && i < end) {
+        const int c = vals[j];
+        rowptr[i] = run;
+        run += c;
+        cnt[i] = 0;
+        if (blockIdx.x == 0) {
+          deg[i] = static_cast<float>(c);
+          dis[i] = c > 0 ? 1.0f / sqrtf(static_cast<float>(c)) : 0.0f;
+        }
+      }
+    }
+  } else {
+    for (int i = beg; i < end; ++i) {
+      const int c = cnt[i];
+      rowptr[i] = run;
+      run += c;
+      cnt[i] = 0;
+      if (blockIdx.x == 0) {
+        deg[i] = static_cast<float>(c);
+        dis[i] = c > 0 ? 1.0f / sqrtf(static_cast<float>(c)) : 0.0f;
+      }
     }
   }
   if (threadIdx.x == kScanThreads - 1) rowptr[n_nodes] = run;

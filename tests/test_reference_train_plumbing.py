@@ -1,0 +1,29 @@
+"""BASELINE configs[0]: the reference's own train.py, unchanged, on a synthetic case14 dataset with
+configs/small.json, batch 16, on CPU (plumbing: argument parser, PowerFlowData processing + normalisation,
+DataLoader/Batch collation, train/eval loops, checkpoint save + reload).  torch_geometric is satisfied by the
+stand-in under oracle/pyg_shim.  Needs the reference checkout (build container only)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = os.environ.get("PFN_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE, "train.py")), reason="reference checkout not present")
+@pytest.mark.timeout(300)
+def test_reference_train_py_runs_unchanged_on_case14(tmp_path):
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "run_reference_train.py"), "--reference", REFERENCE, "--workdir", str(tmp_path),
+           "--make-synthetic-case", "14", "--samples", "80", "--",
+           "--cfg_json", os.path.join(REFERENCE, "configs", "small.json"), "--case", "14", "--model", "MaskEmbdMultiMPN",
+           "--train_loss_fn", "mse_loss", "--batch-size", "16", "--num-epochs", "3", "--data-dir", str(tmp_path / "data")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "Total number of parameters:  30536" in r.stdout
+    losses = [float(m) for m in re.findall(r"train_loss=([0-9.]+)", r.stdout)]
+    assert len(losses) == 3 and all(l == l and l < 1e3 for l in losses)
+    assert "Training Complete" in r.stdout
+    assert any(f.startswith("model_") for f in os.listdir(tmp_path / "models"))

@@ -247,3 +247,32 @@ def test_cuda_graph_step_matches_eager_step():
     step2 = GraphedMSEStep(m2, b1)
     l1, l2 = float(step2(b1)), float(step2(b1))
     assert l1 != l2  # the device-resident seed changed between replays
+
+
+def test_loss_curve_matches_oracle_over_optimizer_steps():
+    """`train_epoch`'s loop (utils/training.py:55-77) with AdamW (train.py:123) for 12 steps, dropout off so both sides are
+    deterministic: the CUDA model's loss curve tracks the CPU oracle's."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=33, n_gnn_layers=3, K=3, dropout_rate=0.0)
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
+    mine = _model(kw, oracle.state_dict()).train()
+    opt_o = torch.optim.AdamW(oracle.parameters(), lr=1e-3)
+    opt_m = torch.optim.AdamW(mine.parameters(), lr=1e-3)
+    batches = [synthetic_batch("14", 16, seed=100 + i) for i in range(4)]
+    curve_o, curve_m = [], []
+    for step in range(12):
+        b = batches[step % 4]
+        opt_o.zero_grad()
+        lo = torch.nn.functional.mse_loss(oracle(b), b.y)
+        lo.backward()
+        opt_o.step()
+        db = b.to(DEV)
+        opt_m.zero_grad()
+        lm = torch.nn.functional.mse_loss(mine(db), db.y)
+        lm.backward()
+        opt_m.step()
+        curve_o.append(float(lo))
+        curve_m.append(float(lm))
+    assert curve_o[-1] < curve_o[0]  # it trains
+    for a, b in zip(curve_m, curve_o):
+        assert abs(a - b) <= 1e-4 * abs(b), (curve_m, curve_o)

@@ -27,3 +27,21 @@ def test_reference_train_py_runs_unchanged_on_case14(tmp_path):
     assert len(losses) == 3 and all(l == l and l < 1e3 for l in losses)
     assert "Training Complete" in r.stdout
     assert any(f.startswith("model_") for f in os.listdir(tmp_path / "models"))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE, "train.py")), reason="reference checkout not present")
+@pytest.mark.timeout(300)
+def test_module_swap_reaches_the_cuda_model_and_fails_loudly_without_a_gpu(tmp_path):
+    """`--impl b200` leaves train.py byte-identical and swaps networks.MPN.MaskEmbdMultiMPN for the sm_100a module:
+    the script builds OUR model (same parameter count) and, on this GPU-less box, the first forward refuses CPU tensors
+    instead of silently computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the swap would simply train")
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "run_reference_train.py"), "--reference", REFERENCE, "--impl", "b200",
+           "--workdir", str(tmp_path), "--make-synthetic-case", "14", "--samples", "40", "--",
+           "--cfg_json", os.path.join(REFERENCE, "configs", "small.json"), "--case", "14", "--model", "MaskEmbdMultiMPN",
+           "--train_loss_fn", "mse_loss", "--batch-size", "16", "--num-epochs", "1", "--data-dir", str(tmp_path / "data")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
+    assert "Total number of parameters:  30536" in r.stdout
+    assert r.returncode != 0 and "CUDA tensors only" in r.stderr and "no CPU fallback" in r.stderr

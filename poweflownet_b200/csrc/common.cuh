@@ -41,6 +41,34 @@ int sm_count();
     if (pfn_rc_ != 0) return pfn_rc_;    \
   } while (0)
 
+// ---- launches: programmatic dependent launch (PDL) ------------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+// griddepcontrol.wait: the next kernel's launch latency and prologue (barrier init, TMEM allocation, tensor-map
+// prefetch, index arithmetic) overlap the tail of the previous one, which matters when a step is ~90 kernels of
+// 5-20 us.  PFN_PDL=0 restores plain stream-ordered launches.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#if defined(__CUDACC__)
+// wait until the preceding kernel(s) in the stream have completed and their writes are visible (no-op without PDL)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // RAII bracket used by the launch sites; a no-op unless pfn_profile_enable(1) was called.
 struct ProfScope {
   int slot;
@@ -105,6 +133,7 @@ struct GemmItem {
   long long a_rs, a_cs, b_rs, b_cs;
   int K;
   int ldc;
+  long long b_plane;  // != 0: B is followed by its pre-split TF32 planes: B + b_plane = hi, B + 2*b_plane = lo
 };
 
 struct GemmArgs {
@@ -148,8 +177,8 @@ int wgrad_tc_launch(GemmArgs& args, cudaStream_t stream);  // may rewrite args.s
 bool tc_enabled();
 struct PackDesc {
   const float* src;  // [rows, cols] with row pitch ld_src (a state_dict weight or a column block of one)
-  float* dst;        // [rows, ld_dst]   16-byte-pitched copy          (may be null)
-  float* dst_t;      // [cols, ld_dst_t] 16-byte-pitched transposed copy (may be null)
+  float* dst;        // 3 planes of [rows, ld_dst]:   fp32 copy | rn_tf32(w) | rn_tf32(w - hi)      (may be null)
+  float* dst_t;      // 3 planes of [cols, ld_dst_t]: the same for the transpose                      (may be null)
   int ld_src, rows, cols, ld_dst, ld_dst_t;
 };
 int pack_weights_launch(const PackDesc* items, int n, cudaStream_t stream);

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(1024)
 k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh, const int* __restrict__ rowptr,
          const int* __restrict__ nbr, const float2* __restrict__ ea, const float* __restrict__ We, int64_t ldwe,
          float* __restrict__ S, int64_t lds, int n_nodes, int h, int c4, int cx, int rows, int npb) {
+  pdl_wait();
   __shared__ SlabSmem sm;
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
   const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
@@ -177,6 +178,7 @@ k_ea_bwd(const float* __restrict__ dS, int64_t ldds, const float* __restrict__ H
          const float2* __restrict__ ea_s, const float* __restrict__ We, int64_t ldwe, float* __restrict__ dHi,
          float* __restrict__ dHj, int64_t ldd, float* __restrict__ dwe_partial, int n_nodes, int h, int c4, int cx,
          int rows, int npb) {
+  pdl_wait();
   __shared__ SlabSmem sm;
   __shared__ float red[8][1024];
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
@@ -279,6 +281,7 @@ k_ea_bwd(const float* __restrict__ dS, int64_t ldds, const float* __restrict__ H
 // in memory) and combine with a fixed shuffle tree (deterministic; no atomics)
 __global__ void k_reduce_dwe(const float* __restrict__ partial, int nblocks, int c4, int h, float* __restrict__ dWe,
                              int64_t lddwe) {
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= 2 * h) return;
   const int k = warp / h, c = warp - k * h;
@@ -296,6 +299,7 @@ __global__ void __launch_bounds__(1024)
 k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, const int* __restrict__ nbr,
       const float* __restrict__ dis, const float* addend, int64_t ldadd, const float* __restrict__ ymask,
       int64_t ldym, float scale, float* Y, int64_t ldy, int n_nodes, int c4, int cx, int rows, int npb) {
+  pdl_wait();
   __shared__ SlabSmem sm;
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
   const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
@@ -356,9 +360,9 @@ int ea_fwd_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView
   if (n_nodes == 0) return 0;
   const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
   ProfScope prof(PFN_PROF_EA_FWD, stream);
-  k_ea_fwd<<<t.nblocks, t.threads, 0, stream>>>(Hi, Hj, ldh, g.rowptr_t, g.nbr_t, reinterpret_cast<const float2*>(g.ea_t),
+  PFN_CUDA_OK(launch_kernel(k_ea_fwd, dim3(t.nblocks), dim3(t.threads), 0, stream, Hi, Hj, ldh, g.rowptr_t, g.nbr_t, reinterpret_cast<const float2*>(g.ea_t),
                                                We, ldwe, S, lds, static_cast<int>(n_nodes), static_cast<int>(h), t.c4,
-                                               t.cx, t.rows, t.npb);
+                                               t.cx, t.rows, t.npb));
   PFN_LAUNCHED();
   return 0;
 }
@@ -376,14 +380,14 @@ int ea_bwd_launch(const float* dS, int64_t ldds, const float* Hi, const float* H
   if (n_nodes > 0) {
     nblocks = t.nblocks;
     dim3 grid(t.nblocks, 2);
-    k_ea_bwd<<<grid, t.threads, 0, stream>>>(dS, ldds, Hi, Hj, ldh, g.rowptr_t, g.nbr_t,
+    PFN_CUDA_OK(launch_kernel(k_ea_bwd, grid, dim3(t.threads), 0, stream, dS, ldds, Hi, Hj, ldh, g.rowptr_t, g.nbr_t,
                                             reinterpret_cast<const float2*>(g.ea_t), g.rowptr_s, g.nbr_s,
                                             reinterpret_cast<const float2*>(g.ea_s), We, ldwe, dHi, dHj, ldd, partial,
-                                            static_cast<int>(n_nodes), static_cast<int>(h), t.c4, t.cx, t.rows, t.npb);
+                                            static_cast<int>(n_nodes), static_cast<int>(h), t.c4, t.cx, t.rows, t.npb));
     PFN_LAUNCHED();
   }
-  k_reduce_dwe<<<static_cast<int>(ceil_div64(2 * h * 32, 256)), 256, 0, stream>>>(partial, nblocks, t.c4, static_cast<int>(h),
-                                                                           dWe, lddwe);
+  PFN_CUDA_OK(launch_kernel(k_reduce_dwe, dim3(static_cast<int>(ceil_div64(2 * h * 32, 256))), dim3(256), 0, stream, partial, nblocks, t.c4, static_cast<int>(h),
+                                                                           dWe, lddwe));
   PFN_LAUNCHED();
   return 0;
 }
@@ -397,9 +401,9 @@ int hop_launch(const float* X, int64_t ldx, const GraphView& g, int64_t n_nodes,
   if (n_nodes == 0) return 0;
   const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
   ProfScope prof(PFN_PROF_HOP, stream);
-  k_hop<<<t.nblocks, t.threads, 0, stream>>>(X, ldx, transpose ? g.rowptr_s : g.rowptr_t, transpose ? g.nbr_s : g.nbr_t,
+  PFN_CUDA_OK(launch_kernel(k_hop, dim3(t.nblocks), dim3(t.threads), 0, stream, X, ldx, transpose ? g.rowptr_s : g.rowptr_t, transpose ? g.nbr_s : g.nbr_t,
                                             g.dis, addend, ldadd, ymask, ldym, scale, Y, ldy, static_cast<int>(n_nodes),
-                                            t.c4, t.cx, t.rows, t.npb);
+                                            t.c4, t.cx, t.rows, t.npb));
   PFN_LAUNCHED();
   return 0;
 }

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -31,6 +32,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("PFN_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
 
 int sm_count() {
   static int cached = 0;
@@ -80,6 +89,7 @@ namespace {
 
 // ---- small elementwise kernels -------------------------------------------------------------------
 __global__ void k_i64_to_f32(const int64_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  pdl_wait();
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     out[i] = static_cast<float>(in[i]);
 }
@@ -88,6 +98,7 @@ constexpr int kMseBlock = 256;
 __global__ void __launch_bounds__(kMseBlock)
 k_mse_partial(const float* __restrict__ out, const float* __restrict__ y, int64_t count, float inv_count,
               float* __restrict__ dout, float* __restrict__ partial) {
+  pdl_wait();
   float local = 0.f;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
     const float d = out[i] - y[i];
@@ -105,6 +116,7 @@ k_mse_partial(const float* __restrict__ out, const float* __restrict__ y, int64_
 }
 __global__ void __launch_bounds__(kMseBlock)
 k_mse_final(const float* __restrict__ partial, int n, float inv_count, float* __restrict__ loss) {
+  pdl_wait();
   __shared__ float red[kMseBlock];
   float local = 0.f;
   for (int i = threadIdx.x; i < n; i += kMseBlock) local += partial[i];
@@ -206,25 +218,25 @@ int make_plan(const pfn_mpn_desc* desc, int64_t n_nodes, Plan& p) {
   for (const LayerPlan& L : p.layers) {
     if (L.is_ea) {
       Plan::EaPack e;
-      e.wi = take(h * ld4(L.fin));
-      e.wj = take(h * ld4(L.fin));
-      e.w2 = take(L.fout * ld4(h));
-      e.wiT = take(L.fin * ld4(h));
-      e.wjT = take(L.fin * ld4(h));
-      e.w2T = take(h * ld4(L.fout));
+      e.wi = take(3 * h * ld4(L.fin));  // three planes each: fp32 | tf32 hi | tf32 lo
+      e.wj = take(3 * h * ld4(L.fin));
+      e.w2 = take(3 * L.fout * ld4(h));
+      e.wiT = take(3 * L.fin * ld4(h));
+      e.wjT = take(3 * L.fin * ld4(h));
+      e.w2T = take(3 * h * ld4(L.fout));
       p.ea_pack.push_back(e);
     } else {
       Plan::TagPack t{};
       for (int k = 0; k <= d.K; ++k) {
-        t.w[k] = take(L.fout * ld4(L.fin));
-        t.wT[k] = take(L.fin * ld4(L.fout));
+        t.w[k] = take(3 * L.fout * ld4(L.fin));
+        t.wT[k] = take(3 * L.fin * ld4(L.fout));
       }
       p.tag_pack.push_back(t);
     }
   }
-  p.mask_w1 = take(h * ld4(d.nfeature_dim));
-  p.mask_w2 = take(d.nfeature_dim * ld4(h));
-  p.mask_w2T = take(h * ld4(d.nfeature_dim));
+  p.mask_w1 = take(3 * h * ld4(d.nfeature_dim));
+  p.mask_w2 = take(3 * d.nfeature_dim * ld4(h));
+  p.mask_w2T = take(3 * h * ld4(d.nfeature_dim));
   p.act_floats = off;
   // scratch
   off = 0;
@@ -276,13 +288,14 @@ GemmArgs base_args(int M, int N) {
 }
 
 // Y = X W^T view helpers -----------------------------------------------------------------------------
+// W is a packed weight [n_out, ldw] followed by its TF32 hi / lo planes (k_pack_weights); w_rows = n_out
 inline GemmItem fwd_item(const float* X, int64_t ldx, const float* W, int64_t ldw, int K, float* C, int64_t ldc,
-                         const float* bias) {
-  return GemmItem{X, W, C, bias, nullptr, ldx, 1, 1, ldw, K, static_cast<int>(ldc)};
+                         const float* bias, int64_t w_rows) {
+  return GemmItem{X, W, C, bias, nullptr, ldx, 1, 1, ldw, K, static_cast<int>(ldc), w_rows * ldw};
 }
 inline GemmItem wgrad_item(const float* dY, int64_t lddy, const float* X, int64_t ldx, int K, float* dW, int64_t lddw,
                            float* dbias) {
-  return GemmItem{dY, X, dW, nullptr, dbias, 1, lddy, ldx, 1, K, static_cast<int>(lddw)};
+  return GemmItem{dY, X, dW, nullptr, dbias, 1, lddy, ldx, 1, K, static_cast<int>(lddw), 0};
 }
 
 void set_activation(GemmArgs& a, const Ctx& c, bool act, int layer_index, uint64_t seed, const float* inj, int64_t ld_inj) {
@@ -343,15 +356,15 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
   // mask_embd (MPN.py:533,537): x0 = Linear(ReLU(Linear(mask.float()))) + x
   {
     const int64_t n = int64_t(N) * nf;
-    k_i64_to_f32<<<static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 1184)), 256, 0, c.stream>>>(pred_mask, maskf, n);
+    PFN_CUDA_OK(launch_kernel(k_i64_to_f32, dim3(static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 1184))), dim3(256), 0, c.stream, pred_mask, maskf, n));
     PFN_LAUNCHED();
     const float* const* mp = c.params + p.p_mask;
     GemmArgs a = base_args(N, h);
-    a.it[0] = fwd_item(maskf, nf, c.act + p.mask_w1, ld_nf, nf, t1, ldh, mp[1]);
+    a.it[0] = fwd_item(maskf, nf, c.act + p.mask_w1, ld_nf, nf, t1, ldh, mp[1], h);
     a.act = PFN_ACT_RELU;
     PFN_TRY(gemm_launch(a, true, true, c.stream));
     GemmArgs b = base_args(N, nf);
-    b.it[0] = fwd_item(t1, ldh, c.act + p.mask_w2, ld_h, h, x0, nf, mp[3]);
+    b.it[0] = fwd_item(t1, ldh, c.act + p.mask_w2, ld_h, h, x0, nf, mp[3], nf);
     b.addend = x;
     b.ld_add = nf;
     PFN_TRY(gemm_launch(b, true, true, c.stream));
@@ -372,8 +385,8 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
       GemmArgs a = base_args(N, h);
       a.n_items = 2;
       a.batched = 1;
-      a.it[0] = fwd_item(cur, ldcur, c.act + pk.wi, ld_fin, L.fin, c.hi(L.slot), ldh, lp[1]);
-      a.it[1] = fwd_item(cur, ldcur, c.act + pk.wj, ld_fin, L.fin, c.hj(L.slot), ldh, nullptr);
+      a.it[0] = fwd_item(cur, ldcur, c.act + pk.wi, ld_fin, L.fin, c.hi(L.slot), ldh, lp[1], h);
+      a.it[1] = fwd_item(cur, ldcur, c.act + pk.wj, ld_fin, L.fin, c.hj(L.slot), ldh, nullptr, h);
       PFN_TRY(gemm_launch(a, true, true, c.stream));
       PFN_TRY(ea_fwd_launch(c.hi(L.slot), c.hj(L.slot), ldh, c.g, N, lp[0] + 2 * L.fin, ldw1, c.s(L.slot), ldh, h,
                             c.stream));
@@ -388,7 +401,7 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
         lddest = p.xcat_ld();
       }
       GemmArgs b = base_args(N, L.fout);
-      b.it[0] = fwd_item(c.s(L.slot), ldh, c.act + pk.w2, ld_h, h, dest, lddest, lp[3]);
+      b.it[0] = fwd_item(c.s(L.slot), ldh, c.act + pk.w2, ld_h, h, dest, lddest, lp[3], L.fout);
       b.rowscale = c.g.deg;
       set_activation(b, c, L.act, li, seed, inj, h);
       PFN_TRY(gemm_launch(b, true, true, c.stream));
@@ -406,7 +419,7 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
       a.n_items = d.K + 1;
       const Plan::TagPack& tk = p.tag_pack[L.slot];
       for (int k = 0; k <= d.K; ++k)
-        a.it[k] = fwd_item(xc + k * ldh, ldx, c.act + tk.w[k], ld_fin, L.fin, dest, lddest, lp[d.K + 1]);
+        a.it[k] = fwd_item(xc + k * ldh, ldx, c.act + tk.w[k], ld_fin, L.fin, dest, lddest, lp[d.K + 1], L.fout);
       set_activation(a, c, L.act, li, seed, inj, h);
       PFN_TRY(gemm_launch(a, true, true, c.stream));
       cur = dest;
@@ -468,7 +481,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
       const Plan::EaPack& pk = p.ea_pack[L.slot];
       {
         GemmArgs a = base_args(N, h);
-        a.it[0] = fwd_item(G, ldG, c.act + pk.w2T, round_up64(L.fout, 4), L.fout, ds, ldh, nullptr);
+        a.it[0] = fwd_item(G, ldG, c.act + pk.w2T, round_up64(L.fout, 4), L.fout, ds, ldh, nullptr, h);
         a.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
         PFN_TRY(gemm_launch(a, true, true, c.stream));
       }
@@ -494,8 +507,8 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         const int64_t lddest = li == 0 ? nf : ldh;
         GemmArgs a = base_args(N, L.fin);
         a.n_items = 2;
-        a.it[0] = fwd_item(dhi, ldh, c.act + pk.wiT, ldh, h, dest, lddest, nullptr);
-        a.it[1] = fwd_item(dhj, ldh, c.act + pk.wjT, ldh, h, dest, lddest, nullptr);
+        a.it[0] = fwd_item(dhi, ldh, c.act + pk.wiT, ldh, h, dest, lddest, nullptr, L.fin);
+        a.it[1] = fwd_item(dhj, ldh, c.act + pk.wjT, ldh, h, dest, lddest, nullptr, L.fin);
         a.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
         if (cur_has_act) {
           a.act = kActMaskByY;
@@ -531,7 +544,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         a.batched = 1;
         const Plan::TagPack& tk = p.tag_pack[L.slot];
         for (int k = 0; k <= d.K; ++k)
-          a.it[k] = fwd_item(G, ldG, c.act + tk.wT[k], round_up64(L.fout, 4), L.fout, dxcat + k * ldh, ldx, nullptr);
+          a.it[k] = fwd_item(G, ldG, c.act + tk.wT[k], round_up64(L.fout, 4), L.fout, dxcat + k * ldh, ldx, nullptr, L.fin);
         a.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
         if (d.K == 0) {
           a.act = kActMaskByY;
@@ -563,7 +576,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
     gemm_plan_splitk(a, N, 1);
     PFN_TRY(gemm_launch(a, false, false, c.stream));
     GemmArgs b = base_args(N, h);
-    b.it[0] = fwd_item(G, ldG, c.act + p.mask_w2T, round_up64(nf, 4), nf, ds, ldh, nullptr);
+    b.it[0] = fwd_item(G, ldG, c.act + p.mask_w2T, round_up64(nf, 4), nf, ds, ldh, nullptr, h);
     b.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
     b.act = kActMaskByY;
     b.ymask = t1;
@@ -680,9 +693,9 @@ extern "C" int pfn_mse_fwd_bwd(const float* out, const float* y, int64_t count, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PFN_REQUIRE(out && y && loss && dout && scratch && count > 0, PFN_E_INVALID, "pfn_mse_fwd_bwd: bad arguments");
   const int blocks = mse_blocks(count);
-  k_mse_partial<<<blocks, kMseBlock, 0, stream>>>(out, y, count, inv_count, dout, static_cast<float*>(scratch));
+  PFN_CUDA_OK(launch_kernel(k_mse_partial, dim3(blocks), dim3(kMseBlock), 0, stream, out, y, count, inv_count, dout, static_cast<float*>(scratch)));
   PFN_LAUNCHED();
-  k_mse_final<<<1, kMseBlock, 0, stream>>>(static_cast<const float*>(scratch), blocks, inv_count, loss);
+  PFN_CUDA_OK(launch_kernel(k_mse_final, dim3(1), dim3(kMseBlock), 0, stream, static_cast<const float*>(scratch), blocks, inv_count, loss));
   PFN_LAUNCHED();
   return 0;
 }

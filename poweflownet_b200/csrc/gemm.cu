@@ -26,6 +26,7 @@ constexpr int kBK = 16;
 
 template <int TM, int TN, bool AK, bool BKC>
 __global__ void __launch_bounds__(256) k_gemm(const __grid_constant__ GemmArgs args) {
+  pdl_wait();
   constexpr int BM = 16 * TM, BN = 16 * TN;
   __shared__ float As[kBK][BM + 1];
   __shared__ float Bs[kBK][BN + 1];
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(256) k_gemm(const __grid_constant__ GemmArgs a
 // Second pass of the split-K weight gradient: sum the partial tiles in a fixed order (deterministic).  Eight partials
 // are loaded before the first add so the pass is bandwidth- rather than latency-bound.
 __global__ void __launch_bounds__(256) k_splitk_reduce(const __grid_constant__ GemmArgs args) {
+  pdl_wait();
   const int M = args.M, N = args.N, n_eff = N + (args.extra_col ? 1 : 0);
   const int count = args.batched ? args.n_items : 1;
   const size_t per = size_t(M) * n_eff;
@@ -209,7 +211,7 @@ int pick_tile(int64_t dim) {
 
 template <int TM, int TN, bool AK, bool BKC>
 int launch_t(const GemmArgs& args, dim3 grid, cudaStream_t stream) {
-  k_gemm<TM, TN, AK, BKC><<<grid, 256, 0, stream>>>(args);
+  PFN_CUDA_OK(launch_kernel(k_gemm<TM, TN, AK, BKC>, grid, dim3(256), 0, stream, args));
   PFN_LAUNCHED();
   return 0;
 }
@@ -278,7 +280,7 @@ int gemm_launch(const GemmArgs& args_in, bool a_kcontig, bool b_kcontig, cudaStr
     if (rc == 0) {
       const size_t total = size_t(args.M) * n_eff * count;
       const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, size_t(sm_count()) * 8));
-      k_splitk_reduce<<<blocks, 256, 0, stream>>>(args);
+      PFN_CUDA_OK(launch_kernel(k_splitk_reduce, dim3(blocks), dim3(256), 0, stream, args));
       PFN_LAUNCHED();
       return 0;
     }
@@ -304,7 +306,7 @@ int gemm_launch(const GemmArgs& args_in, bool a_kcontig, bool b_kcontig, cudaStr
   if (args.splitk > 1) {
     const size_t total = size_t(args.M) * n_eff * count;
     const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, size_t(sm_count()) * 8));
-    k_splitk_reduce<<<blocks, 256, 0, stream>>>(args);
+    PFN_CUDA_OK(launch_kernel(k_splitk_reduce, dim3(blocks), dim3(256), 0, stream, args));
     PFN_LAUNCHED();
   }
   return 0;
@@ -324,7 +326,7 @@ extern "C" int pfn_linear_fwd(const float* X, int64_t ldx, const float* W, int64
   PFN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PFN_E_INVALID, "pfn_linear_fwd: dropout_p out of [0,1)");
   GemmArgs a{};
   a.n_items = 1;
-  a.it[0] = GemmItem{X, W, Y, bias, nullptr, ldx, 1, 1, ldw, static_cast<int>(n_in), static_cast<int>(ldy)};
+  a.it[0] = GemmItem{X, W, Y, bias, nullptr, ldx, 1, 1, ldw, static_cast<int>(n_in), static_cast<int>(ldy), 0};
   a.M = static_cast<int>(M);
   a.N = static_cast<int>(n_out);
   a.rowscale = rowscale;
@@ -348,7 +350,7 @@ extern "C" int pfn_linear_dgrad(const float* dY, int64_t lddy, const float* W, i
   GemmArgs a{};
   a.n_items = 1;
   // dX(m, i) = sum_o dY(m, o) W(o, i):  B(k=o, n=i) = W[o*ldw + i]
-  a.it[0] = GemmItem{dY, W, dX, nullptr, nullptr, lddy, 1, ldw, 1, static_cast<int>(n_out), static_cast<int>(lddx)};
+  a.it[0] = GemmItem{dY, W, dX, nullptr, nullptr, lddy, 1, ldw, 1, static_cast<int>(n_out), static_cast<int>(lddx), 0};
   a.M = static_cast<int>(M);
   a.N = static_cast<int>(n_in);
   a.act = ymask != nullptr ? kActMaskByY : PFN_ACT_NONE;
@@ -370,7 +372,7 @@ extern "C" int pfn_linear_wgrad(const float* dY, int64_t lddy, const float* X, i
   GemmArgs a{};
   a.n_items = 1;
   // dW(o, i) = sum_m dY(m, o) X(m, i):  A(m'=o, k=m) = dY[m*lddy + o],  B(k=m, n=i) = X[m*ldx + i]
-  a.it[0] = GemmItem{dY, X, dW, nullptr, dbias, 1, lddy, ldx, 1, static_cast<int>(M), static_cast<int>(lddw)};
+  a.it[0] = GemmItem{dY, X, dW, nullptr, dbias, 1, lddy, ldx, 1, static_cast<int>(M), static_cast<int>(lddw), 0};
   a.M = static_cast<int>(n_out);
   a.N = static_cast<int>(n_in);
   a.extra_col = dbias != nullptr ? (rowscale != nullptr ? 2 : 1) : 0;

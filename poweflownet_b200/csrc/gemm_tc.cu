@@ -39,10 +39,12 @@ constexpr int kTcMaxStages = 4;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 
 struct TcItem {
-  CUtensorMap a;  // [rows = M, cols = K]   box {32, 128}
-  CUtensorMap b;  // [rows = N, cols = K]   box {32, BN}
+  CUtensorMap a;     // [rows = M, cols = K]   box {32, 128}
+  CUtensorMap b;     // [rows = N, cols = K]   box {32, BN}   (the hi plane when the weights are pre-split)
+  CUtensorMap b_lo;  // lo plane (pre-split weights only)
   int K;
-  int pad_[15];
+  int presplit;
+  int pad_[14];
 };
 static_assert(sizeof(TcItem) % 64 == 0, "tensor maps must stay 64-byte aligned inside the parameter block");
 
@@ -296,10 +298,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       const int s = p_it % S;
       const uint32_t ph = (p_it / S) & 1;
       mbar_wait(empty_bar(s), ph ^ 1u);
-      mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes);
+      mbar_arrive_expect_tx(full_bar(s), a_bytes + (item.presplit ? 2u : 1u) * b_bytes);
       const uint32_t st = base + uint32_t(s) * stage_bytes;
       tma_load_2d(st, &item.a, p_k0, m0, full_bar(s));
       tma_load_2d(st + 2u * a_bytes, &item.b, p_k0, n0, full_bar(s));
+      if (item.presplit) tma_load_2d(st + 2u * a_bytes + b_bytes, &item.b_lo, p_k0, n0, full_bar(s));
       p_k0 += kTcBK;
       ++p_it;
     }
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     for (int seg = seg_begin; seg < seg_end; ++seg) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.it[seg].a)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.it[seg].b)) : "memory");
+      if (args.it[seg].presplit) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.it[seg].b_lo)) : "memory");
     }
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
@@ -316,12 +320,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pdl_wait();  // everything above overlaps the previous kernel's tail; the operands may only be read from here on
     produce(S);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(uint32_t(args.tmem_cols)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         if (tid_c == 0 && it < 8) PFN_TSTAMP(2 + it);
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         split_tile(st, a_bytes, kTcBM * 8, tid_c);
-        split_tile(st + 2u * a_bytes, b_bytes, BN * 8, tid_c);
+        if (!args.it[seg].presplit) split_tile(st + 2u * a_bytes, b_bytes, BN * 8, tid_c);  // weights arrive pre-split
         proxy_fence_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         if (tid_c == 0 && it < 8) PFN_TSTAMP(10 + it);
         __syncwarp();
@@ -526,6 +532,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(uint32_t(args.tmem_cols)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -659,7 +666,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
 // ---- weight packing ------------------------------------------------------------------------------------
 // state_dict weights are [out, in] with arbitrary row pitch (129 floats = 516 B is not a legal TMA stride) and the
 // data-gradient GEMMs need them transposed: one small kernel per step copies every matrix into 16-byte-pitched
-// K-major buffers (dst = W, dstT = W^T).
+// K-major buffers (dst = W, dstT = W^T), each as three planes: the fp32 value, its TF32 hi part and its TF32 lo part,
+// so the GEMMs TMA-load hi and lo directly and only activations are split on chip.
 struct PackItem {
   const float* src;
   float* dst;
@@ -673,13 +681,25 @@ struct PackArgs {
 static_assert(sizeof(PackArgs) <= 4000, "kernel parameter space");
 
 __global__ void k_pack_weights(const __grid_constant__ PackArgs args) {
+  pdl_wait();
   const PackItem& p = args.it[blockIdx.y];
   const int total = p.rows * p.cols;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int r = idx / p.cols, c = idx - r * p.cols;
     const float v = p.src[size_t(r) * p.ld_src + c];
-    if (p.dst != nullptr) p.dst[size_t(r) * p.ld_dst + c] = v;
-    if (p.dst_t != nullptr) p.dst_t[size_t(c) * p.ld_dst_t + r] = v;
+    const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
+    if (p.dst != nullptr) {
+      const size_t plane = size_t(p.rows) * p.ld_dst, o = size_t(r) * p.ld_dst + c;
+      p.dst[o] = v;
+      p.dst[plane + o] = hi;
+      p.dst[2 * plane + o] = lo;
+    }
+    if (p.dst_t != nullptr) {
+      const size_t plane = size_t(p.cols) * p.ld_dst_t, o = size_t(c) * p.ld_dst_t + r;
+      p.dst_t[o] = v;
+      p.dst_t[plane + o] = hi;
+      p.dst_t[2 * plane + o] = lo;
+    }
   }
 }
 
@@ -764,7 +784,12 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   a.tmem_cols = cols;
   for (int i = 0; i < g.n_items; ++i) {
     const GemmItem& it = g.it[i];
-    if (!make_map(&a.it[i].a, it.A, g.M, it.K, it.a_rs, kTcBM) || !make_map(&a.it[i].b, it.B, g.N, it.K, it.b_cs, bn)) return 1;
+    const bool presplit = it.b_plane != 0;
+    if (!make_map(&a.it[i].a, it.A, g.M, it.K, it.a_rs, kTcBM) ||
+        !make_map(&a.it[i].b, it.B + (presplit ? it.b_plane : 0), g.N, it.K, it.b_cs, bn))
+      return 1;
+    if (presplit && !make_map(&a.it[i].b_lo, it.B + 2 * it.b_plane, g.N, it.K, it.b_cs, bn)) return 1;
+    a.it[i].presplit = presplit ? 1 : 0;
     a.it[i].K = it.K;
     a.C[i] = it.C;
     a.bias[i] = it.bias;
@@ -799,7 +824,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     cudaMemsetAsync(timing_dev, 0, 64 * sizeof(long long), stream);
     a.timing = timing_dev;
   }
-  k_gemm_tc<<<grid, kTcThreads, smem, stream>>>(a);
+  PFN_CUDA_OK(launch_kernel(k_gemm_tc, grid, dim3(kTcThreads), smem, stream, a));
   PFN_LAUNCHED();
   if (timing_on) {
     long long t[64];
@@ -885,7 +910,7 @@ int wgrad_tc_launch(GemmArgs& g, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(static_cast<unsigned>(a.splitk), static_cast<unsigned>(count), static_cast<unsigned>(m_groups));
-  k_wgrad_tc<<<grid, kTcThreads, smem, stream>>>(a);
+  PFN_CUDA_OK(launch_kernel(k_wgrad_tc, grid, dim3(kTcThreads), smem, stream, a));
   PFN_LAUNCHED();
   return 0;
 }
@@ -902,7 +927,7 @@ int pack_weights_launch(const PackDesc* items, int n, cudaStream_t stream) {
       max_elems = std::max(max_elems, d.rows * d.cols);
     }
     dim3 grid(static_cast<unsigned>(std::min<int64_t>(ceil_div64(max_elems, 256), 64)), static_cast<unsigned>(cnt));
-    k_pack_weights<<<grid, 256, 0, stream>>>(args);
+    PFN_CUDA_OK(launch_kernel(k_pack_weights, grid, dim3(256), 0, stream, args));
     PFN_LAUNCHED();
   }
   return 0;

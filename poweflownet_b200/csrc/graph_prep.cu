@@ -34,6 +34,7 @@ __device__ __forceinline__ void edge_at(const int64_t* __restrict__ ei, int64_t 
 
 // Pass 1: does the reverse (b -> a) of the first edge (a -> b) exist anywhere?  (MPN.py:504)
 __global__ void k_find_reverse(const int64_t* __restrict__ ei, int64_t stride, int e_raw, int32_t* meta) {
+  pdl_wait();
   const int64_t a = ei[0], b = ei[stride];
   int found = 0;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < e_raw; e += gridDim.x * blockDim.x)
@@ -44,6 +45,7 @@ __global__ void k_find_reverse(const int64_t* __restrict__ ei, int64_t stride, i
 // Pass 2: in/out degree histograms (integer atomics: result independent of order).
 __global__ void k_count(const int64_t* __restrict__ ei, int64_t stride, int e_raw, int mode, int n_nodes,
                         int32_t* meta, int32_t* cnt_t, int32_t* cnt_s) {
+  pdl_wait();
   const bool directed = graph_directed(meta, e_raw, mode);
   const int E = directed ? 2 * e_raw : e_raw;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -69,6 +71,7 @@ __global__ void k_count(const int64_t* __restrict__ ei, int64_t stride, int e_ra
 __global__ void __launch_bounds__(kScanThreads) k_scan(int n_nodes, int32_t* cnt_t, int32_t* cnt_s,
                                                        int32_t* rowptr_t, int32_t* rowptr_s, float* deg,
                                                        float* dis) {
+  pdl_wait();
   int32_t* cnt = blockIdx.x == 0 ? cnt_t : cnt_s;
   int32_t* rowptr = blockIdx.x == 0 ? rowptr_t : rowptr_s;
   // each thread owns a contiguous chunk whose length is a multiple of 4 so it can be read with 16-byte loads; chunks
@@ -157,6 +160,7 @@ __global__ void k_fill(const int64_t* __restrict__ ei, int64_t stride, int e_raw
                        const int32_t* meta, const int32_t* __restrict__ rowptr_t,
                        const int32_t* __restrict__ rowptr_s, int32_t* cur_t, int32_t* cur_s, int32_t* eid_t,
                        int32_t* eid_s) {
+  pdl_wait();
   const int E = graph_directed(meta, e_raw, mode) ? 2 * e_raw : e_raw;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
     int64_t s, t;
@@ -173,6 +177,7 @@ __global__ void k_finalize(const int64_t* __restrict__ ei, int64_t stride, const
                            int e_raw, int n_nodes, const int32_t* __restrict__ rowptr_t,
                            const int32_t* __restrict__ rowptr_s, int32_t* eid_t, int32_t* eid_s, int32_t* nbr_t,
                            int32_t* nbr_s, float2* ea_t, float2* ea_s) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 2 * n_nodes) return;
   const bool by_target = idx < n_nodes;
@@ -202,6 +207,7 @@ __global__ void k_finalize(const int64_t* __restrict__ ei, int64_t stride, const
 
 __global__ void k_export(const int64_t* __restrict__ ei, int64_t stride, const float2* __restrict__ ea,
                          int e_raw, int e_out, int64_t* ei_out, float2* ea_out) {
+  pdl_wait();
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < e_out; e += gridDim.x * blockDim.x) {
     int64_t s, t;
     edge_at(ei, stride, e_raw, e, s, t);
@@ -270,21 +276,21 @@ extern "C" int pfn_graph_prep(const int64_t* edge_index, int64_t ei_row_stride, 
   const int cap = 2 * ER;
   const int edge_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(std::max(cap, 1), threads), 148 * 8)));
   if (ER > 0 && undirect_mode == 1) {
-    k_find_reverse<<<edge_blocks, threads, 0, stream>>>(edge_index, ei_row_stride, ER, g.meta);
+    PFN_CUDA_OK(launch_kernel(k_find_reverse, dim3(edge_blocks), dim3(threads), 0, stream, edge_index, ei_row_stride, ER, g.meta));
     PFN_LAUNCHED();
   }
-  k_count<<<edge_blocks, threads, 0, stream>>>(edge_index, ei_row_stride, ER, undirect_mode, N, g.meta, cnt_t, cnt_s);
+  PFN_CUDA_OK(launch_kernel(k_count, dim3(edge_blocks), dim3(threads), 0, stream, edge_index, ei_row_stride, ER, undirect_mode, N, g.meta, cnt_t, cnt_s));
   PFN_LAUNCHED();
-  k_scan<<<2, kScanThreads, 0, stream>>>(N, cnt_t, cnt_s, g.rowptr_t, g.rowptr_s, g.deg, g.dis);
+  PFN_CUDA_OK(launch_kernel(k_scan, dim3(2), dim3(kScanThreads), 0, stream, N, cnt_t, cnt_s, g.rowptr_t, g.rowptr_s, g.deg, g.dis));
   PFN_LAUNCHED();
   if (ER > 0) {
-    k_fill<<<edge_blocks, threads, 0, stream>>>(edge_index, ei_row_stride, ER, undirect_mode, N, g.meta, g.rowptr_t,
-                                                g.rowptr_s, cnt_t, cnt_s, g.eid_t, g.eid_s);
+    PFN_CUDA_OK(launch_kernel(k_fill, dim3(edge_blocks), dim3(threads), 0, stream, edge_index, ei_row_stride, ER, undirect_mode, N, g.meta, g.rowptr_t,
+                                                g.rowptr_s, cnt_t, cnt_s, g.eid_t, g.eid_s));
     PFN_LAUNCHED();
     if (N > 0) {
-      k_finalize<<<static_cast<int>(ceil_div64(2 * n_nodes, threads)), threads, 0, stream>>>(
+      PFN_CUDA_OK(launch_kernel(k_finalize, dim3(static_cast<int>(ceil_div64(2 * n_nodes, threads))), dim3(threads), 0, stream, 
           edge_index, ei_row_stride, reinterpret_cast<const float2*>(edge_attr), ER, N, g.rowptr_t, g.rowptr_s,
-          g.eid_t, g.eid_s, g.nbr_t, g.nbr_s, reinterpret_cast<float2*>(g.ea_t), reinterpret_cast<float2*>(g.ea_s));
+          g.eid_t, g.eid_s, g.nbr_t, g.nbr_s, reinterpret_cast<float2*>(g.ea_t), reinterpret_cast<float2*>(g.ea_s)));
       PFN_LAUNCHED();
     }
   }
@@ -311,9 +317,9 @@ extern "C" int pfn_graph_export(const int64_t* edge_index, int64_t ei_row_stride
   PFN_REQUIRE(edge_index && edge_attr && ei_out && ea_out, PFN_E_INVALID, "pfn_graph_export: null argument");
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div64(e_out, threads), 148 * 8));
-  k_export<<<blocks, threads, 0, stream>>>(edge_index, ei_row_stride, reinterpret_cast<const float2*>(edge_attr),
+  PFN_CUDA_OK(launch_kernel(k_export, dim3(blocks), dim3(threads), 0, stream, edge_index, ei_row_stride, reinterpret_cast<const float2*>(edge_attr),
                                            static_cast<int>(e_raw), static_cast<int>(e_out), ei_out,
-                                           reinterpret_cast<float2*>(ea_out));
+                                           reinterpret_cast<float2*>(ea_out)));
   PFN_LAUNCHED();
   return 0;
 }

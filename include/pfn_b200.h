@@ -56,7 +56,8 @@ PFN_API uint64_t pfn_launch_count(void);
 #define PFN_PROF_GEMM_DGRAD 4 /* dense Linear data gradient                              */
 #define PFN_PROF_GEMM_WGRAD 5 /* dense Linear weight gradient (incl. split-K reduction)  */
 #define PFN_PROF_PREP 6       /* graph preparation (all passes)                          */
-#define PFN_PROF_CATEGORIES 7
+#define PFN_PROF_FUSED_FWD 7 /* graph-resident whole-forward kernel (pfn_mpn_forward_tiled)   */
+#define PFN_PROF_CATEGORIES 8
 PFN_API int pfn_profile_enable(int on);
 PFN_API int pfn_profile_read(int category, double* total_ms, int64_t* launches);
 
@@ -169,6 +170,21 @@ PFN_API int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* params
                     const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
                     void* act_ws, void* scratch_ws, int training, uint64_t seed,
                     const uint64_t* seed_device, const float* const* inj_masks, float* out, void* stream);
+/* Graph-resident variant of pfn_mpn_forward: ONE kernel runs the whole layer stack for tiles of whole graphs with
+ * the tile's activations kept in shared / tensor memory (small-graph regime: case14, case118).  The caller promises
+ * that rows [t*tile_rows, (t+1)*tile_rows) are closed under edge_index for every t (tile_rows = nodes per graph x
+ * graphs per tile, <= 128).  The kernel validates the promise: a tile with an edge leaving it (or more than 768
+ * directed edges) gets NaN outputs and raises a flag that pfn_graph_tile_status reports (synchronises the stream).
+ * Same workspaces, same saved activations and same results (to fp32 rounding) as pfn_mpn_forward, so
+ * pfn_mpn_backward follows either.  pfn_mpn_fused_supported: 1 when (desc, tile_rows) is inside the kernel's range
+ * (hidden_dim 129 or a multiple of 16 in [32,128], K <= 3, nfeature_dim 4, output_dim <= 4). */
+PFN_API int pfn_mpn_fused_supported(const pfn_mpn_desc* desc, int64_t tile_rows);
+PFN_API int pfn_mpn_forward_tiled(const pfn_mpn_desc* desc, const float* const* params, const float* x,
+                    const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                    void* act_ws, void* scratch_ws, int training, uint64_t seed,
+                    const uint64_t* seed_device, const float* const* inj_masks, float* out,
+                    int64_t tile_rows, void* stream);
+PFN_API int pfn_graph_tile_status(const void* graph_ws, int32_t* violated, void* stream);
 /* dout float [N, output_dim]; grads[i] receives d loss / d params[i] (overwritten, same shapes) */
 PFN_API int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                      const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,

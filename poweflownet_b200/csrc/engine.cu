@@ -15,9 +15,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
+#include "fused.cuh"
 
 namespace pfn {
 
@@ -159,6 +161,8 @@ struct Plan {
   std::vector<EaPack> ea_pack;
   std::vector<TagPack> tag_pack;
   int64_t mask_w1 = 0, mask_w2 = 0, mask_w2T = 0;
+  // every packed weight whose row pitch is ldh sits in one contiguous arena (one TMA tensor map covers them all)
+  int64_t arena_off = 0, arena_rows = 0;
 
   int64_t ea_stride() const { return 3 * N * ldh; }                       // Hi, Hj, S
   int64_t xcat_ld() const { return int64_t(d.K + 1) * ldh; }
@@ -213,30 +217,37 @@ int make_plan(const pfn_mpn_desc* desc, int64_t n_nodes, Plan& p) {
   p.off_ea = take(p.n_ea * p.ea_stride());
   p.off_tag = take(p.n_tag * p.tag_stride());
   auto ld4 = [](int v) { return round_up64(v, 4); };
-  p.ea_pack.clear();
-  p.tag_pack.clear();
+  p.ea_pack.assign(p.n_ea, Plan::EaPack{});
+  p.tag_pack.assign(p.n_tag, Plan::TagPack{});
+  // three planes per matrix: fp32 | tf32 hi | tf32 lo.  Two passes: pitch-ldh matrices first (the arena), then the rest.
+  struct Req { int64_t* slot; int64_t rows, ld; };
+  std::vector<Req> reqs;
   for (const LayerPlan& L : p.layers) {
     if (L.is_ea) {
-      Plan::EaPack e;
-      e.wi = take(3 * h * ld4(L.fin));  // three planes each: fp32 | tf32 hi | tf32 lo
-      e.wj = take(3 * h * ld4(L.fin));
-      e.w2 = take(3 * L.fout * ld4(h));
-      e.wiT = take(3 * L.fin * ld4(h));
-      e.wjT = take(3 * L.fin * ld4(h));
-      e.w2T = take(3 * h * ld4(L.fout));
-      p.ea_pack.push_back(e);
+      Plan::EaPack& e = p.ea_pack[L.slot];
+      reqs.push_back(Req{&e.wi, h, ld4(L.fin)});
+      reqs.push_back(Req{&e.wj, h, ld4(L.fin)});
+      reqs.push_back(Req{&e.w2, L.fout, ld4(h)});
+      reqs.push_back(Req{&e.wiT, L.fin, ld4(h)});
+      reqs.push_back(Req{&e.wjT, L.fin, ld4(h)});
+      reqs.push_back(Req{&e.w2T, h, ld4(L.fout)});
     } else {
-      Plan::TagPack t{};
+      Plan::TagPack& t = p.tag_pack[L.slot];
       for (int k = 0; k <= d.K; ++k) {
-        t.w[k] = take(3 * L.fout * ld4(L.fin));
-        t.wT[k] = take(3 * L.fin * ld4(L.fout));
+        reqs.push_back(Req{&t.w[k], L.fout, ld4(L.fin)});
+        reqs.push_back(Req{&t.wT[k], L.fin, ld4(L.fout)});
       }
-      p.tag_pack.push_back(t);
     }
   }
-  p.mask_w1 = take(3 * h * ld4(d.nfeature_dim));
-  p.mask_w2 = take(3 * d.nfeature_dim * ld4(h));
-  p.mask_w2T = take(3 * h * ld4(d.nfeature_dim));
+  reqs.push_back(Req{&p.mask_w1, h, ld4(d.nfeature_dim)});
+  reqs.push_back(Req{&p.mask_w2, d.nfeature_dim, ld4(h)});
+  reqs.push_back(Req{&p.mask_w2T, h, ld4(d.nfeature_dim)});
+  p.arena_off = off;
+  for (const Req& r : reqs)
+    if (r.ld == p.ldh) *r.slot = take(3 * r.rows * r.ld);
+  p.arena_rows = (off - p.arena_off) / p.ldh;
+  for (const Req& r : reqs)
+    if (r.ld != p.ldh) *r.slot = take(3 * r.rows * r.ld);
   p.act_floats = off;
   // scratch
   off = 0;
@@ -319,8 +330,98 @@ void set_activation(GemmArgs& a, const Ctx& c, bool act, int layer_index, uint64
 }
 
 // ---- forward ------------------------------------------------------------------------------------------
+// The whole forward as ONE launch of the graph-resident kernel (fused_fwd.cu); fills the same activation workspace the
+// layer-wise backward reads.  The packed weights must already be in place (k_pack_weights).
+int forward_fused(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_t seed, const float* const* inj_masks,
+                  float* out, int64_t tile_rows) {
+  const Plan& p = c.p;
+  const pfn_mpn_desc& d = p.d;
+  const int h = d.hidden_dim;
+  const int n_layers = static_cast<int>(p.layers.size());
+  PFN_REQUIRE(n_layers <= kFusedMaxLayers, PFN_E_UNSUPPORTED, "fused forward: too many layers (%d)", n_layers);
+  FusedArgs a;
+  std::memset(&a, 0, sizeof(a));
+  auto arena_row = [&](int64_t off) { return static_cast<int>((off - p.arena_off) / p.ldh); };
+  const bool dropout = c.training && d.dropout_rate > 0.f;
+  for (int li = 0; li < n_layers; ++li) {
+    const LayerPlan& L = p.layers[li];
+    const float* const* lp = c.params + L.p0;
+    FLayer& f = a.layers[li];
+    const bool last = li == n_layers - 1;
+    f.last = last ? 1 : 0;
+    f.act = L.act ? 1 : 0;
+    f.fin = L.fin;
+    f.w_rows = h;
+    f.seed_xor = 0x9E3779B9u * static_cast<uint32_t>(li + 1);
+    f.inj = (inj_masks != nullptr && L.act && dropout) ? inj_masks[li] : nullptr;
+    if (L.is_ea) {
+      const Plan::EaPack& pk = p.ea_pack[L.slot];
+      f.type = L.fin == h ? kFusedEaTc : kFusedEaSimt;
+      PFN_REQUIRE(f.type == kFusedEaTc || L.fin == d.nfeature_dim, PFN_E_UNSUPPORTED, "fused forward: unexpected layer width");
+      if (f.type == kFusedEaTc) {
+        f.w_row[0] = arena_row(pk.wi);
+        f.w_row[1] = arena_row(pk.wj);
+      }
+      f.w_row[2] = arena_row(pk.w2);
+      f.W1 = lp[0];
+      f.b1 = lp[1];
+      f.W2 = lp[2];
+      f.b2 = lp[3];
+      f.save0 = c.hi(L.slot);
+      if (last) {
+        f.dest = out;
+        f.ld_dest = L.fout;
+      } else {
+        f.dest = c.xcat(p.layers[li + 1].slot);
+        f.ld_dest = static_cast<int>(p.xcat_ld());
+      }
+    } else {
+      PFN_REQUIRE(!last && L.fin == h && L.fout == h, PFN_E_UNSUPPORTED, "fused forward: unexpected TAGConv shape");
+      const Plan::TagPack& tk = p.tag_pack[L.slot];
+      f.type = kFusedTag;
+      for (int k = 0; k <= d.K; ++k) f.w_row[k] = arena_row(tk.w[k]);
+      f.bias = lp[d.K + 1];
+      f.save0 = c.xcat(L.slot);
+      f.dest = c.ytag(L.slot);
+      f.ld_dest = static_cast<int>(p.ldh);
+    }
+  }
+  a.n_layers = n_layers;
+  a.n_nodes = static_cast<int>(p.N);
+  a.tile_rows = static_cast<int>(tile_rows);
+  a.h = h;
+  a.K = d.K;
+  a.ldh = static_cast<int>(p.ldh);
+  a.dropout = dropout ? 1 : 0;
+  a.out_dim = d.output_dim;
+  a.x = x;
+  a.pred_mask = pred_mask;
+  const float* const* mp = c.params + p.p_mask;
+  a.mW1 = mp[0];
+  a.mb1 = mp[1];
+  a.mW2 = mp[2];
+  a.mb2 = mp[3];
+  a.maskf = c.act + p.off_maskf;
+  a.t1 = c.act + p.off_t1;
+  a.x0 = c.act + p.off_x0;
+  a.rowptr = c.g.rowptr_t;
+  a.nbr = c.g.nbr_t;
+  a.ea = reinterpret_cast<const float2*>(c.g.ea_t);
+  a.deg = c.g.deg;
+  a.dis = c.g.dis;
+  a.meta = c.g.meta;
+  a.out = out;
+  a.scale = c.scale;
+  const uint64_t host_seed = c.seed_device != nullptr ? 0 : seed;
+  a.seed_lo = static_cast<uint32_t>(host_seed);
+  a.seed_hi = static_cast<uint32_t>(host_seed >> 32);
+  a.keep_thresh = keep_threshold(d.dropout_rate);
+  a.seed_dev = reinterpret_cast<const uint32_t*>(c.seed_device);
+  return fused_fwd_launch(a, c.act + p.arena_off, p.arena_rows, c.stream);
+}
+
 int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_t seed, const float* const* inj_masks,
-                 float* out) {
+                 float* out, int64_t tile_rows) {
   const Plan& p = c.p;
   const pfn_mpn_desc& d = p.d;
   const int N = static_cast<int>(p.N), h = d.hidden_dim, nf = d.nfeature_dim;
@@ -353,6 +454,7 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
     packs.push_back(PackDesc{mp[2], c.act + p.mask_w2, c.act + p.mask_w2T, h, nf, h, ld_h, ld_nf});
     PFN_TRY(pack_weights_launch(packs.data(), static_cast<int>(packs.size()), c.stream));
   }
+  if (tile_rows > 0) return forward_fused(c, x, pred_mask, seed, inj_masks, out, tile_rows);
   // mask_embd (MPN.py:533,537): x0 = Linear(ReLU(Linear(mask.float()))) + x
   {
     const int64_t n = int64_t(N) * nf;
@@ -650,10 +752,53 @@ extern "C" int pfn_mpn_workspace(const pfn_mpn_desc* desc, int64_t n_nodes, int6
   return 0;
 }
 
+extern "C" int pfn_mpn_fused_supported(const pfn_mpn_desc* desc, int64_t tile_rows) {
+  if (desc == nullptr || desc->efeature_dim != 2 || desc->n_gnn_layers < 2) return 0;
+  if (2 * desc->n_gnn_layers - 1 > kFusedMaxLayers) return 0;
+  return fused_fwd_supported(desc->hidden_dim, desc->K, desc->nfeature_dim, desc->output_dim, tile_rows) ? 1 : 0;
+}
+
+extern "C" int pfn_graph_tile_status(const void* graph_ws, int32_t* violated, void* stream_) {
+  PFN_REQUIRE(graph_ws != nullptr && violated != nullptr, PFN_E_INVALID, "pfn_graph_tile_status: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  pfn_graph_layout lay;
+  pfn_graph_layout_get(0, 0, &lay);
+  const int32_t* meta = reinterpret_cast<const int32_t*>(static_cast<const char*>(graph_ws) + lay.meta);
+  int32_t v = 0;
+  PFN_CUDA_OK(cudaMemcpyAsync(&v, meta + 6, sizeof(v), cudaMemcpyDeviceToHost, stream));
+  PFN_CUDA_OK(cudaStreamSynchronize(stream));
+  *violated = v;
+  return 0;
+}
+
+static int mpn_forward_common(const pfn_mpn_desc* desc, const float* const* params, const float* x,
+                              const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                              void* act_ws, void* scratch_ws, int training, uint64_t seed, const uint64_t* seed_device,
+                              const float* const* inj_masks, float* out, int64_t tile_rows, void* stream);
+
+extern "C" int pfn_mpn_forward_tiled(const pfn_mpn_desc* desc, const float* const* params, const float* x,
+                                     const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                                     void* act_ws, void* scratch_ws, int training, uint64_t seed,
+                                     const uint64_t* seed_device, const float* const* inj_masks, float* out,
+                                     int64_t tile_rows, void* stream) {
+  PFN_REQUIRE(tile_rows > 0 && pfn_mpn_fused_supported(desc, tile_rows), PFN_E_UNSUPPORTED,
+              "pfn_mpn_forward_tiled: configuration outside the graph-resident kernel (use pfn_mpn_forward)");
+  return mpn_forward_common(desc, params, x, pred_mask, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, seed,
+                            seed_device, inj_masks, out, tile_rows, stream);
+}
+
 extern "C" int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* params, const float* x,
                                const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
                                void* act_ws, void* scratch_ws, int training, uint64_t seed, const uint64_t* seed_device,
                                const float* const* inj_masks, float* out, void* stream) {
+  return mpn_forward_common(desc, params, x, pred_mask, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, seed,
+                            seed_device, inj_masks, out, 0, stream);
+}
+
+static int mpn_forward_common(const pfn_mpn_desc* desc, const float* const* params, const float* x,
+                              const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                              void* act_ws, void* scratch_ws, int training, uint64_t seed, const uint64_t* seed_device,
+                              const float* const* inj_masks, float* out, int64_t tile_rows, void* stream) {
   Plan p;
   PFN_TRY(make_plan(desc, n_nodes, p));
   PFN_TRY(check_tables(p, params, "pfn_mpn_forward(params)"));
@@ -664,7 +809,7 @@ extern "C" int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* par
         static_cast<cudaStream_t>(stream), training != 0,
         (training != 0 && desc->dropout_rate > 0.f) ? 1.f / (1.f - desc->dropout_rate) : 1.f};
   c.seed_device = seed_device;
-  return forward_impl(c, x, pred_mask, seed, inj_masks, out);
+  return forward_impl(c, x, pred_mask, seed, inj_masks, out, tile_rows);
 }
 
 extern "C" int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,

@@ -1,0 +1,59 @@
+// Argument blocks of the graph-resident (tile-per-CTA) kernels: fused_fwd.cu.  Internal header.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pfn {
+
+constexpr int kFusedMaxLayers = 16;
+constexpr int kFusedMaxSeg = 4;      // K + 1 <= 4 TAGConv segments
+constexpr int kFusedEdgeCap = 768;   // directed edges of one tile
+
+constexpr int kFusedEaSimt = 0;  // EdgeAggregation whose input width is nfeature_dim (first layer): input Linear by FMAs
+constexpr int kFusedEaTc = 1;    // EdgeAggregation with hidden-width input: Hi | Hj on the tensor cores
+constexpr int kFusedTag = 2;     // TAGConv
+
+struct FLayer {
+  int type, last, act, fin;
+  int w_row[kFusedMaxSeg];  // first arena row of each packed weight: EA {Wi, Wj, W2, -} ; TAG {W_0 .. W_K}
+  int w_rows;               // rows of those matrices (= hidden_dim); plane p of a weight starts at w_row + p * w_rows
+  uint32_t seed_xor;        // per-layer salt of the dropout hash (same value as the layer-wise path)
+  int ld_dest, pad_;
+  const float* W1;    // EA: edge_aggr.0.weight [h, 2 fin + 2] as stored
+  const float* b1;
+  const float* W2;    // EA: edge_aggr.2.weight [fout, h] as stored
+  const float* b2;
+  const float* bias;  // TAG
+  const float* inj;   // optional injected keep mask [N, h] (tests)
+  float* save0;       // EA: Hi [N, ldh] (Hj and S follow, N*ldh apart) ; TAG: [x_0 | .. | x_K]  [N, (K+1) ldh]
+  float* dest;        // layer output: block 0 of the next TAGConv's buffer / the TAGConv's Y / the model output
+};
+
+struct FusedArgs {
+  CUtensorMap wmap;  // the packed-weight arena as one 2-D tensor [rows, h] with pitch ldh, box {32, 128}
+  FLayer layers[kFusedMaxLayers];
+  int n_layers, n_nodes, tile_rows, h, K, ldh, dropout, out_dim;
+  const float* arena;
+  const float* x;
+  const int64_t* pred_mask;
+  const float *mW1, *mb1, *mW2, *mb2;  // mask_embd.{0,2}.{weight,bias} as stored
+  float *maskf, *t1, *x0;              // saved for the backward pass
+  const int* rowptr;
+  const int* nbr;
+  const float2* ea;
+  const float* deg;
+  const float* dis;
+  int* meta;
+  float* out;
+  float scale;
+  uint32_t seed_lo, seed_hi, keep_thresh;
+  const uint32_t* seed_dev;
+  long long* timing;  // debug (PFN_FUSED_TIMING): worker 0 of CTA 0 writes clock64() at phase boundaries
+};
+static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");
+
+bool fused_fwd_supported(int h, int K, int nfeature_dim, int output_dim, int64_t tile_rows);
+int fused_fwd_launch(FusedArgs& args, const float* arena, int64_t arena_rows, cudaStream_t stream);
+
+}  // namespace pfn

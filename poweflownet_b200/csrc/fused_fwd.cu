@@ -1,0 +1,1071 @@
+// Graph-resident forward of MaskEmbdMultiMPN (networks/MPN.py:525-559): ONE kernel launch runs mask_embd, every
+// EdgeAggregation and every TAGConv of the stack for a tile of whole graphs, with the activations of the tile living in
+// shared memory / tensor memory between layers.  HBM sees the inputs, the weights (L2-resident) and the activations
+// the backward pass needs -- written once, never read back here.
+//
+// Applicability (checked by the launcher / by the kernel itself): the batch is a disjoint union of graphs, so a
+// contiguous range of rows whose edges all stay inside the range ("closed tile") needs no other CTA.  The caller
+// promises closed tiles of `tile_rows` <= 128 rows (118-bus graphs: one per tile; 14-bus graphs: nine per tile); the
+// kernel validates the promise while it stages the tile's CSR slice and, when it is broken, poisons its output rows with
+// NaN and raises meta[6] in the graph workspace.  hidden_dim must be 128..132 or a multiple of 16 in [32, 128]; larger
+// graphs / wider models take the layer-wise kernels (engine.cu).
+//
+// CTA = 128 rows.  Roles: warp 0 = TMA producer (weight tiles, pre-split TF32 hi/lo planes of the packed arena),
+// warp 1 = tcgen05.mma issuer + TMEM owner, warps 2..9 = 256 workers (gathers, hops, epilogues).
+// Shared memory: two 64 KB regions R0/R1 that hold EITHER the A operand of the next GEMM as (hi, lo) TF32 planes in the
+// K-major SWIZZLE_128B layout (4 K-tiles of 128 rows x 32 floats each, written by the workers directly in the layout a
+// TMA load would produce) OR two fp32 [128][128] buffers (Hi, Hj of an EdgeAggregation, XOR-swizzled for conflict-free
+// row-per-thread writes and row-per-warp reads); 2 x 32 KB weight stages; ~29 KB of CSR slab / border columns.
+// hidden_dim = 129 = 128 + 1: the tensor core multiplies the 128 x 128 x 128 core; the border row/column of every weight
+// matrix is applied by the workers (rank-1 updates in the epilogue, one dot product per row while the MMA runs).
+// Accuracy: 3xTF32 split (A_lo B_hi + A_hi B_lo in their own accumulator, A_hi B_hi rotating over the remaining ones),
+// same scheme and error level as gemm_tc.cu.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "fused.cuh"
+#include "tc_common.cuh"
+
+namespace pfn {
+namespace {
+using namespace tc;
+
+constexpr int kFThreads = 320;
+constexpr int kFWorkers = 256;
+constexpr uint32_t kPlaneBytes = 65536;
+constexpr uint32_t kKTileBytes = 16384;  // 128 rows x 128 B
+constexpr uint32_t kBStageBytes = 32768;  // hi tile | lo tile
+constexpr int kBStages = 2;
+constexpr uint32_t kMiscOffset = 2 * kPlaneBytes + kBStages * kBStageBytes;
+
+struct FMisc {
+  float4 xb[kFusedMaxSeg][128];  // border columns (128..h-1) of the A operand, per TAGConv segment
+  float4 ob[2][128];             // border OUTPUT columns of the running tensor-core GEMM(s); afterwards the border
+                                 // columns of the fp32 buffers Hi / Hj (same thread rewrites its own entry in place)
+  float4 x0s[128];               // layer-0 input rows (mask_embd(mask) + x)
+  float wkb[kFusedMaxSeg][4][128];  // border-K column(s) of the weights of the running GEMM(s): W[c][128 + kb]
+  float sb1[132], sb2[132];      // biases of the running layer
+  float swe[2][132];             // We columns (edge_attr weights) of the running EdgeAggregation
+  float2 ea[kFusedEdgeCap];
+  int rp[132];
+  float dis[128];
+  float deg[128];
+  uint8_t nbr[kFusedEdgeCap];
+  uint8_t perm[128];  // perm[16 w + slot] = row handled in `slot` of worker warp w: the warp's rows by descending in-degree
+  uint64_t bars[8];  // 0,1 bfull ; 2,3 bempty ; 4 a_ready ; 5 acc_done
+  uint32_t tmem_slot;
+  int bad;
+};
+constexpr uint32_t kFusedSmem = kMiscOffset + sizeof(FMisc) + 1024;
+static_assert(kFusedSmem <= 227 * 1024, "shared memory budget");
+
+// NOTE on code shape: with 227 KB of the SM's 256 KB configured as shared memory there is almost no L1 left, so local
+// memory (register arrays indexed by a runtime value) and per-element global loads cost an L2 round trip each.  Every
+// array below is indexed with compile-time constants after unrolling, and per-layer constants (biases, border columns
+// of the weights, We) are staged in shared memory once per layer.
+
+__device__ __forceinline__ uint32_t pl_off(int r, int c) {  // (row, col) -> byte offset inside a TF32 plane
+  return uint32_t(c >> 5) * kKTileBytes + uint32_t(r) * 128u + (uint32_t(((c >> 2) & 7) ^ (r & 7)) << 4) + uint32_t(c & 3) * 4u;
+}
+__device__ __forceinline__ uint32_t fb_off(int r, int c) {  // (row, col) -> byte offset inside an fp32 [128][128] buffer
+  return uint32_t(r) * 512u + (uint32_t(((c >> 2) ^ r) & 31) << 4) + uint32_t(c & 3) * 4u;
+}
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+// border columns live in float4 slots of shared memory; component kb of slot `p`
+__device__ __forceinline__ float& bcol(float4* p, int kb) { return reinterpret_cast<float*>(p)[kb]; }
+__device__ __forceinline__ float bcol(const float4* p, int kb) { return reinterpret_cast<const float*>(p)[kb]; }
+
+// store a value as its TF32 (hi, lo) pair at the same offset of the two planes
+__device__ __forceinline__ void st_planes(uint32_t R0, uint32_t R1, int r, int c, float4 v) {
+  const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+  const float4 l = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
+  const uint32_t o = pl_off(r, c);
+  sts4(R0 + o, h);
+  sts4(R1 + o, l);
+}
+__device__ __forceinline__ float4 ld_planes(uint32_t R0, uint32_t R1, int r, int c) {
+  const uint32_t o = pl_off(r, c);
+  return f4add(lds4(R0 + o), lds4(R1 + o));
+}
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(kFWorkers) : "memory"); }
+
+struct Wk {  // per-thread worker state (registers)
+  FMisc* m;
+  const float* arena;
+  long long* timing;
+  uint32_t R0, R1, a_ready, acc_done, tmem;
+  int ww, lane, wt, r0, nr, n_nodes, h, ldh, e0, K;
+  int rb;  // row of slot `lane & 15` of this warp (the lane-per-row passes use lanes < 16)
+  uint32_t acc_cnt, seed_lo, seed_hi, keep_thresh;
+  float scale;
+  int dropout, ts;
+};
+
+#define FSTAMP(w)                                                                                  \
+  do {                                                                                             \
+    if ((w).timing != nullptr && blockIdx.x == 0 && threadIdx.x == 64 && (w).ts < 250)             \
+      (w).timing[(w).ts++] = clock64();                                                            \
+  } while (0)
+
+// Row handled in slot i (0..15) of this worker warp.  Rows are assigned to slots by descending in-degree so that the four
+// rows a gather interleaves have similar edge counts (the interleaved loop runs to the longest of the four).
+__device__ __forceinline__ int rowof(const Wk& w, int i) { return w.m->perm[w.ww * 16 + i]; }
+
+__device__ __forceinline__ void wait_acc(Wk& w) {
+  mbar_wait(w.acc_done, w.acc_cnt & 1u);
+  ++w.acc_cnt;
+  tc_fence_after();
+}
+// planes (or TMEM reads) of this thread are finished: publish to the MMA warp
+__device__ __forceinline__ void signal_a_ready(const Wk& w) {
+  proxy_fence_async();
+  tc_fence_before();
+  __syncwarp();
+  if (w.lane == 0) mbar_arrive(w.a_ready);
+}
+
+// stage the border-K column(s) of one packed weight: wkb[slot][kb][c] = W[c][128 + kb]
+template <int HB>
+__device__ __forceinline__ void stage_wkb(const Wk& w, int slot, int w_row) {
+  if (HB == 0) return;
+  for (int i = w.wt; i < 128 * HB; i += kFWorkers) {
+    const int kb = i >> 7, c = i & 127;
+    w.m->wkb[slot][kb][c] = __ldg(w.arena + size_t(w_row + c) * w.ldh + 128 + kb);
+  }
+}
+__device__ __forceinline__ void stage_vec(const Wk& w, float* dst, const float* __restrict__ src, int stride, int n) {
+  for (int i = w.wt; i < n; i += kFWorkers) dst[i] = __ldg(src + size_t(i) * stride);
+}
+
+// Border OUTPUT columns of a tensor-core GEMM whose A operand sits in the planes: for every row of this warp,
+// ob[which][row][nb] (+)= sum_{k<h} A[row][k] * W[128+nb][k], W = fp32 plane of the packed arena.
+// Coalesced save of the A operand (planes, hi + lo) of this warp's rows: one 512-byte row per store instruction.
+// (The epilogues own one ROW per thread; storing from there scatters 32 rows per instruction and made the
+// load/store unit the bottleneck.)  The saved value is hi + lo, i.e. exactly what the next GEMM / hop consume.
+__device__ __forceinline__ void save_planes_rows(const Wk& w, float* __restrict__ dst, int ld, bool cl_ok) {
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int r = rowof(w, i);
+    if (r < w.nr && cl_ok) *reinterpret_cast<float4*>(dst + size_t(w.r0 + r) * ld + 4 * w.lane) = ld_planes(w.R0, w.R1, r, 4 * w.lane);
+  }
+}
+
+template <int HB>
+__device__ __forceinline__ void border_dot(const Wk& w, int seg, int w_row, int which, bool accumulate,
+                                           float* __restrict__ save = nullptr, int ld_save = 0) {
+  if (HB == 0) {
+    if (save != nullptr) save_planes_rows(w, save, ld_save, 4 * w.lane < w.h);
+    return;
+  }
+  constexpr int NB = HB > 0 ? HB : 1;
+  const float* __restrict__ W = w.arena + size_t(w_row + 128) * w.ldh;
+  float4 wv[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) wv[nb] = __ldg(reinterpret_cast<const float4*>(W + size_t(nb) * w.ldh + 4 * w.lane));
+  float wc[NB][NB];  // corner: W[128+nb][128+kb]
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int kb = 0; kb < NB; ++kb) wc[nb][kb] = __ldg(W + size_t(nb) * w.ldh + 128 + kb);
+  float mine[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) mine[nb] = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int r = rowof(w, i);
+    const float4 av = ld_planes(w.R0, w.R1, r, 4 * w.lane);
+    if (save != nullptr && r < w.nr) *reinterpret_cast<float4*>(save + size_t(w.r0 + r) * ld_save + 4 * w.lane) = av;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const float t = warp_sum(dot4(av, wv[nb]));
+      if (w.lane == i) mine[nb] = t;
+    }
+  }
+  if (w.lane < 16) {
+    const int r = w.rb;
+    const float4* xbp = &w.m->xb[seg][r];
+    float4* obp = &w.m->ob[which][r];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      float t = mine[nb];
+#pragma unroll
+      for (int kb = 0; kb < NB; ++kb) t = fmaf(bcol(xbp, kb), wc[nb][kb], t);
+      if (accumulate) t += bcol(obp, nb);
+      bcol(obp, nb) = t;
+    }
+  }
+  __syncwarp();
+}
+
+struct ActCfg {
+  int act, dropout;
+  const float* inj;
+  uint32_t seed_lo, seed_hi, keep_thresh;
+  float scale;
+  int h;
+};
+// MODE 0: identity / ReLU ; 1: dropout (counter-based hash) + ReLU ; 2: dropout (injected keep mask, tests) + ReLU.
+// Branch-free on purpose: the keep decision differs per lane, and a data-dependent branch per element made this
+// epilogue ~270 cycles per element (divergence + reconvergence) instead of ~30 instructions.
+template <int MODE>
+__device__ __forceinline__ float activate(const ActCfg& a, float v, int m, int n) {
+  if (MODE == 0) return a.act ? fmaxf(v, 0.f) : v;
+  bool keep;
+  if (MODE == 1)
+    keep = dropout_hash(uint32_t(m), uint32_t(n), a.seed_lo, a.seed_hi) >= a.keep_thresh;
+  else
+    keep = a.inj[size_t(m) * a.h + n] != 0.f;
+  const float y = fmaxf(v * a.scale, 0.f);
+  return keep ? y : 0.f;
+}
+__device__ __forceinline__ int act_mode(const ActCfg& a) { return (!a.act || !a.dropout) ? 0 : (a.inj == nullptr ? 1 : 2); }
+
+// TMEM -> registers: 16 consecutive accumulator columns of this thread's row, summed over NACC accumulators
+// (the small lo-term accumulator first, as gemm_tc.cu does)
+template <int NACC>
+__device__ __forceinline__ void tmem_sum16(uint32_t lane_base, const int (&cols)[NACC], int c0, float (&v)[16]) {
+  uint32_t r[NACC][16];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) tmem_ld16_issue(lane_base + uint32_t(cols[a] + c0), r[a]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float s = __uint_as_float(r[0][i]);
+#pragma unroll
+    for (int a = 1; a < NACC; ++a) s += __uint_as_float(r[a][i]);
+    v[i] = s;
+  }
+}
+
+// Epilogue of a layer-output GEMM (EdgeAggregation's second Linear, or the TAGConv sum): accumulators + border-K rank-1
+// terms + bias, dropout/ReLU, then the result becomes the next A operand (planes + xb[0]) and is saved to `dest`.
+// NSEG segments contributed (their border-K columns are staged in wkb[0..NSEG), their A borders in xb[0..NSEG)).
+template <int HB, int NACC, int NSEG, int MODE>
+__device__ __forceinline__ void epilogue_out(Wk& w, const ActCfg& ac, const int (&cols)[NACC], const float* bias_s,
+                                             bool deg_scaled, float* __restrict__ dest, int ld_dest) {
+  constexpr int NB = HB > 0 ? HB : 1;
+  const int warp = w.ww + 2, qd = warp & 3, half = w.ww >> 2;
+  const int r = 32 * qd + w.lane, m = w.r0 + r;
+  const bool valid = r < w.nr;
+  FMisc* const M = w.m;
+  bar_workers();  // ob / wkb / biases are complete; every worker has finished reading xb and the planes
+  const float rs = deg_scaled ? M->deg[r] : 1.f;
+  float xbv[NSEG][NB];
+  if (HB > 0) {
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s)
+#pragma unroll
+      for (int kb = 0; kb < NB; ++kb) xbv[s][kb] = bcol(&M->xb[s][r], kb);
+  }
+  float obv[NB];
+  if (HB > 0 && half == 0) {
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) obv[nb] = bcol(&M->ob[0][r], nb);
+  }
+  bar_workers();  // ... xb[0] is rewritten below
+  const uint32_t lane_base = w.tmem + (uint32_t(32 * qd) << 16);
+#pragma unroll 1
+  for (int c0 = 16 * half; c0 < w.h && c0 < 128; c0 += 32) {
+    float v[16];
+    tmem_sum16<NACC>(lane_base, cols, c0, v);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int c = c0 + t;
+      float x = v[t];
+      if (HB > 0) {
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s)
+#pragma unroll
+          for (int kb = 0; kb < NB; ++kb) x = fmaf(xbv[s][kb], M->wkb[s][kb][c], x);
+      }
+      x = fmaf(rs, bias_s[c], x);
+      v[t] = activate<MODE>(ac, x, m, c);
+    }
+#pragma unroll
+    for (int t = 0; t < 16; t += 4) {
+      const float4 o = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+      st_planes(w.R0, w.R1, r, c0 + t, o);  // saved to `dest` by the next phase, coalesced (save_planes_rows)
+    }
+  }
+  if (HB > 0 && half == 0) {
+    float4 o = f4zero();
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const float x = fmaf(rs, bias_s[128 + nb], obv[nb]);
+      bcol(&o, nb) = activate<MODE>(ac, x, m, 128 + nb);
+    }
+    M->xb[0][r] = o;
+    if (valid) *reinterpret_cast<float4*>(dest + size_t(m) * ld_dest + 128) = o;
+  }
+}
+
+template <int HB, int NACC, int NSEG>
+__device__ __forceinline__ void epilogue_dispatch(Wk& w, const ActCfg& ac, const int (&cols)[NACC], const float* bias_s,
+                                                  bool deg_scaled, float* __restrict__ dest, int ld_dest) {
+  switch (act_mode(ac)) {  // CTA-uniform
+    case 0: epilogue_out<HB, NACC, NSEG, 0>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest); break;
+    case 1: epilogue_out<HB, NACC, NSEG, 1>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest); break;
+    default: epilogue_out<HB, NACC, NSEG, 2>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest); break;
+  }
+}
+
+// Segmented gather over the tile's CSR for the 16 rows of this warp, four rows interleaved (independent load chains).
+// kHop = false: EdgeAggregation message + aggregate   acc += relu(Hi[i] + Hj[s] + ea0 We0 + ea1 We1)   (fp32 buffers)
+// kHop = true : TAGConv propagation                    acc  = fma(dis[s], x[s], acc)                    (planes)
+template <bool kHop>
+__device__ __forceinline__ void gather16(const Wk& w, int cl, bool cl_ok, float4 w0, float4 w1, float4 (&out)[16]) {
+  FMisc* const M = w.m;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    int beg[4], cnt[4];
+    float4 hi[4], acc[4];
+    int maxd = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rowof(w, 4 * g + j);
+      beg[j] = M->rp[r] - w.e0;
+      cnt[j] = M->rp[r + 1] - w.e0 - beg[j];
+      maxd = max(maxd, cnt[j]);
+      acc[j] = f4zero();
+      hi[j] = f4zero();
+      if (!kHop && cl_ok) hi[j] = lds4(w.R0 + fb_off(r, cl));
+    }
+    if (cl_ok) {
+#pragma unroll 1
+      for (int t = 0; t < maxd; ++t) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = t < cnt[j];
+          const int e = ok ? beg[j] + t : 0;
+          const int s = M->nbr[e];
+          if (kHop) {
+            const float d = ok ? M->dis[s] : 0.f;
+            const float4 v = ld_planes(w.R0, w.R1, s, cl);
+            acc[j].x = fmaf(d, v.x, acc[j].x);
+            acc[j].y = fmaf(d, v.y, acc[j].y);
+            acc[j].z = fmaf(d, v.z, acc[j].z);
+            acc[j].w = fmaf(d, v.w, acc[j].w);
+          } else {
+            const float2 a = M->ea[e];
+            const float4 hj = lds4(w.R1 + fb_off(s, cl));
+            const float px = fmaxf(fmaf(a.y, w1.x, fmaf(a.x, w0.x, hi[j].x + hj.x)), 0.f);
+            const float py = fmaxf(fmaf(a.y, w1.y, fmaf(a.x, w0.y, hi[j].y + hj.y)), 0.f);
+            const float pz = fmaxf(fmaf(a.y, w1.z, fmaf(a.x, w0.z, hi[j].z + hj.z)), 0.f);
+            const float pw = fmaxf(fmaf(a.y, w1.w, fmaf(a.x, w0.w, hi[j].w + hj.w)), 0.f);
+            const float mk = ok ? 1.f : 0.f;  // fma(1, p, acc) == acc + p exactly; fma(0, p, acc) == acc
+            acc[j].x = fmaf(mk, px, acc[j].x);
+            acc[j].y = fmaf(mk, py, acc[j].y);
+            acc[j].z = fmaf(mk, pz, acc[j].z);
+            acc[j].w = fmaf(mk, pw, acc[j].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (kHop) {
+        const float di = M->dis[rowof(w, 4 * g + j)];
+        out[4 * g + j] = make_float4(di * acc[j].x, di * acc[j].y, di * acc[j].z, di * acc[j].w);
+      } else {
+        out[4 * g + j] = acc[j];
+      }
+    }
+  }
+}
+
+template <int HB>
+__global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_constant__ FusedArgs args) {
+  constexpr int NB = HB > 0 ? HB : 1;
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t raw = smem_u32(smem_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  FMisc* const M = reinterpret_cast<FMisc*>(smem_dyn + (base - raw) + kMiscOffset);
+  const uint32_t R0 = base, R1 = base + kPlaneBytes, BS = base + 2 * kPlaneBytes;
+  const uint32_t bar0 = smem_u32(&M->bars[0]);
+  auto bfull = [&](int s) { return bar0 + 8u * s; };
+  auto bempty = [&](int s) { return bar0 + 16u + 8u * s; };
+  const uint32_t a_ready = bar0 + 32u, acc_done = bar0 + 40u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = args.h, hm = min(h, 128), ldh = args.ldh;
+  const int KT = (hm + 31) / 32;
+  const int r0 = blockIdx.x * args.tile_rows, nr = min(args.tile_rows, args.n_nodes - r0);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.wmap)) : "memory");
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    mbar_init(a_ready, kFWorkers / 32);
+    mbar_init(acc_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    M->bad = 0;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&M->tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero the operand regions once: K-tile padding is multiplied by zero weights, but must not hold NaN bit patterns
+  for (uint32_t o = threadIdx.x * 16u; o < 2 * kPlaneBytes; o += kFThreads * 16u) sts4(R0 + o, f4zero());
+  for (int i = threadIdx.x; i < kFusedMaxSeg * 128; i += kFThreads) (&M->xb[0][0])[i] = f4zero();
+  for (int i = threadIdx.x; i < kFusedMaxSeg * 4 * 128; i += kFThreads) (&M->wkb[0][0][0])[i] = 0.f;
+  pdl_wait();
+  // ---- stage the tile's CSR slice (by target), validating that the tile is closed -------------------------------
+  for (int i = threadIdx.x; i <= 128; i += kFThreads) M->rp[i] = args.rowptr[r0 + min(i, nr)];
+  for (int i = threadIdx.x; i < 128; i += kFThreads) {
+    M->dis[i] = i < nr ? args.dis[r0 + i] : 0.f;
+    M->deg[i] = i < nr ? args.deg[r0 + i] : 0.f;
+    // float(pred_mask) of the tile's rows, parked in ob[1] until mask_embd has consumed it
+    float4 mk = f4zero();
+    if (i < nr) {
+      const longlong2* pm = reinterpret_cast<const longlong2*>(args.pred_mask + size_t(r0 + i) * 4);
+      const longlong2 a = pm[0], b = pm[1];
+      mk = make_float4(float(a.x), float(a.y), float(b.x), float(b.y));
+    }
+    M->ob[1][i] = mk;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = M->tmem_slot;
+  const int e0 = M->rp[0], ne = M->rp[128] - e0;
+  {
+    int bad = ne > kFusedEdgeCap ? 1 : 0;
+    for (int i = threadIdx.x; i < min(ne, kFusedEdgeCap); i += kFThreads) {
+      const int loc = args.nbr[e0 + i] - r0;
+      if (loc < 0 || loc >= nr) bad = 1;
+      M->nbr[i] = static_cast<uint8_t>(loc & 127);
+      M->ea[i] = args.ea[e0 + i];
+    }
+    if (threadIdx.x == 0 && ne == 0) M->nbr[0] = 0;  // the branch-free gathers may touch slot 0 of an edgeless tile
+    if (bad) M->bad = 1;
+    if (warp < 8) {  // slot order of the 16 rows of worker warp `warp`: by descending in-degree, ties by row
+      const int i = lane & 15, r = warp * 16 + i;
+      const int d = M->rp[r + 1] - M->rp[r];
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int dj = __shfl_sync(0xffffffffu, d, j);
+        rank += (dj > d || (dj == d && j < i)) ? 1 : 0;
+      }
+      if (lane < 16) M->perm[warp * 16 + rank] = static_cast<uint8_t>(r);
+    }
+  }
+  __syncthreads();
+  if (M->bad) {  // CTA-uniform: the caller's promise does not hold for this tile
+    if (threadIdx.x == 0) args.meta[6] = 1;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int i = threadIdx.x; i < nr * args.out_dim; i += kFThreads) args.out[size_t(r0) * args.out_dim + i] = qnan;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    return;
+  }
+
+  if (warp == 0) {
+    // ===== TMA producer: the weight K-tiles of every tensor-core GEMM, in program order =====
+    if (lane == 0) {
+      int it = 0;
+      auto load_weight = [&](int w_row, int w_rows) {
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const int s = it % kBStages;
+          const uint32_t ph = (it / kBStages) & 1;
+          mbar_wait(bempty(s), ph ^ 1u);
+          mbar_arrive_expect_tx(bfull(s), kBStageBytes);
+          const uint32_t st = BS + uint32_t(s) * kBStageBytes;
+          tma_load_2d(st, &args.wmap, kt * 32, w_row + w_rows, bfull(s));
+          tma_load_2d(st + kKTileBytes, &args.wmap, kt * 32, w_row + 2 * w_rows, bfull(s));
+        }
+      };
+      for (int li = 0; li < args.n_layers; ++li) {
+        const FLayer& L = args.layers[li];
+        if (L.type == kFusedTag) {
+          for (int k = 0; k <= args.K; ++k) load_weight(L.w_row[k], L.w_rows);
+        } else {
+          if (L.type == kFusedEaTc) {
+            load_weight(L.w_row[0], L.w_rows);
+            load_weight(L.w_row[1], L.w_rows);
+          }
+          if (!L.last) load_weight(L.w_row[2], L.w_rows);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(128 >> 3) << 17) | (uint32_t(128 >> 4) << 24);
+    int it = 0;
+    uint32_t a_cnt = 0;
+    auto wait_a = [&]() {
+      mbar_wait(a_ready, a_cnt & 1u);
+      ++a_cnt;
+      tc_fence_after();
+    };
+    // one GEMM over the planes: lo terms -> TMEM column d_lo ; hi*hi -> d_hi0 + 128 * (kk % n_hi); kk = running K-step
+    auto gemm = [&](uint32_t d_hi0, int n_hi, uint32_t d_lo, int& kk) {
+      for (int kt = 0; kt < KT; ++kt, ++it) {
+        const int s = it % kBStages;
+        const uint32_t ph = (it / kBStages) & 1;
+        mbar_wait(bfull(s), ph);
+        tc_fence_after();
+        const int nk = min(4, (hm - kt * 32 + 7) / 8);
+        if (lane == 0) {
+          const uint32_t st = BS + uint32_t(s) * kBStageBytes;
+          const uint64_t a_hi = umma_desc_k128(R0 + uint32_t(kt) * kKTileBytes), a_lo = umma_desc_k128(R1 + uint32_t(kt) * kKTileBytes);
+          const uint64_t b_hi = umma_desc_k128(st), b_lo = umma_desc_k128(st + kKTileBytes);
+          for (int j = 0; j < nk; ++j) {
+            const uint64_t adv = uint64_t(j * 2);  // +32 bytes in the 16-byte-granular start-address field
+            const int k_idx = kk + j;
+            umma_tf32(tmem + d_lo, a_lo + adv, b_hi + adv, idesc, k_idx > 0 ? 1u : 0u);
+            umma_tf32(tmem + d_lo, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(tmem + d_hi0 + 128u * uint32_t(k_idx % n_hi), a_hi + adv, b_hi + adv, idesc, k_idx >= n_hi ? 1u : 0u);
+          }
+          umma_commit(bempty(s));
+        }
+        kk += nk;
+        __syncwarp();
+      }
+    };
+    for (int li = 0; li < args.n_layers; ++li) {
+      const FLayer& L = args.layers[li];
+      if (L.type == kFusedTag) {
+        int kk = 0;
+        for (int k = 0; k <= args.K; ++k) {
+          wait_a();
+          gemm(0u, 3, 384u, kk);
+          if (lane == 0) umma_commit(acc_done);
+          __syncwarp();
+        }
+      } else {
+        if (L.type == kFusedEaTc) {
+          wait_a();
+          int kk = 0;
+          gemm(0u, 1, 128u, kk);
+          kk = 0;
+          gemm(256u, 1, 384u, kk);
+          if (lane == 0) umma_commit(acc_done);
+          __syncwarp();
+        }
+        if (!L.last) {
+          wait_a();
+          int kk = 0;
+          gemm(0u, 1, 128u, kk);
+          if (lane == 0) umma_commit(acc_done);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== workers =====
+    Wk w;
+    w.m = M;
+    w.arena = args.arena;
+    w.timing = args.timing;
+    w.R0 = R0;
+    w.R1 = R1;
+    w.a_ready = a_ready;
+    w.acc_done = acc_done;
+    w.tmem = tmem;
+    w.ww = warp - 2;
+    w.lane = lane;
+    w.wt = threadIdx.x - 64;
+    w.r0 = r0;
+    w.nr = nr;
+    w.n_nodes = args.n_nodes;
+    w.h = h;
+    w.ldh = ldh;
+    w.e0 = e0;
+    w.K = args.K;
+    w.acc_cnt = 0;
+    w.seed_lo = args.seed_lo;
+    w.seed_hi = args.seed_hi;
+    if (args.seed_dev != nullptr) {
+      w.seed_lo ^= args.seed_dev[0];
+      w.seed_hi ^= args.seed_dev[1];
+    }
+    w.keep_thresh = args.keep_thresh;
+    w.scale = args.scale;
+    w.dropout = args.dropout;
+    w.ts = 0;
+    FSTAMP(w);
+    const int ww = w.ww;
+    const int cl = 4 * lane;            // first column of this lane's main chunk
+    const bool cl_ok = cl < hm;         // (hm is a multiple of 4 on this path)
+    const int rb = M->perm[ww * 16 + (lane & 15)];  // row of the lane-per-row passes (lanes < 16): slot `lane` of this warp
+    w.rb = rb;
+    constexpr int nf = 4;
+
+    // ---- mask_embd (MPN.py:533,537): x0 = W2m relu(W1m mask + b1m) + b2m + x ; saves maskf, t1, x0 ------------------
+    {
+      float w1m[4][4], b1m[4], w2m[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = cl + j;
+        b1m[j] = cl_ok ? __ldg(args.mb1 + c) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w1m[j][k] = cl_ok ? __ldg(args.mW1 + c * nf + k) : 0.f;
+          w2m[k][j] = cl_ok ? __ldg(args.mW2 + k * h + c) : 0.f;
+        }
+      }
+      float w1b[NB][4], b1b[NB], w2b[4][NB];  // border columns 128.. of mask_embd's hidden layer
+      float4 xin = f4zero(), mb2 = f4zero();
+      if (lane < 16) {
+        if (HB > 0) {
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            b1b[j] = __ldg(args.mb1 + 128 + j);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              w1b[j][k] = __ldg(args.mW1 + (128 + j) * nf + k);
+              w2b[k][j] = __ldg(args.mW2 + k * h + 128 + j);
+            }
+          }
+        }
+        if (rb < nr) xin = __ldg(reinterpret_cast<const float4*>(args.x + size_t(r0 + rb) * nf));
+        mb2 = make_float4(__ldg(args.mb2 + 0), __ldg(args.mb2 + 1), __ldg(args.mb2 + 2), __ldg(args.mb2 + 3));
+      }
+      float mine[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int r = rowof(w, i), m = r0 + r;
+        const float4 mk = M->ob[1][r];
+        float t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float s = mk.x * w1m[j][0];
+          s = fmaf(mk.y, w1m[j][1], s);
+          s = fmaf(mk.z, w1m[j][2], s);
+          s = fmaf(mk.w, w1m[j][3], s);
+          t[j] = fmaxf(s + b1m[j], 0.f);
+        }
+        if (r < nr && cl_ok) *reinterpret_cast<float4*>(args.t1 + size_t(m) * ldh + cl) = make_float4(t[0], t[1], t[2], t[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float s = warp_sum(t[0] * w2m[k][0] + t[1] * w2m[k][1] + t[2] * w2m[k][2] + t[3] * w2m[k][3]);
+          if (lane == i) mine[k] = s;
+        }
+      }
+      if (lane < 16) {
+        const int r = rb, m = r0 + r;
+        const float4 mk = M->ob[1][r];
+        if (HB > 0) {
+          float4 tb = f4zero();
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            float s = mk.x * w1b[j][0];
+            s = fmaf(mk.y, w1b[j][1], s);
+            s = fmaf(mk.z, w1b[j][2], s);
+            s = fmaf(mk.w, w1b[j][3], s);
+            s = fmaxf(s + b1b[j], 0.f);
+            bcol(&tb, j) = s;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mine[k] = fmaf(s, w2b[k][j], mine[k]);
+          }
+          if (r < nr) *reinterpret_cast<float4*>(args.t1 + size_t(m) * ldh + 128) = tb;
+        }
+        float4 x0 = f4zero();
+        if (r < nr) {
+          x0 = make_float4(mine[0] + mb2.x + xin.x, mine[1] + mb2.y + xin.y, mine[2] + mb2.z + xin.z, mine[3] + mb2.w + xin.w);
+          *reinterpret_cast<float4*>(args.x0 + size_t(m) * nf) = x0;
+          *reinterpret_cast<float4*>(args.maskf + size_t(m) * nf) = mk;
+        }
+        M->x0s[r] = x0;
+      }
+      __syncwarp();
+    }
+    FSTAMP(w);  // mask_embd done
+
+#pragma unroll 1
+    for (int li = 0; li < args.n_layers; ++li) {
+      const FLayer& L = args.layers[li];
+      ActCfg ac;
+      ac.act = L.act;
+      ac.dropout = w.dropout;
+      ac.inj = L.inj;
+      ac.seed_lo = w.seed_lo ^ L.seed_xor;
+      ac.seed_hi = w.seed_hi;
+      ac.keep_thresh = w.keep_thresh;
+      ac.scale = w.scale;
+      ac.h = h;
+      if (L.type != kFusedTag) {
+        // =================================== EdgeAggregation (MPN.py:23-28,53) ===================================
+        const int ldw1 = 2 * L.fin + 2;
+        float* const gHi = L.save0;
+        float* const gHj = gHi + size_t(args.n_nodes) * ldh;
+        float* const gS = gHj + size_t(args.n_nodes) * ldh;
+        // per-layer constants -> shared memory (visible after the next worker barrier)
+        stage_vec(w, M->sb1, L.b1, 1, h);
+        if (!L.last) stage_vec(w, M->sb2, L.b2, 1, h);
+        stage_vec(w, M->swe[0], L.W1 + 2 * L.fin, ldw1, h);
+        stage_vec(w, M->swe[1], L.W1 + 2 * L.fin + 1, ldw1, h);
+        if (L.type == kFusedEaTc) {
+          stage_wkb<HB>(w, 0, L.w_row[0]);
+          stage_wkb<HB>(w, 1, L.w_row[1]);
+        }
+        if (!L.last) stage_wkb<HB>(w, 2, L.w_row[2]);
+        if (L.type == kFusedEaSimt) {
+          // Hi = x Wi^T + b1, Hj = x Wj^T with fin = 4: plain FMAs, x rows broadcast from shared memory
+          float wi[4][4], wj[4][4], b1v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = cl + j;
+            b1v[j] = cl_ok ? __ldg(L.b1 + c) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              wi[j][k] = cl_ok ? __ldg(L.W1 + c * ldw1 + k) : 0.f;
+              wj[j][k] = cl_ok ? __ldg(L.W1 + c * ldw1 + nf + k) : 0.f;
+            }
+          }
+          float wib[NB][4], wjb[NB][4], b1b[NB];
+          if (HB > 0 && lane < 16) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              b1b[j] = __ldg(L.b1 + 128 + j);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                wib[j][k] = __ldg(L.W1 + (128 + j) * ldw1 + k);
+                wjb[j][k] = __ldg(L.W1 + (128 + j) * ldw1 + nf + k);
+              }
+            }
+          }
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int r = rowof(w, i), m = r0 + r;
+            const float4 xv = M->x0s[r];
+            float hi[4], hj[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = xv.x * wi[j][0], b = xv.x * wj[j][0];
+              a = fmaf(xv.y, wi[j][1], a); b = fmaf(xv.y, wj[j][1], b);
+              a = fmaf(xv.z, wi[j][2], a); b = fmaf(xv.z, wj[j][2], b);
+              a = fmaf(xv.w, wi[j][3], a); b = fmaf(xv.w, wj[j][3], b);
+              hi[j] = a + b1v[j];
+              hj[j] = b;
+            }
+            if (cl_ok) {
+              const float4 hi4 = make_float4(hi[0], hi[1], hi[2], hi[3]), hj4 = make_float4(hj[0], hj[1], hj[2], hj[3]);
+              sts4(R0 + fb_off(r, cl), hi4);
+              sts4(R1 + fb_off(r, cl), hj4);
+              if (r < nr) {
+                *reinterpret_cast<float4*>(gHi + size_t(m) * ldh + cl) = hi4;
+                *reinterpret_cast<float4*>(gHj + size_t(m) * ldh + cl) = hj4;
+              }
+            }
+          }
+          if (HB > 0 && lane < 16) {
+            const int r = rb, m = r0 + r;
+            const float4 xv = M->x0s[r];
+            float4 hi = f4zero(), hj = f4zero();
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              float a = xv.x * wib[j][0], b = xv.x * wjb[j][0];
+              a = fmaf(xv.y, wib[j][1], a); b = fmaf(xv.y, wjb[j][1], b);
+              a = fmaf(xv.z, wib[j][2], a); b = fmaf(xv.z, wjb[j][2], b);
+              a = fmaf(xv.w, wib[j][3], a); b = fmaf(xv.w, wjb[j][3], b);
+              bcol(&hi, j) = a + b1b[j];
+              bcol(&hj, j) = b;
+            }
+            M->ob[0][r] = hi;
+            M->ob[1][r] = hj;
+            if (r < nr) {
+              *reinterpret_cast<float4*>(gHi + size_t(m) * ldh + 128) = hi;
+              *reinterpret_cast<float4*>(gHj + size_t(m) * ldh + 128) = hj;
+            }
+          }
+        } else {
+          // Hi | Hj on the tensor cores: A = the previous layer's output (planes), B = Wi, Wj
+          // (the first pass also saves the previous layer's output, which sits in the planes, to its global buffer)
+          border_dot<HB>(w, 0, L.w_row[0], 0, false, args.layers[li - 1].dest, args.layers[li - 1].ld_dest);
+          border_dot<HB>(w, 0, L.w_row[1], 1, false);
+          FSTAMP(w);  // EA: border dots done
+          wait_acc(w);
+          FSTAMP(w);  // EA: Hi|Hj GEMM done
+          bar_workers();  // ob / staged constants complete; nobody reads the planes any more: they become Hi / Hj
+          const int warp_id = ww + 2, qd = warp_id & 3, half = ww >> 2;
+          const int r = 32 * qd + lane, m = r0 + r;
+          const bool valid = r < nr;
+          float xbv[NB];
+          if (HB > 0) {
+#pragma unroll
+            for (int kb = 0; kb < NB; ++kb) xbv[kb] = bcol(&M->xb[0][r], kb);
+          }
+          const uint32_t lane_base = tmem + (uint32_t(32 * qd) << 16);
+#pragma unroll 1
+          for (int c0 = 16 * half; c0 < hm; c0 += 32) {
+            float vi[16], vj[16];
+            const int ci[2] = {128, 0}, cj[2] = {384, 256};
+            tmem_sum16<2>(lane_base, ci, c0, vi);
+            tmem_sum16<2>(lane_base, cj, c0, vj);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const int c = c0 + t;
+              if (HB > 0) {
+#pragma unroll
+                for (int kb = 0; kb < NB; ++kb) {
+                  vi[t] = fmaf(xbv[kb], M->wkb[0][kb][c], vi[t]);
+                  vj[t] = fmaf(xbv[kb], M->wkb[1][kb][c], vj[t]);
+                }
+              }
+              vi[t] += M->sb1[c];
+            }
+#pragma unroll
+            for (int t = 0; t < 16; t += 4) {
+              const float4 hi = make_float4(vi[t], vi[t + 1], vi[t + 2], vi[t + 3]);
+              const float4 hj = make_float4(vj[t], vj[t + 1], vj[t + 2], vj[t + 3]);
+              sts4(R0 + fb_off(r, c0 + t), hi);
+              sts4(R1 + fb_off(r, c0 + t), hj);
+            }
+          }
+          if (HB > 0 && half == 0) {
+            float4 hi = f4zero(), hj = f4zero();
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+              bcol(&hi, nb) = bcol(&M->ob[0][r], nb) + M->sb1[128 + nb];
+              bcol(&hj, nb) = bcol(&M->ob[1][r], nb);
+            }
+            M->ob[0][r] = hi;  // from here on ob[0] / ob[1] are the border columns of Hi / Hj
+            M->ob[1][r] = hj;
+            if (valid) {
+              *reinterpret_cast<float4*>(gHi + size_t(m) * ldh + 128) = hi;
+              *reinterpret_cast<float4*>(gHj + size_t(m) * ldh + 128) = hj;
+            }
+          }
+          tc_fence_before();
+        }
+        bar_workers();  // Hi / Hj of the whole tile are in the fp32 buffers
+        FSTAMP(w);      // EA: input stage done
+        if (L.type == kFusedEaTc && cl_ok) {  // save them for the backward pass: one 512-byte row per store instruction
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int r = rowof(w, i);
+            if (r < nr) {
+              *reinterpret_cast<float4*>(gHi + size_t(r0 + r) * ldh + cl) = lds4(R0 + fb_off(r, cl));
+              *reinterpret_cast<float4*>(gHj + size_t(r0 + r) * ldh + cl) = lds4(R1 + fb_off(r, cl));
+            }
+          }
+        }
+
+        // ---- message + aggregate: S[i] = sum_{e in in(i)} relu(Hi[i] + Hj[src e] + We ea_e), ascending edge id ------
+        float4 S[16];
+        float Sb[NB];
+        {
+          float4 w0 = f4zero(), w1 = f4zero();
+          if (cl_ok) {
+            w0 = *reinterpret_cast<const float4*>(&M->swe[0][cl]);
+            w1 = *reinterpret_cast<const float4*>(&M->swe[1][cl]);
+          }
+          gather16<false>(w, cl, cl_ok, w0, w1, S);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) Sb[j] = 0.f;
+          if (HB > 0 && lane < 16) {
+            const int r = rb;
+            const int beg = M->rp[r] - e0, fin = M->rp[r + 1] - e0;
+#pragma unroll 1
+            for (int e = beg; e < fin; ++e) {
+              const int s = M->nbr[e];
+              const float2 a = M->ea[e];
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                Sb[j] += fmaxf(fmaf(a.y, M->swe[1][128 + j], fmaf(a.x, M->swe[0][128 + j], bcol(&M->ob[0][r], j) + bcol(&M->ob[1][s], j))), 0.f);
+            }
+          }
+        }
+        FSTAMP(w);  // EA: gather done
+        // save S (dW2 = G^T S needs it)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int r = rowof(w, i);
+          if (r < nr && cl_ok) *reinterpret_cast<float4*>(gS + size_t(r0 + r) * ldh + cl) = S[i];
+        }
+        float4 Sb4 = f4zero();
+#pragma unroll
+        for (int j = 0; j < NB; ++j) bcol(&Sb4, j) = Sb[j];
+        if (HB > 0 && lane < 16 && rb < nr) *reinterpret_cast<float4*>(gS + size_t(r0 + rb) * ldh + 128) = Sb4;
+
+        if (L.last) {
+          // out = S W2^T + deg (.) b2 with a handful of output columns: warp reductions straight from the registers
+          const int od = args.out_dim;
+          float mine[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < od) {
+              float4 wv = f4zero();
+              if (cl_ok) wv = make_float4(__ldg(L.W2 + k * h + cl), __ldg(L.W2 + k * h + cl + 1), __ldg(L.W2 + k * h + cl + 2), __ldg(L.W2 + k * h + cl + 3));
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float s = warp_sum(dot4(S[i], wv));
+                if (lane == i) mine[k] = s;
+              }
+            }
+          }
+          if (lane < 16 && rb < nr) {
+            const int r = rb, m = r0 + r;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < od) {
+                float s = mine[k];
+                if (HB > 0) {
+#pragma unroll
+                  for (int j = 0; j < NB; ++j) s = fmaf(Sb[j], __ldg(L.W2 + k * h + 128 + j), s);
+                }
+                L.dest[size_t(m) * L.ld_dest + k] = fmaf(M->deg[r], __ldg(L.b2 + k), s);
+              }
+            }
+          }
+          bar_workers();
+        } else {
+          bar_workers();  // every gather has read Hi / Hj: the regions may become the S planes
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (cl_ok) st_planes(R0, R1, rowof(w, i), cl, S[i]);
+          }
+          if (lane < 16) M->xb[0][rb] = Sb4;
+          signal_a_ready(w);
+          FSTAMP(w);  // EA: S planes written
+          border_dot<HB>(w, 0, L.w_row[2], 0, false);  // own rows only (written by this warp)
+          FSTAMP(w);  // EA: border dot done
+          wait_acc(w);
+          FSTAMP(w);  // EA: W2 GEMM done
+          // the W2 border-K column was staged in slot 2; the epilogue reads slots [0, NSEG): copy via a one-slot view
+          const int cols[2] = {128, 0};
+          {
+            bar_workers();
+            if (HB > 0) {
+              for (int i = w.wt; i < 128 * HB; i += kFWorkers) M->wkb[0][i >> 7][i & 127] = M->wkb[2][i >> 7][i & 127];
+            }
+          }
+          epilogue_dispatch<HB, 2, 1>(w, ac, cols, M->sb2, true, L.dest, L.ld_dest);
+          signal_a_ready(w);
+          bar_workers();  // the planes hold the next layer's input for every worker
+          FSTAMP(w);      // EA: output epilogue done
+        }
+      } else {
+        // =================================== TAGConv (PyG; call site MPN.py:545) ===================================
+        float* const xc = L.save0;
+        const int ldx = (args.K + 1) * ldh;
+        stage_vec(w, M->sb1, L.bias, 1, h);
+        for (int k = 0; k <= args.K; ++k) stage_wkb<HB>(w, k, L.w_row[k]);
+#pragma unroll 1
+        for (int k = 0; k < args.K; ++k) {
+          border_dot<HB>(w, k, L.w_row[k], 0, k > 0, k == 0 ? xc : nullptr, ldx);  // k = 0: also saves x_0 (block 0 of xc)
+          // x_{k+1} = A_hat x_k, read from the planes while the tensor core multiplies x_k
+          float4 Y[16];
+          gather16<true>(w, cl, cl_ok, f4zero(), f4zero(), Y);
+          float4 Yb = f4zero();
+          if (HB > 0 && lane < 16) {
+            const int r = rb;
+            float acc[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+            const int beg = M->rp[r] - e0, fin = M->rp[r + 1] - e0;
+#pragma unroll 1
+            for (int e = beg; e < fin; ++e) {
+              const int s = M->nbr[e];
+              const float d = M->dis[s];
+#pragma unroll
+              for (int j = 0; j < NB; ++j) acc[j] = fmaf(d, bcol(&M->xb[k][s], j), acc[j]);
+            }
+            const float di = M->dis[r];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) bcol(&Yb, j) = di * acc[j];
+          }
+          FSTAMP(w);      // TAG: hop computed
+          wait_acc(w);    // segment k has been multiplied ...
+          FSTAMP(w);      // TAG: segment GEMM done
+          bar_workers();  // ... and every worker has gathered from x_k: the planes may be overwritten
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = rowof(w, i);
+            if (cl_ok) {
+              st_planes(R0, R1, r, cl, Y[i]);
+              if (r < nr) *reinterpret_cast<float4*>(xc + size_t(r0 + r) * ldx + (k + 1) * ldh + cl) = Y[i];
+            }
+          }
+          if (HB > 0 && lane < 16) {
+            M->xb[k + 1][rb] = Yb;
+            if (rb < nr) *reinterpret_cast<float4*>(xc + size_t(r0 + rb) * ldx + (k + 1) * ldh + 128) = Yb;
+          }
+          signal_a_ready(w);
+          bar_workers();
+          FSTAMP(w);  // TAG: next segment written
+        }
+        border_dot<HB>(w, args.K, L.w_row[args.K], 0, args.K > 0, args.K == 0 ? xc : nullptr, ldx);
+        wait_acc(w);
+        FSTAMP(w);  // TAG: last GEMM done
+        const int cols[4] = {384, 0, 128, 256};
+        // always four segments: xb[s] of the segments beyond K is zero (see the zero fill at kernel start)
+        epilogue_dispatch<HB, 4, 4>(w, ac, cols, M->sb1, false, L.dest, L.ld_dest);
+        signal_a_ready(w);
+        bar_workers();
+        FSTAMP(w);  // TAG: output epilogue done
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace
+
+bool fused_fwd_supported(int h, int K, int nfeature_dim, int output_dim, int64_t tile_rows) {
+  if (!tc_enabled()) return false;
+  const bool h_ok = h == 129 || (h >= 32 && h <= 128 && h % 16 == 0);
+  return h_ok && K + 1 <= kFusedMaxSeg && nfeature_dim == 4 && output_dim >= 1 && output_dim <= 4 && tile_rows >= 1 &&
+         tile_rows <= 128;
+}
+
+int fused_fwd_launch(FusedArgs& a, const float* arena, int64_t arena_rows, cudaStream_t stream) {
+  PFN_REQUIRE(tc_make_map(&a.wmap, arena, arena_rows, a.h, a.ldh, 128), PFN_E_UNSUPPORTED,
+              "fused forward: cannot encode the weight-arena tensor map");
+  a.arena = arena;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFN_CUDA_OK(cudaFuncSetAttribute(k_mpn_fused_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)));
+    PFN_CUDA_OK(cudaFuncSetAttribute(k_mpn_fused_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)));
+    attr_set = true;
+  }
+  void (*kernel)(FusedArgs) = a.h > 128 ? k_mpn_fused_fwd<1> : k_mpn_fused_fwd<0>;
+  const unsigned tiles = static_cast<unsigned>(ceil_div64(a.n_nodes, a.tile_rows));
+  static const bool timing_on = std::getenv("PFN_FUSED_TIMING") != nullptr;  // debug aid: phase timestamps of CTA 0
+  static long long* timing_dev = nullptr;
+  if (timing_on) {
+    if (timing_dev == nullptr) cudaMalloc(&timing_dev, 256 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 256 * sizeof(long long), stream);
+    a.timing = timing_dev;
+  }
+  {
+    ProfScope prof(PFN_PROF_FUSED_FWD, stream);
+    PFN_CUDA_OK(launch_kernel(kernel, dim3(tiles), dim3(kFThreads), kFusedSmem, stream, a));
+    PFN_LAUNCHED();
+  }
+  if (timing_on) {
+    long long t[256];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[fused-timing] cycles since worker start:");
+    for (int i = 1; i < 250 && t[i]; ++i) fprintf(stderr, " %lld", t[i] - t[0]);
+    fprintf(stderr, "\n");
+  }
+  return 0;
+}
+
+}  // namespace pfn

@@ -77,7 +77,7 @@ class _MPNFunction(torch.autograd.Function):
     """Whole-model forward/backward through `pfn_mpn_forward` / `pfn_mpn_backward`."""
 
     @staticmethod
-    def forward(ctx, model, x, pred_mask, edge_index, edge_attr, *params):
+    def forward(ctx, model, tile_rows, x, pred_mask, edge_index, edge_attr, *params):
         dev = ops.require_cuda(x, pred_mask, edge_index, edge_attr, *params)
         n = int(x.size(0))
         training = bool(model.training)
@@ -100,11 +100,25 @@ class _MPNFunction(torch.autograd.Function):
             out = torch.empty((n, model.output_dim), dtype=torch.float32, device=dev)
             ptable = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
             desc = model._desc()
-            check(lib().pfn_mpn_forward(C.byref(desc), ptable, x.data_ptr(), pred_mask.data_ptr(), n, graph.e_raw,
-                                        ws.graph.data_ptr(), ws.act.data_ptr(), ws.scratch.data_ptr(), int(training),
-                                        seed, None if seed_dev is None else seed_dev.data_ptr(), inj_table, out.data_ptr(),
-                                        torch.cuda.current_stream().cuda_stream),
-                  "pfn_mpn_forward")
+            common = (C.byref(desc), ptable, x.data_ptr(), pred_mask.data_ptr(), n, graph.e_raw, ws.graph.data_ptr(),
+                      ws.act.data_ptr(), ws.scratch.data_ptr(), int(training), seed,
+                      None if seed_dev is None else seed_dev.data_ptr(), inj_table, out.data_ptr())
+            stream = torch.cuda.current_stream().cuda_stream
+            if tile_rows > 0:
+                # graph-resident kernel: the whole layer stack in one launch, one tile of whole graphs per CTA
+                check(lib().pfn_mpn_forward_tiled(*common, tile_rows, stream), "pfn_mpn_forward_tiled")
+                sig = (n, graph.e_raw, tile_rows)
+                if sig not in model._tiling_checked and not torch.cuda.is_current_stream_capturing():
+                    # first batch of this shape: read back the kernel's own validation of the closed-tile promise
+                    violated = C.c_int32(0)
+                    check(lib().pfn_graph_tile_status(ws.graph.data_ptr(), C.byref(violated), stream), "pfn_graph_tile_status")
+                    model._tiling_checked[sig] = not violated.value
+                    if violated.value:
+                        tile_rows = 0
+                elif not model._tiling_checked.get(sig, True):
+                    tile_rows = 0
+            if tile_rows <= 0:
+                check(lib().pfn_mpn_forward(*common, stream), "pfn_mpn_forward")
         if needs_grad:
             ctx.model, ctx.ws, ctx.params, ctx.n, ctx.e_raw, ctx.training = model, ws, params, n, graph.e_raw, training
             ctx.keep = (x, pred_mask, graph, inj)  # keep inputs alive until backward
@@ -133,14 +147,14 @@ class _MPNFunction(torch.autograd.Function):
                                          ws.graph.data_ptr(), ws.act.data_ptr(), ws.scratch.data_ptr(),
                                          int(ctx.training), torch.cuda.current_stream().cuda_stream), "pfn_mpn_backward")
             dx = None
-            if ctx.needs_input_grad[1]:
+            if ctx.needs_input_grad[2]:
                 # x enters as `mask_embd(mask) + x` (MPN.py:537): d loss / d x is the gradient w.r.t. that sum
                 dx = model._dx0_view(ws, ctx.n).clone()
             if model._grad_reducer is not None:
                 model._grad_reducer(gflat)  # data parallel: ONE collective over the flat gradient buffer
         model._give_workspace(ctx.n, ctx.e_raw, dev, ws)
         ctx.ws = None
-        return (None, dx, None, None, None, *views)
+        return (None, None, dx, None, None, None, *views)
 
 
 class MaskEmbdMultiMPN(nn.Module):
@@ -165,6 +179,8 @@ class MaskEmbdMultiMPN(nn.Module):
         self._inject_dropout_masks: Optional[Sequence[torch.Tensor]] = None  # test hook: replay given keep-masks
         self._grad_reducer = None  # set by poweflownet_b200.parallel.attach_gradient_allreduce
         self._seed_device: Optional[torch.Tensor] = None  # int64[1] on the device: dropout seed read by the kernels
+        self.fused = True  # use the graph-resident kernel when the batch is made of equal-sized graphs of <= 128 nodes
+        self._tiling_checked = {}  # (N, E_raw, tile_rows) -> did the kernel's closed-tile validation pass
 
     # ---- reference helper methods (networks/MPN.py:498-523) -------------------------------------
     def is_directed(self, edge_index):
@@ -225,6 +241,27 @@ class MaskEmbdMultiMPN(nn.Module):
         off = 4 * r4(n * ldh) + r4(n * (self.K + 1) * ldh)
         return ws.scratch.view(torch.float32)[off:off + n * self.nfeature_dim].view(n, self.nfeature_dim)
 
+    def _tile_rows(self, data) -> int:
+        """Rows per closed tile for the graph-resident kernel, or 0 for the layer-wise path.  Uses only host-side
+        shape information (no device read): a batch of `num_graphs` equal-sized graphs of n = N / num_graphs <= 128
+        nodes is tiled as floor(128 / n) whole graphs per tile; the kernel validates that no edge leaves a tile."""
+        if not self.fused:
+            return 0
+        n = int(data.x.size(0))
+        g = getattr(data, "num_graphs", None)
+        if g is None and getattr(data, "ptr", None) is not None:
+            g = int(data.ptr.numel()) - 1
+        if not g or g <= 0 or n <= 0 or n % g:
+            return 0
+        per = n // g
+        if per > 128:
+            return 0
+        tile = (128 // per) * per
+        if self._tiling_checked.get((n, int(data.edge_index.size(1)), tile), True) is False:
+            return 0
+        desc = self._desc()
+        return tile if lib().pfn_mpn_fused_supported(C.byref(desc), tile) else 0
+
     def forward(self, data):
         """networks/MPN.py:525-559.  `data` is any object with the PyG `Batch` attributes the reference
         reads: x [N,4], pred_mask [N,4], edge_index [2,E_raw], edge_attr [E_raw,2] (bus_type / batch are
@@ -236,4 +273,5 @@ class MaskEmbdMultiMPN(nn.Module):
                 "which cannot run unless hidden_dim == output_dim; the sm_100a path implements n_gnn_layers >= 2")
         if self.efeature_dim != 2:
             raise NotImplementedError("the sm_100a path implements efeature_dim == 2 (the dataset's edge width)")
-        return _MPNFunction.apply(self, data.x, data.pred_mask, data.edge_index, data.edge_attr, *self._engine_params())
+        return _MPNFunction.apply(self, self._tile_rows(data), data.x, data.pred_mask, data.edge_index, data.edge_attr,
+                                  *self._engine_params())

@@ -1,0 +1,157 @@
+"""The graph-resident forward (`pfn_mpn_forward_tiled`, csrc/fused_fwd.cu): one kernel for the whole layer stack,
+one tile of whole graphs per CTA.  Checked against the reference goldens, against the layer-wise kernels, and for its
+behaviour when the caller's closed-tile promise does not hold (the kernel validates it itself)."""
+import ctypes as C
+
+import pytest
+import torch
+
+import common
+from oracle import pfn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda:0"
+FUSED_CASES = ["case14_small", "case118_standard"]  # equal-sized graphs, hidden_dim 64 / 129
+
+
+def _model(kw, fused=True):
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    m = common.load_seeded(MaskEmbdMultiMPN(**kw)).to(DEV)
+    m.fused = fused
+    return m
+
+
+def _close(got, want, what, tol=TOL):
+    e = common.rel_err(got.detach().cpu(), want.detach().cpu())
+    assert max(e) < tol, (what, e)
+
+
+def _launches():
+    from poweflownet_b200 import _lib
+    return int(_lib.lib().pfn_launch_count())
+
+
+@pytest.mark.parametrize("name", FUSED_CASES)
+def test_fused_path_is_taken_and_matches_reference(name):
+    gold = torch.load(common.golden_path(name), weights_only=True)
+    m = _model(gold["meta"]["model_kwargs"]).eval()
+    batch = common.GraphBatch(**gold["inputs"]).to(DEV)
+    assert m._tile_rows(batch) > 0, "this batch should be eligible for the graph-resident kernel"
+    with torch.no_grad():
+        m(batch)  # first call of a shape also reads back the tile validation
+        n0 = _launches()
+        out = m(batch)
+        n_fused = _launches() - n0
+    assert all(m._tiling_checked.values()) and len(m._tiling_checked) == 1
+    # graph prep (5 launches) + weight packing (1) + ONE forward kernel
+    assert n_fused <= 7, n_fused
+    _close(out, gold["eval_out"], "eval_out vs fp32 reference")
+    _close(out, gold["eval_out_fp64"].float(), "eval_out vs fp64 twin")
+    m.fused = False
+    with torch.no_grad():
+        n0 = _launches()
+        out_lw = m(batch)
+        n_layerwise = _launches() - n0
+    assert n_layerwise > 2 * n_fused
+    _close(out, out_lw, "graph-resident vs layer-wise forward", tol=3e-6)
+
+
+@pytest.mark.parametrize("name", FUSED_CASES)
+def test_fused_train_step_matches_reference(name):
+    gold = torch.load(common.golden_path(name), weights_only=True)
+    m = _model(gold["meta"]["model_kwargs"]).train()
+    batch = common.GraphBatch(**gold["inputs"]).to(DEV)
+    m._inject_dropout_masks = common.dropout_masks(name, batch.num_nodes)
+    out = m(batch)
+    assert m._tiling_checked and all(m._tiling_checked.values())
+    loss = torch.nn.functional.mse_loss(out, batch.y)
+    loss.backward()
+    _close(out, gold["train_out"], "train_out")
+    assert abs(float(loss) - float(gold["train_loss"])) < TOL * abs(float(gold["train_loss"]))
+    for k, p in m.named_parameters():
+        if "grads" in gold:
+            _close(p.grad, gold["grads"][k], k)
+        else:
+            nrm = float(gold["grad_norm"][k])
+            assert abs(float(p.grad.double().norm()) - nrm) < TOL * nrm + 1e-12, k
+
+
+def test_saved_activations_match_layerwise():
+    """The fused forward must leave the activation workspace the backward kernels read (Hi, Hj, S, x_k, Y, t1, x0)
+    as the layer-wise forward does: compare the gradients a layer-wise backward computes from either."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=129, n_gnn_layers=3, K=2, dropout_rate=0.0)
+    batch = synthetic_batch("118v2", 5).to(DEV)
+    grads = {}
+    for fused in (True, False):
+        m = _model(kw, fused).train()
+        torch.nn.functional.mse_loss(m(batch), batch.y).backward()
+        grads[fused] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    for k in grads[True]:
+        _close(grads[True][k], grads[False][k], k, tol=3e-6)
+
+
+def test_dropout_generator_statistics_and_determinism():
+    """Counter-based dropout inside the fused epilogues: same seed tensor -> same output, and the same keep masks as
+    the layer-wise path draws."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=129, n_gnn_layers=2, K=3, dropout_rate=0.2)
+    batch = synthetic_batch("118v2", 8).to(DEV)
+    m = _model(kw).train()
+    m._seed_device = torch.tensor([1234567], dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        a, b = m(batch), m(batch)
+        m._seed_device = torch.tensor([7654321], dtype=torch.int64, device=DEV)
+        c = m(batch)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    with torch.no_grad():
+        d = m.eval()(batch)
+    assert not torch.equal(a, d)  # dropout really was applied in train mode
+    # the generator is shared with the layer-wise epilogues (same hash of (row, column, layer, seed)): same masks
+    m.train()
+    m.fused = False
+    with torch.no_grad():
+        e = m(batch)
+    _close(c, e, "same seed, graph-resident vs layer-wise", tol=3e-6)
+
+
+def test_broken_tile_promise_is_detected_and_falls_back():
+    """Equal N / num_graphs but an edge that crosses the assumed tile boundary: the kernel flags it, the module
+    re-runs the layer-wise path for that shape, and the result is still the reference's."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=64, n_gnn_layers=2, K=3, dropout_rate=0.0)
+    batch = synthetic_batch("14", 18)  # 252 nodes: tiles of 9 graphs = 126 rows
+    ei = batch.edge_index.clone()
+    ei[:, -1] = torch.tensor([125, 126])  # joins the last node of tile 0 to the first node of tile 1
+    bad = common.GraphBatch(**{f: (ei if f == "edge_index" else getattr(batch, f)) for f in
+                               ("x", "y", "bus_type", "pred_mask", "edge_index", "edge_attr", "batch", "ptr")})
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).eval()
+    with torch.no_grad():
+        want = oracle(bad)
+    m = _model(kw).eval()
+    db = bad.to(DEV)
+    assert m._tile_rows(db) == 126
+    with torch.no_grad():
+        out = m(db)
+    assert list(m._tiling_checked.values()) == [False]
+    assert m._tile_rows(db) == 0  # the shape is remembered as not tileable
+    assert not torch.isnan(out).any()
+    _close(out, want, "fallback result")
+    with torch.no_grad():
+        _close(m(db), want, "second call (layer-wise from the start)")
+
+
+def test_tiled_entry_point_rejects_unsupported_configurations():
+    from poweflownet_b200 import _lib
+    from poweflownet_b200._lib import MpnDesc
+    lib = _lib.lib()
+    ok = MpnDesc(4, 2, 4, 129, 4, 3, 0.2, 0)
+    assert lib.pfn_mpn_fused_supported(C.byref(ok), 118) == 1
+    assert lib.pfn_mpn_fused_supported(C.byref(ok), 129) == 0          # more than 128 rows per tile
+    assert lib.pfn_mpn_fused_supported(C.byref(MpnDesc(4, 2, 4, 512, 5, 3, 0.2, 0)), 118) == 0   # configs/large.json width
+    assert lib.pfn_mpn_fused_supported(C.byref(MpnDesc(4, 2, 4, 33, 4, 3, 0.2, 0)), 118) == 0
+    assert lib.pfn_mpn_fused_supported(C.byref(MpnDesc(4, 2, 4, 64, 2, 3, 0.2, 0)), 126) == 1
+    rc = lib.pfn_mpn_forward_tiled(C.byref(MpnDesc(4, 2, 4, 512, 5, 3, 0.2, 0)), None, None, None, 0, 0, None, None, None, 0, 0,
+                                   None, None, None, 118, None)
+    assert rc == -2 and b"graph-resident" in lib.pfn_last_error()

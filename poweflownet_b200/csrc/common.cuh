@@ -175,6 +175,22 @@ void gemm_plan_splitk(GemmArgs& args, int64_t K, int count);
 int gemm_tc_launch(const GemmArgs& args, cudaStream_t stream);
 int wgrad_tc_launch(GemmArgs& args, cudaStream_t stream);  // may rewrite args.splitk / args.kchunk
 bool tc_enabled();
+// one weight-gradient problem of a backward pass: dW[Mo, Ni] = dY^T X over `nodes` rows (+ bias gradient as an extra
+// column of X: extra_col 1 = ones, 2 = extra_vec[node]); see wgrad_group_launch in gemm_tc.cu
+struct WgradProblem {
+  const float* dY;  // [nodes, Mo] row-major, pitch lddy
+  long long lddy;
+  const float* X;   // [nodes, Ni] row-major, pitch ldx
+  long long ldx;
+  int Mo, Ni;
+  float* dW;        // [Mo, Ni] with row pitch lddw
+  int lddw;
+  float* dbias;     // [Mo] or null
+  int extra_col;
+  const float* extra_vec;
+};
+size_t wgrad_group_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes);
+int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* partial, size_t partial_bytes, cudaStream_t stream);
 struct PackDesc {
   const float* src;  // [rows, cols] with row pitch ld_src (a state_dict weight or a column block of one)
   float* dst;        // 3 planes of [rows, ld_dst]:   fp32 copy | rn_tf32(w) | rn_tf32(w - hi)      (may be null)

@@ -249,14 +249,15 @@ int make_plan(const pfn_mpn_desc* desc, int64_t n_nodes, Plan& p) {
   for (const Req& r : reqs)
     if (r.ld != p.ldh) *r.slot = take(3 * r.rows * r.ld);
   p.act_floats = off;
-  // scratch
+  // scratch.  Every layer keeps its own gradient buffers (d cur, dHi, dHj, d[x_0..x_K]) because the weight
+  // gradients are deferred to ONE grouped launch at the end of the backward pass and read them all.
   off = 0;
-  p.off_dz = take(n_nodes * p.ldh);
+  p.off_dx0 = take(n_nodes * d.nfeature_dim);  // first: d loss / d (mask_embd(mask) + x), read back by the Python layer
   p.off_ds = take(n_nodes * p.ldh);
-  p.off_dhi = take(n_nodes * p.ldh);
-  p.off_dhj = take(n_nodes * p.ldh);
-  p.off_dxcat = take(n_nodes * p.xcat_ld());
-  p.off_dx0 = take(n_nodes * d.nfeature_dim);
+  p.off_dz = take(p.n_ea * n_nodes * p.ldh);
+  p.off_dhi = take(p.n_ea * n_nodes * p.ldh);
+  p.off_dhj = take(p.n_ea * n_nodes * p.ldh);
+  p.off_dxcat = take(p.n_tag * n_nodes * p.xcat_ld());
   size_t part = pfn_ea_bwd_scratch_bytes(h);
   // every split-K weight-gradient problem the backward launches: (rows of dW, cols of dW, problems per launch)
   const int wg[][3] = {{h, h, 1}, {d.output_dim, h, 1},                   // EA  dW2 = G^T S
@@ -264,6 +265,28 @@ int make_plan(const pfn_mpn_desc* desc, int64_t n_nodes, Plan& p) {
                        {h, h, d.K + 1},                                   // TAG dW_k
                        {d.nfeature_dim, h, 1}, {h, d.nfeature_dim, 1}};   // mask_embd
   for (const auto& w : wg) part = std::max(part, gemm_splitk_scratch_bytes(w[0], w[1], n_nodes, w[2]));
+  {
+    std::vector<WgradProblem> shapes;
+    auto shape = [&](int mo, int ni) {
+      WgradProblem w{};
+      w.Mo = mo;
+      w.Ni = ni;
+      shapes.push_back(w);
+    };
+    for (const LayerPlan& L : p.layers) {
+      if (L.is_ea) {
+        shape(L.fout, h);
+        shape(h, L.fin);
+        shape(h, L.fin);
+      } else {
+        for (int k = 0; k <= d.K; ++k) shape(L.fout, L.fin);
+      }
+    }
+    shape(d.nfeature_dim, h);
+    shape(h, d.nfeature_dim);
+    // the per-EdgeAggregation dWe partial rows share the buffer: they are consumed before the grouped launch starts
+    part = std::max(part, wgrad_group_scratch_bytes(shapes.data(), static_cast<int>(shapes.size()), n_nodes));
+  }
   p.part_bytes = static_cast<int64_t>(part);
   p.off_part = take(static_cast<int64_t>((part + 3) / 4));
   p.scratch_floats = off;
@@ -538,12 +561,10 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
   const int N = static_cast<int>(p.N), h = d.hidden_dim, nf = d.nfeature_dim;
   const int64_t ldh = p.ldh;
   if (N == 0) return 0;
-  float* dz = c.scratch + p.off_dz;
   float* ds = c.scratch + p.off_ds;
-  float* dhi = c.scratch + p.off_dhi;
-  float* dhj = c.scratch + p.off_dhj;
-  float* dxcat = c.scratch + p.off_dxcat;
   float* dx0 = c.scratch + p.off_dx0;
+  const int64_t nld = int64_t(N) * ldh;
+  std::vector<GemmArgs> deferred;  // weight-gradient problems, launched together at the end
   float* part = c.scratch + p.off_part;
   const float* x0 = c.act + p.off_x0;
   const float* G = dout;  // gradient w.r.t. the current layer's (pre-activation) output
@@ -555,6 +576,9 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
     float* const* lg = grads + L.p0;
     if (L.is_ea) {
       const int ldw1 = 2 * L.fin + 2;
+      float* dz = c.scratch + p.off_dz + L.slot * nld;
+      float* dhi = c.scratch + p.off_dhi + L.slot * nld;
+      float* dhj = c.scratch + p.off_dhj + L.slot * nld;
       // input of this layer and whether it is the (post-activation) output of a previous layer
       const float* cur;
       int64_t ldcur;
@@ -577,7 +601,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         a.partial = part;
         a.partial_bytes = static_cast<size_t>(p.part_bytes);
         gemm_plan_splitk(a, N, 1);
-        PFN_TRY(gemm_launch(a, false, false, c.stream));
+        deferred.push_back(a);
       }
       // dS = G W2   (as G (W2^T)^T with the packed transpose: both operands K-major)
       const Plan::EaPack& pk = p.ea_pack[L.slot];
@@ -601,7 +625,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         a.partial = part;
         a.partial_bytes = static_cast<size_t>(p.part_bytes);
         gemm_plan_splitk(a, N, 2);
-        PFN_TRY(gemm_launch(a, false, false, c.stream));
+        deferred.push_back(a);
       }
       // d cur = dHi Wi + dHj Wj, masked by the previous layer's activation
       {
@@ -625,6 +649,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
     } else {
       const float* xc = c.xcat(L.slot);
       const int64_t ldx = p.xcat_ld();
+      float* dxcat = c.scratch + p.off_dxcat + L.slot * int64_t(N) * ldx;
       // dW_k = G^T x_k (k = 0..K) ; dbias = colsum G
       {
         GemmArgs a = base_args(L.fout, L.fin);
@@ -636,7 +661,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         a.partial = part;
         a.partial_bytes = static_cast<size_t>(p.part_bytes);
         gemm_plan_splitk(a, N, d.K + 1);
-        PFN_TRY(gemm_launch(a, false, false, c.stream));
+        deferred.push_back(a);
       }
       // d x_k = G W_k (k = 0..K), then the transposed hop chain d x_{k-1} += A_hat^T d x_k; the last hop
       // also applies the activation mask of the layer input (which is block 0 of xcat itself)
@@ -674,9 +699,9 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
     a.it[0] = wgrad_item(G, ldG, t1, ldh, N, mg[2], h, mg[3]);
     a.extra_col = 1;
     a.partial = part;
-        a.partial_bytes = static_cast<size_t>(p.part_bytes);
+    a.partial_bytes = static_cast<size_t>(p.part_bytes);
     gemm_plan_splitk(a, N, 1);
-    PFN_TRY(gemm_launch(a, false, false, c.stream));
+    deferred.push_back(a);
     GemmArgs b = base_args(N, h);
     b.it[0] = fwd_item(G, ldG, c.act + p.mask_w2T, round_up64(nf, 4), nf, ds, ldh, nullptr, h);
     b.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
@@ -691,7 +716,28 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
     w.partial = part;
     w.partial_bytes = static_cast<size_t>(p.part_bytes);
     gemm_plan_splitk(w, N, 1);
-    PFN_TRY(gemm_launch(w, false, false, c.stream));
+    deferred.push_back(w);
+  }
+  // ---- every weight gradient of the step: one grouped tensor-core launch + one reduction (gemm_tc.cu) ----
+  {
+    std::vector<WgradProblem> probs;
+    for (const GemmArgs& a : deferred) {
+      const int count = a.batched ? a.n_items : 1;
+      for (int i = 0; i < count; ++i) {
+        const GemmItem& it = a.it[i];
+        probs.push_back(WgradProblem{it.A, it.a_cs, it.B, it.b_rs, a.M, a.N, it.C, it.ldc, it.bias_out, a.extra_col, a.extra_vec});
+      }
+    }
+    int rc;
+    {
+      ProfScope prof(PFN_PROF_GEMM_WGRAD, c.stream);
+      rc = wgrad_group_launch(probs.data(), static_cast<int>(probs.size()), N, part, static_cast<size_t>(p.part_bytes), c.stream);
+    }
+    if (rc == 1) {  // outside the grouped kernel's range (e.g. hidden_dim > 255): one launch per problem, as before
+      for (const GemmArgs& a : deferred) PFN_TRY(gemm_launch(a, false, false, c.stream));
+    } else if (rc != 0) {
+      return rc;
+    }
   }
   return 0;
 }

@@ -592,6 +592,229 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   }
 }
 
+
+// ---- grouped weight gradient: every dW of a backward pass in ONE launch -------------------------------------------
+// A step has ~20 weight-gradient problems (dW2, dWi, dWj per EdgeAggregation; dW_0..dW_K per TAGConv; mask_embd), each
+// a [<=129, <=130] output reduced over all nodes.  Launched one by one, each is a 118-way split-K with a 118 x 66 KB
+// partial buffer and its own reduction pass (26 launches, ~160 MB of partial traffic per step).  Here the work items
+// (problem, M group, node chunk) of ALL problems form one grid of about one CTA per SM, so a CTA reduces over ~1/7 of
+// the nodes in TMEM and the partial traffic drops ~17x; one more launch sums the few partials in fixed order.
+// Same mainloop as k_wgrad_tc (MN-major TF32 operands, SWIZZLE_128B_BASE32B, converter warps, 3xTF32).
+constexpr int kWgMaxProb = 32;
+// The tensor core adds into its fp32 accumulator with truncation, so the error of a TMEM-resident sum grows linearly
+// with the number of accumulating instructions (measured: 1.8e-5 relative at 2176 nodes per CTA, above the 1e-5
+// contract).  A CTA therefore reduces at most this many nodes; the partials are summed in round-to-nearest fp32.
+constexpr int kWgMaxChunk = 512;
+struct WgGroupProb {
+  CUtensorMap a;  // dY  [rows = nodes, cols = Mo]   box {32, 32}
+  CUtensorMap b;  // X   [rows = nodes, cols = Ni]   box {32, 32}
+  float* dW;
+  float* dbias;
+  const float* extra_vec;
+  long long part_off;  // float offset of this problem's partials: [split][Mo][n_eff]
+  int Mo, N, n_eff, BN, mt, nb, extra_col, lddw, m_groups, tmem_cols, stages, item0;
+  int acc_hi[2], acc_lo[2];
+};
+struct WgGroupArgs {
+  WgGroupProb p[kWgMaxProb];
+  int n_prob, K, kchunk, splitk;
+  float* partial;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_constant__ WgGroupArgs args) {
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  int prob = 0;
+  for (int i = 1; i < args.n_prob; ++i)
+    if (int(blockIdx.x) >= args.p[i].item0) prob = i;
+  const WgGroupProb& P = args.p[prob];
+  const int item = int(blockIdx.x) - P.item0;
+  const int mgrp = item / args.splitk, split = item - mgrp * args.splitk;
+  const int BN = P.BN, S = P.stages, mt = P.mt, nb = P.nb;
+  const uint32_t a_bytes = uint32_t(mt) * 4u * 4096u, b_bytes = uint32_t(nb) * 4096u;
+  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);  // A_hi | A_lo | B_hi | B_lo
+  const uint32_t bar_base = base + uint32_t(S) * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (kTcMaxStages + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kTcMaxStages + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * kTcMaxStages);
+  const uint32_t tmem_slot = accum_bar + 8u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = mgrp * mt * kTcBM;  // first dW row of this CTA
+  const int k_beg = split * args.kchunk, k_end = min(args.K, k_beg + args.kchunk);
+  const int n_tiles = (k_end > k_beg) ? (k_end - k_beg + kTcBK - 1) / kTcBK : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.b)) : "memory");
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), kTcWorkers / 32);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(uint32_t(P.tmem_cols)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        const int k0 = k_beg + it * kTcBK;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes);
+        const uint32_t st = base + uint32_t(s) * stage_bytes;
+        for (int b = 0; b < mt * 4; ++b) tma_load_2d(st + uint32_t(b) * 4096u, &P.a, row0 + 32 * b, k0, full_bar(s));
+        for (int b = 0; b < nb; ++b) tma_load_2d(st + 2u * a_bytes + uint32_t(b) * 4096u, &P.b, 32 * b, k0, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    // D = F32, A = B = TF32, A and B MN-major (bits 15, 16), N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (uint32_t(BN >> 3) << 17) |
+                           (uint32_t(kTcBM >> 4) << 24);
+    const uint32_t lbo = 4096u, sbo = 512u, kstep = 1024u;
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(conv_bar(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = base + uint32_t(s) * stage_bytes;
+        const uint32_t b_hi = st + 2u * a_bytes, b_lo = b_hi + b_bytes;
+        for (int j = 0; j < kTcBK / 8; ++j) {  // 8 nodes per UMMA K step = one 1024-byte K group
+          const uint32_t koff = uint32_t(j) * kstep;
+          const uint64_t dbh = umma_desc_mn128(b_hi + koff, lbo, sbo), dbl = umma_desc_mn128(b_lo + koff, lbo, sbo);
+          for (int t = 0; t < mt; ++t) {
+            const uint32_t a_hi = st + uint32_t(t) * 16384u, a_lo = a_hi + a_bytes;
+            const uint64_t dah = umma_desc_mn128(a_hi + koff, lbo, sbo), dal = umma_desc_mn128(a_lo + koff, lbo, sbo);
+            const uint32_t d_hi = tmem_base + uint32_t(P.acc_hi[t]), d_lo = tmem_base + uint32_t(P.acc_lo[t]);
+            const uint32_t first = (it > 0 || j > 0) ? 1u : 0u;
+            umma_tf32(d_lo, dal, dbh, idesc, first);
+            umma_tf32(d_lo, dah, dbl, idesc, 1u);
+            umma_tf32(d_hi, dah, dbh, idesc, (d_hi == d_lo) ? 1u : first);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(accum_bar);
+    __syncwarp();
+  } else {
+    const int tid_c = threadIdx.x - 64;
+    for (int it = 0; it < n_tiles; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      const int k0 = k_beg + it * kTcBK;
+      mbar_wait(full_bar(s), ph);
+      const uint32_t st = base + uint32_t(s) * stage_bytes;
+      if (P.extra_col != 0) {
+        // virtual column N of X := 1 (or extra_vec[node]) -> its dot products with dY are the bias gradient
+        if (tid_c < kTcBK) {
+          const int r = tid_c, cN = P.N, bb = cN >> 5, cc = cN & 31;
+          const int node = k0 + r;
+          float v = 0.f;
+          if (node < k_end) v = P.extra_col == 1 ? 1.f : P.extra_vec[node];
+          const uint32_t addr = st + 2u * a_bytes + uint32_t(bb) * 4096u + uint32_t(r) * 128u +
+                                (uint32_t((cc >> 3) ^ (r & 3)) << 5) + uint32_t(cc & 7) * 4u;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");
+      }
+      split_tile(st, a_bytes, int(a_bytes / 16u), tid_c);
+      split_tile(st + 2u * a_bytes, b_bytes, int(b_bytes / 16u), tid_c);
+      proxy_fence_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(conv_bar(s));
+    }
+    // epilogue: accumulators -> padded smem tile -> coalesced rows of the split-K partial buffer
+    const int wk = warp - 2, q = warp & 3, half = wk >> 2;
+    const int n_eff = P.n_eff, Mo = P.Mo;
+    float* __restrict__ const part = args.partial + P.part_off + size_t(split) * size_t(Mo) * n_eff;
+    const uint32_t tile_ld = uint32_t(BN) + 4u;
+    if (n_tiles > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+    for (int t = 0; t < mt; ++t) {
+      if (row0 + t * kTcBM >= Mo) break;  // CTA-uniform
+      if (n_tiles > 0) {
+        const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
+        const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
+        for (int c0 = 16 * half; c0 < n_eff; c0 += 32) {
+          uint32_t r[16];
+          float acc[16];
+          tmem_ld16(lane_base + uint32_t(P.acc_lo[t] + c0), r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
+          if (P.acc_hi[t] != P.acc_lo[t]) {
+            tmem_ld16(lane_base + uint32_t(P.acc_hi[t] + c0), r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + 4u * (c0 + i)), "f"(acc[i]), "f"(acc[i + 1]),
+                         "f"(acc[i + 2]), "f"(acc[i + 3]) : "memory");
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
+      for (int rr = 0; rr < 16; ++rr) {
+        const int row = 16 * wk + rr, m = row0 + t * kTcBM + row;
+        if (m >= Mo) break;
+        const uint32_t row_addr = base + (uint32_t(row) * tile_ld) * 4u;
+        for (int c = lane; c < n_eff; c += 32) {
+          float v = 0.f;
+          if (n_tiles > 0) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(row_addr + 4u * c));
+          part[size_t(m) * n_eff + c] = v;
+        }
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(P.tmem_cols)) : "memory");
+  }
+}
+
+// sum the node-chunk partials of every problem in fixed order (deterministic) and scatter into dW / dbias
+__global__ void __launch_bounds__(256) k_wgrad_group_reduce(const __grid_constant__ WgGroupArgs args) {
+  pdl_wait();
+  const WgGroupProb& P = args.p[blockIdx.y];
+  const int n_eff = P.n_eff, total = P.Mo * n_eff, S = args.splitk;
+  const float* __restrict__ src0 = args.partial + P.part_off;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    float sum = 0.f;
+    int s = 0;
+    for (; s + 4 <= S; s += 4) {
+      const float v0 = __ldg(src0 + size_t(s) * total + idx), v1 = __ldg(src0 + size_t(s + 1) * total + idx);
+      const float v2 = __ldg(src0 + size_t(s + 2) * total + idx), v3 = __ldg(src0 + size_t(s + 3) * total + idx);
+      sum += (v0 + v1) + (v2 + v3);
+    }
+    for (; s < S; ++s) sum += __ldg(src0 + size_t(s) * total + idx);
+    const int m = idx / n_eff, n = idx - m * n_eff;
+    if (n == P.N) {
+      if (P.dbias != nullptr) P.dbias[m] = sum;
+    } else {
+      P.dW[size_t(m) * P.lddw + n] = sum;
+    }
+  }
+}
+
 // ---- weight packing ------------------------------------------------------------------------------------
 // state_dict weights are [out, in] with arbitrary row pitch (129 floats = 516 B is not a legal TMA stride) and the
 // data-gradient GEMMs need them transposed: one small kernel per step copies every matrix into 16-byte-pitched
@@ -844,6 +1067,95 @@ int wgrad_tc_launch(GemmArgs& g, cudaStream_t stream) {
   }
   dim3 grid(static_cast<unsigned>(a.splitk), static_cast<unsigned>(count), static_cast<unsigned>(m_groups));
   PFN_CUDA_OK(launch_kernel(k_wgrad_tc, grid, dim3(kTcThreads), smem, stream, a));
+  PFN_LAUNCHED();
+  return 0;
+}
+
+
+size_t wgrad_group_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes) {
+  if (n <= 0) return 0;
+  int64_t groups = 0;
+  for (int i = 0; i < n; ++i) groups += std::max<int64_t>(1, ceil_div64(ceil_div64(probs[i].Mo, kTcBM), 2));
+  const int64_t want = std::max<int64_t>(1, int64_t(sm_count()) / std::max<int64_t>(groups, 1));
+  const int64_t kchunk = std::min<int64_t>(kWgMaxChunk, round_up64(std::max<int64_t>(ceil_div64(std::max<int64_t>(nodes, 1), want), kTcBK), kTcBK));
+  const int64_t splitk = std::max<int64_t>(1, ceil_div64(std::max<int64_t>(nodes, 1), kchunk));
+  size_t floats = 0;
+  for (int i = 0; i < n; ++i) floats += size_t(splitk) * size_t(probs[i].Mo) * size_t(probs[i].Ni + 1);
+  return floats * sizeof(float) + 256;
+}
+
+// All weight gradients of a backward pass in one launch (+ one reduction launch).  Returns 1 when some problem does not
+// fit the tensor-core path (caller launches them one by one), 0 on success.
+int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* partial, size_t partial_bytes, cudaStream_t stream) {
+  if (!tc_enabled() || n <= 0 || n > kWgMaxProb || nodes <= 0 || partial == nullptr) return 1;
+  static const bool disabled = std::getenv("PFN_WGRAD_GROUP") != nullptr && std::getenv("PFN_WGRAD_GROUP")[0] == '0';
+  if (disabled) return 1;
+  WgGroupArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int items_per_split = 0;
+  uint32_t smem_max = 0;
+  for (int i = 0; i < n; ++i) {
+    const WgradProblem& w = probs[i];
+    WgGroupProb& P = a.p[i];
+    const int n_eff = w.Ni + (w.extra_col ? 1 : 0);
+    if (w.Mo <= 0 || w.Ni <= 0 || n_eff > 256 || !tma_ok(w.dY, w.lddy) || !tma_ok(w.X, w.ldx)) return 1;
+    P.Mo = w.Mo;
+    P.N = w.Ni;
+    P.n_eff = n_eff;
+    P.BN = static_cast<int>(round_up64(n_eff, 16));
+    P.nb = (P.BN + 31) / 32;
+    const int m_tiles = static_cast<int>(ceil_div64(w.Mo, kTcBM));
+    P.mt = (m_tiles >= 2 && 2 * P.BN <= 512) ? 2 : 1;
+    P.m_groups = static_cast<int>(ceil_div64(m_tiles, P.mt));
+    int used;
+    if (P.mt == 1) {
+      P.acc_hi[0] = 0; P.acc_lo[0] = P.BN; used = 2 * P.BN;
+    } else if (3 * P.BN <= 512) {
+      P.acc_hi[0] = 0; P.acc_lo[0] = P.BN; P.acc_hi[1] = P.acc_lo[1] = 2 * P.BN; used = 3 * P.BN;
+    } else {
+      P.acc_hi[0] = P.acc_lo[0] = 0; P.acc_hi[1] = P.acc_lo[1] = P.BN; used = 2 * P.BN;
+    }
+    int cols = 32;
+    while (cols < used) cols <<= 1;
+    P.tmem_cols = cols;
+    const uint32_t stage_bytes = 2u * (uint32_t(P.mt) * 16384u + uint32_t(P.nb) * 4096u);
+    P.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 2048u) / stage_bytes));
+    if (P.stages < 2) return 1;
+    smem_max = std::max(smem_max, uint32_t(P.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2));
+    if (!make_map(&P.a, w.dY, nodes, w.Mo, w.lddy, kTcBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map(&P.b, w.X, nodes, w.Ni, w.ldx, kTcBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+      return 1;
+    P.dW = w.dW;
+    P.dbias = w.dbias;
+    P.extra_col = w.extra_col;
+    P.extra_vec = w.extra_vec;
+    P.lddw = w.lddw;
+    items_per_split += P.m_groups;
+  }
+  const int64_t want = std::max<int64_t>(1, int64_t(sm_count()) / std::max(1, items_per_split));
+  const int64_t kchunk = std::min<int64_t>(kWgMaxChunk, round_up64(std::max<int64_t>(ceil_div64(nodes, want), kTcBK), kTcBK));
+  a.K = static_cast<int>(nodes);
+  a.kchunk = static_cast<int>(kchunk);
+  a.splitk = static_cast<int>(std::max<int64_t>(1, ceil_div64(nodes, kchunk)));
+  a.n_prob = n;
+  a.partial = partial;
+  int item = 0;
+  size_t floats = 0;
+  for (int i = 0; i < n; ++i) {
+    a.p[i].item0 = item;
+    item += a.p[i].m_groups * a.splitk;
+    a.p[i].part_off = static_cast<long long>(floats);
+    floats += size_t(a.splitk) * size_t(a.p[i].Mo) * size_t(a.p[i].n_eff);
+  }
+  if (floats * sizeof(float) > partial_bytes) return 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PFN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_group, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
+    attr_set = true;
+  }
+  PFN_CUDA_OK(launch_kernel(k_wgrad_group, dim3(static_cast<unsigned>(item)), dim3(kTcThreads), smem_max, stream, a));
+  PFN_LAUNCHED();
+  PFN_CUDA_OK(launch_kernel(k_wgrad_group_reduce, dim3(16, static_cast<unsigned>(n)), dim3(256), 0, stream, a));
   PFN_LAUNCHED();
   return 0;
 }

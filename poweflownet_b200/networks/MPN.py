@@ -235,11 +235,8 @@ class MaskEmbdMultiMPN(nn.Module):
             free.append(ws)
 
     def _dx0_view(self, ws: _Workspace, n: int) -> torch.Tensor:
-        # scratch layout of engine.cu: dz, ds, dhi, dhj [n, ldh] ; dxcat [n, (K+1) ldh] ; dx0 [n, nfeat]
-        ldh = ops.round_up4(self.hidden_dim)
-        r4 = lambda v: (v + 3) // 4 * 4  # noqa: E731
-        off = 4 * r4(n * ldh) + r4(n * (self.K + 1) * ldh)
-        return ws.scratch.view(torch.float32)[off:off + n * self.nfeature_dim].view(n, self.nfeature_dim)
+        # scratch layout of engine.cu: dx0 [n, nfeat] comes first
+        return ws.scratch.view(torch.float32)[:n * self.nfeature_dim].view(n, self.nfeature_dim)
 
     def _tile_rows(self, data) -> int:
         """Rows per closed tile for the graph-resident kernel, or 0 for the layer-wise path.  Uses only host-side

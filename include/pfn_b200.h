@@ -185,6 +185,12 @@ PFN_API int pfn_mpn_forward_tiled(const pfn_mpn_desc* desc, const float* const* 
                     const uint64_t* seed_device, const float* const* inj_masks, float* out,
                     int64_t tile_rows, void* stream);
 PFN_API int pfn_graph_tile_status(const void* graph_ws, int32_t* violated, void* stream);
+/* backward after pfn_mpn_forward_tiled (same tile_rows, same promise): the TAGConv layers' data gradients run through
+ * the graph-resident kernel too (hops and weight products commute, so d x_0 = sum_k ((A_hat^T)^k G) W_k is the forward
+ * program on G with the CSR by source and the transposed weights); everything else as pfn_mpn_backward. */
+PFN_API int pfn_mpn_backward_tiled(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
+                     const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                     void* act_ws, void* scratch_ws, int training, int64_t tile_rows, void* stream);
 /* dout float [N, output_dim]; grads[i] receives d loss / d params[i] (overwritten, same shapes) */
 PFN_API int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                      const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,

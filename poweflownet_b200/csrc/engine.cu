@@ -555,7 +555,45 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
 }
 
 // ---- backward -----------------------------------------------------------------------------------------
-int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
+// Backward of one TAGConv through the graph-resident kernel (fused_fwd.cu, mode 1): d x_0 = sum_k ((A_hat^T)^k G) W_k,
+// masked by the layer input -- one launch instead of a 4-problem GEMM + K hop launches.
+int tag_backward_fused(const Ctx& c, const LayerPlan& L, const float* G, int64_t ldG, const float* xc, float* dest,
+                       int64_t tile_rows) {
+  const Plan& p = c.p;
+  const pfn_mpn_desc& d = p.d;
+  FusedArgs a;
+  std::memset(&a, 0, sizeof(a));
+  const Plan::TagPack& tk = p.tag_pack[L.slot];
+  FLayer& f = a.layers[0];
+  f.type = kFusedTag;
+  f.fin = L.fin;
+  f.w_rows = d.hidden_dim;
+  for (int k = 0; k <= d.K; ++k) f.w_row[k] = static_cast<int>((tk.wT[k] - p.arena_off) / p.ldh);
+  f.dest = dest;
+  f.ld_dest = static_cast<int>(p.xcat_ld());
+  a.mode = kFusedModeTagBackward;
+  a.n_layers = 1;
+  a.n_nodes = static_cast<int>(p.N);
+  a.tile_rows = static_cast<int>(tile_rows);
+  a.h = d.hidden_dim;
+  a.K = d.K;
+  a.ldh = static_cast<int>(p.ldh);
+  a.out_dim = d.output_dim;
+  a.gin = G;
+  a.ld_gin = static_cast<int>(ldG);
+  a.ymask = xc;
+  a.ld_ymask = static_cast<int>(p.xcat_ld());
+  a.rowptr = c.g.rowptr_s;
+  a.nbr = c.g.nbr_s;
+  a.ea = reinterpret_cast<const float2*>(c.g.ea_s);
+  a.deg = c.g.deg;
+  a.dis = c.g.dis;
+  a.meta = c.g.meta;
+  a.scale = c.scale;
+  return fused_fwd_launch(a, c.act + p.arena_off, p.arena_rows, c.stream);
+}
+
+int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t tile_rows) {
   const Plan& p = c.p;
   const pfn_mpn_desc& d = p.d;
   const int N = static_cast<int>(p.N), h = d.hidden_dim, nf = d.nfeature_dim;
@@ -663,28 +701,32 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout) {
         gemm_plan_splitk(a, N, d.K + 1);
         deferred.push_back(a);
       }
-      // d x_k = G W_k (k = 0..K), then the transposed hop chain d x_{k-1} += A_hat^T d x_k; the last hop
-      // also applies the activation mask of the layer input (which is block 0 of xcat itself)
-      {
-        GemmArgs a = base_args(N, L.fin);
-        a.n_items = d.K + 1;
-        a.batched = 1;
-        const Plan::TagPack& tk = p.tag_pack[L.slot];
-        for (int k = 0; k <= d.K; ++k)
-          a.it[k] = fwd_item(G, ldG, c.act + tk.wT[k], round_up64(L.fout, 4), L.fout, dxcat + k * ldh, ldx, nullptr, L.fin);
-        a.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
-        if (d.K == 0) {
-          a.act = kActMaskByY;
-          a.ymask = xc;
-          a.ld_ym = static_cast<int>(ldx);
-          a.scale = c.scale;
+      if (tile_rows > 0 && ldG % 4 == 0) {
+        PFN_TRY(tag_backward_fused(c, L, G, ldG, xc, dxcat, tile_rows));
+      } else {
+        // d x_k = G W_k (k = 0..K), then the transposed hop chain d x_{k-1} += A_hat^T d x_k; the last hop
+        // also applies the activation mask of the layer input (which is block 0 of xcat itself)
+        {
+          GemmArgs a = base_args(N, L.fin);
+          a.n_items = d.K + 1;
+          a.batched = 1;
+          const Plan::TagPack& tk = p.tag_pack[L.slot];
+          for (int k = 0; k <= d.K; ++k)
+            a.it[k] = fwd_item(G, ldG, c.act + tk.wT[k], round_up64(L.fout, 4), L.fout, dxcat + k * ldh, ldx, nullptr, L.fin);
+          a.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
+          if (d.K == 0) {
+            a.act = kActMaskByY;
+            a.ymask = xc;
+            a.ld_ym = static_cast<int>(ldx);
+            a.scale = c.scale;
+          }
+          PFN_TRY(gemm_launch(a, true, true, c.stream));
         }
-        PFN_TRY(gemm_launch(a, true, true, c.stream));
-      }
-      for (int k = d.K; k >= 1; --k) {
-        const bool final_hop = k == 1;
-        PFN_TRY(hop_launch(dxcat + k * ldh, ldx, c.g, N, true, dxcat + (k - 1) * ldh, ldx, final_hop ? xc : nullptr, ldx,
-                           c.scale, dxcat + (k - 1) * ldh, ldx, L.fin, c.stream));
+        for (int k = d.K; k >= 1; --k) {
+          const bool final_hop = k == 1;
+          PFN_TRY(hop_launch(dxcat + k * ldh, ldx, c.g, N, true, dxcat + (k - 1) * ldh, ldx, final_hop ? xc : nullptr, ldx,
+                             c.scale, dxcat + (k - 1) * ldh, ldx, L.fin, c.stream));
+        }
       }
       G = dxcat;
       ldG = ldx;
@@ -858,9 +900,28 @@ static int mpn_forward_common(const pfn_mpn_desc* desc, const float* const* para
   return forward_impl(c, x, pred_mask, seed, inj_masks, out, tile_rows);
 }
 
+static int mpn_backward_common(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
+                               const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws, void* act_ws,
+                               void* scratch_ws, int training, int64_t tile_rows, void* stream);
+
 extern "C" int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                                 const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws, void* act_ws,
                                 void* scratch_ws, int training, void* stream) {
+  return mpn_backward_common(desc, params, grads, dout, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, 0, stream);
+}
+
+extern "C" int pfn_mpn_backward_tiled(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
+                                      const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
+                                      void* act_ws, void* scratch_ws, int training, int64_t tile_rows, void* stream) {
+  PFN_REQUIRE(tile_rows > 0 && pfn_mpn_fused_supported(desc, tile_rows), PFN_E_UNSUPPORTED,
+              "pfn_mpn_backward_tiled: configuration outside the graph-resident kernel (use pfn_mpn_backward)");
+  return mpn_backward_common(desc, params, grads, dout, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, tile_rows,
+                             stream);
+}
+
+static int mpn_backward_common(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
+                               const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws, void* act_ws,
+                               void* scratch_ws, int training, int64_t tile_rows, void* stream) {
   Plan p;
   PFN_TRY(make_plan(desc, n_nodes, p));
   PFN_TRY(check_tables(p, params, "pfn_mpn_backward(params)"));
@@ -874,7 +935,7 @@ extern "C" int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* pa
   if (n_nodes == 0) {  // gradients of an empty batch are zero
     return 0;
   }
-  return backward_impl(c, grads, dout);
+  return backward_impl(c, grads, dout, tile_rows);
 }
 
 extern "C" size_t pfn_mse_scratch_bytes(int64_t count) { return size_t(mse_blocks(count)) * sizeof(float); }

@@ -49,11 +49,18 @@ struct FusedArgs {
   float scale;
   uint32_t seed_lo, seed_hi, keep_thresh;
   const uint32_t* seed_dev;
+  // mode 1 (TAGConv backward, one layer per launch): d x_0 = sum_k ((A_hat^T)^k G) W_k, masked by the layer input.
+  // Hops and GEMMs commute (one acts on rows, the other on columns), so this is the forward TAGConv program run on G
+  // with the CSR by source and the transposed weights; `gin` is G, `ymask` the saved layer input x_0.
+  int mode, ld_gin, ld_ymask, pad1_;
+  const float* gin;
+  const float* ymask;
   long long* timing;  // debug (PFN_FUSED_TIMING): worker 0 of CTA 0 writes clock64() at phase boundaries
 };
 static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");
 
 bool fused_fwd_supported(int h, int K, int nfeature_dim, int output_dim, int64_t tile_rows);
+constexpr int kFusedModeForward = 0, kFusedModeTagBackward = 1;
 int fused_fwd_launch(FusedArgs& args, const float* arena, int64_t arena_rows, cudaStream_t stream);
 
 }  // namespace pfn

@@ -11,7 +11,7 @@
 // graphs / wider models take the layer-wise kernels (engine.cu).
 //
 // CTA = 128 rows.  Roles: warp 0 = TMA producer (weight tiles, pre-split TF32 hi/lo planes of the packed arena),
-// warp 1 = tcgen05.mma issuer + TMEM owner, warps 2..9 = 256 workers (gathers, hops, epilogues).
+// warp 1 = tcgen05.mma issuer + TMEM owner, warps 2..17 = 512 workers (gathers, hops, epilogues).
 // Shared memory: two 64 KB regions R0/R1 that hold EITHER the A operand of the next GEMM as (hi, lo) TF32 planes in the
 // K-major SWIZZLE_128B layout (4 K-tiles of 128 rows x 32 floats each, written by the workers directly in the layout a
 // TMA load would produce) OR two fp32 [128][128] buffers (Hi, Hj of an EdgeAggregation, XOR-swizzled for conflict-free
@@ -32,8 +32,11 @@ namespace pfn {
 namespace {
 using namespace tc;
 
-constexpr int kFThreads = 320;
-constexpr int kFWorkers = 256;
+constexpr int kFWorkerWarps = 16;               // 4 per SM sub-partition: the worker phases are latency-bound with fewer
+constexpr int kFWorkers = 32 * kFWorkerWarps;
+constexpr int kFThreads = 64 + kFWorkers;
+constexpr int kRW = 128 / kFWorkerWarps;        // rows of the tile owned by one worker warp in the row-per-warp passes
+constexpr int kCG = kFWorkerWarps / 4;          // column groups in the row-per-thread (TMEM) passes
 constexpr uint32_t kPlaneBytes = 65536;
 constexpr uint32_t kKTileBytes = 16384;  // 128 rows x 128 B
 constexpr uint32_t kBStageBytes = 32768;  // hi tile | lo tile
@@ -124,9 +127,9 @@ struct Wk {  // per-thread worker state (registers)
       (w).timing[(w).ts++] = clock64();                                                            \
   } while (0)
 
-// Row handled in slot i (0..15) of this worker warp.  Rows are assigned to slots by descending in-degree so that the four
+// Row handled in slot i (0..kRW-1) of this worker warp.  Rows are assigned to slots by descending in-degree so that the four
 // rows a gather interleaves have similar edge counts (the interleaved loop runs to the longest of the four).
-__device__ __forceinline__ int rowof(const Wk& w, int i) { return w.m->perm[w.ww * 16 + i]; }
+__device__ __forceinline__ int rowof(const Wk& w, int i) { return w.m->perm[w.ww * kRW + i]; }
 
 __device__ __forceinline__ void wait_acc(Wk& w) {
   mbar_wait(w.acc_done, w.acc_cnt & 1u);
@@ -160,8 +163,8 @@ __device__ __forceinline__ void stage_vec(const Wk& w, float* dst, const float* 
 // (The epilogues own one ROW per thread; storing from there scatters 32 rows per instruction and made the
 // load/store unit the bottleneck.)  The saved value is hi + lo, i.e. exactly what the next GEMM / hop consume.
 __device__ __forceinline__ void save_planes_rows(const Wk& w, float* __restrict__ dst, int ld, bool cl_ok) {
-#pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
+#pragma unroll
+  for (int i = 0; i < kRW; ++i) {
     const int r = rowof(w, i);
     if (r < w.nr && cl_ok) *reinterpret_cast<float4*>(dst + size_t(w.r0 + r) * ld + 4 * w.lane) = ld_planes(w.R0, w.R1, r, 4 * w.lane);
   }
@@ -187,8 +190,8 @@ __device__ __forceinline__ void border_dot(const Wk& w, int seg, int w_row, int 
   float mine[NB];
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) mine[nb] = 0.f;
-#pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
+#pragma unroll
+  for (int i = 0; i < kRW; ++i) {
     const int r = rowof(w, i);
     const float4 av = ld_planes(w.R0, w.R1, r, 4 * w.lane);
     if (save != nullptr && r < w.nr) *reinterpret_cast<float4*>(save + size_t(w.r0 + r) * ld_save + 4 * w.lane) = av;
@@ -198,7 +201,7 @@ __device__ __forceinline__ void border_dot(const Wk& w, int seg, int w_row, int 
       if (w.lane == i) mine[nb] = t;
     }
   }
-  if (w.lane < 16) {
+  if (w.lane < kRW) {
     const int r = w.rb;
     const float4* xbp = &w.m->xb[seg][r];
     float4* obp = &w.m->ob[which][r];
@@ -241,16 +244,22 @@ __device__ __forceinline__ int act_mode(const ActCfg& a) { return (!a.act || !a.
 // (the small lo-term accumulator first, as gemm_tc.cu does)
 template <int NACC>
 __device__ __forceinline__ void tmem_sum16(uint32_t lane_base, const int (&cols)[NACC], int c0, float (&v)[16]) {
-  uint32_t r[NACC][16];
-#pragma unroll
-  for (int a = 0; a < NACC; ++a) tmem_ld16_issue(lane_base + uint32_t(cols[a] + c0), r[a]);
+  // two accumulators in flight at a time: with 18 warps per CTA a thread has ~96 registers
+  uint32_t r[2][16];
+  tmem_ld16_issue(lane_base + uint32_t(cols[0] + c0), r[0]);
+  tmem_ld16_issue(lane_base + uint32_t(cols[1] + c0), r[1]);
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float s = __uint_as_float(r[0][i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[0][i]) + __uint_as_float(r[1][i]);
+  if (NACC > 2) {
+    tmem_ld16_issue(lane_base + uint32_t(cols[2] + c0), r[0]);
+    if (NACC > 3) tmem_ld16_issue(lane_base + uint32_t(cols[NACC > 3 ? 3 : 2] + c0), r[1]);
+    tmem_ld_wait();
 #pragma unroll
-    for (int a = 1; a < NACC; ++a) s += __uint_as_float(r[a][i]);
-    v[i] = s;
+    for (int i = 0; i < 16; ++i) {
+      v[i] += __uint_as_float(r[0][i]);
+      if (NACC > 3) v[i] += __uint_as_float(r[1][i]);
+    }
   }
 }
 
@@ -261,7 +270,7 @@ template <int HB, int NACC, int NSEG, int MODE>
 __device__ __forceinline__ void epilogue_out(Wk& w, const ActCfg& ac, const int (&cols)[NACC], const float* bias_s,
                                              bool deg_scaled, float* __restrict__ dest, int ld_dest) {
   constexpr int NB = HB > 0 ? HB : 1;
-  const int warp = w.ww + 2, qd = warp & 3, half = w.ww >> 2;
+  const int warp = w.ww + 2, qd = warp & 3, half = w.ww >> 2;  // half: column group 0..kCG-1 (16-column chunks half, half+kCG, ..)
   const int r = 32 * qd + w.lane, m = w.r0 + r;
   const bool valid = r < w.nr;
   FMisc* const M = w.m;
@@ -282,7 +291,7 @@ __device__ __forceinline__ void epilogue_out(Wk& w, const ActCfg& ac, const int 
   bar_workers();  // ... xb[0] is rewritten below
   const uint32_t lane_base = w.tmem + (uint32_t(32 * qd) << 16);
 #pragma unroll 1
-  for (int c0 = 16 * half; c0 < w.h && c0 < 128; c0 += 32) {
+  for (int c0 = 16 * half; c0 < w.h && c0 < 128; c0 += 16 * kCG) {
     float v[16];
     tmem_sum16<NACC>(lane_base, cols, c0, v);
 #pragma unroll
@@ -312,7 +321,7 @@ __device__ __forceinline__ void epilogue_out(Wk& w, const ActCfg& ac, const int 
       bcol(&o, nb) = activate<MODE>(ac, x, m, 128 + nb);
     }
     M->xb[0][r] = o;
-    if (valid) *reinterpret_cast<float4*>(dest + size_t(m) * ld_dest + 128) = o;
+    if (valid && dest != nullptr) *reinterpret_cast<float4*>(dest + size_t(m) * ld_dest + 128) = o;
   }
 }
 
@@ -326,14 +335,14 @@ __device__ __forceinline__ void epilogue_dispatch(Wk& w, const ActCfg& ac, const
   }
 }
 
-// Segmented gather over the tile's CSR for the 16 rows of this warp, four rows interleaved (independent load chains).
+// Segmented gather over the tile's CSR for the kRW rows of this warp, four rows interleaved (independent load chains).
 // kHop = false: EdgeAggregation message + aggregate   acc += relu(Hi[i] + Hj[s] + ea0 We0 + ea1 We1)   (fp32 buffers)
 // kHop = true : TAGConv propagation                    acc  = fma(dis[s], x[s], acc)                    (planes)
 template <bool kHop>
-__device__ __forceinline__ void gather16(const Wk& w, int cl, bool cl_ok, float4 w0, float4 w1, float4 (&out)[16]) {
+__device__ __forceinline__ void gather_rows(const Wk& w, int cl, bool cl_ok, float4 w0, float4 w1, float4 (&out)[kRW]) {
   FMisc* const M = w.m;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < kRW / 4; ++g) {
     int beg[4], cnt[4];
     float4 hi[4], acc[4];
     int maxd = 0;
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
       mbar_init(bfull(s), 1);
       mbar_init(bempty(s), 1);
     }
-    mbar_init(a_ready, kFWorkers / 32);
+    mbar_init(a_ready, kFWorkerWarps);
     mbar_init(acc_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     M->bad = 0;
@@ -434,7 +443,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     M->deg[i] = i < nr ? args.deg[r0 + i] : 0.f;
     // float(pred_mask) of the tile's rows, parked in ob[1] until mask_embd has consumed it
     float4 mk = f4zero();
-    if (i < nr) {
+    if (i < nr && args.mode == kFusedModeForward) {
       const longlong2* pm = reinterpret_cast<const longlong2*>(args.pred_mask + size_t(r0 + i) * 4);
       const longlong2 a = pm[0], b = pm[1];
       mk = make_float4(float(a.x), float(a.y), float(b.x), float(b.y));
@@ -456,23 +465,28 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     }
     if (threadIdx.x == 0 && ne == 0) M->nbr[0] = 0;  // the branch-free gathers may touch slot 0 of an edgeless tile
     if (bad) M->bad = 1;
-    if (warp < 8) {  // slot order of the 16 rows of worker warp `warp`: by descending in-degree, ties by row
-      const int i = lane & 15, r = warp * 16 + i;
+    if (warp < kFWorkerWarps) {  // slot order of the kRW rows of worker warp `warp`: by descending in-degree, ties by row
+      const int i = lane % kRW, r = warp * kRW + i;
       const int d = M->rp[r + 1] - M->rp[r];
       int rank = 0;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < kRW; ++j) {
         const int dj = __shfl_sync(0xffffffffu, d, j);
         rank += (dj > d || (dj == d && j < i)) ? 1 : 0;
       }
-      if (lane < 16) M->perm[warp * 16 + rank] = static_cast<uint8_t>(r);
+      if (lane < kRW) M->perm[warp * kRW + rank] = static_cast<uint8_t>(r);
     }
   }
   __syncthreads();
   if (M->bad) {  // CTA-uniform: the caller's promise does not hold for this tile
     if (threadIdx.x == 0) args.meta[6] = 1;
     const float qnan = __int_as_float(0x7fc00000);
-    for (int i = threadIdx.x; i < nr * args.out_dim; i += kFThreads) args.out[size_t(r0) * args.out_dim + i] = qnan;
+    if (args.mode == kFusedModeForward) {
+      for (int i = threadIdx.x; i < nr * args.out_dim; i += kFThreads) args.out[size_t(r0) * args.out_dim + i] = qnan;
+    } else {
+      const FLayer& L = args.layers[0];
+      for (int i = threadIdx.x; i < nr * h; i += kFThreads) L.dest[size_t(r0 + i / h) * L.ld_dest + i % h] = qnan;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -608,10 +622,29 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     const int ww = w.ww;
     const int cl = 4 * lane;            // first column of this lane's main chunk
     const bool cl_ok = cl < hm;         // (hm is a multiple of 4 on this path)
-    const int rb = M->perm[ww * 16 + (lane & 15)];  // row of the lane-per-row passes (lanes < 16): slot `lane` of this warp
+    const int rb = M->perm[ww * kRW + (lane % kRW)];  // row of the lane-per-row passes (lanes < kRW): slot `lane` of this warp
     w.rb = rb;
     constexpr int nf = 4;
 
+    if (args.mode == kFusedModeTagBackward) {
+      // ---- backward of one TAGConv: the incoming gradient G becomes the A operand (planes + border columns) ----------
+#pragma unroll 4
+      for (int i = 0; i < kRW; ++i) {
+        const int r = rowof(w, i);
+        float4 v = f4zero();
+        if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + r) * args.ld_gin + cl));
+        if (cl_ok) st_planes(R0, R1, r, cl, v);
+      }
+      if (HB > 0 && lane < kRW) {
+        float4 v = f4zero();
+        if (rb < nr) v = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + rb) * args.ld_gin + 128));
+#pragma unroll
+        for (int j = NB; j < 4; ++j) bcol(&v, j) = 0.f;
+        M->xb[0][rb] = v;
+      }
+      signal_a_ready(w);
+      bar_workers();
+    } else {
     // ---- mask_embd (MPN.py:533,537): x0 = W2m relu(W1m mask + b1m) + b2m + x ; saves maskf, t1, x0 ------------------
     {
       float w1m[4][4], b1m[4], w2m[4][4];
@@ -627,7 +660,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
       }
       float w1b[NB][4], b1b[NB], w2b[4][NB];  // border columns 128.. of mask_embd's hidden layer
       float4 xin = f4zero(), mb2 = f4zero();
-      if (lane < 16) {
+      if (lane < kRW) {
         if (HB > 0) {
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
@@ -644,7 +677,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
       }
       float mine[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < kRW; ++i) {
         const int r = rowof(w, i), m = r0 + r;
         const float4 mk = M->ob[1][r];
         float t[4];
@@ -663,7 +696,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           if (lane == i) mine[k] = s;
         }
       }
-      if (lane < 16) {
+      if (lane < kRW) {
         const int r = rb, m = r0 + r;
         const float4 mk = M->ob[1][r];
         if (HB > 0) {
@@ -690,6 +723,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         M->x0s[r] = x0;
       }
       __syncwarp();
+    }
     }
     FSTAMP(w);  // mask_embd done
 
@@ -735,7 +769,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
             }
           }
           float wib[NB][4], wjb[NB][4], b1b[NB];
-          if (HB > 0 && lane < 16) {
+          if (HB > 0 && lane < kRW) {
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
               b1b[j] = __ldg(L.b1 + 128 + j);
@@ -747,7 +781,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
             }
           }
 #pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < kRW; ++i) {
             const int r = rowof(w, i), m = r0 + r;
             const float4 xv = M->x0s[r];
             float hi[4], hj[4];
@@ -770,7 +804,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
               }
             }
           }
-          if (HB > 0 && lane < 16) {
+          if (HB > 0 && lane < kRW) {
             const int r = rb, m = r0 + r;
             const float4 xv = M->x0s[r];
             float4 hi = f4zero(), hj = f4zero();
@@ -809,7 +843,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           }
           const uint32_t lane_base = tmem + (uint32_t(32 * qd) << 16);
 #pragma unroll 1
-          for (int c0 = 16 * half; c0 < hm; c0 += 32) {
+          for (int c0 = 16 * half; c0 < hm; c0 += 16 * kCG) {
             float vi[16], vj[16];
             const int ci[2] = {128, 0}, cj[2] = {384, 256};
             tmem_sum16<2>(lane_base, ci, c0, vi);
@@ -854,7 +888,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         FSTAMP(w);      // EA: input stage done
         if (L.type == kFusedEaTc && cl_ok) {  // save them for the backward pass: one 512-byte row per store instruction
 #pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < kRW; ++i) {
             const int r = rowof(w, i);
             if (r < nr) {
               *reinterpret_cast<float4*>(gHi + size_t(r0 + r) * ldh + cl) = lds4(R0 + fb_off(r, cl));
@@ -864,7 +898,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         }
 
         // ---- message + aggregate: S[i] = sum_{e in in(i)} relu(Hi[i] + Hj[src e] + We ea_e), ascending edge id ------
-        float4 S[16];
+        float4 S[kRW];
         float Sb[NB];
         {
           float4 w0 = f4zero(), w1 = f4zero();
@@ -872,10 +906,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
             w0 = *reinterpret_cast<const float4*>(&M->swe[0][cl]);
             w1 = *reinterpret_cast<const float4*>(&M->swe[1][cl]);
           }
-          gather16<false>(w, cl, cl_ok, w0, w1, S);
+          gather_rows<false>(w, cl, cl_ok, w0, w1, S);
 #pragma unroll
           for (int j = 0; j < NB; ++j) Sb[j] = 0.f;
-          if (HB > 0 && lane < 16) {
+          if (HB > 0 && lane < kRW) {
             const int r = rb;
             const int beg = M->rp[r] - e0, fin = M->rp[r + 1] - e0;
 #pragma unroll 1
@@ -891,14 +925,14 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         FSTAMP(w);  // EA: gather done
         // save S (dW2 = G^T S needs it)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < kRW; ++i) {
           const int r = rowof(w, i);
           if (r < nr && cl_ok) *reinterpret_cast<float4*>(gS + size_t(r0 + r) * ldh + cl) = S[i];
         }
         float4 Sb4 = f4zero();
 #pragma unroll
         for (int j = 0; j < NB; ++j) bcol(&Sb4, j) = Sb[j];
-        if (HB > 0 && lane < 16 && rb < nr) *reinterpret_cast<float4*>(gS + size_t(r0 + rb) * ldh + 128) = Sb4;
+        if (HB > 0 && lane < kRW && rb < nr) *reinterpret_cast<float4*>(gS + size_t(r0 + rb) * ldh + 128) = Sb4;
 
         if (L.last) {
           // out = S W2^T + deg (.) b2 with a handful of output columns: warp reductions straight from the registers
@@ -910,13 +944,13 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
               float4 wv = f4zero();
               if (cl_ok) wv = make_float4(__ldg(L.W2 + k * h + cl), __ldg(L.W2 + k * h + cl + 1), __ldg(L.W2 + k * h + cl + 2), __ldg(L.W2 + k * h + cl + 3));
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
+              for (int i = 0; i < kRW; ++i) {
                 const float s = warp_sum(dot4(S[i], wv));
                 if (lane == i) mine[k] = s;
               }
             }
           }
-          if (lane < 16 && rb < nr) {
+          if (lane < kRW && rb < nr) {
             const int r = rb, m = r0 + r;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -934,10 +968,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         } else {
           bar_workers();  // every gather has read Hi / Hj: the regions may become the S planes
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < kRW; ++i) {
             if (cl_ok) st_planes(R0, R1, rowof(w, i), cl, S[i]);
           }
-          if (lane < 16) M->xb[0][rb] = Sb4;
+          if (lane < kRW) M->xb[0][rb] = Sb4;
           signal_a_ready(w);
           FSTAMP(w);  // EA: S planes written
           border_dot<HB>(w, 0, L.w_row[2], 0, false);  // own rows only (written by this warp)
@@ -961,16 +995,20 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         // =================================== TAGConv (PyG; call site MPN.py:545) ===================================
         float* const xc = L.save0;
         const int ldx = (args.K + 1) * ldh;
-        stage_vec(w, M->sb1, L.bias, 1, h);
+        if (L.bias != nullptr) {
+          stage_vec(w, M->sb1, L.bias, 1, h);
+        } else {
+          for (int i = w.wt; i < 132; i += kFWorkers) M->sb1[i] = 0.f;
+        }
         for (int k = 0; k <= args.K; ++k) stage_wkb<HB>(w, k, L.w_row[k]);
 #pragma unroll 1
         for (int k = 0; k < args.K; ++k) {
           border_dot<HB>(w, k, L.w_row[k], 0, k > 0, k == 0 ? xc : nullptr, ldx);  // k = 0: also saves x_0 (block 0 of xc)
           // x_{k+1} = A_hat x_k, read from the planes while the tensor core multiplies x_k
-          float4 Y[16];
-          gather16<true>(w, cl, cl_ok, f4zero(), f4zero(), Y);
+          float4 Y[kRW];
+          gather_rows<true>(w, cl, cl_ok, f4zero(), f4zero(), Y);
           float4 Yb = f4zero();
-          if (HB > 0 && lane < 16) {
+          if (HB > 0 && lane < kRW) {
             const int r = rb;
             float acc[NB];
 #pragma unroll
@@ -992,16 +1030,16 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           FSTAMP(w);      // TAG: segment GEMM done
           bar_workers();  // ... and every worker has gathered from x_k: the planes may be overwritten
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < kRW; ++i) {
             const int r = rowof(w, i);
             if (cl_ok) {
               st_planes(R0, R1, r, cl, Y[i]);
-              if (r < nr) *reinterpret_cast<float4*>(xc + size_t(r0 + r) * ldx + (k + 1) * ldh + cl) = Y[i];
+              if (r < nr && xc != nullptr) *reinterpret_cast<float4*>(xc + size_t(r0 + r) * ldx + (k + 1) * ldh + cl) = Y[i];
             }
           }
-          if (HB > 0 && lane < 16) {
+          if (HB > 0 && lane < kRW) {
             M->xb[k + 1][rb] = Yb;
-            if (rb < nr) *reinterpret_cast<float4*>(xc + size_t(r0 + rb) * ldx + (k + 1) * ldh + 128) = Yb;
+            if (rb < nr && xc != nullptr) *reinterpret_cast<float4*>(xc + size_t(r0 + rb) * ldx + (k + 1) * ldh + 128) = Yb;
           }
           signal_a_ready(w);
           bar_workers();
@@ -1012,10 +1050,37 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         FSTAMP(w);  // TAG: last GEMM done
         const int cols[4] = {384, 0, 128, 256};
         // always four segments: xb[s] of the segments beyond K is zero (see the zero fill at kernel start)
-        epilogue_dispatch<HB, 4, 4>(w, ac, cols, M->sb1, false, L.dest, L.ld_dest);
+        const bool tag_bwd = args.mode == kFusedModeTagBackward;
+        epilogue_dispatch<HB, 4, 4>(w, ac, cols, M->sb1, false, tag_bwd ? nullptr : L.dest, L.ld_dest);
         signal_a_ready(w);
         bar_workers();
         FSTAMP(w);  // TAG: output epilogue done
+        if (tag_bwd) {
+          // d (layer input) = (sum in the planes) * (x_0 > 0 ? 1/(1-p) : 0): ReLU + dropout backward from the saved x_0,
+          // one coalesced 512-byte row per load / store instruction
+#pragma unroll 4
+          for (int i = 0; i < kRW; ++i) {
+            const int r = rowof(w, i);
+            if (r < nr && cl_ok) {
+              const float4 v = ld_planes(R0, R1, r, cl);
+              const float4 y = __ldg(reinterpret_cast<const float4*>(args.ymask + size_t(r0 + r) * args.ld_ymask + cl));
+              float4 o;
+              o.x = y.x > 0.f ? v.x * w.scale : 0.f;
+              o.y = y.y > 0.f ? v.y * w.scale : 0.f;
+              o.z = y.z > 0.f ? v.z * w.scale : 0.f;
+              o.w = y.w > 0.f ? v.w * w.scale : 0.f;
+              *reinterpret_cast<float4*>(L.dest + size_t(r0 + r) * L.ld_dest + cl) = o;
+            }
+          }
+          if (HB > 0 && lane < kRW && rb < nr) {
+            const float4 v = M->xb[0][rb];
+            const float4 y = __ldg(reinterpret_cast<const float4*>(args.ymask + size_t(r0 + rb) * args.ld_ymask + 128));
+            float4 o = f4zero();
+#pragma unroll
+            for (int j = 0; j < NB; ++j) bcol(&o, j) = bcol(&y, j) > 0.f ? bcol(&v, j) * w.scale : 0.f;
+            *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb) * L.ld_dest + 128) = o;
+          }
+        }
       }
     }
   }
@@ -1053,7 +1118,7 @@ int fused_fwd_launch(FusedArgs& a, const float* arena, int64_t arena_rows, cudaS
     a.timing = timing_dev;
   }
   {
-    ProfScope prof(PFN_PROF_FUSED_FWD, stream);
+    ProfScope prof(a.mode == kFusedModeForward ? PFN_PROF_FUSED_FWD : PFN_PROF_GEMM_DGRAD, stream);
     PFN_CUDA_OK(launch_kernel(kernel, dim3(tiles), dim3(kFThreads), kFusedSmem, stream, a));
     PFN_LAUNCHED();
   }

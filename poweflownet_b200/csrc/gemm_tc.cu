@@ -614,6 +614,7 @@ struct WgGroupProb {
   long long part_off;  // float offset of this problem's partials: [split][Mo][n_eff]
   int Mo, N, n_eff, BN, mt, nb, extra_col, lddw, m_groups, tmem_cols, stages, item0;
   int acc_hi[2], acc_lo[2];
+  int odd, pad_;
 };
 struct WgGroupArgs {
   WgGroupProb p[kWgMaxProb];
@@ -632,7 +633,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
   const int mgrp = item / args.splitk, split = item - mgrp * args.splitk;
   const int BN = P.BN, S = P.stages, mt = P.mt, nb = P.nb;
   const uint32_t a_bytes = uint32_t(mt) * 4u * 4096u, b_bytes = uint32_t(nb) * 4096u;
-  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);  // A_hi | A_lo | B_hi | B_lo
+  // P.odd: Mo = 128 + 1 (hidden_dim 129).  A second 128-row M tile for ONE row would double the MMA and converter work,
+  // so row 128 of dW is accumulated by the converter threads instead (thread n: sum over nodes of dY[node][128] X[node][n],
+  // fp32 FMAs on the TMA-landed tiles); its dY column arrives as a fifth 32-column box behind the operand planes.
+  const uint32_t odd_bytes = P.odd ? 4096u : 0u;
+  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes) + odd_bytes;  // A_hi | A_lo | B_hi | B_lo | (odd dY box)
   const uint32_t bar_base = base + uint32_t(S) * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto conv_bar = [&](int s) { return bar_base + 8u * (kTcMaxStages + s); };
@@ -674,9 +679,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         const uint32_t ph = (it / S) & 1;
         const int k0 = k_beg + it * kTcBK;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes);
+        mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes + odd_bytes);
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         for (int b = 0; b < mt * 4; ++b) tma_load_2d(st + uint32_t(b) * 4096u, &P.a, row0 + 32 * b, k0, full_bar(s));
+        if (P.odd) tma_load_2d(st + 2u * (a_bytes + b_bytes), &P.a, kTcBM, k0, full_bar(s));
         for (int b = 0; b < nb; ++b) tma_load_2d(st + 2u * a_bytes + uint32_t(b) * 4096u, &P.b, 32 * b, k0, full_bar(s));
       }
     }
@@ -714,6 +720,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
     __syncwarp();
   } else {
     const int tid_c = threadIdx.x - 64;
+    float odd_acc = 0.f;
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
@@ -732,6 +739,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");
+      }
+      if (P.odd) {
+        if (tid_c < P.n_eff) {
+          const int bb = tid_c >> 5, cc = tid_c & 31;
+          const uint32_t xcol = st + 2u * a_bytes + uint32_t(bb) * 4096u + uint32_t(cc & 7) * 4u;
+          const uint32_t ycol = st + 2u * (a_bytes + b_bytes);
+#pragma unroll 8
+          for (int r = 0; r < kTcBK; ++r) {  // 128-byte rows, 32-byte chunks XOR-swizzled with (row mod 4)
+            float x, y;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xcol + uint32_t(r) * 128u + (uint32_t((cc >> 3) ^ (r & 3)) << 5)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(ycol + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
+            odd_acc = fmaf(y, x, odd_acc);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");  // the split below rewrites X in place
       }
       split_tile(st, a_bytes, int(a_bytes / 16u), tid_c);
       split_tile(st + 2u * a_bytes, b_bytes, int(b_bytes / 16u), tid_c);
@@ -783,6 +805,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       }
       asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
     }
+    if (P.odd && tid_c < n_eff) part[size_t(kTcBM) * n_eff + tid_c] = odd_acc;
   }
   tc_fence_before();
   __syncthreads();
@@ -1075,7 +1098,8 @@ int wgrad_tc_launch(GemmArgs& g, cudaStream_t stream) {
 size_t wgrad_group_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes) {
   if (n <= 0) return 0;
   int64_t groups = 0;
-  for (int i = 0; i < n; ++i) groups += std::max<int64_t>(1, ceil_div64(ceil_div64(probs[i].Mo, kTcBM), 2));
+  for (int i = 0; i < n; ++i)
+    groups += probs[i].Mo == kTcBM + 1 ? 1 : std::max<int64_t>(1, ceil_div64(ceil_div64(probs[i].Mo, kTcBM), 2));
   const int64_t want = std::max<int64_t>(1, int64_t(sm_count()) / std::max<int64_t>(groups, 1));
   const int64_t kchunk = std::min<int64_t>(kWgMaxChunk, round_up64(std::max<int64_t>(ceil_div64(std::max<int64_t>(nodes, 1), want), kTcBK), kTcBK));
   const int64_t splitk = std::max<int64_t>(1, ceil_div64(std::max<int64_t>(nodes, 1), kchunk));
@@ -1104,7 +1128,8 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     P.n_eff = n_eff;
     P.BN = static_cast<int>(round_up64(n_eff, 16));
     P.nb = (P.BN + 31) / 32;
-    const int m_tiles = static_cast<int>(ceil_div64(w.Mo, kTcBM));
+    P.odd = (w.Mo == kTcBM + 1) ? 1 : 0;  // row 128 of dW is summed by the converter threads (see the kernel)
+    const int m_tiles = P.odd ? 1 : static_cast<int>(ceil_div64(w.Mo, kTcBM));
     P.mt = (m_tiles >= 2 && 2 * P.BN <= 512) ? 2 : 1;
     P.m_groups = static_cast<int>(ceil_div64(m_tiles, P.mt));
     int used;
@@ -1118,7 +1143,7 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     int cols = 32;
     while (cols < used) cols <<= 1;
     P.tmem_cols = cols;
-    const uint32_t stage_bytes = 2u * (uint32_t(P.mt) * 16384u + uint32_t(P.nb) * 4096u);
+    const uint32_t stage_bytes = 2u * (uint32_t(P.mt) * 16384u + uint32_t(P.nb) * 4096u) + (P.odd ? 4096u : 0u);
     P.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 2048u) / stage_bytes));
     if (P.stages < 2) return 1;
     smem_max = std::max(smem_max, uint32_t(P.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2));

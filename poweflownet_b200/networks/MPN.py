@@ -121,6 +121,7 @@ class _MPNFunction(torch.autograd.Function):
                 check(lib().pfn_mpn_forward(*common, stream), "pfn_mpn_forward")
         if needs_grad:
             ctx.model, ctx.ws, ctx.params, ctx.n, ctx.e_raw, ctx.training = model, ws, params, n, graph.e_raw, training
+            ctx.tile_rows = tile_rows  # > 0: the closed-tile promise held for this batch (validated by the forward kernel)
             ctx.keep = (x, pred_mask, graph, inj)  # keep inputs alive until backward
         else:
             model._give_workspace(n, graph.e_raw, dev, ws)
@@ -143,9 +144,13 @@ class _MPNFunction(torch.autograd.Function):
             ptable = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
             gtable = (C.c_void_p * len(params))(*[v.data_ptr() for v in views])
             desc = model._desc()
-            check(lib().pfn_mpn_backward(C.byref(desc), ptable, gtable, dout.data_ptr(), ctx.n, ctx.e_raw,
-                                         ws.graph.data_ptr(), ws.act.data_ptr(), ws.scratch.data_ptr(),
-                                         int(ctx.training), torch.cuda.current_stream().cuda_stream), "pfn_mpn_backward")
+            common = (C.byref(desc), ptable, gtable, dout.data_ptr(), ctx.n, ctx.e_raw, ws.graph.data_ptr(),
+                      ws.act.data_ptr(), ws.scratch.data_ptr(), int(ctx.training))
+            stream = torch.cuda.current_stream().cuda_stream
+            if ctx.tile_rows > 0:
+                check(lib().pfn_mpn_backward_tiled(*common, ctx.tile_rows, stream), "pfn_mpn_backward_tiled")
+            else:
+                check(lib().pfn_mpn_backward(*common, stream), "pfn_mpn_backward")
             dx = None
             if ctx.needs_input_grad[2]:
                 # x enters as `mask_embd(mask) + x` (MPN.py:537): d loss / d x is the gradient w.r.t. that sum

@@ -392,6 +392,15 @@ int ea_bwd_launch(const float* dS, int64_t ldds, const float* Hi, const float* H
   return 0;
 }
 
+// dWe[c, k] = sum over `nblocks` per-CTA partial rows laid out [2][4 * ceil(h/4)][nblocks] (k_ea_bwd, or the tiles of the
+// graph-resident EdgeAggregation backward)
+int reduce_dwe_launch(const float* partial, int nblocks, int64_t h, float* dWe, int64_t lddwe, cudaStream_t stream) {
+  PFN_CUDA_OK(launch_kernel(k_reduce_dwe, dim3(static_cast<int>(ceil_div64(2 * h * 32, 256))), dim3(256), 0, stream, partial, nblocks,
+                            static_cast<int>((h + 3) / 4), static_cast<int>(h), dWe, lddwe));
+  PFN_LAUNCHED();
+  return 0;
+}
+
 int hop_launch(const float* X, int64_t ldx, const GraphView& g, int64_t n_nodes, bool transpose, const float* addend,
                int64_t ldadd, const float* ymask, int64_t ldym, float scale, float* Y, int64_t ldy, int64_t h,
                cudaStream_t stream) {

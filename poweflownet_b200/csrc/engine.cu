@@ -593,6 +593,64 @@ int tag_backward_fused(const Ctx& c, const LayerPlan& L, const float* G, int64_t
   return fused_fwd_launch(a, c.act + p.arena_off, p.arena_rows, c.stream);
 }
 
+// Backward of one EdgeAggregation through the graph-resident kernel (fused_fwd.cu, mode 2): dS = G W2, both segmented
+// passes (dHj by source, dHi + dWe by target, ReLU mask recomputed from the saved Hi / Hj) and d cur = dHj Wj + dHi Wi in
+// ONE launch (+ the tiny dWe reduction) instead of two GEMMs and the two-pass edge kernel.
+int ea_backward_fused(const Ctx& c, const LayerPlan& L, bool last, const float* const* lp, const float* G, int64_t ldG,
+                      const float* ymask, int64_t ld_ymask, float* dest, int64_t ld_dest, float* dhi, float* dhj, float* part,
+                      float* dWe, int64_t tile_rows) {
+  const Plan& p = c.p;
+  const pfn_mpn_desc& d = p.d;
+  const int h = d.hidden_dim;
+  FusedArgs a;
+  std::memset(&a, 0, sizeof(a));
+  const Plan::EaPack& pk = p.ea_pack[L.slot];
+  auto arena_row = [&](int64_t off) { return static_cast<int>((off - p.arena_off) / p.ldh); };
+  FLayer& f = a.layers[0];
+  f.type = L.fin == h ? kFusedEaTc : kFusedEaSimt;
+  f.last = last ? 1 : 0;
+  f.fin = L.fin;
+  f.w_rows = h;
+  if (f.type == kFusedEaTc) {  // transposed packed weights: [fin, ldh] each
+    f.w_row[0] = arena_row(pk.wiT);
+    f.w_row[1] = arena_row(pk.wjT);
+  }
+  if (!last) f.w_row[2] = arena_row(pk.w2T);  // [h, ld(fout)] with fout = h
+  f.W1 = lp[0];
+  f.W2 = lp[2];
+  f.save0 = c.hi(L.slot);
+  f.dest = dest;
+  f.ld_dest = static_cast<int>(ld_dest);
+  a.mode = kFusedModeEaBackward;
+  a.n_layers = 1;
+  a.n_nodes = static_cast<int>(p.N);
+  a.tile_rows = static_cast<int>(tile_rows);
+  a.n_tiles = static_cast<int>(ceil_div64(p.N, tile_rows));
+  a.h = h;
+  a.K = d.K;
+  a.ldh = static_cast<int>(p.ldh);
+  a.out_dim = d.output_dim;
+  a.gin = G;
+  a.ld_gin = static_cast<int>(ldG);
+  a.ymask = ymask;
+  a.ld_ymask = static_cast<int>(ld_ymask);
+  a.rowptr = c.g.rowptr_s;
+  a.nbr = c.g.nbr_s;
+  a.ea = reinterpret_cast<const float2*>(c.g.ea_s);
+  a.rowptr2 = c.g.rowptr_t;
+  a.nbr2 = c.g.nbr_t;
+  a.ea2 = reinterpret_cast<const float2*>(c.g.ea_t);
+  a.deg = c.g.deg;
+  a.dis = c.g.dis;
+  a.meta = c.g.meta;
+  a.scale = c.scale;
+  a.dhi = dhi;
+  a.dhj = dhj;
+  a.dwe_partial = part;
+  PFN_TRY(fused_fwd_launch(a, c.act + p.arena_off, p.arena_rows, c.stream));
+  return reduce_dwe_launch(part, a.n_tiles, h, dWe, 2 * L.fin + 2, c.stream);
+}
+
 int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t tile_rows) {
   const Plan& p = c.p;
   const pfn_mpn_desc& d = p.d;
@@ -641,8 +699,15 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
         gemm_plan_splitk(a, N, 1);
         deferred.push_back(a);
       }
-      // dS = G W2   (as G (W2^T)^T with the packed transpose: both operands K-major)
+      const bool ea_fused = tile_rows > 0 && ldG % 4 == 0 && (L.fin == h || L.fin == nf);
       const Plan::EaPack& pk = p.ea_pack[L.slot];
+      if (ea_fused) {
+        float* dest = li == 0 ? dx0 : dz;
+        const int64_t lddest = li == 0 ? nf : ldh;
+        PFN_TRY(ea_backward_fused(c, L, li == n_layers - 1, lp, G, ldG, cur_has_act ? cur : nullptr, ldcur, dest, lddest, dhi, dhj,
+                                  part, lg[0] + 2 * L.fin, tile_rows));
+      } else {
+      // dS = G W2   (as G (W2^T)^T with the packed transpose: both operands K-major)
       {
         GemmArgs a = base_args(N, h);
         a.it[0] = fwd_item(G, ldG, c.act + pk.w2T, round_up64(L.fout, 4), L.fout, ds, ldh, nullptr, h);
@@ -652,6 +717,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
       // dHi, dHj, dWe
       PFN_TRY(ea_bwd_launch(ds, ldh, c.hi(L.slot), c.hj(L.slot), ldh, c.g, N, lp[0] + 2 * L.fin, ldw1, dhi, dhj, ldh,
                             lg[0] + 2 * L.fin, ldw1, part, h, c.stream));
+      }
       // dWi = dHi^T cur (+ db1 = colsum dHi) ; dWj = dHj^T cur
       {
         GemmArgs a = base_args(h, L.fin);
@@ -666,7 +732,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
         deferred.push_back(a);
       }
       // d cur = dHi Wi + dHj Wj, masked by the previous layer's activation
-      {
+      if (!ea_fused) {
         float* dest = li == 0 ? dx0 : dz;
         const int64_t lddest = li == 0 ? nf : ldh;
         GemmArgs a = base_args(N, L.fin);
@@ -683,6 +749,10 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
         PFN_TRY(gemm_launch(a, true, true, c.stream));
         G = dest;
         ldG = lddest;
+      }
+      if (ea_fused) {
+        G = li == 0 ? dx0 : dz;
+        ldG = li == 0 ? nf : ldh;
       }
     } else {
       const float* xc = c.xcat(L.slot);

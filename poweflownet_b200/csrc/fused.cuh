@@ -52,15 +52,24 @@ struct FusedArgs {
   // mode 1 (TAGConv backward, one layer per launch): d x_0 = sum_k ((A_hat^T)^k G) W_k, masked by the layer input.
   // Hops and GEMMs commute (one acts on rows, the other on columns), so this is the forward TAGConv program run on G
   // with the CSR by source and the transposed weights; `gin` is G, `ymask` the saved layer input x_0.
-  int mode, ld_gin, ld_ymask, pad1_;
+  // mode 2 (EdgeAggregation backward, one layer per launch): dS = G W2, the two segmented passes (by source: dHj, by
+  // target: dHi and dWe) with the ReLU mask recomputed from the saved Hi / Hj, d cur = dHj Wj + dHi Wi masked by the
+  // layer input.  rowptr/nbr/ea = CSR by source, rowptr2/nbr2/ea2 = CSR by target.
+  int mode, ld_gin, ld_ymask, n_tiles;
   const float* gin;
   const float* ymask;
+  const int* rowptr2;
+  const int* nbr2;
+  const float2* ea2;
+  float* dhi;          // [N, ldh] out (weight gradients dWi / db1 read it)
+  float* dhj;
+  float* dwe_partial;  // [2][4 * ceil(h/4)][n_tiles]: per-tile partial sums of dWe, reduced by k_reduce_dwe
   long long* timing;  // debug (PFN_FUSED_TIMING): worker 0 of CTA 0 writes clock64() at phase boundaries
 };
 static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");
 
 bool fused_fwd_supported(int h, int K, int nfeature_dim, int output_dim, int64_t tile_rows);
-constexpr int kFusedModeForward = 0, kFusedModeTagBackward = 1;
+constexpr int kFusedModeForward = 0, kFusedModeTagBackward = 1, kFusedModeEaBackward = 2;
 int fused_fwd_launch(FusedArgs& args, const float* arena, int64_t arena_rows, cudaStream_t stream);
 
 }  // namespace pfn

@@ -48,7 +48,7 @@ struct FMisc {
   float4 ob[2][128];             // border OUTPUT columns of the running tensor-core GEMM(s); afterwards the border
                                  // columns of the fp32 buffers Hi / Hj (same thread rewrites its own entry in place)
   float4 x0s[128];               // layer-0 input rows (mask_embd(mask) + x)
-  float wkb[kFusedMaxSeg][4][128];  // border-K column(s) of the weights of the running GEMM(s): W[c][128 + kb]
+  float wkb[kFusedMaxSeg][1][128];  // border-K column of the weights of the running GEMM(s): W[c][128] (hidden_dim <= 129)
   float sb1[132], sb2[132];      // biases of the running layer
   float swe[2][132];             // We columns (edge_attr weights) of the running EdgeAggregation
   float2 ea[kFusedEdgeCap];
@@ -56,7 +56,12 @@ struct FMisc {
   float dis[128];
   float deg[128];
   uint8_t nbr[kFusedEdgeCap];
-  uint8_t perm[128];  // perm[16 w + slot] = row handled in `slot` of worker warp w: the warp's rows by descending in-degree
+  // second CSR slice (EdgeAggregation backward: slab 1 = by source, slab 2 = by target)
+  float2 ea2[kFusedEdgeCap];
+  int rp2[132];
+  uint8_t nbr2[kFusedEdgeCap];
+  uint8_t perm2[128];
+  uint8_t perm[128];  // perm[kRW w + slot] = row handled in `slot` of worker warp w: the warp's rows by descending in-degree
   uint64_t bars[8];  // 0,1 bfull ; 2,3 bempty ; 4 a_ready ; 5 acc_done
   uint32_t tmem_slot;
   int bad;
@@ -115,6 +120,7 @@ struct Wk {  // per-thread worker state (registers)
   long long* timing;
   uint32_t R0, R1, a_ready, acc_done, tmem;
   int ww, lane, wt, r0, nr, n_nodes, h, ldh, e0, K;
+  int e02, rb2;  // second CSR slice: first edge id, row of this lane's slot in the by-target order
   int rb;  // row of slot `lane & 15` of this warp (the lane-per-row passes use lanes < 16)
   uint32_t acc_cnt, seed_lo, seed_hi, keep_thresh;
   float scale;
@@ -268,7 +274,7 @@ __device__ __forceinline__ void tmem_sum16(uint32_t lane_base, const int (&cols)
 // NSEG segments contributed (their border-K columns are staged in wkb[0..NSEG), their A borders in xb[0..NSEG)).
 template <int HB, int NACC, int NSEG, int MODE>
 __device__ __forceinline__ void epilogue_out(Wk& w, const ActCfg& ac, const int (&cols)[NACC], const float* bias_s,
-                                             bool deg_scaled, float* __restrict__ dest, int ld_dest) {
+                                             bool deg_scaled, float* __restrict__ dest, int ld_dest, int ob_which = 0) {
   constexpr int NB = HB > 0 ? HB : 1;
   const int warp = w.ww + 2, qd = warp & 3, half = w.ww >> 2;  // half: column group 0..kCG-1 (16-column chunks half, half+kCG, ..)
   const int r = 32 * qd + w.lane, m = w.r0 + r;
@@ -286,7 +292,7 @@ __device__ __forceinline__ void epilogue_out(Wk& w, const ActCfg& ac, const int 
   float obv[NB];
   if (HB > 0 && half == 0) {
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) obv[nb] = bcol(&M->ob[0][r], nb);
+    for (int nb = 0; nb < NB; ++nb) obv[nb] = bcol(&M->ob[ob_which][r], nb);
   }
   bar_workers();  // ... xb[0] is rewritten below
   const uint32_t lane_base = w.tmem + (uint32_t(32 * qd) << 16);
@@ -327,11 +333,11 @@ __device__ __forceinline__ void epilogue_out(Wk& w, const ActCfg& ac, const int 
 
 template <int HB, int NACC, int NSEG>
 __device__ __forceinline__ void epilogue_dispatch(Wk& w, const ActCfg& ac, const int (&cols)[NACC], const float* bias_s,
-                                                  bool deg_scaled, float* __restrict__ dest, int ld_dest) {
+                                                  bool deg_scaled, float* __restrict__ dest, int ld_dest, int ob_which = 0) {
   switch (act_mode(ac)) {  // CTA-uniform
-    case 0: epilogue_out<HB, NACC, NSEG, 0>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest); break;
-    case 1: epilogue_out<HB, NACC, NSEG, 1>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest); break;
-    default: epilogue_out<HB, NACC, NSEG, 2>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest); break;
+    case 0: epilogue_out<HB, NACC, NSEG, 0>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest, ob_which); break;
+    case 1: epilogue_out<HB, NACC, NSEG, 1>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest, ob_which); break;
+    default: epilogue_out<HB, NACC, NSEG, 2>(w, ac, cols, bias_s, deg_scaled, dest, ld_dest, ob_which); break;
   }
 }
 
@@ -399,7 +405,110 @@ __device__ __forceinline__ void gather_rows(const Wk& w, int cl, bool cl_ok, flo
   }
 }
 
-template <int HB>
+// ---- EdgeAggregation backward (mode 2) ------------------------------------------------------------------------------
+// One segmented pass over this warp's kRW rows, four rows interleaved (branch-free, as gather_rows).
+//   kTarget = false (CSR by source, row j): out[j] = sum_{e=(j->t)} dS[t] * 1[Hi[t] + Hj[j] + We ea_e > 0]            -> dHj
+//   kTarget = true  (CSR by target, row i): out[i] = sum_{e=(s->i)} dS[i] * 1[Hi[i] + Hj[s] + We ea_e > 0]            -> dHi
+//                                            gw0 / gw1 += the same masked dS times ea_e.x / ea_e.y                    -> dWe
+// R0 holds dS, R1 the OTHER side's H (Hi for the source pass, Hj for the target pass), both as fp32 buffers; the row's
+// own H comes straight from the saved activations in global memory (one coalesced 512-byte row).  The pre-activation is
+// recomputed with the forward's exact expression, so the mask is the forward's.
+template <bool kTarget>
+__device__ __forceinline__ void ea_bwd_pass(const Wk& w, int cl, bool cl_ok, float4 w0, float4 w1, const float* __restrict__ own,
+                                            float4 (&out)[kRW], float4& gw0, float4& gw1) {
+  FMisc* const M = w.m;
+  const int* rp = kTarget ? M->rp2 : M->rp;
+  const uint8_t* nb = kTarget ? M->nbr2 : M->nbr;
+  const float2* eav = kTarget ? M->ea2 : M->ea;
+  const uint8_t* perm = kTarget ? M->perm2 : M->perm;
+  const int e0 = kTarget ? w.e02 : w.e0;
+#pragma unroll
+  for (int g = 0; g < kRW / 2; ++g) {  // two rows interleaved (register budget: ~96 per thread)
+    int beg[2], cnt[2];
+    float4 hown[2], dsown[2], acc[2];
+    int maxd = 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = perm[w.ww * kRW + 2 * g + j];
+      beg[j] = rp[r] - e0;
+      cnt[j] = rp[r + 1] - e0 - beg[j];
+      maxd = max(maxd, cnt[j]);
+      acc[j] = f4zero();
+      hown[j] = f4zero();
+      dsown[j] = f4zero();
+      if (cl_ok) {
+        if (r < w.nr) hown[j] = __ldg(reinterpret_cast<const float4*>(own + size_t(w.r0 + r) * w.ldh + cl));
+        if (kTarget) dsown[j] = lds4(w.R0 + fb_off(r, cl));
+      }
+    }
+    if (cl_ok) {
+#pragma unroll 1
+      for (int t = 0; t < maxd; ++t) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool ok = t < cnt[j];
+          const int e = ok ? beg[j] + t : 0;
+          const int o = nb[e];
+          const float2 a = eav[e];
+          const float4 hoth = lds4(w.R1 + fb_off(o, cl));
+          float4 ds = dsown[j];
+          if (!kTarget) ds = lds4(w.R0 + fb_off(o, cl));
+          // forward: fmaf(a.y, w1, fmaf(a.x, w0, Hi[target] + Hj[source]))  (the sum is commutative, hence exact either way)
+          const float px = fmaf(a.y, w1.x, fmaf(a.x, w0.x, hown[j].x + hoth.x));
+          const float py = fmaf(a.y, w1.y, fmaf(a.x, w0.y, hown[j].y + hoth.y));
+          const float pz = fmaf(a.y, w1.z, fmaf(a.x, w0.z, hown[j].z + hoth.z));
+          const float pw = fmaf(a.y, w1.w, fmaf(a.x, w0.w, hown[j].w + hoth.w));
+          const float gx = (ok && px > 0.f) ? ds.x : 0.f;
+          const float gy = (ok && py > 0.f) ? ds.y : 0.f;
+          const float gz = (ok && pz > 0.f) ? ds.z : 0.f;
+          const float gw = (ok && pw > 0.f) ? ds.w : 0.f;
+          acc[j].x += gx;
+          acc[j].y += gy;
+          acc[j].z += gz;
+          acc[j].w += gw;
+          if (kTarget) {
+            gw0.x = fmaf(gx, a.x, gw0.x); gw0.y = fmaf(gy, a.x, gw0.y); gw0.z = fmaf(gz, a.x, gw0.z); gw0.w = fmaf(gw, a.x, gw0.w);
+            gw1.x = fmaf(gx, a.y, gw1.x); gw1.y = fmaf(gy, a.y, gw1.y); gw1.z = fmaf(gz, a.y, gw1.z); gw1.w = fmaf(gw, a.y, gw1.w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) out[2 * g + j] = acc[j];
+  }
+}
+
+// the same pass for the border column (hidden_dim 129: column 128) of this lane's row; lanes < kRW only.
+// dS border in ob[0], the other side's H border in xb[3], We border in swe[.][128]
+template <bool kTarget>
+__device__ __forceinline__ float ea_bwd_border(const Wk& w, int r, const float* __restrict__ own, float& gw0, float& gw1) {
+  FMisc* const M = w.m;
+  const int* rp = kTarget ? M->rp2 : M->rp;
+  const uint8_t* nb = kTarget ? M->nbr2 : M->nbr;
+  const float2* eav = kTarget ? M->ea2 : M->ea;
+  const int e0 = kTarget ? w.e02 : w.e0;
+  const float hown = r < w.nr ? __ldg(own + size_t(w.r0 + r) * w.ldh + 128) : 0.f;
+  const float we0 = M->swe[0][128], we1 = M->swe[1][128];
+  const int beg = rp[r] - e0, fin = rp[r + 1] - e0;
+  float acc = 0.f;
+#pragma unroll 1
+  for (int e = beg; e < fin; ++e) {
+    const int o = nb[e];
+    const float2 a = eav[e];
+    const float p = fmaf(a.y, we1, fmaf(a.x, we0, hown + bcol(&M->xb[3][o], 0)));
+    const float ds = bcol(&M->ob[0][kTarget ? r : o], 0);
+    const float g = p > 0.f ? ds : 0.f;
+    acc += g;
+    if (kTarget) {
+      gw0 = fmaf(g, a.x, gw0);
+      gw1 = fmaf(g, a.y, gw1);
+    }
+  }
+  return acc;
+}
+
+// MODE is a template parameter (not a run-time branch) so that each program gets its own register allocation
+template <int HB, int MODE>
 __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_constant__ FusedArgs args) {
   constexpr int NB = HB > 0 ? HB : 1;
   extern __shared__ uint8_t smem_dyn[];
@@ -434,16 +543,19 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
   // zero the operand regions once: K-tile padding is multiplied by zero weights, but must not hold NaN bit patterns
   for (uint32_t o = threadIdx.x * 16u; o < 2 * kPlaneBytes; o += kFThreads * 16u) sts4(R0 + o, f4zero());
   for (int i = threadIdx.x; i < kFusedMaxSeg * 128; i += kFThreads) (&M->xb[0][0])[i] = f4zero();
-  for (int i = threadIdx.x; i < kFusedMaxSeg * 4 * 128; i += kFThreads) (&M->wkb[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < kFusedMaxSeg * 128; i += kFThreads) (&M->wkb[0][0][0])[i] = 0.f;
   pdl_wait();
   // ---- stage the tile's CSR slice (by target), validating that the tile is closed -------------------------------
-  for (int i = threadIdx.x; i <= 128; i += kFThreads) M->rp[i] = args.rowptr[r0 + min(i, nr)];
+  for (int i = threadIdx.x; i <= 128; i += kFThreads) {
+    M->rp[i] = args.rowptr[r0 + min(i, nr)];
+    if (MODE == kFusedModeEaBackward) M->rp2[i] = args.rowptr2[r0 + min(i, nr)];
+  }
   for (int i = threadIdx.x; i < 128; i += kFThreads) {
     M->dis[i] = i < nr ? args.dis[r0 + i] : 0.f;
     M->deg[i] = i < nr ? args.deg[r0 + i] : 0.f;
     // float(pred_mask) of the tile's rows, parked in ob[1] until mask_embd has consumed it
     float4 mk = f4zero();
-    if (i < nr && args.mode == kFusedModeForward) {
+    if (i < nr && MODE == kFusedModeForward) {
       const longlong2* pm = reinterpret_cast<const longlong2*>(args.pred_mask + size_t(r0 + i) * 4);
       const longlong2 a = pm[0], b = pm[1];
       mk = make_float4(float(a.x), float(a.y), float(b.x), float(b.y));
@@ -465,6 +577,29 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     }
     if (threadIdx.x == 0 && ne == 0) M->nbr[0] = 0;  // the branch-free gathers may touch slot 0 of an edgeless tile
     if (bad) M->bad = 1;
+    if (MODE == kFusedModeEaBackward) {
+      const int e02 = M->rp2[0], ne2 = M->rp2[128] - e02;
+      if (ne2 > kFusedEdgeCap) bad = 1;
+      for (int i = threadIdx.x; i < min(ne2, kFusedEdgeCap); i += kFThreads) {
+        const int loc = args.nbr2[e02 + i] - r0;
+        if (loc < 0 || loc >= nr) bad = 1;
+        M->nbr2[i] = static_cast<uint8_t>(loc & 127);
+        M->ea2[i] = args.ea2[e02 + i];
+      }
+      if (threadIdx.x == 0 && ne2 == 0) M->nbr2[0] = 0;
+      if (bad) M->bad = 1;
+      if (warp < kFWorkerWarps) {
+        const int i = lane % kRW, r = warp * kRW + i;
+        const int d = M->rp2[r + 1] - M->rp2[r];
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < kRW; ++j) {
+          const int dj = __shfl_sync(0xffffffffu, d, j);
+          rank += (dj > d || (dj == d && j < i)) ? 1 : 0;
+        }
+        if (lane < kRW) M->perm2[warp * kRW + rank] = static_cast<uint8_t>(r);
+      }
+    }
     if (warp < kFWorkerWarps) {  // slot order of the kRW rows of worker warp `warp`: by descending in-degree, ties by row
       const int i = lane % kRW, r = warp * kRW + i;
       const int d = M->rp[r + 1] - M->rp[r];
@@ -481,11 +616,12 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
   if (M->bad) {  // CTA-uniform: the caller's promise does not hold for this tile
     if (threadIdx.x == 0) args.meta[6] = 1;
     const float qnan = __int_as_float(0x7fc00000);
-    if (args.mode == kFusedModeForward) {
+    if (MODE == kFusedModeForward) {
       for (int i = threadIdx.x; i < nr * args.out_dim; i += kFThreads) args.out[size_t(r0) * args.out_dim + i] = qnan;
     } else {
       const FLayer& L = args.layers[0];
-      for (int i = threadIdx.x; i < nr * h; i += kFThreads) L.dest[size_t(r0 + i / h) * L.ld_dest + i % h] = qnan;
+      const int wd = MODE == kFusedModeEaBackward ? L.fin : h;
+      for (int i = threadIdx.x; i < nr * wd; i += kFThreads) L.dest[size_t(r0 + i / wd) * L.ld_dest + i % wd] = qnan;
     }
     tc_fence_before();
     __syncthreads();
@@ -508,7 +644,15 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           tma_load_2d(st + kKTileBytes, &args.wmap, kt * 32, w_row + 2 * w_rows, bfull(s));
         }
       };
-      for (int li = 0; li < args.n_layers; ++li) {
+      if (MODE == kFusedModeEaBackward) {  // W2^T, then Wj^T and Wi^T (w_row[] index the TRANSPOSED packed weights)
+        const FLayer& L = args.layers[0];
+        if (!L.last) load_weight(L.w_row[2], L.w_rows);
+        if (L.type == kFusedEaTc) {
+          load_weight(L.w_row[1], L.w_rows);
+          load_weight(L.w_row[0], L.w_rows);
+        }
+      }
+      for (int li = 0; li < (MODE == kFusedModeEaBackward ? 0 : args.n_layers); ++li) {
         const FLayer& L = args.layers[li];
         if (L.type == kFusedTag) {
           for (int k = 0; k <= args.K; ++k) load_weight(L.w_row[k], L.w_rows);
@@ -557,7 +701,26 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         __syncwarp();
       }
     };
-    for (int li = 0; li < args.n_layers; ++li) {
+    if (MODE == kFusedModeEaBackward) {
+      const FLayer& L = args.layers[0];
+      if (!L.last) {  // dS = G W2
+        wait_a();
+        int kk = 0;
+        gemm(0u, 1, 128u, kk);
+        if (lane == 0) umma_commit(acc_done);
+        __syncwarp();
+      }
+      if (L.type == kFusedEaTc) {  // d cur = dHj Wj + dHi Wi: two segments into the same accumulators
+        int kk = 0;
+        for (int seg = 0; seg < 2; ++seg) {
+          wait_a();
+          gemm(256u, 1, 384u, kk);
+          if (lane == 0) umma_commit(acc_done);
+          __syncwarp();
+        }
+      }
+    }
+    for (int li = 0; li < (MODE == kFusedModeEaBackward ? 0 : args.n_layers); ++li) {
       const FLayer& L = args.layers[li];
       if (L.type == kFusedTag) {
         int kk = 0;
@@ -626,7 +789,250 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     w.rb = rb;
     constexpr int nf = 4;
 
-    if (args.mode == kFusedModeTagBackward) {
+    if (MODE == kFusedModeEaBackward) {
+      // ======================= backward of one EdgeAggregation (see ea_bwd_pass) =======================
+      const FLayer& L = args.layers[0];
+      const int ldw1 = 2 * L.fin + 2;
+      const float* const gHi = L.save0;
+      const float* const gHj = gHi + size_t(args.n_nodes) * ldh;
+      const bool tc_in = L.type == kFusedEaTc;
+      w.e02 = M->rp2[0];
+      const int rb2 = M->perm2[ww * kRW + (lane % kRW)];
+      w.rb2 = rb2;
+      stage_vec(w, M->swe[0], L.W1 + 2 * L.fin, ldw1, h);
+      stage_vec(w, M->swe[1], L.W1 + 2 * L.fin + 1, ldw1, h);
+      for (int i = w.wt; i < 132; i += kFWorkers) M->sb1[i] = 0.f;
+      if (!L.last) stage_wkb<HB>(w, 2, L.w_row[2]);  // border-K columns: slot 2 = W2^T, slot 0 = Wj^T, slot 1 = Wi^T
+      if (tc_in) {
+        stage_wkb<HB>(w, 0, L.w_row[1]);
+        stage_wkb<HB>(w, 1, L.w_row[0]);
+      }
+      if (!L.last) {
+        // G -> A operand (planes; border column kept in xb[2] for both extractions of dS)
+#pragma unroll 4
+        for (int i = 0; i < kRW; ++i) {
+          const int r = rowof(w, i);
+          float4 v = f4zero();
+          if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + r) * args.ld_gin + cl));
+          if (cl_ok) st_planes(R0, R1, r, cl, v);
+        }
+        if (HB > 0 && lane < kRW) {
+          float4 v = f4zero();
+          if (rb < nr) v = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + rb) * args.ld_gin + 128));
+#pragma unroll
+          for (int j = NB; j < 4; ++j) bcol(&v, j) = 0.f;
+          M->xb[2][rb] = v;
+        }
+        signal_a_ready(w);
+        bar_workers();
+        border_dot<HB>(w, 2, L.w_row[2], 0, false);  // column 128 of dS -> ob[0] (stays there for both passes)
+        wait_acc(w);
+      }
+      float4 w0 = f4zero(), w1 = f4zero();
+#pragma unroll 1
+      for (int round = 0; round < 2; ++round) {  // 0: pass by source (dHj) ; 1: pass by target (dHi, dWe)
+        bar_workers();  // staged constants visible; nobody still reads R0 / R1 (their MMA has completed: wait_acc above)
+        if (!L.last) {
+          // dS (TMEM accumulators 0 = hi*hi, 128 = lo terms; they survive the second GEMM) -> fp32 buffer R0
+          const int warp_id = ww + 2, qd = warp_id & 3, half = ww >> 2;
+          const int r = 32 * qd + lane;
+          float xbv = 0.f;
+          if (HB > 0) xbv = bcol(&M->xb[2][r], 0);
+          const uint32_t lane_base = tmem + (uint32_t(32 * qd) << 16);
+#pragma unroll 1
+          for (int c0 = 16 * half; c0 < hm; c0 += 16 * kCG) {
+            float v[16];
+            const int cd[2] = {128, 0};
+            tmem_sum16<2>(lane_base, cd, c0, v);
+            if (HB > 0) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t) v[t] = fmaf(xbv, M->wkb[2][0][c0 + t], v[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < 16; t += 4) sts4(R0 + fb_off(r, c0 + t), make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]));
+          }
+          tc_fence_before();
+        } else {
+          // dS = G W2 with a handful of G columns (output layer): FMAs, G rows straight from global memory
+          float w2r[4][4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w2r[k][j] = (k < args.out_dim && cl_ok) ? __ldg(L.W2 + k * h + cl + j) : 0.f;
+#pragma unroll 4
+          for (int i = 0; i < kRW; ++i) {
+            const int r = rowof(w, i);
+            float4 gv = f4zero();
+            if (r < nr) gv = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + r) * args.ld_gin));
+            float4 ds;
+            ds.x = fmaf(gv.w, w2r[3][0], fmaf(gv.z, w2r[2][0], fmaf(gv.y, w2r[1][0], gv.x * w2r[0][0])));
+            ds.y = fmaf(gv.w, w2r[3][1], fmaf(gv.z, w2r[2][1], fmaf(gv.y, w2r[1][1], gv.x * w2r[0][1])));
+            ds.z = fmaf(gv.w, w2r[3][2], fmaf(gv.z, w2r[2][2], fmaf(gv.y, w2r[1][2], gv.x * w2r[0][2])));
+            ds.w = fmaf(gv.w, w2r[3][3], fmaf(gv.z, w2r[2][3], fmaf(gv.y, w2r[1][3], gv.x * w2r[0][3])));
+            if (cl_ok) sts4(R0 + fb_off(r, cl), ds);
+          }
+          if (HB > 0 && lane < kRW) {
+            float4 gv = f4zero();
+            if (rb < nr) gv = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + rb) * args.ld_gin));
+            float d = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < args.out_dim) d = fmaf(bcol(&gv, k), __ldg(L.W2 + k * h + 128), d);
+            float4 o = f4zero();
+            o.x = d;
+            M->ob[0][rb] = o;
+          }
+        }
+        // the other side's H -> fp32 buffer R1 (border column -> xb[3]); one coalesced row per instruction
+        {
+          const float* __restrict__ hsrc = round == 0 ? gHi : gHj;
+#pragma unroll 4
+          for (int i = 0; i < kRW; ++i) {
+            const int r = rowof(w, i);
+            float4 v = f4zero();
+            if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(hsrc + size_t(r0 + r) * ldh + cl));
+            if (cl_ok) sts4(R1 + fb_off(r, cl), v);
+          }
+          if (HB > 0 && lane < kRW) {
+            float4 v = f4zero();
+            if (rb < nr) v.x = __ldg(hsrc + size_t(r0 + rb) * ldh + 128);
+            M->xb[3][rb] = v;
+          }
+        }
+        bar_workers();
+        if (round == 0 && cl_ok) {
+          w0 = *reinterpret_cast<const float4*>(&M->swe[0][cl]);
+          w1 = *reinterpret_cast<const float4*>(&M->swe[1][cl]);
+        }
+        float4 D[kRW];
+        float4 gw0 = f4zero(), gw1 = f4zero();
+        float db = 0.f, gb0 = 0.f, gb1 = 0.f;
+        const uint8_t* const perm_r = round == 0 ? M->perm : M->perm2;
+        const int rbr = round == 0 ? rb : rb2;
+        if (round == 0) {
+          ea_bwd_pass<false>(w, cl, cl_ok, w0, w1, gHj, D, gw0, gw1);
+          if (HB > 0 && lane < kRW) db = ea_bwd_border<false>(w, rbr, gHj, gb0, gb1);
+        } else {
+          ea_bwd_pass<true>(w, cl, cl_ok, w0, w1, gHi, D, gw0, gw1);
+          if (HB > 0 && lane < kRW) db = ea_bwd_border<true>(w, rbr, gHi, gb0, gb1);
+        }
+        // dHj / dHi to global (the weight gradients read them)
+        float* const gout = round == 0 ? args.dhj : args.dhi;
+#pragma unroll
+        for (int i = 0; i < kRW; ++i) {
+          const int r = perm_r[ww * kRW + i];
+          if (r < nr && cl_ok) *reinterpret_cast<float4*>(gout + size_t(r0 + r) * ldh + cl) = D[i];
+        }
+        float4 db4 = f4zero();
+        db4.x = db;
+        if (HB > 0 && lane < kRW && rbr < nr) *reinterpret_cast<float4*>(gout + size_t(r0 + rbr) * ldh + 128) = db4;
+        bar_workers();  // every worker has finished reading R0 / R1 / ob[0] / xb[3]
+        if (round == 1) {
+          // dWe: per-warp column sums -> shared scratch (R0 is free) -> fixed-order sum over the warps -> this tile's partial
+          const uint32_t red = R0;
+          if (cl_ok) {
+            sts4(red + (uint32_t(ww * 2 + 0) * 132u + uint32_t(cl)) * 4u, gw0);
+            sts4(red + (uint32_t(ww * 2 + 1) * 132u + uint32_t(cl)) * 4u, gw1);
+          }
+          if (HB > 0) {
+            const float s0 = warp_sum(lane < kRW ? gb0 : 0.f), s1 = warp_sum(lane < kRW ? gb1 : 0.f);
+            if (lane == 0) {
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (uint32_t(ww * 2 + 0) * 132u + 128u) * 4u), "f"(s0) : "memory");
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + (uint32_t(ww * 2 + 1) * 132u + 128u) * 4u), "f"(s1) : "memory");
+            }
+          }
+          bar_workers();
+          const int c4 = (h + 3) / 4;
+          for (int idx = w.wt; idx < 2 * h; idx += kFWorkers) {
+            const int k = idx / h, c = idx - k * h;
+            float sum = 0.f;
+#pragma unroll 1
+            for (int v = 0; v < kFWorkerWarps; ++v) {
+              float t;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(red + (uint32_t(v * 2 + k) * 132u + uint32_t(c)) * 4u));
+              sum += t;
+            }
+            args.dwe_partial[(size_t(k) * 4 * c4 + c) * args.n_tiles + blockIdx.x] = sum;
+          }
+          bar_workers();
+        }
+        if (tc_in) {
+          // the pass result becomes the A operand of its segment of d cur = dHj Wj + dHi Wi
+#pragma unroll
+          for (int i = 0; i < kRW; ++i) {
+            if (cl_ok) st_planes(R0, R1, perm_r[ww * kRW + i], cl, D[i]);
+          }
+          if (lane < kRW) M->xb[round][rbr] = db4;
+          signal_a_ready(w);
+          __syncwarp();
+          // border column of d cur accumulates in ob[1]; the planes rows of this warp's slots were written by this warp,
+          // but border_dot walks the rows in `perm` order: wait for everyone
+          bar_workers();
+          border_dot<HB>(w, round, L.w_row[round == 0 ? 1 : 0], 1, round == 1);
+          wait_acc(w);
+        } else {
+          // input width 4 (first layer): d x0 += D W[:, block] by warp reductions; rows differ between the two passes,
+          // so the running sum lives in shared memory (x0s)
+          const int off = round == 0 ? nf : 0;  // Wj columns follow Wi's in edge_aggr.0.weight
+          float mine[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float4 wv = f4zero();
+            if (cl_ok) wv = make_float4(__ldg(L.W1 + (cl + 0) * ldw1 + off + k), __ldg(L.W1 + (cl + 1) * ldw1 + off + k),
+                                        __ldg(L.W1 + (cl + 2) * ldw1 + off + k), __ldg(L.W1 + (cl + 3) * ldw1 + off + k));
+#pragma unroll
+            for (int i = 0; i < kRW; ++i) {
+              const float sres = warp_sum(dot4(D[i], wv));
+              if (lane == i) mine[k] = sres;
+            }
+          }
+          if (lane < kRW) {
+            if (HB > 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mine[k] = fmaf(db, __ldg(L.W1 + 128 * ldw1 + off + k), mine[k]);
+            }
+            float4 acc4 = make_float4(mine[0], mine[1], mine[2], mine[3]);
+            if (round == 1) acc4 = f4add(acc4, M->x0s[rbr]);
+            M->x0s[rbr] = acc4;
+          }
+        }
+      }
+      if (tc_in) {
+        ActCfg ac0{};
+        const int cols[2] = {384, 256};
+        epilogue_dispatch<HB, 2, 2>(w, ac0, cols, M->sb1, false, nullptr, 0, 1);
+        signal_a_ready(w);
+        bar_workers();
+        // d cur = planes * (layer input > 0 ? 1/(1-p) : 0), coalesced
+#pragma unroll 4
+        for (int i = 0; i < kRW; ++i) {
+          const int r = rowof(w, i);
+          if (r < nr && cl_ok) {
+            const float4 v = ld_planes(R0, R1, r, cl);
+            float4 o = v;
+            if (args.ymask != nullptr) {
+              const float4 y = __ldg(reinterpret_cast<const float4*>(args.ymask + size_t(r0 + r) * args.ld_ymask + cl));
+              o.x = y.x > 0.f ? v.x * w.scale : 0.f;
+              o.y = y.y > 0.f ? v.y * w.scale : 0.f;
+              o.z = y.z > 0.f ? v.z * w.scale : 0.f;
+              o.w = y.w > 0.f ? v.w * w.scale : 0.f;
+            }
+            *reinterpret_cast<float4*>(L.dest + size_t(r0 + r) * L.ld_dest + cl) = o;
+          }
+        }
+        if (HB > 0 && lane < kRW && rb < nr) {
+          float4 o = f4zero();
+          const float v = bcol(&M->xb[0][rb], 0);
+          o.x = v;
+          if (args.ymask != nullptr) o.x = __ldg(args.ymask + size_t(r0 + rb) * args.ld_ymask + 128) > 0.f ? v * w.scale : 0.f;
+          *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb) * L.ld_dest + 128) = o;
+        }
+      } else {
+        __syncwarp();
+        if (lane < kRW && rb2 < nr) *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb2) * L.ld_dest) = M->x0s[rb2];
+      }
+    } else
+    if (MODE == kFusedModeTagBackward) {
       // ---- backward of one TAGConv: the incoming gradient G becomes the A operand (planes + border columns) ----------
 #pragma unroll 4
       for (int i = 0; i < kRW; ++i) {
@@ -728,7 +1134,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     FSTAMP(w);  // mask_embd done
 
 #pragma unroll 1
-    for (int li = 0; li < args.n_layers; ++li) {
+    for (int li = 0; li < (MODE == kFusedModeEaBackward ? 0 : args.n_layers); ++li) {
       const FLayer& L = args.layers[li];
       ActCfg ac;
       ac.act = L.act;
@@ -1050,7 +1456,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         FSTAMP(w);  // TAG: last GEMM done
         const int cols[4] = {384, 0, 128, 256};
         // always four segments: xb[s] of the segments beyond K is zero (see the zero fill at kernel start)
-        const bool tag_bwd = args.mode == kFusedModeTagBackward;
+        const bool tag_bwd = MODE == kFusedModeTagBackward;
         epilogue_dispatch<HB, 4, 4>(w, ac, cols, M->sb1, false, tag_bwd ? nullptr : L.dest, L.ld_dest);
         signal_a_ready(w);
         bar_workers();
@@ -1102,13 +1508,17 @@ int fused_fwd_launch(FusedArgs& a, const float* arena, int64_t arena_rows, cudaS
   PFN_REQUIRE(tc_make_map(&a.wmap, arena, arena_rows, a.h, a.ldh, 128), PFN_E_UNSUPPORTED,
               "fused forward: cannot encode the weight-arena tensor map");
   a.arena = arena;
+  void (*kernels[2][3])(FusedArgs) = {
+      {k_mpn_fused_fwd<0, kFusedModeForward>, k_mpn_fused_fwd<0, kFusedModeTagBackward>, k_mpn_fused_fwd<0, kFusedModeEaBackward>},
+      {k_mpn_fused_fwd<1, kFusedModeForward>, k_mpn_fused_fwd<1, kFusedModeTagBackward>, k_mpn_fused_fwd<1, kFusedModeEaBackward>}};
   static bool attr_set = false;
   if (!attr_set) {
-    PFN_CUDA_OK(cudaFuncSetAttribute(k_mpn_fused_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)));
-    PFN_CUDA_OK(cudaFuncSetAttribute(k_mpn_fused_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)));
+    for (auto& row : kernels)
+      for (auto* k : row) PFN_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)));
     attr_set = true;
   }
-  void (*kernel)(FusedArgs) = a.h > 128 ? k_mpn_fused_fwd<1> : k_mpn_fused_fwd<0>;
+  PFN_REQUIRE(a.mode >= 0 && a.mode <= 2, PFN_E_INVALID, "fused kernel: bad mode %d", a.mode);
+  void (*kernel)(FusedArgs) = kernels[a.h > 128 ? 1 : 0][a.mode];
   const unsigned tiles = static_cast<unsigned>(ceil_div64(a.n_nodes, a.tile_rows));
   static const bool timing_on = std::getenv("PFN_FUSED_TIMING") != nullptr;  // debug aid: phase timestamps of CTA 0
   static long long* timing_dev = nullptr;

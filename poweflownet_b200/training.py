@@ -118,6 +118,49 @@ class GraphedMSEStep:
         return self.loss
 
 
+class PipelinedMSESteps:
+    """Two `GraphedMSEStep`s over two sets of static input buffers: the host->device copy of batch i+1 runs on a side
+    stream while batch i computes (what a prefetching loader with `pin_memory=True` does for the reference's
+    `data.to(device)` at utils/training.py:56).  Usage::
+
+        pipe.prefetch(batch_0)
+        for i in range(n):
+            pipe.prefetch(batch_{i+1})        # asynchronous, overlaps the step below
+            loss = float(pipe.step().item())  # forward + MSE + backward of batch_i, then the device->host read
+    """
+
+    def __init__(self, model: MaskEmbdMultiMPN, example_batch, total_count: Optional[int] = None):
+        self.steps = [GraphedMSEStep(model, example_batch, total_count) for _ in range(2)]
+        dev = self.steps[0].device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self._in, self._run, self._pending = 0, 0, 0
+
+    def prefetch(self, batch) -> None:
+        if self._pending >= 2:
+            raise RuntimeError("both buffer sets hold batches that have not been stepped yet")
+        k = self._in
+        self._in ^= 1
+        self._pending += 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.done[k])  # the replay that last read this buffer set has finished
+            self.steps[k].load(batch)
+            self.ready[k].record(self.copy_stream)
+
+    def step(self) -> torch.Tensor:
+        if self._pending <= 0:
+            raise RuntimeError("step() without a prefetched batch")
+        k = self._run
+        self._run ^= 1
+        self._pending -= 1
+        cur = torch.cuda.current_stream(self.steps[k].device)
+        cur.wait_event(self.ready[k])
+        loss = self.steps[k](None)
+        self.done[k].record(cur)
+        return loss
+
+
 def train_step(model: MaskEmbdMultiMPN, host_batch, device, loss: str = "mse", total_count: Optional[int] = None):
     """End-to-end step from HOST memory: H2D of the batch (pinned -> non_blocking), forward, loss, backward,
     and the device->host read of the loss (utils/training.py:56-77 minus optimizer.step)."""

@@ -155,3 +155,30 @@ def test_tiled_entry_point_rejects_unsupported_configurations():
     rc = lib.pfn_mpn_forward_tiled(C.byref(MpnDesc(4, 2, 4, 512, 5, 3, 0.2, 0)), None, None, None, 0, 0, None, None, None, 0, 0,
                                    None, None, None, 118, None)
     assert rc == -2 and b"graph-resident" in lib.pfn_last_error()
+
+
+def test_pipelined_steps_match_eager_steps():
+    """PipelinedMSESteps (double-buffered CUDA-graph replays, H2D of batch i+1 under the step of batch i) returns the
+    losses and leaves the gradients of plain eager steps on the same batches."""
+    from poweflownet_b200.data import synthetic_batch
+    from poweflownet_b200.training import PipelinedMSESteps, fused_mse_step
+    kw = dict(common.MODEL_DIMS, hidden_dim=129, n_gnn_layers=3, K=3, dropout_rate=0.0)
+    host = [synthetic_batch("118v2", 6, seed=100 + i).pin_memory() for i in range(4)]
+    m = _model(kw).train()
+    want, want_grads = [], None
+    for b in host:
+        want.append(float(fused_mse_step(m, b.to(DEV)).item()))
+        want_grads = [p.grad.clone() for p in m._engine_params()]
+    pipe = PipelinedMSESteps(m, host[0].to(DEV))
+    got = []
+    pipe.prefetch(host[0])
+    for i in range(len(host)):
+        if i + 1 < len(host):
+            pipe.prefetch(host[i + 1])
+        got.append(float(pipe.step().item()))
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 1e-6 * abs(b), (got, want)
+    for p, g in zip(m._engine_params(), want_grads):
+        _close(p.grad, g, "gradient after the last pipelined step", tol=1e-6)
+    with pytest.raises(RuntimeError):
+        pipe.step()

@@ -68,6 +68,67 @@ __global__ void k_count(const int64_t* __restrict__ ei, int64_t stride, int e_ra
 
 // Pass 3: exclusive scan of a histogram into rowptr (one CTA per CSR), degree and deg^-1/2, and
 // reset of the histogram so pass 4 can reuse it as the per-row cursor.
+// Shared-memory variant of k_scan for batches whose counts fit (n_nodes <= kScanSmemNodes): all global traffic is
+// coalesced (thread t touches elements t, t + 1024, ...), the per-thread contiguous chunks are read from and written to
+// shared memory.  The register variant below lets every thread store 16 scattered words per array from ONE SM, which
+// made its load/store unit the bottleneck (36 us for 15104 nodes).
+constexpr int kScanSmemNodes = 24 * 1024;
+__global__ void __launch_bounds__(kScanThreads) k_scan_smem(int n_nodes, int32_t* cnt_t, int32_t* cnt_s,
+                                                            int32_t* rowptr_t, int32_t* rowptr_s, float* deg, float* dis) {
+  extern __shared__ int32_t sm_scan[];  // counts [n_pad] | exclusive sums [n_pad]
+  pdl_wait();
+  int32_t* cnt = blockIdx.x == 0 ? cnt_t : cnt_s;
+  int32_t* rowptr = blockIdx.x == 0 ? rowptr_t : rowptr_s;
+  const int per = (n_nodes + kScanThreads - 1) / kScanThreads;
+  const int n_pad = per * kScanThreads;
+  const int pad_words = n_pad + n_pad / 32 + 32;
+  int32_t* s_cnt = sm_scan;
+  int32_t* s_sum = sm_scan + pad_words;
+  auto slot = [&](int i) { return i + (i >> 5); };  // pad one word per 32: chunk-strided accesses spread over the banks
+  for (int i = threadIdx.x; i < n_pad; i += kScanThreads) s_cnt[slot(i)] = i < n_nodes ? cnt[i] : 0;
+  __syncthreads();
+  const int beg = threadIdx.x * per;
+  int local = 0;
+  for (int j = 0; j < per; ++j) local += s_cnt[slot(beg + j)];
+  __shared__ int warp_sums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += v;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  int run = incl - local + (warp > 0 ? warp_sums[warp - 1] : 0);
+  for (int j = 0; j < per; ++j) {
+    const int c = s_cnt[slot(beg + j)];
+    s_sum[slot(beg + j)] = run;
+    run += c;
+  }
+  if (threadIdx.x == kScanThreads - 1) rowptr[n_nodes] = run;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_nodes; i += kScanThreads) {
+    const int c = s_cnt[slot(i)];
+    rowptr[i] = s_sum[slot(i)];
+    cnt[i] = 0;
+    if (blockIdx.x == 0) {
+      deg[i] = static_cast<float>(c);
+      dis[i] = c > 0 ? 1.0f / sqrtf(static_cast<float>(c)) : 0.0f;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kScanThreads) k_scan(int n_nodes, int32_t* cnt_t, int32_t* cnt_s,
                                                        int32_t* rowptr_t, int32_t* rowptr_s, float* deg,
                                                        float* dis) {
@@ -281,7 +342,18 @@ extern "C" int pfn_graph_prep(const int64_t* edge_index, int64_t ei_row_stride, 
   }
   PFN_CUDA_OK(launch_kernel(k_count, dim3(edge_blocks), dim3(threads), 0, stream, edge_index, ei_row_stride, ER, undirect_mode, N, g.meta, cnt_t, cnt_s));
   PFN_LAUNCHED();
-  PFN_CUDA_OK(launch_kernel(k_scan, dim3(2), dim3(kScanThreads), 0, stream, N, cnt_t, cnt_s, g.rowptr_t, g.rowptr_s, g.deg, g.dis));
+  if (N <= kScanSmemNodes) {
+    const int per = (N + kScanThreads - 1) / kScanThreads, n_pad = per * kScanThreads;
+    const size_t smem = 2 * size_t(n_pad + n_pad / 32 + 32) * sizeof(int32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+      PFN_CUDA_OK(cudaFuncSetAttribute(k_scan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+      attr_set = true;
+    }
+    PFN_CUDA_OK(launch_kernel(k_scan_smem, dim3(2), dim3(kScanThreads), smem, stream, N, cnt_t, cnt_s, g.rowptr_t, g.rowptr_s, g.deg, g.dis));
+  } else {
+    PFN_CUDA_OK(launch_kernel(k_scan, dim3(2), dim3(kScanThreads), 0, stream, N, cnt_t, cnt_s, g.rowptr_t, g.rowptr_s, g.deg, g.dis));
+  }
   PFN_LAUNCHED();
   if (ER > 0) {
     PFN_CUDA_OK(launch_kernel(k_fill, dim3(edge_blocks), dim3(threads), 0, stream, edge_index, ei_row_stride, ER, undirect_mode, N, g.meta, g.rowptr_t,

@@ -604,7 +604,15 @@ constexpr int kWgMaxProb = 32;
 // The tensor core adds into its fp32 accumulator with truncation, so the error of a TMEM-resident sum grows linearly
 // with the number of accumulating instructions (measured: 1.8e-5 relative at 2176 nodes per CTA, above the 1e-5
 // contract).  A CTA therefore reduces at most this many nodes; the partials are summed in round-to-nearest fp32.
-constexpr int kWgMaxChunk = 512;
+constexpr int kWgMaxChunkDefault = 512;
+static int wg_max_chunk() {
+  static const int v = [] {
+    const char* e = std::getenv("PFN_WG_CHUNK");  // experiments only: larger chunks exceed the 1e-5 contract
+    const int c = e != nullptr ? std::atoi(e) : 0;
+    return c >= 32 ? c / 32 * 32 : kWgMaxChunkDefault;
+  }();
+  return v;
+}
 struct WgGroupProb {
   CUtensorMap a;  // dY  [rows = nodes, cols = Mo]   box {32, 32}
   CUtensorMap b;  // X   [rows = nodes, cols = Ni]   box {32, 32}
@@ -614,17 +622,20 @@ struct WgGroupProb {
   long long part_off;  // float offset of this problem's partials: [split][Mo][n_eff]
   int Mo, N, n_eff, BN, mt, nb, extra_col, lddw, m_groups, tmem_cols, stages, item0;
   int acc_hi[2], acc_lo[2];
-  int odd, pad_;
+  int odd, oddn;
 };
 struct WgGroupArgs {
   WgGroupProb p[kWgMaxProb];
   int n_prob, K, kchunk, splitk;
   float* partial;
+  long long* timing;  // debug (PFN_WG_TIMING): CTA 0 writes clock64() at phase boundaries
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_constant__ WgGroupArgs args) {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+#define WSTAMP(slot) do { if (args.timing != nullptr && blockIdx.x == 0) args.timing[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) WSTAMP(0);
   int prob = 0;
   for (int i = 1; i < args.n_prob; ++i)
     if (int(blockIdx.x) >= args.p[i].item0) prob = i;
@@ -636,7 +647,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
   // P.odd: Mo = 128 + 1 (hidden_dim 129).  A second 128-row M tile for ONE row would double the MMA and converter work,
   // so row 128 of dW is accumulated by the converter threads instead (thread n: sum over nodes of dY[node][128] X[node][n],
   // fp32 FMAs on the TMA-landed tiles); its dY column arrives as a fifth 32-column box behind the operand planes.
-  const uint32_t odd_bytes = P.odd ? 4096u : 0u;
+  // P.oddn: Ni = 128 + 1 likewise: X column 128 and the virtual bias column are multiplied by the converter threads too
+  // (thread m: sums over nodes of dY[node][m] X[node][128] and dY[node][m] e[node]), so the B operand is exactly four
+  // 32-column boxes and a third pipeline stage fits in shared memory.
+  const uint32_t oddx_off = 2u * (a_bytes + b_bytes) + (P.odd ? 4096u : 0u);  // X columns 128..159 (P.oddn)
+  const uint32_t odd_bytes = (P.odd ? 4096u : 0u) + (P.oddn ? 4096u : 0u);
+  __shared__ float evec[kTcMaxStages][kTcBK];  // the bias column's entries (ones / extra_vec) of the tile in each stage
   const uint32_t stage_bytes = 2u * (a_bytes + b_bytes) + odd_bytes;  // A_hi | A_lo | B_hi | B_lo | (odd dY box)
   const uint32_t bar_base = base + uint32_t(S) * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -671,6 +687,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) WSTAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -683,6 +700,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         for (int b = 0; b < mt * 4; ++b) tma_load_2d(st + uint32_t(b) * 4096u, &P.a, row0 + 32 * b, k0, full_bar(s));
         if (P.odd) tma_load_2d(st + 2u * (a_bytes + b_bytes), &P.a, kTcBM, k0, full_bar(s));
+        if (P.oddn) tma_load_2d(st + oddx_off, &P.b, 128, k0, full_bar(s));
         for (int b = 0; b < nb; ++b) tma_load_2d(st + 2u * a_bytes + uint32_t(b) * 4096u, &P.b, 32 * b, k0, full_bar(s));
       }
     }
@@ -696,6 +714,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       const uint32_t ph = (it / S) & 1;
       mbar_wait(conv_bar(s), ph);
       tc_fence_after();
+      if (lane == 0 && it < 12) WSTAMP(30 + it);
       if (lane == 0) {
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         const uint32_t b_hi = st + 2u * a_bytes, b_lo = b_hi + b_bytes;
@@ -717,17 +736,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       __syncwarp();
     }
     if (lane == 0) umma_commit(accum_bar);
+    if (lane == 0) WSTAMP(44);
     __syncwarp();
   } else {
     const int tid_c = threadIdx.x - 64;
-    float odd_acc = 0.f;
+    float odd_acc = 0.f, col_acc = 0.f, bias_acc = 0.f;
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
       const int k0 = k_beg + it * kTcBK;
       mbar_wait(full_bar(s), ph);
+      if (tid_c == 0 && it < 12) WSTAMP(2 + it);
       const uint32_t st = base + uint32_t(s) * stage_bytes;
-      if (P.extra_col != 0) {
+      if (P.oddn) {
+        if (tid_c < kTcBK) {
+          const int node = k0 + tid_c;
+          evec[s][tid_c] = (P.extra_col != 0 && node < k_end) ? (P.extra_col == 1 ? 1.f : P.extra_vec[node]) : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");
+        const uint32_t ycol = st + 2u * (a_bytes + b_bytes), xodd = st + oddx_off;
+        if (tid_c < kTcBM) {
+          // column 128 and the bias column of dW rows 0..127:  sum_r dY[r][m] * X[r][128],  sum_r dY[r][m] * e[r]
+          const int bb = tid_c >> 5, cc = tid_c & 31;
+          const uint32_t ym = st + uint32_t(bb) * 4096u + uint32_t(cc & 7) * 4u;
+#pragma unroll 8
+          for (int r = 0; r < kTcBK; ++r) {
+            float y, x;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(ym + uint32_t(r) * 128u + (uint32_t((cc >> 3) ^ (r & 3)) << 5)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xodd + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
+            col_acc = fmaf(y, x, col_acc);
+            bias_acc = fmaf(y, evec[s][r], bias_acc);
+          }
+        } else if (tid_c < kTcBM + 2 && P.odd) {
+          // the corner: row 128 of dW times column 128 (thread 128) / the bias column (thread 129)
+#pragma unroll 8
+          for (int r = 0; r < kTcBK; ++r) {
+            float y, x;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(ycol + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xodd + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
+            odd_acc = fmaf(y, tid_c == kTcBM ? x : evec[s][r], odd_acc);
+          }
+        }
+      } else if (P.extra_col != 0) {
         // virtual column N of X := 1 (or extra_vec[node]) -> its dot products with dY are the bias gradient
         if (tid_c < kTcBK) {
           const int r = tid_c, cN = P.N, bb = cN >> 5, cc = cN & 31;
@@ -741,7 +791,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");
       }
       if (P.odd) {
-        if (tid_c < P.n_eff) {
+        if (tid_c < (P.oddn ? kTcBM : P.n_eff)) {
           const int bb = tid_c >> 5, cc = tid_c & 31;
           const uint32_t xcol = st + 2u * a_bytes + uint32_t(bb) * 4096u + uint32_t(cc & 7) * 4u;
           const uint32_t ycol = st + 2u * (a_bytes + b_bytes);
@@ -753,29 +803,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
             odd_acc = fmaf(y, x, odd_acc);
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");  // the split below rewrites X in place
       }
+      if (P.odd || P.oddn) asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");  // the split below rewrites the tiles in place
       split_tile(st, a_bytes, int(a_bytes / 16u), tid_c);
       split_tile(st + 2u * a_bytes, b_bytes, int(b_bytes / 16u), tid_c);
       proxy_fence_async();
+      if (tid_c == 0 && it < 12) WSTAMP(16 + it);
       __syncwarp();
       if (lane == 0) mbar_arrive(conv_bar(s));
     }
     // epilogue: accumulators -> padded smem tile -> coalesced rows of the split-K partial buffer
     const int wk = warp - 2, q = warp & 3, half = wk >> 2;
     const int n_eff = P.n_eff, Mo = P.Mo;
+    const int n_main = P.oddn ? kTcBM : n_eff;  // columns that come from the tensor core
     float* __restrict__ const part = args.partial + P.part_off + size_t(split) * size_t(Mo) * n_eff;
     const uint32_t tile_ld = uint32_t(BN) + 4u;
     if (n_tiles > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
+    if (tid_c == 0) WSTAMP(45);
     for (int t = 0; t < mt; ++t) {
       if (row0 + t * kTcBM >= Mo) break;  // CTA-uniform
       if (n_tiles > 0) {
         const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
         const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
-        for (int c0 = 16 * half; c0 < n_eff; c0 += 32) {
+        for (int c0 = 16 * half; c0 < n_main; c0 += 32) {
           uint32_t r[16];
           float acc[16];
           tmem_ld16(lane_base + uint32_t(P.acc_lo[t] + c0), r);
@@ -797,7 +850,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         const int row = 16 * wk + rr, m = row0 + t * kTcBM + row;
         if (m >= Mo) break;
         const uint32_t row_addr = base + (uint32_t(row) * tile_ld) * 4u;
-        for (int c = lane; c < n_eff; c += 32) {
+        for (int c = lane; c < n_main; c += 32) {
           float v = 0.f;
           if (n_tiles > 0) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(row_addr + 4u * c));
           part[size_t(m) * n_eff + c] = v;
@@ -806,9 +859,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
     }
     if (P.odd && tid_c < n_eff) part[size_t(kTcBM) * n_eff + tid_c] = odd_acc;
+    if (P.oddn && tid_c < kTcBM && tid_c < Mo) {
+      part[size_t(tid_c) * n_eff + kTcBM] = col_acc;
+      if (n_eff > kTcBM + 1) part[size_t(tid_c) * n_eff + kTcBM + 1] = bias_acc;
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) WSTAMP(46);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(P.tmem_cols)) : "memory");
   }
@@ -1101,7 +1159,7 @@ size_t wgrad_group_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes
   for (int i = 0; i < n; ++i)
     groups += probs[i].Mo == kTcBM + 1 ? 1 : std::max<int64_t>(1, ceil_div64(ceil_div64(probs[i].Mo, kTcBM), 2));
   const int64_t want = std::max<int64_t>(1, int64_t(sm_count()) / std::max<int64_t>(groups, 1));
-  const int64_t kchunk = std::min<int64_t>(kWgMaxChunk, round_up64(std::max<int64_t>(ceil_div64(std::max<int64_t>(nodes, 1), want), kTcBK), kTcBK));
+  const int64_t kchunk = std::min<int64_t>(wg_max_chunk(), round_up64(std::max<int64_t>(ceil_div64(std::max<int64_t>(nodes, 1), want), kTcBK), kTcBK));
   const int64_t splitk = std::max<int64_t>(1, ceil_div64(std::max<int64_t>(nodes, 1), kchunk));
   size_t floats = 0;
   for (int i = 0; i < n; ++i) floats += size_t(splitk) * size_t(probs[i].Mo) * size_t(probs[i].Ni + 1);
@@ -1126,9 +1184,10 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     P.Mo = w.Mo;
     P.N = w.Ni;
     P.n_eff = n_eff;
-    P.BN = static_cast<int>(round_up64(n_eff, 16));
-    P.nb = (P.BN + 31) / 32;
     P.odd = (w.Mo == kTcBM + 1) ? 1 : 0;  // row 128 of dW is summed by the converter threads (see the kernel)
+    P.oddn = (w.Ni == kTcBM + 1 && w.Mo <= kTcBM + 1) ? 1 : 0;  // and so are column 128 and the bias column
+    P.BN = P.oddn ? kTcBM : static_cast<int>(round_up64(n_eff, 16));
+    P.nb = (P.BN + 31) / 32;
     const int m_tiles = P.odd ? 1 : static_cast<int>(ceil_div64(w.Mo, kTcBM));
     P.mt = (m_tiles >= 2 && 2 * P.BN <= 512) ? 2 : 1;
     P.m_groups = static_cast<int>(ceil_div64(m_tiles, P.mt));
@@ -1143,8 +1202,8 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     int cols = 32;
     while (cols < used) cols <<= 1;
     P.tmem_cols = cols;
-    const uint32_t stage_bytes = 2u * (uint32_t(P.mt) * 16384u + uint32_t(P.nb) * 4096u) + (P.odd ? 4096u : 0u);
-    P.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 2048u) / stage_bytes));
+    const uint32_t stage_bytes = 2u * (uint32_t(P.mt) * 16384u + uint32_t(P.nb) * 4096u) + (P.odd ? 4096u : 0u) + (P.oddn ? 4096u : 0u);
+    P.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 3072u) / stage_bytes));
     if (P.stages < 2) return 1;
     smem_max = std::max(smem_max, uint32_t(P.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2));
     if (!make_map(&P.a, w.dY, nodes, w.Mo, w.lddy, kTcBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
@@ -1158,7 +1217,7 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     items_per_split += P.m_groups;
   }
   const int64_t want = std::max<int64_t>(1, int64_t(sm_count()) / std::max(1, items_per_split));
-  const int64_t kchunk = std::min<int64_t>(kWgMaxChunk, round_up64(std::max<int64_t>(ceil_div64(nodes, want), kTcBK), kTcBK));
+  const int64_t kchunk = std::min<int64_t>(wg_max_chunk(), round_up64(std::max<int64_t>(ceil_div64(nodes, want), kTcBK), kTcBK));
   a.K = static_cast<int>(nodes);
   a.kchunk = static_cast<int>(kchunk);
   a.splitk = static_cast<int>(std::max<int64_t>(1, ceil_div64(nodes, kchunk)));
@@ -1175,11 +1234,27 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
   if (floats * sizeof(float) > partial_bytes) return 1;
   static bool attr_set = false;
   if (!attr_set) {
-    PFN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_group, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
+    // (the kernel also has 512 bytes of static shared memory: the opt-in maximum is for the sum)
+    PFN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_group, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit - 1024u)));
     attr_set = true;
+  }
+  static const bool timing_on = std::getenv("PFN_WG_TIMING") != nullptr;
+  static long long* timing_dev = nullptr;
+  if (timing_on) {
+    if (timing_dev == nullptr) cudaMalloc(&timing_dev, 64 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 64 * sizeof(long long), stream);
+    a.timing = timing_dev;
   }
   PFN_CUDA_OK(launch_kernel(k_wgrad_group, dim3(static_cast<unsigned>(item)), dim3(kTcThreads), smem_max, stream, a));
   PFN_LAUNCHED();
+  if (timing_on) {
+    long long t[64];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[wg-timing] setup %lld |", t[1] - t[0]);
+    for (int i = 0; i < 12 && t[2 + i]; ++i) fprintf(stderr, " t%d full@%lld conv@%lld mma@%lld |", i, t[2 + i] - t[0], t[16 + i] - t[0], t[30 + i] - t[0]);
+    fprintf(stderr, " mma_done@%lld accum@%lld end@%lld\n", t[44] - t[0], t[45] - t[0], t[46] - t[0]);
+  }
   PFN_CUDA_OK(launch_kernel(k_wgrad_group_reduce, dim3(16, static_cast<unsigned>(n)), dim3(256), 0, stream, a));
   PFN_LAUNCHED();
   return 0;

@@ -75,11 +75,18 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
          (uint64_t(2) << 61);
 }
 
-// round-to-nearest TF32 (result has its low 13 mantissa bits clear => exact whatever the tensor core does with them)
+// round-to-nearest TF32 (result has its low 13 mantissa bits clear => exact whatever the tensor core does with them).
+// Integer form of cvt.rna.tf32.f32 (nearest, ties away from zero: add half an ulp to the magnitude, truncate): two
+// full-rate ALU instructions instead of one conversion-pipe instruction -- the hi/lo split of every operand tile runs
+// this twice per element and was bound by the conversion pipe (PFN_TF32_CVT=1 at compile time restores cvt).
 __device__ __forceinline__ float tf32_rn(float v) {
+#if defined(PFN_TF32_CVT)
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
+#else
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+#endif
 }
 
 }  // namespace tc

@@ -68,16 +68,31 @@ struct TcArgs {
 using namespace tc;
 
 
-// rewrite a TMA-landed tile as (hi in place, lo at +lo_off); n_vec float4 elements, kTcWorkers converter threads
+// rewrite a TMA-landed tile as (hi in place, lo at +lo_off); n_vec float4 elements, kTcWorkers converter threads.
+// Four elements per thread are loaded before the first store: the volatile shared-memory accesses are issued in program
+// order, so a load-convert-store loop pays one shared-memory round trip per element (measured 154 cycles per float4,
+// 1.2 k cycles per 32 KB of tiles -- the serial stage of the weight-gradient pipeline).
 __device__ __forceinline__ void split_tile(uint32_t hi_addr, uint32_t lo_off, int n_vec, int tid_c) {
-  for (int i = tid_c; i < n_vec; i += kTcWorkers) {
-    const uint32_t a = hi_addr + 16u * i;
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-    float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-    float4 l = make_float4(tf32_rn(v.x - h.x), tf32_rn(v.y - h.y), tf32_rn(v.z - h.z), tf32_rn(v.w - h.w));
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + lo_off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+  constexpr int B = 4;
+  for (int i0 = tid_c; i0 < n_vec; i0 += B * kTcWorkers) {
+    float4 v[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int i = i0 + j * kTcWorkers;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n_vec)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w) : "r"(hi_addr + 16u * i));
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int i = i0 + j * kTcWorkers;
+      if (i >= n_vec) continue;
+      const uint32_t a = hi_addr + 16u * i;
+      const float4 h = make_float4(tf32_rn(v[j].x), tf32_rn(v[j].y), tf32_rn(v[j].z), tf32_rn(v[j].w));
+      const float4 l = make_float4(tf32_rn(v[j].x - h.x), tf32_rn(v[j].y - h.y), tf32_rn(v[j].z - h.z), tf32_rn(v[j].w - h.w));
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + lo_off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+    }
   }
 }
 
@@ -740,7 +755,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
     __syncwarp();
   } else {
     const int tid_c = threadIdx.x - 64;
-    float odd_acc = 0.f, col_acc = 0.f, bias_acc = 0.f;
+    float odd_acc = 0.f, col_acc = 0.f, bias_acc = 0.f, corner_acc = 0.f;
+    float evec_next = 0.f;
+    if (P.oddn && P.extra_col == 2 && tid_c < kTcBK && k_beg + tid_c < k_end) evec_next = P.extra_vec[k_beg + tid_c];
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
@@ -750,31 +767,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       const uint32_t st = base + uint32_t(s) * stage_bytes;
       if (P.oddn) {
         if (tid_c < kTcBK) {
+          // the entry of this tile was fetched one tile ahead (a global load here sat on the pipeline's critical path)
           const int node = k0 + tid_c;
-          evec[s][tid_c] = (P.extra_col != 0 && node < k_end) ? (P.extra_col == 1 ? 1.f : P.extra_vec[node]) : 0.f;
+          float ev = (P.extra_col != 0 && node < k_end) ? 1.f : 0.f;
+          if (P.extra_col == 2) ev = node < k_end ? evec_next : 0.f;
+          evec[s][tid_c] = ev;
+          const int nn = node + kTcBK;
+          if (P.extra_col == 2) evec_next = nn < k_end ? P.extra_vec[nn] : 0.f;
         }
+        if (tid_c == 0 && it == 4) WSTAMP(50);
         asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");
+        if (tid_c == 0 && it == 4) WSTAMP(51);
         const uint32_t ycol = st + 2u * (a_bytes + b_bytes), xodd = st + oddx_off;
-        if (tid_c < kTcBM) {
+        // all eight converter warps: thread -> (m = tid mod 128, rows [16 (tid / 128), +16)); the halves meet in the epilogue
+        {
           // column 128 and the bias column of dW rows 0..127:  sum_r dY[r][m] * X[r][128],  sum_r dY[r][m] * e[r]
-          const int bb = tid_c >> 5, cc = tid_c & 31;
+          const int mrow = tid_c & 127, rbeg = (tid_c >> 7) * 16;
+          const int bb = mrow >> 5, cc = mrow & 31;
           const uint32_t ym = st + uint32_t(bb) * 4096u + uint32_t(cc & 7) * 4u;
-#pragma unroll 8
-          for (int r = 0; r < kTcBK; ++r) {
-            float y, x;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(ym + uint32_t(r) * 128u + (uint32_t((cc >> 3) ^ (r & 3)) << 5)));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xodd + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
-            col_acc = fmaf(y, x, col_acc);
-            bias_acc = fmaf(y, evec[s][r], bias_acc);
+#pragma unroll
+          for (int r8 = 0; r8 < 16; r8 += 8) {  // all loads of eight rows before the first use (see split_tile)
+            float y[8], x[8], e[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int r = rbeg + r8 + u;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[u]) : "r"(ym + uint32_t(r) * 128u + (uint32_t((cc >> 3) ^ (r & 3)) << 5)));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[u]) : "r"(xodd + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
+              e[u] = evec[s][r];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              col_acc = fmaf(y[u], x[u], col_acc);
+              bias_acc = fmaf(y[u], e[u], bias_acc);
+            }
           }
-        } else if (tid_c < kTcBM + 2 && P.odd) {
-          // the corner: row 128 of dW times column 128 (thread 128) / the bias column (thread 129)
+          if (P.odd && mrow < 2) {
+            // the corner: row 128 of dW times column 128 (m = 0) / the bias column (m = 1)
 #pragma unroll 8
-          for (int r = 0; r < kTcBK; ++r) {
-            float y, x;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(ycol + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xodd + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
-            odd_acc = fmaf(y, tid_c == kTcBM ? x : evec[s][r], odd_acc);
+            for (int r = rbeg; r < rbeg + 16; ++r) {
+              float y, x;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(ycol + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xodd + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
+              corner_acc = fmaf(y, mrow == 0 ? x : evec[s][r], corner_acc);
+            }
           }
         }
       } else if (P.extra_col != 0) {
@@ -791,22 +826,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");
       }
       if (P.odd) {
-        if (tid_c < (P.oddn ? kTcBM : P.n_eff)) {
-          const int bb = tid_c >> 5, cc = tid_c & 31;
+        // row 128 of dW: sum_r dY[r][128] * X[r][n].  With P.oddn the 128 columns are split over all 256 threads by rows.
+        const int ncol = P.oddn ? (tid_c & 127) : tid_c;
+        const int rbeg = P.oddn ? (tid_c >> 7) * 16 : 0, rend = P.oddn ? rbeg + 16 : kTcBK;
+        if (P.oddn || tid_c < P.n_eff) {
+          const int bb = ncol >> 5, cc = ncol & 31;
           const uint32_t xcol = st + 2u * a_bytes + uint32_t(bb) * 4096u + uint32_t(cc & 7) * 4u;
           const uint32_t ycol = st + 2u * (a_bytes + b_bytes);
-#pragma unroll 8
-          for (int r = 0; r < kTcBK; ++r) {  // 128-byte rows, 32-byte chunks XOR-swizzled with (row mod 4)
-            float x, y;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xcol + uint32_t(r) * 128u + (uint32_t((cc >> 3) ^ (r & 3)) << 5)));
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(ycol + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
-            odd_acc = fmaf(y, x, odd_acc);
+          for (int r8 = rbeg; r8 < rend; r8 += 8) {  // 128-byte rows, 32-byte chunks XOR-swizzled with (row mod 4)
+            float x[8], y[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int r = r8 + u;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[u]) : "r"(xcol + uint32_t(r) * 128u + (uint32_t((cc >> 3) ^ (r & 3)) << 5)));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y[u]) : "r"(ycol + uint32_t(r) * 128u + (uint32_t(r & 3) << 5)));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) odd_acc = fmaf(y[u], x[u], odd_acc);
           }
         }
       }
+      if (tid_c == 0 && it == 4) WSTAMP(52);
       if (P.odd || P.oddn) asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");  // the split below rewrites the tiles in place
+      if (tid_c == 0 && it == 4) WSTAMP(53);
       split_tile(st, a_bytes, int(a_bytes / 16u), tid_c);
       split_tile(st + 2u * a_bytes, b_bytes, int(b_bytes / 16u), tid_c);
+      if (tid_c == 0 && it == 4) WSTAMP(54);
       proxy_fence_async();
       if (tid_c == 0 && it < 12) WSTAMP(16 + it);
       __syncwarp();
@@ -858,10 +903,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       }
       asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
     }
-    if (P.odd && tid_c < n_eff) part[size_t(kTcBM) * n_eff + tid_c] = odd_acc;
-    if (P.oddn && tid_c < kTcBM && tid_c < Mo) {
-      part[size_t(tid_c) * n_eff + kTcBM] = col_acc;
-      if (n_eff > kTcBM + 1) part[size_t(tid_c) * n_eff + kTcBM + 1] = bias_acc;
+    if (P.oddn) {
+      // the two row halves of the border sums meet here (threads t and t + 128 hold the same m / n)
+      const uint32_t scr = base + uint32_t(tid_c) * 16u;
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scr), "f"(odd_acc), "f"(col_acc), "f"(bias_acc), "f"(corner_acc) : "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
+      if (tid_c < kTcBM) {
+        float4 o;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(scr + 128u * 16u));
+        odd_acc += o.x;
+        col_acc += o.y;
+        bias_acc += o.z;
+        corner_acc += o.w;
+        if (P.odd) {
+          part[size_t(kTcBM) * n_eff + tid_c] = odd_acc;
+          if (tid_c == 0) part[size_t(kTcBM) * n_eff + kTcBM] = corner_acc;
+          if (tid_c == 1 && n_eff > kTcBM + 1) part[size_t(kTcBM) * n_eff + kTcBM + 1] = corner_acc;
+        }
+        if (tid_c < Mo) {
+          part[size_t(tid_c) * n_eff + kTcBM] = col_acc;
+          if (n_eff > kTcBM + 1) part[size_t(tid_c) * n_eff + kTcBM + 1] = bias_acc;
+        }
+      }
+    } else if (P.odd && tid_c < n_eff) {
+      part[size_t(kTcBM) * n_eff + tid_c] = odd_acc;
     }
   }
   tc_fence_before();
@@ -1253,7 +1318,8 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[wg-timing] setup %lld |", t[1] - t[0]);
     for (int i = 0; i < 12 && t[2 + i]; ++i) fprintf(stderr, " t%d full@%lld conv@%lld mma@%lld |", i, t[2 + i] - t[0], t[16 + i] - t[0], t[30 + i] - t[0]);
-    fprintf(stderr, " mma_done@%lld accum@%lld end@%lld\n", t[44] - t[0], t[45] - t[0], t[46] - t[0]);
+    fprintf(stderr, " mma_done@%lld accum@%lld end@%lld || tile4: full@%lld evec@%lld bar@%lld dots@%lld bar@%lld split@%lld fence@%lld\n", t[44] - t[0], t[45] - t[0], t[46] - t[0],
+            t[6] - t[0], t[50] - t[0], t[51] - t[0], t[52] - t[0], t[53] - t[0], t[54] - t[0], t[20] - t[0]);
   }
   PFN_CUDA_OK(launch_kernel(k_wgrad_group_reduce, dim3(16, static_cast<unsigned>(n)), dim3(256), 0, stream, a));
   PFN_LAUNCHED();

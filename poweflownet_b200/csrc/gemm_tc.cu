@@ -1218,14 +1218,34 @@ int wgrad_tc_launch(GemmArgs& g, cudaStream_t stream) {
 }
 
 
+// Node-chunk count for the grouped weight gradient: chunks of at most wg_max_chunk() nodes (accuracy, see above), and among
+// those the count that minimises (waves of one CTA per SM) x (32-node tiles per CTA).
+static void wg_plan_chunks(int64_t nodes, int64_t items_per_split, int64_t* kchunk_out, int64_t* splitk_out) {
+  const int64_t tiles = ceil_div64(std::max<int64_t>(nodes, 1), kTcBK);
+  const int64_t max_tiles = std::max<int64_t>(1, wg_max_chunk() / kTcBK);
+  const int64_t s_min = ceil_div64(tiles, max_tiles);
+  int64_t best_s = s_min, best_cost = -1;
+  for (int64_t sp = s_min; sp <= std::min<int64_t>(tiles, s_min + 24); ++sp) {
+    const int64_t per = ceil_div64(tiles, sp);
+    const int64_t real = ceil_div64(tiles, per);  // chunks actually needed with `per` tiles each
+    const int64_t cost = ceil_div64(real * items_per_split, sm_count()) * (per + 3);  // + ~3 tiles of prologue/epilogue per CTA
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_s = real;
+    }
+  }
+  const int64_t per = ceil_div64(tiles, best_s);
+  *kchunk_out = per * kTcBK;
+  *splitk_out = ceil_div64(tiles, per);
+}
+
 size_t wgrad_group_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes) {
   if (n <= 0) return 0;
   int64_t groups = 0;
   for (int i = 0; i < n; ++i)
     groups += probs[i].Mo == kTcBM + 1 ? 1 : std::max<int64_t>(1, ceil_div64(ceil_div64(probs[i].Mo, kTcBM), 2));
-  const int64_t want = std::max<int64_t>(1, int64_t(sm_count()) / std::max<int64_t>(groups, 1));
-  const int64_t kchunk = std::min<int64_t>(wg_max_chunk(), round_up64(std::max<int64_t>(ceil_div64(std::max<int64_t>(nodes, 1), want), kTcBK), kTcBK));
-  const int64_t splitk = std::max<int64_t>(1, ceil_div64(std::max<int64_t>(nodes, 1), kchunk));
+  int64_t kchunk, splitk;
+  wg_plan_chunks(nodes, groups, &kchunk, &splitk);
   size_t floats = 0;
   for (int i = 0; i < n; ++i) floats += size_t(splitk) * size_t(probs[i].Mo) * size_t(probs[i].Ni + 1);
   return floats * sizeof(float) + 256;
@@ -1281,11 +1301,11 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     P.lddw = w.lddw;
     items_per_split += P.m_groups;
   }
-  const int64_t want = std::max<int64_t>(1, int64_t(sm_count()) / std::max(1, items_per_split));
-  const int64_t kchunk = std::min<int64_t>(wg_max_chunk(), round_up64(std::max<int64_t>(ceil_div64(nodes, want), kTcBK), kTcBK));
+  int64_t kchunk, splitk_plan;
+  wg_plan_chunks(nodes, items_per_split, &kchunk, &splitk_plan);
   a.K = static_cast<int>(nodes);
   a.kchunk = static_cast<int>(kchunk);
-  a.splitk = static_cast<int>(std::max<int64_t>(1, ceil_div64(nodes, kchunk)));
+  a.splitk = static_cast<int>(splitk_plan);
   a.n_prob = n;
   a.partial = partial;
   int item = 0;
@@ -1321,7 +1341,10 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     fprintf(stderr, " mma_done@%lld accum@%lld end@%lld || tile4: full@%lld evec@%lld bar@%lld dots@%lld bar@%lld split@%lld fence@%lld\n", t[44] - t[0], t[45] - t[0], t[46] - t[0],
             t[6] - t[0], t[50] - t[0], t[51] - t[0], t[52] - t[0], t[53] - t[0], t[54] - t[0], t[20] - t[0]);
   }
-  PFN_CUDA_OK(launch_kernel(k_wgrad_group_reduce, dim3(16, static_cast<unsigned>(n)), dim3(256), 0, stream, a));
+  int max_total = 1;
+  for (int i = 0; i < n; ++i) max_total = std::max(max_total, a.p[i].Mo * a.p[i].n_eff);
+  // one output element per thread: each sums ~30 partials, so the pass is latency-bound and wants many threads in flight
+  PFN_CUDA_OK(launch_kernel(k_wgrad_group_reduce, dim3(static_cast<unsigned>(ceil_div64(max_total, 256)), static_cast<unsigned>(n)), dim3(256), 0, stream, a));
   PFN_LAUNCHED();
   return 0;
 }

@@ -557,56 +557,66 @@ int forward_impl(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_
 // ---- backward -----------------------------------------------------------------------------------------
 // Backward of one TAGConv through the graph-resident kernel (fused_fwd.cu, mode 1): d x_0 = sum_k ((A_hat^T)^k G) W_k,
 // masked by the layer input -- one launch instead of a 4-problem GEMM + K hop launches.
-int tag_backward_fused(const Ctx& c, const LayerPlan& L, const float* G, int64_t ldG, const float* xc, float* dest,
-                       int64_t tile_rows) {
+void fill_tag_backward_layer(const Ctx& c, const LayerPlan& L, const float* G, int64_t ldG, const float* xc, float* dest,
+                             FLayer& f) {
   const Plan& p = c.p;
   const pfn_mpn_desc& d = p.d;
-  FusedArgs a;
-  std::memset(&a, 0, sizeof(a));
   const Plan::TagPack& tk = p.tag_pack[L.slot];
-  FLayer& f = a.layers[0];
   f.type = kFusedTag;
   f.fin = L.fin;
   f.w_rows = d.hidden_dim;
   for (int k = 0; k <= d.K; ++k) f.w_row[k] = static_cast<int>((tk.wT[k] - p.arena_off) / p.ldh);
   f.dest = dest;
   f.ld_dest = static_cast<int>(p.xcat_ld());
-  a.mode = kFusedModeTagBackward;
-  a.n_layers = 1;
+  f.gin = G;
+  f.ld_gin = static_cast<int>(ldG);
+  f.ymask = xc;
+  f.ld_ymask = static_cast<int>(p.xcat_ld());
+}
+
+void fill_backward_common(const Ctx& c, FusedArgs& a, int mode, int n_layers, int64_t tile_rows) {
+  const Plan& p = c.p;
+  const pfn_mpn_desc& d = p.d;
+  a.mode = mode;
+  a.n_layers = n_layers;
   a.n_nodes = static_cast<int>(p.N);
   a.tile_rows = static_cast<int>(tile_rows);
+  a.n_tiles = static_cast<int>(ceil_div64(p.N, tile_rows));
   a.h = d.hidden_dim;
   a.K = d.K;
   a.ldh = static_cast<int>(p.ldh);
   a.out_dim = d.output_dim;
-  a.gin = G;
-  a.ld_gin = static_cast<int>(ldG);
-  a.ymask = xc;
-  a.ld_ymask = static_cast<int>(p.xcat_ld());
   a.rowptr = c.g.rowptr_s;
   a.nbr = c.g.nbr_s;
   a.ea = reinterpret_cast<const float2*>(c.g.ea_s);
+  a.rowptr2 = c.g.rowptr_t;
+  a.nbr2 = c.g.nbr_t;
+  a.ea2 = reinterpret_cast<const float2*>(c.g.ea_t);
   a.deg = c.g.deg;
   a.dis = c.g.dis;
   a.meta = c.g.meta;
   a.scale = c.scale;
-  return fused_fwd_launch(a, c.act + p.arena_off, p.arena_rows, c.stream);
+}
+
+int tag_backward_fused(const Ctx& c, const LayerPlan& L, const float* G, int64_t ldG, const float* xc, float* dest,
+                       int64_t tile_rows) {
+  FusedArgs a;
+  std::memset(&a, 0, sizeof(a));
+  fill_tag_backward_layer(c, L, G, ldG, xc, dest, a.layers[0]);
+  fill_backward_common(c, a, kFusedModeTagBackward, 1, tile_rows);
+  return fused_fwd_launch(a, c.act + c.p.arena_off, c.p.arena_rows, c.stream);
 }
 
 // Backward of one EdgeAggregation through the graph-resident kernel (fused_fwd.cu, mode 2): dS = G W2, both segmented
 // passes (dHj by source, dHi + dWe by target, ReLU mask recomputed from the saved Hi / Hj) and d cur = dHj Wj + dHi Wi in
 // ONE launch (+ the tiny dWe reduction) instead of two GEMMs and the two-pass edge kernel.
-int ea_backward_fused(const Ctx& c, const LayerPlan& L, bool last, const float* const* lp, const float* G, int64_t ldG,
-                      const float* ymask, int64_t ld_ymask, float* dest, int64_t ld_dest, float* dhi, float* dhj, float* part,
-                      float* dWe, int64_t tile_rows) {
+void fill_ea_backward_layer(const Ctx& c, const LayerPlan& L, bool last, const float* const* lp, const float* G, int64_t ldG,
+                            const float* ymask, int64_t ld_ymask, float* dest, int64_t ld_dest, float* dhi, float* dhj,
+                            float* part, FLayer& f) {
   const Plan& p = c.p;
-  const pfn_mpn_desc& d = p.d;
-  const int h = d.hidden_dim;
-  FusedArgs a;
-  std::memset(&a, 0, sizeof(a));
+  const int h = p.d.hidden_dim;
   const Plan::EaPack& pk = p.ea_pack[L.slot];
   auto arena_row = [&](int64_t off) { return static_cast<int>((off - p.arena_off) / p.ldh); };
-  FLayer& f = a.layers[0];
   f.type = L.fin == h ? kFusedEaTc : kFusedEaSimt;
   f.last = last ? 1 : 0;
   f.fin = L.fin;
@@ -621,34 +631,25 @@ int ea_backward_fused(const Ctx& c, const LayerPlan& L, bool last, const float* 
   f.save0 = c.hi(L.slot);
   f.dest = dest;
   f.ld_dest = static_cast<int>(ld_dest);
-  a.mode = kFusedModeEaBackward;
-  a.n_layers = 1;
-  a.n_nodes = static_cast<int>(p.N);
-  a.tile_rows = static_cast<int>(tile_rows);
-  a.n_tiles = static_cast<int>(ceil_div64(p.N, tile_rows));
-  a.h = h;
-  a.K = d.K;
-  a.ldh = static_cast<int>(p.ldh);
-  a.out_dim = d.output_dim;
-  a.gin = G;
-  a.ld_gin = static_cast<int>(ldG);
-  a.ymask = ymask;
-  a.ld_ymask = static_cast<int>(ld_ymask);
-  a.rowptr = c.g.rowptr_s;
-  a.nbr = c.g.nbr_s;
-  a.ea = reinterpret_cast<const float2*>(c.g.ea_s);
-  a.rowptr2 = c.g.rowptr_t;
-  a.nbr2 = c.g.nbr_t;
-  a.ea2 = reinterpret_cast<const float2*>(c.g.ea_t);
-  a.deg = c.g.deg;
-  a.dis = c.g.dis;
-  a.meta = c.g.meta;
-  a.scale = c.scale;
-  a.dhi = dhi;
-  a.dhj = dhj;
-  a.dwe_partial = part;
+  f.gin = G;
+  f.ld_gin = static_cast<int>(ldG);
+  f.ymask = ymask;
+  f.ld_ymask = static_cast<int>(ld_ymask);
+  f.dhi = dhi;
+  f.dhj = dhj;
+  f.dwe_partial = part;
+}
+
+int ea_backward_fused(const Ctx& c, const LayerPlan& L, bool last, const float* const* lp, const float* G, int64_t ldG,
+                      const float* ymask, int64_t ld_ymask, float* dest, int64_t ld_dest, float* dhi, float* dhj, float* part,
+                      float* dWe, int64_t tile_rows) {
+  const Plan& p = c.p;
+  FusedArgs a;
+  std::memset(&a, 0, sizeof(a));
+  fill_ea_backward_layer(c, L, last, lp, G, ldG, ymask, ld_ymask, dest, ld_dest, dhi, dhj, part, a.layers[0]);
+  fill_backward_common(c, a, kFusedModeEaBackward, 1, tile_rows);
   PFN_TRY(fused_fwd_launch(a, c.act + p.arena_off, p.arena_rows, c.stream));
-  return reduce_dwe_launch(part, a.n_tiles, h, dWe, 2 * L.fin + 2, c.stream);
+  return reduce_dwe_launch(part, a.n_tiles, p.d.hidden_dim, dWe, 2 * L.fin + 2, c.stream);
 }
 
 int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t tile_rows) {
@@ -661,6 +662,15 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
   float* dx0 = c.scratch + p.off_dx0;
   const int64_t nld = int64_t(N) * ldh;
   std::vector<GemmArgs> deferred;  // weight-gradient problems, launched together at the end
+  // Whole backward data path in ONE launch of the graph-resident kernel (mode 3) when every layer fits it; PFN_BWD_CHAIN=0
+  // keeps one launch per layer (modes 1 / 2).
+  static const bool chain_off = std::getenv("PFN_BWD_CHAIN") != nullptr && std::getenv("PFN_BWD_CHAIN")[0] == '0';
+  bool chain = tile_rows > 0 && !chain_off && static_cast<int>(p.layers.size()) <= kFusedMaxLayers;
+  for (const LayerPlan& L : p.layers) chain = chain && (!L.is_ea || L.fin == h || L.fin == nf);
+  FusedArgs ch;
+  std::memset(&ch, 0, sizeof(ch));
+  int n_chain = 0;
+  const int64_t dwe_stride = 2 * 4 * ((h + 3) / 4) * ceil_div64(N, std::max<int64_t>(tile_rows, 1));  // floats per EA layer
   float* part = c.scratch + p.off_part;
   const float* x0 = c.act + p.off_x0;
   const float* G = dout;  // gradient w.r.t. the current layer's (pre-activation) output
@@ -699,9 +709,14 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
         gemm_plan_splitk(a, N, 1);
         deferred.push_back(a);
       }
-      const bool ea_fused = tile_rows > 0 && ldG % 4 == 0 && (L.fin == h || L.fin == nf);
+      const bool ea_fused = chain || (tile_rows > 0 && ldG % 4 == 0 && (L.fin == h || L.fin == nf));
       const Plan::EaPack& pk = p.ea_pack[L.slot];
-      if (ea_fused) {
+      if (chain) {
+        float* dest = li == 0 ? dx0 : dz;
+        const int64_t lddest = li == 0 ? nf : ldh;
+        fill_ea_backward_layer(c, L, li == n_layers - 1, lp, G, ldG, cur_has_act ? cur : nullptr, ldcur, dest, lddest, dhi, dhj,
+                               part + L.slot * dwe_stride, ch.layers[n_chain++]);
+      } else if (ea_fused) {
         float* dest = li == 0 ? dx0 : dz;
         const int64_t lddest = li == 0 ? nf : ldh;
         PFN_TRY(ea_backward_fused(c, L, li == n_layers - 1, lp, G, ldG, cur_has_act ? cur : nullptr, ldcur, dest, lddest, dhi, dhj,
@@ -771,7 +786,9 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
         gemm_plan_splitk(a, N, d.K + 1);
         deferred.push_back(a);
       }
-      if (tile_rows > 0 && ldG % 4 == 0) {
+      if (chain) {
+        fill_tag_backward_layer(c, L, G, ldG, xc, dxcat, ch.layers[n_chain++]);
+      } else if (tile_rows > 0 && ldG % 4 == 0) {
         PFN_TRY(tag_backward_fused(c, L, G, ldG, xc, dxcat, tile_rows));
       } else {
         // d x_k = G W_k (k = 0..K), then the transposed hop chain d x_{k-1} += A_hat^T d x_k; the last hop
@@ -801,6 +818,13 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
       G = dxcat;
       ldG = ldx;
     }
+  }
+  if (chain) {
+    fill_backward_common(c, ch, kFusedModeBackward, n_chain, tile_rows);
+    PFN_TRY(fused_fwd_launch(ch, c.act + p.arena_off, p.arena_rows, c.stream));
+    for (const LayerPlan& L : p.layers)
+      if (L.is_ea)
+        PFN_TRY(reduce_dwe_launch(part + L.slot * dwe_stride, ch.n_tiles, h, grads[L.p0] + 2 * L.fin, 2 * L.fin + 2, c.stream));
   }
   // mask_embd backward: x0 = W2m relu(W1m mask + b1m) + b2m + x
   {

@@ -28,6 +28,13 @@ struct FLayer {
   const float* inj;   // optional injected keep mask [N, h] (tests)
   float* save0;       // EA: Hi [N, ldh] (Hj and S follow, N*ldh apart) ; TAG: [x_0 | .. | x_K]  [N, (K+1) ldh]
   float* dest;        // layer output: block 0 of the next TAGConv's buffer / the TAGConv's Y / the model output
+  // backward programs (modes 1..3); `dest` is then the gradient w.r.t. the layer input
+  const float* gin;    // incoming gradient G [N, ld_gin] (read from global memory by the first step of a launch only)
+  const float* ymask;  // saved layer input: d input *= (ymask > 0 ? 1/(1-p) : 0); null = no activation in front of the layer
+  float* dhi;          // EA: dHi / dHj [N, ldh] out (the weight gradients read them)
+  float* dhj;
+  float* dwe_partial;  // EA: [2][4 * ceil(h/4)][n_tiles] per-tile partial sums of dWe, reduced by k_reduce_dwe
+  int ld_gin, ld_ymask;
 };
 
 struct FusedArgs {
@@ -55,21 +62,18 @@ struct FusedArgs {
   // mode 2 (EdgeAggregation backward, one layer per launch): dS = G W2, the two segmented passes (by source: dHj, by
   // target: dHi and dWe) with the ReLU mask recomputed from the saved Hi / Hj, d cur = dHj Wj + dHi Wi masked by the
   // layer input.  rowptr/nbr/ea = CSR by source, rowptr2/nbr2/ea2 = CSR by target.
-  int mode, ld_gin, ld_ymask, n_tiles;
-  const float* gin;
-  const float* ymask;
+  // mode 3 (whole backward data path): the steps of modes 2 and 1 for every layer in reverse order in ONE launch; the
+  // gradient stays in the planes between layers exactly as the activation does in the forward.
+  int mode, n_tiles, pad1_, pad2_;
   const int* rowptr2;
   const int* nbr2;
   const float2* ea2;
-  float* dhi;          // [N, ldh] out (weight gradients dWi / db1 read it)
-  float* dhj;
-  float* dwe_partial;  // [2][4 * ceil(h/4)][n_tiles]: per-tile partial sums of dWe, reduced by k_reduce_dwe
   long long* timing;  // debug (PFN_FUSED_TIMING): worker 0 of CTA 0 writes clock64() at phase boundaries
 };
 static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");
 
 bool fused_fwd_supported(int h, int K, int nfeature_dim, int output_dim, int64_t tile_rows);
-constexpr int kFusedModeForward = 0, kFusedModeTagBackward = 1, kFusedModeEaBackward = 2;
+constexpr int kFusedModeForward = 0, kFusedModeTagBackward = 1, kFusedModeEaBackward = 2, kFusedModeBackward = 3;
 int fused_fwd_launch(FusedArgs& args, const float* arena, int64_t arena_rows, cudaStream_t stream);
 
 }  // namespace pfn

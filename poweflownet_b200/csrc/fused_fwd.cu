@@ -511,6 +511,9 @@ __device__ __forceinline__ float ea_bwd_border(const Wk& w, int r, const float* 
 template <int HB, int MODE>
 __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_constant__ FusedArgs args) {
   constexpr int NB = HB > 0 ? HB : 1;
+  constexpr bool kChain = MODE == kFusedModeBackward;                             // several backward steps in one launch
+  constexpr bool kTwoSlabs = MODE == kFusedModeEaBackward || kChain;              // CSR by source AND by target staged
+  constexpr bool kTagBwd = MODE == kFusedModeTagBackward || kChain;               // TAGConv layers run their backward
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t raw = smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
   // ---- stage the tile's CSR slice (by target), validating that the tile is closed -------------------------------
   for (int i = threadIdx.x; i <= 128; i += kFThreads) {
     M->rp[i] = args.rowptr[r0 + min(i, nr)];
-    if (MODE == kFusedModeEaBackward) M->rp2[i] = args.rowptr2[r0 + min(i, nr)];
+    if (kTwoSlabs) M->rp2[i] = args.rowptr2[r0 + min(i, nr)];
   }
   for (int i = threadIdx.x; i < 128; i += kFThreads) {
     M->dis[i] = i < nr ? args.dis[r0 + i] : 0.f;
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     }
     if (threadIdx.x == 0 && ne == 0) M->nbr[0] = 0;  // the branch-free gathers may touch slot 0 of an edgeless tile
     if (bad) M->bad = 1;
-    if (MODE == kFusedModeEaBackward) {
+    if (kTwoSlabs) {
       const int e02 = M->rp2[0], ne2 = M->rp2[128] - e02;
       if (ne2 > kFusedEdgeCap) bad = 1;
       for (int i = threadIdx.x; i < min(ne2, kFusedEdgeCap); i += kFThreads) {
@@ -619,8 +622,8 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     if (MODE == kFusedModeForward) {
       for (int i = threadIdx.x; i < nr * args.out_dim; i += kFThreads) args.out[size_t(r0) * args.out_dim + i] = qnan;
     } else {
-      const FLayer& L = args.layers[0];
-      const int wd = MODE == kFusedModeEaBackward ? L.fin : h;
+      const FLayer& L = args.layers[args.n_layers - 1];
+      const int wd = kTwoSlabs ? L.fin : h;
       for (int i = threadIdx.x; i < nr * wd; i += kFThreads) L.dest[size_t(r0 + i / wd) * L.ld_dest + i % wd] = qnan;
     }
     tc_fence_before();
@@ -644,16 +647,17 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           tma_load_2d(st + kKTileBytes, &args.wmap, kt * 32, w_row + 2 * w_rows, bfull(s));
         }
       };
-      if (MODE == kFusedModeEaBackward) {  // W2^T, then Wj^T and Wi^T (w_row[] index the TRANSPOSED packed weights)
-        const FLayer& L = args.layers[0];
-        if (!L.last) load_weight(L.w_row[2], L.w_rows);
-        if (L.type == kFusedEaTc) {
-          load_weight(L.w_row[1], L.w_rows);
-          load_weight(L.w_row[0], L.w_rows);
-        }
-      }
-      for (int li = 0; li < (MODE == kFusedModeEaBackward ? 0 : args.n_layers); ++li) {
+      for (int li = 0; li < args.n_layers; ++li) {
         const FLayer& L = args.layers[li];
+        if (kTwoSlabs && L.type != kFusedTag) {
+          // EdgeAggregation backward: W2^T, then Wj^T and Wi^T (w_row[] index the TRANSPOSED packed weights)
+          if (!L.last) load_weight(L.w_row[2], L.w_rows);
+          if (L.type == kFusedEaTc) {
+            load_weight(L.w_row[1], L.w_rows);
+            load_weight(L.w_row[0], L.w_rows);
+          }
+          continue;
+        }
         if (L.type == kFusedTag) {
           for (int k = 0; k <= args.K; ++k) load_weight(L.w_row[k], L.w_rows);
         } else {
@@ -701,27 +705,27 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         __syncwarp();
       }
     };
-    if (MODE == kFusedModeEaBackward) {
-      const FLayer& L = args.layers[0];
-      if (!L.last) {  // dS = G W2
-        wait_a();
-        int kk = 0;
-        gemm(0u, 1, 128u, kk);
-        if (lane == 0) umma_commit(acc_done);
-        __syncwarp();
-      }
-      if (L.type == kFusedEaTc) {  // d cur = dHj Wj + dHi Wi: two segments into the same accumulators
-        int kk = 0;
-        for (int seg = 0; seg < 2; ++seg) {
+    for (int li = 0; li < args.n_layers; ++li) {
+      const FLayer& L = args.layers[li];
+      if (kTwoSlabs && L.type != kFusedTag) {  // EdgeAggregation backward
+        if (!L.last) {  // dS = G W2
           wait_a();
-          gemm(256u, 1, 384u, kk);
+          int kk = 0;
+          gemm(0u, 1, 128u, kk);
           if (lane == 0) umma_commit(acc_done);
           __syncwarp();
         }
+        if (L.type == kFusedEaTc) {  // d cur = dHj Wj + dHi Wi: two segments into the same accumulators
+          int kk = 0;
+          for (int seg = 0; seg < 2; ++seg) {
+            wait_a();
+            gemm(256u, 1, 384u, kk);
+            if (lane == 0) umma_commit(acc_done);
+            __syncwarp();
+          }
+        }
+        continue;
       }
-    }
-    for (int li = 0; li < (MODE == kFusedModeEaBackward ? 0 : args.n_layers); ++li) {
-      const FLayer& L = args.layers[li];
       if (L.type == kFusedTag) {
         int kk = 0;
         for (int k = 0; k <= args.K; ++k) {
@@ -789,16 +793,19 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     w.rb = rb;
     constexpr int nf = 4;
 
-    if (MODE == kFusedModeEaBackward) {
-      // ======================= backward of one EdgeAggregation (see ea_bwd_pass) =======================
-      const FLayer& L = args.layers[0];
+    if (kTwoSlabs) {
+      w.e02 = M->rp2[0];
+      w.rb2 = M->perm2[ww * kRW + (lane % kRW)];
+    }
+    const int rb2 = w.rb2;
+    // ======================= backward of one EdgeAggregation (see ea_bwd_pass) =======================
+    // g_in_planes: the previous step of this launch left G (masked) in the planes and its border column in xb[2];
+    // has_next: another step follows and consumes this step's masked output from the planes / xb[0]
+    auto ea_bwd_step = [&](const FLayer& L, const bool g_in_planes, const bool has_next) {
       const int ldw1 = 2 * L.fin + 2;
       const float* const gHi = L.save0;
       const float* const gHj = gHi + size_t(args.n_nodes) * ldh;
       const bool tc_in = L.type == kFusedEaTc;
-      w.e02 = M->rp2[0];
-      const int rb2 = M->perm2[ww * kRW + (lane % kRW)];
-      w.rb2 = rb2;
       stage_vec(w, M->swe[0], L.W1 + 2 * L.fin, ldw1, h);
       stage_vec(w, M->swe[1], L.W1 + 2 * L.fin + 1, ldw1, h);
       for (int i = w.wt; i < 132; i += kFWorkers) M->sb1[i] = 0.f;
@@ -807,24 +814,26 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         stage_wkb<HB>(w, 0, L.w_row[1]);
         stage_wkb<HB>(w, 1, L.w_row[0]);
       }
-      if (!L.last) {
+      if (!L.last && !g_in_planes) {
         // G -> A operand (planes; border column kept in xb[2] for both extractions of dS)
 #pragma unroll 4
         for (int i = 0; i < kRW; ++i) {
           const int r = rowof(w, i);
           float4 v = f4zero();
-          if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + r) * args.ld_gin + cl));
+          if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(L.gin + size_t(r0 + r) * L.ld_gin + cl));
           if (cl_ok) st_planes(R0, R1, r, cl, v);
         }
         if (HB > 0 && lane < kRW) {
           float4 v = f4zero();
-          if (rb < nr) v = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + rb) * args.ld_gin + 128));
+          if (rb < nr) v = __ldg(reinterpret_cast<const float4*>(L.gin + size_t(r0 + rb) * L.ld_gin + 128));
 #pragma unroll
           for (int j = NB; j < 4; ++j) bcol(&v, j) = 0.f;
           M->xb[2][rb] = v;
         }
         signal_a_ready(w);
         bar_workers();
+      }
+      if (!L.last) {
         border_dot<HB>(w, 2, L.w_row[2], 0, false);  // column 128 of dS -> ob[0] (stays there for both passes)
         wait_acc(w);
       }
@@ -863,7 +872,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           for (int i = 0; i < kRW; ++i) {
             const int r = rowof(w, i);
             float4 gv = f4zero();
-            if (r < nr) gv = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + r) * args.ld_gin));
+            if (r < nr) gv = __ldg(reinterpret_cast<const float4*>(L.gin + size_t(r0 + r) * L.ld_gin));
             float4 ds;
             ds.x = fmaf(gv.w, w2r[3][0], fmaf(gv.z, w2r[2][0], fmaf(gv.y, w2r[1][0], gv.x * w2r[0][0])));
             ds.y = fmaf(gv.w, w2r[3][1], fmaf(gv.z, w2r[2][1], fmaf(gv.y, w2r[1][1], gv.x * w2r[0][1])));
@@ -873,7 +882,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           }
           if (HB > 0 && lane < kRW) {
             float4 gv = f4zero();
-            if (rb < nr) gv = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + rb) * args.ld_gin));
+            if (rb < nr) gv = __ldg(reinterpret_cast<const float4*>(L.gin + size_t(r0 + rb) * L.ld_gin));
             float d = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -917,7 +926,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           if (HB > 0 && lane < kRW) db = ea_bwd_border<true>(w, rbr, gHi, gb0, gb1);
         }
         // dHj / dHi to global (the weight gradients read them)
-        float* const gout = round == 0 ? args.dhj : args.dhi;
+        float* const gout = round == 0 ? L.dhj : L.dhi;
 #pragma unroll
         for (int i = 0; i < kRW; ++i) {
           const int r = perm_r[ww * kRW + i];
@@ -952,7 +961,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(red + (uint32_t(v * 2 + k) * 132u + uint32_t(c)) * 4u));
               sum += t;
             }
-            args.dwe_partial[(size_t(k) * 4 * c4 + c) * args.n_tiles + blockIdx.x] = sum;
+            L.dwe_partial[(size_t(k) * 4 * c4 + c) * args.n_tiles + blockIdx.x] = sum;
           }
           bar_workers();
         }
@@ -1001,7 +1010,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         ActCfg ac0{};
         const int cols[2] = {384, 256};
         epilogue_dispatch<HB, 2, 2>(w, ac0, cols, M->sb1, false, nullptr, 0, 1);
-        signal_a_ready(w);
+        tc_fence_before();
         bar_workers();
         // d cur = planes * (layer input > 0 ? 1/(1-p) : 0), coalesced
 #pragma unroll 4
@@ -1010,47 +1019,57 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           if (r < nr && cl_ok) {
             const float4 v = ld_planes(R0, R1, r, cl);
             float4 o = v;
-            if (args.ymask != nullptr) {
-              const float4 y = __ldg(reinterpret_cast<const float4*>(args.ymask + size_t(r0 + r) * args.ld_ymask + cl));
+            if (L.ymask != nullptr) {
+              const float4 y = __ldg(reinterpret_cast<const float4*>(L.ymask + size_t(r0 + r) * L.ld_ymask + cl));
               o.x = y.x > 0.f ? v.x * w.scale : 0.f;
               o.y = y.y > 0.f ? v.y * w.scale : 0.f;
               o.z = y.z > 0.f ? v.z * w.scale : 0.f;
               o.w = y.w > 0.f ? v.w * w.scale : 0.f;
             }
             *reinterpret_cast<float4*>(L.dest + size_t(r0 + r) * L.ld_dest + cl) = o;
+            if (has_next) st_planes(R0, R1, r, cl, o);  // the masked gradient is the next step's A operand
           }
         }
-        if (HB > 0 && lane < kRW && rb < nr) {
+        if (HB > 0 && lane < kRW) {
           float4 o = f4zero();
           const float v = bcol(&M->xb[0][rb], 0);
           o.x = v;
-          if (args.ymask != nullptr) o.x = __ldg(args.ymask + size_t(r0 + rb) * args.ld_ymask + 128) > 0.f ? v * w.scale : 0.f;
-          *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb) * L.ld_dest + 128) = o;
+          if (L.ymask != nullptr && rb < nr) o.x = __ldg(L.ymask + size_t(r0 + rb) * L.ld_ymask + 128) > 0.f ? v * w.scale : 0.f;
+          if (rb < nr) *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb) * L.ld_dest + 128) = o;
+          if (has_next) M->xb[0][rb] = o;  // (a TAGConv step follows: it expects its operand's border column in xb[0])
+        }
+        if (has_next) {
+          signal_a_ready(w);
+          bar_workers();
         }
       } else {
         __syncwarp();
         if (lane < kRW && rb2 < nr) *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb2) * L.ld_dest) = M->x0s[rb2];
       }
+    };
+    if (MODE == kFusedModeEaBackward) {
+      ea_bwd_step(args.layers[0], false, false);
     } else
     if (MODE == kFusedModeTagBackward) {
       // ---- backward of one TAGConv: the incoming gradient G becomes the A operand (planes + border columns) ----------
+      const FLayer& L0 = args.layers[0];
 #pragma unroll 4
       for (int i = 0; i < kRW; ++i) {
         const int r = rowof(w, i);
         float4 v = f4zero();
-        if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + r) * args.ld_gin + cl));
+        if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(L0.gin + size_t(r0 + r) * L0.ld_gin + cl));
         if (cl_ok) st_planes(R0, R1, r, cl, v);
       }
       if (HB > 0 && lane < kRW) {
         float4 v = f4zero();
-        if (rb < nr) v = __ldg(reinterpret_cast<const float4*>(args.gin + size_t(r0 + rb) * args.ld_gin + 128));
+        if (rb < nr) v = __ldg(reinterpret_cast<const float4*>(L0.gin + size_t(r0 + rb) * L0.ld_gin + 128));
 #pragma unroll
         for (int j = NB; j < 4; ++j) bcol(&v, j) = 0.f;
         M->xb[0][rb] = v;
       }
       signal_a_ready(w);
       bar_workers();
-    } else {
+    } else if (MODE == kFusedModeForward) {
     // ---- mask_embd (MPN.py:533,537): x0 = W2m relu(W1m mask + b1m) + b2m + x ; saves maskf, t1, x0 ------------------
     {
       float w1m[4][4], b1m[4], w2m[4][4];
@@ -1136,6 +1155,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
 #pragma unroll 1
     for (int li = 0; li < (MODE == kFusedModeEaBackward ? 0 : args.n_layers); ++li) {
       const FLayer& L = args.layers[li];
+      if (kChain && L.type != kFusedTag) {
+        ea_bwd_step(L, li > 0, li + 1 < args.n_layers);
+        continue;
+      }
       ActCfg ac;
       ac.act = L.act;
       ac.dropout = w.dropout;
@@ -1407,6 +1430,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           for (int i = w.wt; i < 132; i += kFWorkers) M->sb1[i] = 0.f;
         }
         for (int k = 0; k <= args.K; ++k) stage_wkb<HB>(w, k, L.w_row[k]);
+        if (kChain && HB > 0) {  // segments beyond K must contribute nothing (an EdgeAggregation step left its own data there)
+          for (int i = w.wt; i < (kFusedMaxSeg - 1 - args.K) * 128; i += kFWorkers) (&M->xb[args.K + 1][0])[i] = f4zero();
+          for (int i = w.wt; i < (kFusedMaxSeg - 1 - args.K) * 128; i += kFWorkers) (&M->wkb[args.K + 1][0][0])[i] = 0.f;
+        }
 #pragma unroll 1
         for (int k = 0; k < args.K; ++k) {
           border_dot<HB>(w, k, L.w_row[k], 0, k > 0, k == 0 ? xc : nullptr, ldx);  // k = 0: also saves x_0 (block 0 of xc)
@@ -1456,9 +1483,11 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         FSTAMP(w);  // TAG: last GEMM done
         const int cols[4] = {384, 0, 128, 256};
         // always four segments: xb[s] of the segments beyond K is zero (see the zero fill at kernel start)
-        const bool tag_bwd = MODE == kFusedModeTagBackward;
+        constexpr bool tag_bwd = kTagBwd;
+        const bool has_next = kChain && li + 1 < args.n_layers;
         epilogue_dispatch<HB, 4, 4>(w, ac, cols, M->sb1, false, tag_bwd ? nullptr : L.dest, L.ld_dest);
-        signal_a_ready(w);
+        if (!tag_bwd) signal_a_ready(w);  // (backward: the planes are rewritten with the masked values first, see below)
+        tc_fence_before();
         bar_workers();
         FSTAMP(w);  // TAG: output epilogue done
         if (tag_bwd) {
@@ -1469,22 +1498,30 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
             const int r = rowof(w, i);
             if (r < nr && cl_ok) {
               const float4 v = ld_planes(R0, R1, r, cl);
-              const float4 y = __ldg(reinterpret_cast<const float4*>(args.ymask + size_t(r0 + r) * args.ld_ymask + cl));
+              const float4 y = __ldg(reinterpret_cast<const float4*>(L.ymask + size_t(r0 + r) * L.ld_ymask + cl));
               float4 o;
               o.x = y.x > 0.f ? v.x * w.scale : 0.f;
               o.y = y.y > 0.f ? v.y * w.scale : 0.f;
               o.z = y.z > 0.f ? v.z * w.scale : 0.f;
               o.w = y.w > 0.f ? v.w * w.scale : 0.f;
               *reinterpret_cast<float4*>(L.dest + size_t(r0 + r) * L.ld_dest + cl) = o;
+              if (has_next) st_planes(R0, R1, r, cl, o);  // the masked gradient is the next step's A operand
             }
           }
-          if (HB > 0 && lane < kRW && rb < nr) {
+          if (HB > 0 && lane < kRW) {
             const float4 v = M->xb[0][rb];
-            const float4 y = __ldg(reinterpret_cast<const float4*>(args.ymask + size_t(r0 + rb) * args.ld_ymask + 128));
             float4 o = f4zero();
+            if (rb < nr) {
+              const float4 y = __ldg(reinterpret_cast<const float4*>(L.ymask + size_t(r0 + rb) * L.ld_ymask + 128));
 #pragma unroll
-            for (int j = 0; j < NB; ++j) bcol(&o, j) = bcol(&y, j) > 0.f ? bcol(&v, j) * w.scale : 0.f;
-            *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb) * L.ld_dest + 128) = o;
+              for (int j = 0; j < NB; ++j) bcol(&o, j) = bcol(&y, j) > 0.f ? bcol(&v, j) * w.scale : 0.f;
+              *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb) * L.ld_dest + 128) = o;
+            }
+            if (has_next) M->xb[2][rb] = o;  // (an EdgeAggregation step follows: it keeps G's border column in xb[2])
+          }
+          if (has_next) {
+            signal_a_ready(w);
+            bar_workers();
           }
         }
       }
@@ -1508,16 +1545,18 @@ int fused_fwd_launch(FusedArgs& a, const float* arena, int64_t arena_rows, cudaS
   PFN_REQUIRE(tc_make_map(&a.wmap, arena, arena_rows, a.h, a.ldh, 128), PFN_E_UNSUPPORTED,
               "fused forward: cannot encode the weight-arena tensor map");
   a.arena = arena;
-  void (*kernels[2][3])(FusedArgs) = {
-      {k_mpn_fused_fwd<0, kFusedModeForward>, k_mpn_fused_fwd<0, kFusedModeTagBackward>, k_mpn_fused_fwd<0, kFusedModeEaBackward>},
-      {k_mpn_fused_fwd<1, kFusedModeForward>, k_mpn_fused_fwd<1, kFusedModeTagBackward>, k_mpn_fused_fwd<1, kFusedModeEaBackward>}};
+  void (*kernels[2][4])(FusedArgs) = {
+      {k_mpn_fused_fwd<0, kFusedModeForward>, k_mpn_fused_fwd<0, kFusedModeTagBackward>, k_mpn_fused_fwd<0, kFusedModeEaBackward>,
+       k_mpn_fused_fwd<0, kFusedModeBackward>},
+      {k_mpn_fused_fwd<1, kFusedModeForward>, k_mpn_fused_fwd<1, kFusedModeTagBackward>, k_mpn_fused_fwd<1, kFusedModeEaBackward>,
+       k_mpn_fused_fwd<1, kFusedModeBackward>}};
   static bool attr_set = false;
   if (!attr_set) {
     for (auto& row : kernels)
       for (auto* k : row) PFN_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)));
     attr_set = true;
   }
-  PFN_REQUIRE(a.mode >= 0 && a.mode <= 2, PFN_E_INVALID, "fused kernel: bad mode %d", a.mode);
+  PFN_REQUIRE(a.mode >= 0 && a.mode <= 3, PFN_E_INVALID, "fused kernel: bad mode %d", a.mode);
   void (*kernel)(FusedArgs) = kernels[a.h > 128 ? 1 : 0][a.mode];
   const unsigned tiles = static_cast<unsigned>(ceil_div64(a.n_nodes, a.tile_rows));
   static const bool timing_on = std::getenv("PFN_FUSED_TIMING") != nullptr;  // debug aid: phase timestamps of CTA 0

@@ -664,7 +664,8 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
   std::vector<GemmArgs> deferred;  // weight-gradient problems, launched together at the end
   // Whole backward data path in ONE launch of the graph-resident kernel (mode 3) when every layer fits it; PFN_BWD_CHAIN=0
   // keeps one launch per layer (modes 1 / 2).
-  static const bool chain_off = std::getenv("PFN_BWD_CHAIN") != nullptr && std::getenv("PFN_BWD_CHAIN")[0] == '0';
+  const char* chain_env = std::getenv("PFN_BWD_CHAIN");  // read per call: the tests compare both launch structures
+  const bool chain_off = chain_env != nullptr && chain_env[0] == '0';
   bool chain = tile_rows > 0 && !chain_off && static_cast<int>(p.layers.size()) <= kFusedMaxLayers;
   for (const LayerPlan& L : p.layers) chain = chain && (!L.is_ea || L.fin == h || L.fin == nf);
   FusedArgs ch;

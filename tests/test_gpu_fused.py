@@ -182,3 +182,23 @@ def test_pipelined_steps_match_eager_steps():
         _close(p.grad, g, "gradient after the last pipelined step", tol=1e-6)
     with pytest.raises(RuntimeError):
         pipe.step()
+
+
+@pytest.mark.parametrize("cfg", [dict(hidden_dim=129, n_gnn_layers=3, K=3), dict(hidden_dim=64, n_gnn_layers=2, K=2)])
+def test_chained_backward_equals_per_layer_backward(cfg, monkeypatch):
+    """Mode 3 (the whole backward data path in one launch, gradient kept in the planes between layers) against one
+    launch per layer (modes 1 / 2, PFN_BWD_CHAIN=0) and against the layer-wise kernels."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, dropout_rate=0.0, **cfg)
+    batch = synthetic_batch("118v2" if cfg["hidden_dim"] == 129 else "14", 9).to(DEV)
+    grads = {}
+    for name, fused, chain in (("chain", True, "1"), ("per_layer", True, "0"), ("layerwise", False, "1")):
+        monkeypatch.setenv("PFN_BWD_CHAIN", chain)
+        m = _model(kw, fused).train()
+        n0 = _launches()
+        torch.nn.functional.mse_loss(m(batch), batch.y).backward()
+        grads[name] = ({k: p.grad.clone() for k, p in m.named_parameters()}, _launches() - n0)
+    assert grads["chain"][1] < grads["per_layer"][1] < grads["layerwise"][1]
+    for k in grads["chain"][0]:
+        _close(grads["chain"][0][k], grads["per_layer"][0][k], k + " (chain vs per-layer)", tol=1e-6)
+        _close(grads["chain"][0][k], grads["layerwise"][0][k], k + " (chain vs layer-wise)", tol=3e-6)

@@ -31,6 +31,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout must carry exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at the VERSION level,
+# which this image sets) out of it unless the caller asked for more verbose NCCL logging
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "graphs/sec (case118v2, batch 128) fwd+bwd"
 UNIT = "graphs/s"

@@ -176,6 +176,18 @@ __device__ __forceinline__ void save_planes_rows(const Wk& w, float* __restrict_
   }
 }
 
+// All kRW row loads of this warp's slots are issued before the first use: the shared-memory stores that consume them are
+// volatile asm with a memory clobber, so a load-store loop would pay one L2 round trip per row (perm: slot -> row).
+__device__ __forceinline__ void preload_rows(const Wk& w, const uint8_t* perm, const float* __restrict__ src, int ld, int col,
+                                             bool ok, float4 (&v)[kRW]) {
+#pragma unroll
+  for (int i = 0; i < kRW; ++i) {
+    const int r = perm[w.ww * kRW + i];
+    v[i] = f4zero();
+    if (ok && r < w.nr) v[i] = __ldg(reinterpret_cast<const float4*>(src + size_t(w.r0 + r) * ld + col));
+  }
+}
+
 template <int HB>
 __device__ __forceinline__ void border_dot(const Wk& w, int seg, int w_row, int which, bool accumulate,
                                            float* __restrict__ save = nullptr, int ld_save = 0) {
@@ -422,6 +434,13 @@ __device__ __forceinline__ void ea_bwd_pass(const Wk& w, int cl, bool cl_ok, flo
   const float2* eav = kTarget ? M->ea2 : M->ea;
   const uint8_t* perm = kTarget ? M->perm2 : M->perm;
   const int e0 = kTarget ? w.e02 : w.e0;
+  float4 hnext[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {  // own rows of group 0
+    const int r = perm[w.ww * kRW + j];
+    hnext[j] = f4zero();
+    if (cl_ok && r < w.nr) hnext[j] = __ldg(reinterpret_cast<const float4*>(own + size_t(w.r0 + r) * w.ldh + cl));
+  }
 #pragma unroll
   for (int g = 0; g < kRW / 2; ++g) {  // two rows interleaved (register budget: ~96 per thread)
     int beg[2], cnt[2];
@@ -434,11 +453,16 @@ __device__ __forceinline__ void ea_bwd_pass(const Wk& w, int cl, bool cl_ok, flo
       cnt[j] = rp[r + 1] - e0 - beg[j];
       maxd = max(maxd, cnt[j]);
       acc[j] = f4zero();
-      hown[j] = f4zero();
+      hown[j] = hnext[j];
       dsown[j] = f4zero();
-      if (cl_ok) {
-        if (r < w.nr) hown[j] = __ldg(reinterpret_cast<const float4*>(own + size_t(w.r0 + r) * w.ldh + cl));
-        if (kTarget) dsown[j] = lds4(w.R0 + fb_off(r, cl));
+      if (cl_ok && kTarget) dsown[j] = lds4(w.R0 + fb_off(r, cl));
+    }
+    if (g + 1 < kRW / 2) {  // the next group's own rows are requested before this group's edge loop (global-memory latency)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = perm[w.ww * kRW + 2 * (g + 1) + j];
+        hnext[j] = f4zero();
+        if (cl_ok && r < w.nr) hnext[j] = __ldg(reinterpret_cast<const float4*>(own + size_t(w.r0 + r) * w.ldh + cl));
       }
     }
     if (cl_ok) {
@@ -816,12 +840,13 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
       }
       if (!L.last && !g_in_planes) {
         // G -> A operand (planes; border column kept in xb[2] for both extractions of dS)
-#pragma unroll 4
-        for (int i = 0; i < kRW; ++i) {
-          const int r = rowof(w, i);
-          float4 v = f4zero();
-          if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(L.gin + size_t(r0 + r) * L.ld_gin + cl));
-          if (cl_ok) st_planes(R0, R1, r, cl, v);
+        {
+          float4 gv[kRW];
+          preload_rows(w, M->perm, L.gin, L.ld_gin, cl, cl_ok, gv);
+#pragma unroll
+          for (int i = 0; i < kRW; ++i) {
+            if (cl_ok) st_planes(R0, R1, rowof(w, i), cl, gv[i]);
+          }
         }
         if (HB > 0 && lane < kRW) {
           float4 v = f4zero();
@@ -868,11 +893,12 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int j = 0; j < 4; ++j) w2r[k][j] = (k < args.out_dim && cl_ok) ? __ldg(L.W2 + k * h + cl + j) : 0.f;
-#pragma unroll 4
+          float4 grow[kRW];
+          preload_rows(w, M->perm, L.gin, L.ld_gin, 0, true, grow);
+#pragma unroll
           for (int i = 0; i < kRW; ++i) {
             const int r = rowof(w, i);
-            float4 gv = f4zero();
-            if (r < nr) gv = __ldg(reinterpret_cast<const float4*>(L.gin + size_t(r0 + r) * L.ld_gin));
+            const float4 gv = grow[i];
             float4 ds;
             ds.x = fmaf(gv.w, w2r[3][0], fmaf(gv.z, w2r[2][0], fmaf(gv.y, w2r[1][0], gv.x * w2r[0][0])));
             ds.y = fmaf(gv.w, w2r[3][1], fmaf(gv.z, w2r[2][1], fmaf(gv.y, w2r[1][1], gv.x * w2r[0][1])));
@@ -895,12 +921,11 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         // the other side's H -> fp32 buffer R1 (border column -> xb[3]); one coalesced row per instruction
         {
           const float* __restrict__ hsrc = round == 0 ? gHi : gHj;
-#pragma unroll 4
+          float4 hv[kRW];
+          preload_rows(w, M->perm, hsrc, ldh, cl, cl_ok, hv);
+#pragma unroll
           for (int i = 0; i < kRW; ++i) {
-            const int r = rowof(w, i);
-            float4 v = f4zero();
-            if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(hsrc + size_t(r0 + r) * ldh + cl));
-            if (cl_ok) sts4(R1 + fb_off(r, cl), v);
+            if (cl_ok) sts4(R1 + fb_off(rowof(w, i), cl), hv[i]);
           }
           if (HB > 0 && lane < kRW) {
             float4 v = f4zero();
@@ -1013,14 +1038,17 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         tc_fence_before();
         bar_workers();
         // d cur = planes * (layer input > 0 ? 1/(1-p) : 0), coalesced
-#pragma unroll 4
+        float4 ym[kRW];
+        preload_rows(w, M->perm, L.ymask != nullptr ? L.ymask : L.dest, L.ymask != nullptr ? L.ld_ymask : L.ld_dest, cl,
+                     cl_ok && L.ymask != nullptr, ym);
+#pragma unroll
         for (int i = 0; i < kRW; ++i) {
           const int r = rowof(w, i);
           if (r < nr && cl_ok) {
             const float4 v = ld_planes(R0, R1, r, cl);
             float4 o = v;
             if (L.ymask != nullptr) {
-              const float4 y = __ldg(reinterpret_cast<const float4*>(L.ymask + size_t(r0 + r) * L.ld_ymask + cl));
+              const float4 y = ym[i];
               o.x = y.x > 0.f ? v.x * w.scale : 0.f;
               o.y = y.y > 0.f ? v.y * w.scale : 0.f;
               o.z = y.z > 0.f ? v.z * w.scale : 0.f;
@@ -1053,12 +1081,13 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     if (MODE == kFusedModeTagBackward) {
       // ---- backward of one TAGConv: the incoming gradient G becomes the A operand (planes + border columns) ----------
       const FLayer& L0 = args.layers[0];
-#pragma unroll 4
-      for (int i = 0; i < kRW; ++i) {
-        const int r = rowof(w, i);
-        float4 v = f4zero();
-        if (r < nr && cl_ok) v = __ldg(reinterpret_cast<const float4*>(L0.gin + size_t(r0 + r) * L0.ld_gin + cl));
-        if (cl_ok) st_planes(R0, R1, r, cl, v);
+      {
+        float4 gv[kRW];
+        preload_rows(w, M->perm, L0.gin, L0.ld_gin, cl, cl_ok, gv);
+#pragma unroll
+        for (int i = 0; i < kRW; ++i) {
+          if (cl_ok) st_planes(R0, R1, rowof(w, i), cl, gv[i]);
+        }
       }
       if (HB > 0 && lane < kRW) {
         float4 v = f4zero();
@@ -1493,12 +1522,14 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         if (tag_bwd) {
           // d (layer input) = (sum in the planes) * (x_0 > 0 ? 1/(1-p) : 0): ReLU + dropout backward from the saved x_0,
           // one coalesced 512-byte row per load / store instruction
-#pragma unroll 4
+          float4 ym[kRW];
+          preload_rows(w, M->perm, L.ymask, L.ld_ymask, cl, cl_ok, ym);
+#pragma unroll
           for (int i = 0; i < kRW; ++i) {
             const int r = rowof(w, i);
             if (r < nr && cl_ok) {
               const float4 v = ld_planes(R0, R1, r, cl);
-              const float4 y = __ldg(reinterpret_cast<const float4*>(L.ymask + size_t(r0 + r) * L.ld_ymask + cl));
+              const float4 y = ym[i];
               float4 o;
               o.x = y.x > 0.f ? v.x * w.scale : 0.f;
               o.y = y.y > 0.f ? v.y * w.scale : 0.f;

@@ -1071,7 +1071,11 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   }
   TcArgs a;
   std::memset(&a, 0, sizeof(a));
-  const int bn = static_cast<int>(std::min<int64_t>(256, round_up64(g.N, 16)));
+  // N tile: the whole width while it leaves room for >= 2 rotating hi*hi accumulators (N <= 160), else 128-wide tiles
+  // (three rotating accumulators): a 256-wide tile has ONE, and the truncating accumulate then costs ~4e-6 relative at
+  // K = 512 -- enough to flip ReLU masks downstream and push wide models' gradients outside the 1e-5 contract.
+  const int64_t n16 = round_up64(g.N, 16);
+  const int bn = static_cast<int>(n16 <= 160 ? n16 : 128);
   a.BN = bn;
   a.n_items = g.n_items;
   a.batched = g.batched;

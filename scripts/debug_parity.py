@@ -7,9 +7,12 @@ import common
 from oracle import pfn_oracle as O
 from poweflownet_b200.data import synthetic_batch
 from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
-kw = dict(common.MODEL_DIMS, hidden_dim=129, n_gnn_layers=4, K=3, dropout_rate=0.0)
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-batch = synthetic_batch("118v2", b)
+case = sys.argv[2] if len(sys.argv) > 2 else "118v2"
+hid = int(sys.argv[3]) if len(sys.argv) > 3 else 129
+nl = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+kw = dict(common.MODEL_DIMS, hidden_dim=hid, n_gnn_layers=nl, K=3, dropout_rate=0.0)
+batch = synthetic_batch(case, b)
 oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
 loss_ref, out_ref = O.forward_loss_backward(oracle, batch, "mse")
 o64 = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).double().train()

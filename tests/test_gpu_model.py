@@ -88,9 +88,15 @@ def test_fused_mse_step_equals_autograd_step():
         _close(p.grad, gold["grads"][k], k)
 
 
-@pytest.mark.parametrize("case,b,cfg", [("118v2", 128, dict(hidden_dim=129, n_gnn_layers=4, K=3, dropout_rate=0.2)),
-                                        ("6470rte", 2, dict(hidden_dim=64, n_gnn_layers=3, K=3, dropout_rate=0.2))])
-def test_full_size_against_oracle(case, b, cfg):
+@pytest.mark.parametrize("case,b,cfg,tol", [
+    ("118v2", 128, dict(hidden_dim=129, n_gnn_layers=4, K=3, dropout_rate=0.2), TOL),
+    ("6470rte", 2, dict(hidden_dim=64, n_gnn_layers=3, K=3, dropout_rate=0.2), TOL),
+    # configs/large.json width (layer-wise kernels, per-problem weight gradients).  KNOWN GAP, see DESIGN.md section 3: the
+    # output is within 3e-6, but a few ReLU pre-activations of magnitude < 1e-6 |Hi| flip sign under the 3xTF32 GEMMs'
+    # ~5e-7 error at K = 512, which moves single entries of the last layer's gradient by up to 6e-5 of the tensor's maximum
+    # (Frobenius 1.1e-5; the fp32 reference itself is up to 5.5e-5 from its fp64 twin here).  Checked at 1e-4.
+    ("6470rte", 1, dict(hidden_dim=512, n_gnn_layers=3, K=3, dropout_rate=0.2), 1e-4)])
+def test_full_size_against_oracle(case, b, cfg, tol):
     """BASELINE configs[1] (case118v2, batch 128, standard.json) forward+backward vs the CPU oracle, dropout off
     (p=0 in train mode exercises the train path deterministically), plus a 6470-bus large-graph case."""
     from poweflownet_b200.data import synthetic_batch
@@ -113,14 +119,15 @@ def test_full_size_against_oracle(case, b, cfg):
     loss.backward()
     _close(out, out_ref, "out")
     assert abs(float(loss) - float(loss_ref)) < TOL * float(loss_ref)
+    TOL_G = tol
     for (k, p), (_, q), (_, r) in zip(m.named_parameters(), oracle.named_parameters(), twin.named_parameters()):
         exact = r.grad
         ours_vs_exact = max(common.rel_err(p.grad.cpu().double(), exact))
         ref_vs_exact = max(common.rel_err(q.grad.double(), exact))
         # within 1e-5 of the exact gradient and of the fp32 reference, each relaxed only by the reference's OWN distance
         # from the exact value (its fp32 rounding floor, up to ~1.4e-5 on bias gradients summed over 15104 nodes)
-        assert ours_vs_exact < TOL + ref_vs_exact, (k, "vs fp64 twin", ours_vs_exact, ref_vs_exact)
-        assert max(common.rel_err(p.grad.cpu(), q.grad)) < TOL + ref_vs_exact, (k, "vs fp32 oracle", ref_vs_exact)
+        assert ours_vs_exact < TOL_G + ref_vs_exact, (k, "vs fp64 twin", ours_vs_exact, ref_vs_exact)
+        assert max(common.rel_err(p.grad.cpu(), q.grad)) < TOL_G + ref_vs_exact, (k, "vs fp32 oracle", ref_vs_exact)
 
 
 def test_masked_l2_loss_through_autograd():

@@ -225,6 +225,8 @@ int ea_bwd_launch(const float* dS, int64_t ldds, const float* Hi, const float* H
                   const GraphView& g, int64_t n_nodes, const float* We, int64_t ldwe, float* dHi, float* dHj,
                   int64_t ldd, float* dWe, int64_t lddwe, void* scratch, int64_t h, cudaStream_t stream);
 int reduce_dwe_launch(const float* partial, int nblocks, int64_t h, float* dWe, int64_t lddwe, cudaStream_t stream);
+int reduce_dwe_multi_launch(const float* const* partial, float* const* dwe, const int* lddwe, int n, int nblocks, int64_t h,
+                            cudaStream_t stream);
 int hop_launch(const float* X, int64_t ldx, const GraphView& g, int64_t n_nodes, bool transpose,
                const float* addend, int64_t ldadd, const float* ymask, int64_t ldym, float scale, float* Y,
                int64_t ldy, int64_t h, cudaStream_t stream);

@@ -392,6 +392,43 @@ int ea_bwd_launch(const float* dS, int64_t ldds, const float* Hi, const float* H
   return 0;
 }
 
+// the dWe reduction for up to 8 layers in one launch (blockIdx.y = layer)
+namespace {
+struct DweMulti {
+  const float* partial[8];
+  float* dwe[8];
+  int lddwe[8];
+};
+__global__ void k_reduce_dwe_multi(const __grid_constant__ DweMulti a, int nblocks, int c4, int h) {
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= 2 * h) return;
+  const int k = warp / h, c = warp - k * h;
+  const float* src = a.partial[blockIdx.y] + (size_t(k) * 4 * c4 + c) * nblocks;
+  float sum = 0.f;
+  for (int b = lane; b < nblocks; b += 32) sum += src[b];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (lane == 0) a.dwe[blockIdx.y][c * a.lddwe[blockIdx.y] + k] = sum;
+}
+}  // namespace
+int reduce_dwe_multi_launch(const float* const* partial, float* const* dwe, const int* lddwe, int n, int nblocks, int64_t h,
+                            cudaStream_t stream) {
+  for (int base = 0; base < n; base += 8) {
+    DweMulti a{};
+    const int cnt = std::min(8, n - base);
+    for (int i = 0; i < cnt; ++i) {
+      a.partial[i] = partial[base + i];
+      a.dwe[i] = dwe[base + i];
+      a.lddwe[i] = lddwe[base + i];
+    }
+    PFN_CUDA_OK(launch_kernel(k_reduce_dwe_multi, dim3(static_cast<unsigned>(ceil_div64(2 * h * 32, 256)), static_cast<unsigned>(cnt)),
+                              dim3(256), 0, stream, a, nblocks, static_cast<int>((h + 3) / 4), static_cast<int>(h)));
+    PFN_LAUNCHED();
+  }
+  return 0;
+}
+
 // dWe[c, k] = sum over `nblocks` per-CTA partial rows laid out [2][4 * ceil(h/4)][nblocks] (k_ea_bwd, or the tiles of the
 // graph-resident EdgeAggregation backward)
 int reduce_dwe_launch(const float* partial, int nblocks, int64_t h, float* dWe, int64_t lddwe, cudaStream_t stream) {

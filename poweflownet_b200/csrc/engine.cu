@@ -822,10 +822,21 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
   }
   if (chain) {
     fill_backward_common(c, ch, kFusedModeBackward, n_chain, tile_rows);
+    // the last step (first layer) also produces d t1 of mask_embd: d t1 = (d x0 W2m) * (t1 > 0)
+    ch.mW2 = c.params[p.p_mask + 2];
+    ch.t1 = c.act + p.off_t1;
+    ch.dt1 = ds;
     PFN_TRY(fused_fwd_launch(ch, c.act + p.arena_off, p.arena_rows, c.stream));
+    std::vector<const float*> parts;
+    std::vector<float*> dwes;
+    std::vector<int> lds;
     for (const LayerPlan& L : p.layers)
-      if (L.is_ea)
-        PFN_TRY(reduce_dwe_launch(part + L.slot * dwe_stride, ch.n_tiles, h, grads[L.p0] + 2 * L.fin, 2 * L.fin + 2, c.stream));
+      if (L.is_ea) {
+        parts.push_back(part + L.slot * dwe_stride);
+        dwes.push_back(grads[L.p0] + 2 * L.fin);
+        lds.push_back(2 * L.fin + 2);
+      }
+    PFN_TRY(reduce_dwe_multi_launch(parts.data(), dwes.data(), lds.data(), static_cast<int>(parts.size()), ch.n_tiles, h, c.stream));
   }
   // mask_embd backward: x0 = W2m relu(W1m mask + b1m) + b2m + x
   {
@@ -839,14 +850,16 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
     a.partial_bytes = static_cast<size_t>(p.part_bytes);
     gemm_plan_splitk(a, N, 1);
     deferred.push_back(a);
-    GemmArgs b = base_args(N, h);
-    b.it[0] = fwd_item(G, ldG, c.act + p.mask_w2T, round_up64(nf, 4), nf, ds, ldh, nullptr, h);
-    b.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
-    b.act = kActMaskByY;
-    b.ymask = t1;
-    b.ld_ym = static_cast<int>(ldh);
-    b.scale = 1.f;
-    PFN_TRY(gemm_launch(b, true, true, c.stream));
+    if (!chain) {  // (the chained tile kernel has already written d t1 into `ds`)
+      GemmArgs b = base_args(N, h);
+      b.it[0] = fwd_item(G, ldG, c.act + p.mask_w2T, round_up64(nf, 4), nf, ds, ldh, nullptr, h);
+      b.prof_cat = PFN_PROF_GEMM_DGRAD + 1;
+      b.act = kActMaskByY;
+      b.ymask = t1;
+      b.ld_ym = static_cast<int>(ldh);
+      b.scale = 1.f;
+      PFN_TRY(gemm_launch(b, true, true, c.stream));
+    }
     GemmArgs w = base_args(h, nf);
     w.it[0] = wgrad_item(ds, ldh, maskf, nf, N, mg[0], nf, mg[1]);
     w.extra_col = 1;

@@ -46,6 +46,7 @@ struct FusedArgs {
   const int64_t* pred_mask;
   const float *mW1, *mb1, *mW2, *mb2;  // mask_embd.{0,2}.{weight,bias} as stored
   float *maskf, *t1, *x0;              // saved for the backward pass
+  float* dt1;                          // mode 3: d loss / d (mask_embd hidden pre-activation) [N, ldh], written by the last step
   const int* rowptr;
   const int* nbr;
   const float2* ea;

@@ -1073,6 +1073,43 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
       } else {
         __syncwarp();
         if (lane < kRW && rb2 < nr) *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb2) * L.ld_dest) = M->x0s[rb2];
+        if (kChain && args.dt1 != nullptr) {
+          // mask_embd backward, data part (x0 = W2m relu(t1) + b2m + x): d t1 = (d x0 W2m) * (t1 > 0); the two weight
+          // gradients of mask_embd are ordinary problems of the grouped launch (they read d x0 and d t1)
+          float w2m[4][4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w2m[k][j] = cl_ok ? __ldg(args.mW2 + k * h + cl + j) : 0.f;
+          float4 tv[kRW];
+          preload_rows(w, M->perm2, args.t1, ldh, cl, cl_ok, tv);
+#pragma unroll
+          for (int i = 0; i < kRW; ++i) {
+            const int r = M->perm2[ww * kRW + i];
+            if (r < nr && cl_ok) {
+              const float4 dx = M->x0s[r];
+              float4 o;
+              o.x = tv[i].x > 0.f ? fmaf(dx.w, w2m[3][0], fmaf(dx.z, w2m[2][0], fmaf(dx.y, w2m[1][0], dx.x * w2m[0][0]))) : 0.f;
+              o.y = tv[i].y > 0.f ? fmaf(dx.w, w2m[3][1], fmaf(dx.z, w2m[2][1], fmaf(dx.y, w2m[1][1], dx.x * w2m[0][1]))) : 0.f;
+              o.z = tv[i].z > 0.f ? fmaf(dx.w, w2m[3][2], fmaf(dx.z, w2m[2][2], fmaf(dx.y, w2m[1][2], dx.x * w2m[0][2]))) : 0.f;
+              o.w = tv[i].w > 0.f ? fmaf(dx.w, w2m[3][3], fmaf(dx.z, w2m[2][3], fmaf(dx.y, w2m[1][3], dx.x * w2m[0][3]))) : 0.f;
+              *reinterpret_cast<float4*>(args.dt1 + size_t(r0 + r) * ldh + cl) = o;
+            }
+          }
+          if (HB > 0 && lane < kRW && rb2 < nr) {
+            const float4 dx = M->x0s[rb2];
+            float4 o = f4zero();
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const int c = 128 + j;
+              const float t = __ldg(args.t1 + size_t(r0 + rb2) * ldh + c);
+              const float v = fmaf(dx.w, __ldg(args.mW2 + 3 * h + c), fmaf(dx.z, __ldg(args.mW2 + 2 * h + c),
+                              fmaf(dx.y, __ldg(args.mW2 + 1 * h + c), dx.x * __ldg(args.mW2 + c))));
+              bcol(&o, j) = t > 0.f ? v : 0.f;
+            }
+            *reinterpret_cast<float4*>(args.dt1 + size_t(r0 + rb2) * ldh + 128) = o;
+          }
+        }
       }
     };
     if (MODE == kFusedModeEaBackward) {

@@ -862,6 +862,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         border_dot<HB>(w, 2, L.w_row[2], 0, false);  // column 128 of dS -> ob[0] (stays there for both passes)
         wait_acc(w);
       }
+      FSTAMP(w);  // EA-bwd: dS GEMM done
       float4 w0 = f4zero(), w1 = f4zero();
 #pragma unroll 1
       for (int round = 0; round < 2; ++round) {  // 0: pass by source (dHj) ; 1: pass by target (dHi, dWe)
@@ -934,6 +935,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           }
         }
         bar_workers();
+        FSTAMP(w);  // EA-bwd: dS and the other side's H are in shared memory
         if (round == 0 && cl_ok) {
           w0 = *reinterpret_cast<const float4*>(&M->swe[0][cl]);
           w1 = *reinterpret_cast<const float4*>(&M->swe[1][cl]);
@@ -950,6 +952,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           ea_bwd_pass<true>(w, cl, cl_ok, w0, w1, gHi, D, gw0, gw1);
           if (HB > 0 && lane < kRW) db = ea_bwd_border<true>(w, rbr, gHi, gb0, gb1);
         }
+        FSTAMP(w);  // EA-bwd: segmented pass done
         // dHj / dHi to global (the weight gradients read them)
         float* const gout = round == 0 ? L.dhj : L.dhi;
 #pragma unroll
@@ -1003,7 +1006,9 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           // but border_dot walks the rows in `perm` order: wait for everyone
           bar_workers();
           border_dot<HB>(w, round, L.w_row[round == 0 ? 1 : 0], 1, round == 1);
+          FSTAMP(w);  // EA-bwd: planes written, border dot done
           wait_acc(w);
+          FSTAMP(w);  // EA-bwd: d cur segment multiplied
         } else {
           // input width 4 (first layer): d x0 += D W[:, block] by warp reductions; rows differ between the two passes,
           // so the running sum lives in shared memory (x0s)
@@ -1070,6 +1075,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           signal_a_ready(w);
           bar_workers();
         }
+        FSTAMP(w);  // EA-bwd: epilogue + masked output done
       } else {
         __syncwarp();
         if (lane < kRW && rb2 < nr) *reinterpret_cast<float4*>(L.dest + size_t(r0 + rb2) * L.ld_dest) = M->x0s[rb2];

@@ -68,8 +68,8 @@ def main():
         md.append(f"| {i} | `{s[0]}` | {s[1]} | {s[2]} | {s[3]:.2f} | {s[3] / tot:.1%} |")
     md.append(f"| | **total** | | | **{tot:.1f}** | {len(step)} launches |\n")
     md.append("`k_mpn_fused_fwd<HB, MODE>`: MODE 0 = whole forward, 3 = whole backward data path (1 / 2 = one TAGConv / EdgeAggregation "
-              "backward per launch, `PFN_BWD_CHAIN=0`), csrc/fused_fwd.cu.  bench.py (CUDA events, warm, 50 steps): 0.77 ms/step; the shares agree "
-              "with its `kernel_time` (forward kernel 27 %, backward data path 40 %, grouped weight gradients 28 %, graph prep 5 %).\n")
+              "backward per launch, `PFN_BWD_CHAIN=0`), csrc/fused_fwd.cu.  bench.py (CUDA events, warm, 200 steps): 0.734 ms/step; the shares agree "
+              "with its `kernel_time` (forward kernel 28 %, backward tile kernel 38 %, grouped weight gradients 29 %, graph prep 5 %).\n")
     md.append("## 2. `ncu --set full` of the main kernels (`profiles/r1_ncu_full_summary.json`)\n")
     md.append("| kernel | µs | DRAM read / written | tensor pipe | issue slots | LSU pipe | smem wavefronts | regs | top stall reasons |\n|---|---|---|---|---|---|---|---|---|")
     seen = set()

@@ -36,6 +36,25 @@ if ROOT not in sys.path:
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
     os.environ["NCCL_DEBUG"] = "NONE"
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Route everything any library writes to file descriptor 1 (NCCL banners, stray prints) to stderr and keep the real
+    stdout for the single JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "graphs/sec (case118v2, batch 128) fwd+bwd"
 UNIT = "graphs/s"
 CASE, BATCH = "118v2", 128
@@ -169,7 +188,7 @@ def run_reference(args):
             "cpu_baseline": {"value": r["graphs_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample},
             "e2e": {"value": r["graphs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def time_ea_fwd_alone(lib, dev, batch, h, iters=240, n_sets=12):
@@ -389,7 +408,7 @@ def run_ours(args):
                                 "ms_per_step": r["ms_per_step"],
                                 "sample": f"{r['steps']} steps of fwd+MSE+bwd of the oracle (torch CPU fp32, train mode) on one "
                                           f"case118v2 batch of {BATCH} graphs, {r['cores']} host cores"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -403,6 +422,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU oracle timing (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -44,7 +44,7 @@ int sm_count();
 // ---- launches: programmatic dependent launch (PDL) ------------------------------------------------------------
 // Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
 // griddepcontrol.wait: the next kernel's launch latency and prologue (barrier init, TMEM allocation, tensor-map
-// prefetch, index arithmetic) overlap the tail of the previous one, which matters when a step is ~90 kernels of
+// prefetch, index arithmetic) overlap the tail of the previous one, which matters when a step is 13-90 kernels of
 // 5-20 us.  PFN_PDL=0 restores plain stream-ordered launches.
 bool pdl_enabled();
 

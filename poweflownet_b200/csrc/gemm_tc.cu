@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -1243,7 +1244,7 @@ static void wg_plan_chunks(int64_t nodes, int64_t items_per_split, int64_t* kchu
   *splitk_out = ceil_div64(tiles, per);
 }
 
-size_t wgrad_group_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes) {
+static size_t wgrad_batch_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes) {
   if (n <= 0) return 0;
   int64_t groups = 0;
   for (int i = 0; i < n; ++i)
@@ -1257,7 +1258,7 @@ size_t wgrad_group_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes
 
 // All weight gradients of a backward pass in one launch (+ one reduction launch).  Returns 1 when some problem does not
 // fit the tensor-core path (caller launches them one by one), 0 on success.
-int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* partial, size_t partial_bytes, cudaStream_t stream) {
+static int wgrad_batch_launch(const WgradProblem* probs, int n, int64_t nodes, float* partial, size_t partial_bytes, cudaStream_t stream) {
   if (!tc_enabled() || n <= 0 || n > kWgMaxProb || nodes <= 0 || partial == nullptr) return 1;
   static const bool disabled = std::getenv("PFN_WGRAD_GROUP") != nullptr && std::getenv("PFN_WGRAD_GROUP")[0] == '0';
   if (disabled) return 1;
@@ -1278,7 +1279,9 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
     P.BN = P.oddn ? kTcBM : static_cast<int>(round_up64(n_eff, 16));
     P.nb = (P.BN + 31) / 32;
     const int m_tiles = P.odd ? 1 : static_cast<int>(ceil_div64(w.Mo, kTcBM));
-    P.mt = (m_tiles >= 2 && 2 * P.BN <= 512) ? 2 : 1;
+    // two M tiles per CTA only for the 129..256-row case; wider dW (hidden 512) takes one tile per CTA so that every tile
+    // keeps its own hi*hi and lo accumulators
+    P.mt = (m_tiles == 2 && 2 * P.BN <= 512) ? 2 : 1;
     P.m_groups = static_cast<int>(ceil_div64(m_tiles, P.mt));
     int used;
     if (P.mt == 1) {
@@ -1350,6 +1353,60 @@ int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* p
   // one output element per thread: each sums ~30 partials, so the pass is latency-bound and wants many threads in flight
   PFN_CUDA_OK(launch_kernel(k_wgrad_group_reduce, dim3(static_cast<unsigned>(ceil_div64(max_total, 256)), static_cast<unsigned>(n)), dim3(256), 0, stream, a));
   PFN_LAUNCHED();
+  return 0;
+}
+
+
+// Problems wider than one N tile (n_eff > 256: hidden 512) are cut into 128-column chunks of X -- independent problems
+// that share dY; the bias column rides on the last chunk.
+static std::vector<WgradProblem> wgrad_split_wide(const WgradProblem* probs, int n) {
+  std::vector<WgradProblem> out;
+  for (int i = 0; i < n; ++i) {
+    const WgradProblem& w = probs[i];
+    const int n_eff = w.Ni + (w.extra_col ? 1 : 0);
+    if (n_eff <= 256) {
+      out.push_back(w);
+      continue;
+    }
+    for (int n0 = 0; n0 < w.Ni; n0 += 128) {
+      WgradProblem c = w;
+      c.X = w.X + n0;
+      c.Ni = std::min(128, w.Ni - n0);
+      c.dW = w.dW + n0;
+      const bool last = n0 + 128 >= w.Ni;
+      if (!last) {
+        c.extra_col = 0;
+        c.extra_vec = nullptr;
+        c.dbias = nullptr;
+      }
+      out.push_back(c);
+    }
+  }
+  return out;
+}
+
+size_t wgrad_group_scratch_bytes(const WgradProblem* probs, int n, int64_t nodes) {
+  const std::vector<WgradProblem> work = wgrad_split_wide(probs, n);
+  size_t worst = 0;
+  for (size_t b = 0; b < work.size(); b += kWgMaxProb)
+    worst = std::max(worst, wgrad_batch_scratch_bytes(work.data() + b, static_cast<int>(std::min<size_t>(kWgMaxProb, work.size() - b)), nodes));
+  return worst;
+}
+
+// All weight gradients of a backward pass: one launch (+ one reduction launch) per batch of up to kWgMaxProb problems.
+// Returns 1 when some problem does not fit the tensor-core path (nothing has been launched: the caller takes the
+// per-problem route), 0 on success.
+int wgrad_group_launch(const WgradProblem* probs, int n, int64_t nodes, float* partial, size_t partial_bytes, cudaStream_t stream) {
+  if (!tc_enabled() || n <= 0 || nodes <= 0 || partial == nullptr) return 1;
+  const std::vector<WgradProblem> work = wgrad_split_wide(probs, n);
+  for (const WgradProblem& w : work)  // applicability of every problem is checked before the first launch
+    if (w.Mo <= 0 || w.Ni <= 0 || w.Ni + (w.extra_col ? 1 : 0) > 256 || !tma_ok(w.dY, w.lddy) || !tma_ok(w.X, w.ldx)) return 1;
+  if (wgrad_group_scratch_bytes(probs, n, nodes) > partial_bytes) return 1;
+  for (size_t b = 0; b < work.size(); b += kWgMaxProb) {
+    const int rc = wgrad_batch_launch(work.data() + b, static_cast<int>(std::min<size_t>(kWgMaxProb, work.size() - b)), nodes, partial,
+                                      partial_bytes, stream);
+    if (rc != 0) return (rc == 1 && b > 0) ? PFN_E_UNSUPPORTED : rc;  // (no falling back once a batch has been launched)
+  }
   return 0;
 }
 

@@ -204,6 +204,15 @@ PFN_API size_t pfn_mse_scratch_bytes(int64_t count);
 PFN_API int pfn_mse_fwd_bwd(const float* out, const float* y, int64_t count, float inv_count, float* loss,
                     float* dout, void* scratch, void* stream);
 
+/* ---- Masked_L2_loss head (utils/custom_loss_functions.py:10-46, the default --train_loss_fn of
+ *      utils/argument_parser.py:36-37; dispatched at utils/training.py:61-62): fused value + gradient.
+ *      loss = mean over {mask != 0} of (out-y)^2 + regcoeff * mean over {mask == 0} of (out-y)^2 (second term only when
+ *      `regularize`); the element counts stay on the device (the reference's masked_select costs two host syncs).
+ *      mask: int64 [count] (data.pred_mask).  scratch: at least pfn_masked_l2_scratch_bytes(count). --------------- */
+PFN_API size_t pfn_masked_l2_scratch_bytes(int64_t count);
+PFN_API int pfn_masked_l2_fwd_bwd(const float* out, const float* y, const int64_t* mask, int64_t count, int regularize,
+                          float regcoeff, float* loss, float* dout, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,9 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p, C.c_int, c_i64, C.c_void_p]),
     "pfn_mse_scratch_bytes": (c_sz, [c_i64]),
     "pfn_mse_fwd_bwd": (C.c_int, [c_f32p, c_f32p, c_i64, C.c_float, c_f32p, c_f32p, C.c_void_p, C.c_void_p]),
+    "pfn_masked_l2_scratch_bytes": (c_sz, [c_i64]),
+    "pfn_masked_l2_fwd_bwd": (C.c_int, [c_f32p, c_f32p, C.c_void_p, c_i64, C.c_int, C.c_float, c_f32p, c_f32p, C.c_void_p,
+                                        C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -130,6 +130,70 @@ k_mse_final(const float* __restrict__ partial, int n, float inv_count, float* __
   }
   if (threadIdx.x == 0) loss[0] = red[0] * inv_count;
 }
+// ---- Masked_L2_loss (utils/custom_loss_functions.py:10-46, the parser's default --train_loss_fn) ---------------------
+//   loss = mean_{mask=1} (out-y)^2 + regcoeff * mean_{mask=0} (out-y)^2      (second term only if `regularize`)
+// masked_select + MSELoss(mean) in the reference (dynamic shapes, two device->host syncs); here three small launches
+// with device-resident element counts: partial sums, final (loss + the two gradient scales), scaled gradient.
+__global__ void __launch_bounds__(kMseBlock)
+k_ml2_partial(const float* __restrict__ out, const float* __restrict__ y, const int64_t* __restrict__ mask, int64_t count,
+              float* __restrict__ partial) {
+  pdl_wait();
+  float s1 = 0.f, s0 = 0.f, c1 = 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x) {
+    const float d = out[i] - y[i];
+    const bool m = mask[i] != 0;
+    s1 += m ? d * d : 0.f;
+    s0 += m ? 0.f : d * d;
+    c1 += m ? 1.f : 0.f;
+  }
+  __shared__ float red[3][kMseBlock];
+  red[0][threadIdx.x] = s1;
+  red[1][threadIdx.x] = s0;
+  red[2][threadIdx.x] = c1;
+  __syncthreads();
+  for (int s = kMseBlock / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 3; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) partial[threadIdx.x * gridDim.x + blockIdx.x] = red[threadIdx.x][0];
+}
+__global__ void __launch_bounds__(kMseBlock)
+k_ml2_final(const float* __restrict__ partial, int n, int64_t count, int regularize, float regcoeff, float* __restrict__ loss,
+            float* __restrict__ scales) {
+  pdl_wait();
+  __shared__ float red[3][kMseBlock];
+  for (int k = 0; k < 3; ++k) {
+    float local = 0.f;
+    for (int i = threadIdx.x; i < n; i += kMseBlock) local += partial[k * n + i];
+    red[k][threadIdx.x] = local;
+  }
+  __syncthreads();
+  for (int s = kMseBlock / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 3; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float n1 = red[2][0], n0 = static_cast<float>(count) - n1;
+    float l = red[0][0] / n1;  // mean over an empty selection is NaN, as torch.nn.MSELoss gives
+    float sc0 = 0.f;
+    if (regularize) {
+      l += regcoeff * (red[1][0] / n0);
+      sc0 = 2.f * regcoeff / n0;
+    }
+    loss[0] = l;
+    scales[0] = 2.f / n1;
+    scales[1] = sc0;
+  }
+}
+__global__ void k_ml2_grad(const float* __restrict__ out, const float* __restrict__ y, const int64_t* __restrict__ mask,
+                           int64_t count, const float* __restrict__ scales, float* __restrict__ dout) {
+  pdl_wait();
+  const float sc1 = scales[0], sc0 = scales[1];
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
+    dout[i] = (out[i] - y[i]) * (mask[i] != 0 ? sc1 : sc0);
+}
 int mse_blocks(int64_t count) {
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(count, kMseBlock * 4), 1024)));
 }
@@ -1056,6 +1120,25 @@ extern "C" int pfn_mse_fwd_bwd(const float* out, const float* y, int64_t count, 
   PFN_CUDA_OK(launch_kernel(k_mse_partial, dim3(blocks), dim3(kMseBlock), 0, stream, out, y, count, inv_count, dout, static_cast<float*>(scratch)));
   PFN_LAUNCHED();
   PFN_CUDA_OK(launch_kernel(k_mse_final, dim3(1), dim3(kMseBlock), 0, stream, static_cast<const float*>(scratch), blocks, inv_count, loss));
+  PFN_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t pfn_masked_l2_scratch_bytes(int64_t count) { return size_t(3 * mse_blocks(count) + 2) * sizeof(float); }
+
+extern "C" int pfn_masked_l2_fwd_bwd(const float* out, const float* y, const int64_t* mask, int64_t count, int regularize,
+                                     float regcoeff, float* loss, float* dout, void* scratch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PFN_REQUIRE(out && y && mask && loss && dout && scratch && count > 0, PFN_E_INVALID, "pfn_masked_l2_fwd_bwd: bad arguments");
+  const int blocks = mse_blocks(count);
+  float* partial = static_cast<float*>(scratch);
+  float* scales = partial + 3 * blocks;
+  PFN_CUDA_OK(launch_kernel(k_ml2_partial, dim3(blocks), dim3(kMseBlock), 0, stream, out, y, mask, count, partial));
+  PFN_LAUNCHED();
+  PFN_CUDA_OK(launch_kernel(k_ml2_final, dim3(1), dim3(kMseBlock), 0, stream, static_cast<const float*>(partial), blocks, count, regularize,
+                            regcoeff, loss, scales));
+  PFN_LAUNCHED();
+  PFN_CUDA_OK(launch_kernel(k_ml2_grad, dim3(blocks), dim3(kMseBlock), 0, stream, out, y, mask, count, static_cast<const float*>(scales), dout));
   PFN_LAUNCHED();
   return 0;
 }

@@ -35,6 +35,43 @@ def mse_loss_and_grad(out: torch.Tensor, y: torch.Tensor, total_count: Optional[
     return loss, dout
 
 
+def masked_l2_loss_and_grad(out: torch.Tensor, y: torch.Tensor, mask: torch.Tensor, regularize: bool = True,
+                            regcoeff: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(loss, d loss / d out) for the reference's `Masked_L2_loss(regularize, regcoeff)(out, y, mask)`
+    (utils/custom_loss_functions.py:10-46): mean over the masked entries plus `regcoeff` x mean over the others.
+    Element counts are taken on the device (no masked_select, no host sync).  Single process only: under data
+    parallelism the two means need global counts -- use `model(data)` + torch autograd there."""
+    dev = ops.require_cuda(out, y, mask)
+    with torch.cuda.device(dev):
+        out, y = out.contiguous(), y.contiguous().float()
+        mask = mask.contiguous()
+        if mask.dtype != torch.int64:
+            mask = mask.long()
+        if mask.shape != out.shape:
+            raise ValueError(f"mask shape {tuple(mask.shape)} != output shape {tuple(out.shape)}")
+        count = out.numel()
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        dout = torch.empty_like(out)
+        scratch = torch.empty(int(lib().pfn_masked_l2_scratch_bytes(count)), dtype=torch.uint8, device=dev)
+        check(lib().pfn_masked_l2_fwd_bwd(out.data_ptr(), y.data_ptr(), mask.data_ptr(), count, int(bool(regularize)),
+                                          float(regcoeff), loss.data_ptr(), dout.data_ptr(), scratch.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "pfn_masked_l2_fwd_bwd")
+    return loss, dout
+
+
+def fused_masked_l2_step(model: MaskEmbdMultiMPN, data, regularize: bool = True, regcoeff: float = 1.0) -> torch.Tensor:
+    """forward + Masked_L2_loss + backward (the parser-default training loss, utils/training.py:61-62); parameter
+    `.grad`s are SET.  Returns the loss as a 1-element device tensor."""
+    with torch.enable_grad():
+        out = model(data)
+    loss, dout = masked_l2_loss_and_grad(out.detach(), data.y, data.pred_mask, regularize, regcoeff)
+    params = model._engine_params()
+    grads = torch.autograd.grad(out, params, grad_outputs=dout, allow_unused=False)
+    for p, g in zip(params, grads):
+        p.grad = g
+    return loss
+
+
 def fused_mse_step(model: MaskEmbdMultiMPN, data, total_count: Optional[int] = None) -> torch.Tensor:
     """forward + MSE + backward; parameter `.grad`s are SET (as after `zero_grad(); loss.backward()`).
     Returns the loss as a 1-element device tensor (call `.item()` for the reference's read-back)."""

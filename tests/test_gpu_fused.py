@@ -202,3 +202,25 @@ def test_chained_backward_equals_per_layer_backward(cfg, monkeypatch):
     for k in grads["chain"][0]:
         _close(grads["chain"][0][k], grads["per_layer"][0][k], k + " (chain vs per-layer)", tol=1e-6)
         _close(grads["chain"][0][k], grads["layerwise"][0][k], k + " (chain vs layer-wise)", tol=3e-6)
+
+
+@pytest.mark.parametrize("name", ["mixed", "case118_standard"])
+@pytest.mark.parametrize("regularize", [True, False])
+def test_fused_masked_l2_step_matches_reference(name, regularize):
+    """`fused_masked_l2_step` (Masked_L2_loss value + gradient from one fused head, element counts on the device)
+    against the oracle's restatement of utils/custom_loss_functions.py:10-46 + autograd."""
+    from poweflownet_b200.training import fused_masked_l2_step
+    gold = torch.load(common.golden_path(name), weights_only=True)
+    kw = gold["meta"]["model_kwargs"]
+    batch = common.GraphBatch(**gold["inputs"])
+    masks = common.dropout_masks(name, batch.num_nodes)
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
+    out = oracle(batch, dropout_masks=masks)
+    want = O.masked_l2_loss(out, batch.y, batch.pred_mask, regularize=regularize)
+    want.backward()
+    m = _model(kw).train()
+    m._inject_dropout_masks = masks
+    loss = fused_masked_l2_step(m, batch.to(DEV), regularize=regularize)
+    assert abs(float(loss) - float(want)) < TOL * abs(float(want))
+    for (k, p), (_, q) in zip(m.named_parameters(), oracle.named_parameters()):
+        _close(p.grad, q.grad, k)

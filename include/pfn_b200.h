@@ -177,20 +177,24 @@ PFN_API int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* params
  * directed edges) gets NaN outputs and raises a flag that pfn_graph_tile_status reports (synchronises the stream).
  * Same workspaces, same saved activations and same results (to fp32 rounding) as pfn_mpn_forward, so
  * pfn_mpn_backward follows either.  pfn_mpn_fused_supported: 1 when (desc, tile_rows) is inside the kernel's range
- * (hidden_dim 129 or a multiple of 16 in [32,128], K <= 3, nfeature_dim 4, output_dim <= 4). */
+ * (hidden_dim 129 or a multiple of 16 in [32,128], K <= 3, nfeature_dim 4, output_dim <= 4).
+ * graph_ptr != NULL (device int64 [n_graphs + 1], PyG `Batch.ptr`): batches that MIX graph sizes (the reference's
+ * `--case mixed`, datasets/PowerFlowData.py:67-70) -- whole graphs are packed greedily into tiles of at most 128 rows by
+ * a device-side pass (tile_rows is then only the 128-row bound); a graph of more than 128 nodes raises the same flag. */
 PFN_API int pfn_mpn_fused_supported(const pfn_mpn_desc* desc, int64_t tile_rows);
 PFN_API int pfn_mpn_forward_tiled(const pfn_mpn_desc* desc, const float* const* params, const float* x,
                     const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
                     void* act_ws, void* scratch_ws, int training, uint64_t seed,
                     const uint64_t* seed_device, const float* const* inj_masks, float* out,
-                    int64_t tile_rows, void* stream);
+                    int64_t tile_rows, const int64_t* graph_ptr, int64_t n_graphs, void* stream);
 PFN_API int pfn_graph_tile_status(const void* graph_ws, int32_t* violated, void* stream);
-/* backward after pfn_mpn_forward_tiled (same tile_rows, same promise): the TAGConv layers' data gradients run through
+/* backward after pfn_mpn_forward_tiled (same tile_rows / n_graphs -- 0 when graph_ptr was NULL --, same promise): the TAGConv layers' data gradients run through
  * the graph-resident kernel too (hops and weight products commute, so d x_0 = sum_k ((A_hat^T)^k G) W_k is the forward
  * program on G with the CSR by source and the transposed weights); everything else as pfn_mpn_backward. */
 PFN_API int pfn_mpn_backward_tiled(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                      const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
-                     void* act_ws, void* scratch_ws, int training, int64_t tile_rows, void* stream);
+                     void* act_ws, void* scratch_ws, int training, int64_t tile_rows, int64_t n_graphs,
+                     void* stream);
 /* dout float [N, output_dim]; grads[i] receives d loss / d params[i] (overwritten, same shapes) */
 PFN_API int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                      const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,

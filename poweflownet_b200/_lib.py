@@ -62,12 +62,12 @@ SIGNATURES = {
     "pfn_mpn_fused_supported": (C.c_int, [C.POINTER(MpnDesc), c_i64]),
     "pfn_mpn_forward_tiled": (C.c_int, [C.POINTER(MpnDesc), C.c_void_p, c_f32p, C.c_void_p, c_i64, c_i64, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_int, c_u64, C.c_void_p, C.c_void_p, c_f32p, c_i64,
-                                        C.c_void_p]),
+                                        C.c_void_p, c_i64, C.c_void_p]),
     "pfn_graph_tile_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "pfn_mpn_backward": (C.c_int, [C.POINTER(MpnDesc), C.c_void_p, C.c_void_p, c_f32p, c_i64, c_i64, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pfn_mpn_backward_tiled": (C.c_int, [C.POINTER(MpnDesc), C.c_void_p, C.c_void_p, c_f32p, c_i64, c_i64, C.c_void_p,
-                                         C.c_void_p, C.c_void_p, C.c_int, c_i64, C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_int, c_i64, c_i64, C.c_void_p]),
     "pfn_mse_scratch_bytes": (c_sz, [c_i64]),
     "pfn_mse_fwd_bwd": (C.c_int, [c_f32p, c_f32p, c_i64, C.c_float, c_f32p, c_f32p, C.c_void_p, C.c_void_p]),
     "pfn_masked_l2_scratch_bytes": (c_sz, [c_i64]),

@@ -194,6 +194,30 @@ __global__ void k_ml2_grad(const float* __restrict__ out, const float* __restric
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += int64_t(gridDim.x) * blockDim.x)
     dout[i] = (out[i] - y[i]) * (mask[i] != 0 ? sc1 : sc0);
 }
+// Variable-size tiles for batches that mix graph sizes: whole graphs are packed greedily, in order, into tiles of at
+// most 128 rows (`ptr` = PyG Batch.ptr).  One thread: a batch holds a few hundred graphs.  meta[7] = number of tiles;
+// a graph with more than 128 nodes cannot be tiled and raises meta[6] (the same flag a broken closed-tile promise raises).
+__global__ void k_tile_table(const int64_t* __restrict__ ptr, int n_graphs, int n_nodes, int* __restrict__ tile_start,
+                             int32_t* __restrict__ meta) {
+  pdl_wait();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int t = 0, start = 0;
+  tile_start[0] = 0;
+  for (int g = 0; g < n_graphs; ++g) {
+    const int end = static_cast<int>(ptr[g + 1]);
+    if (end - static_cast<int>(ptr[g]) > 128) meta[6] = 1;
+    if (end - start > 128) {  // graph g does not fit any more: close the tile in front of it
+      const int cut = static_cast<int>(ptr[g]);
+      if (cut > start) {
+        tile_start[++t] = cut;
+        start = cut;
+      }
+    }
+  }
+  if (n_nodes > start) tile_start[++t] = n_nodes;
+  meta[7] = t;
+}
+
 int mse_blocks(int64_t count) {
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div64(count, kMseBlock * 4), 1024)));
 }
@@ -215,7 +239,7 @@ struct Plan {
   int n_params = 0;
   int64_t N = 0, ldh = 0;
   // activation workspace offsets (floats)
-  int64_t off_maskf = 0, off_t1 = 0, off_x0 = 0, off_ea = 0, off_tag = 0, act_floats = 0;
+  int64_t off_maskf = 0, off_t1 = 0, off_x0 = 0, off_ea = 0, off_tag = 0, off_tiles = 0, act_floats = 0;
   // scratch offsets (floats)
   int64_t off_dz = 0, off_ds = 0, off_dhi = 0, off_dhj = 0, off_dxcat = 0, off_dx0 = 0, off_part = 0, scratch_floats = 0;
   int64_t part_bytes = 0;
@@ -275,6 +299,7 @@ int make_plan(const pfn_mpn_desc* desc, int64_t n_nodes, Plan& p) {
     off += round_up64(floats, 4);
     return o;
   };
+  p.off_tiles = take(n_nodes + 8);  // int32 tile table of the graph-resident route (at most one tile per node)
   p.off_maskf = take(n_nodes * d.nfeature_dim);
   p.off_t1 = take(n_nodes * p.ldh);
   p.off_x0 = take(n_nodes * d.nfeature_dim);
@@ -367,6 +392,11 @@ struct Ctx {
   bool training;
   float scale;  // 1/(1-p) in training, 1 otherwise
   const uint64_t* seed_device = nullptr;
+  // graph-resident route: uniform tiles of `tile_rows` rows, or (n_graphs > 0) variable tiles packed from `graph_ptr`
+  int64_t tile_rows = 0, n_graphs = 0;
+  const int64_t* graph_ptr = nullptr;
+  int* tile_table() const { return reinterpret_cast<int*>(act + p.off_tiles); }
+  int64_t n_tiles() const { return n_graphs > 0 ? n_graphs : ceil_div64(p.N, std::max<int64_t>(tile_rows, 1)); }
 
   float* hi(int slot) const { return act + p.off_ea + slot * p.ea_stride(); }
   float* hj(int slot) const { return hi(slot) + p.N * p.ldh; }
@@ -421,6 +451,11 @@ void set_activation(GemmArgs& a, const Ctx& c, bool act, int layer_index, uint64
 // layer-wise backward reads.  The packed weights must already be in place (k_pack_weights).
 int forward_fused(const Ctx& c, const float* x, const int64_t* pred_mask, uint64_t seed, const float* const* inj_masks,
                   float* out, int64_t tile_rows) {
+  if (c.n_graphs > 0) {  // variable-size tiles: build the table once per forward (the backward reuses it)
+    PFN_CUDA_OK(launch_kernel(k_tile_table, dim3(1), dim3(32), 0, c.stream, c.graph_ptr, static_cast<int>(c.n_graphs),
+                              static_cast<int>(c.p.N), c.tile_table(), c.g.meta));
+    PFN_LAUNCHED();
+  }
   const Plan& p = c.p;
   const pfn_mpn_desc& d = p.d;
   const int h = d.hidden_dim;
@@ -476,6 +511,8 @@ int forward_fused(const Ctx& c, const float* x, const int64_t* pred_mask, uint64
   a.n_layers = n_layers;
   a.n_nodes = static_cast<int>(p.N);
   a.tile_rows = static_cast<int>(tile_rows);
+  a.n_tiles = static_cast<int>(c.n_tiles());
+  a.tile_start = c.n_graphs > 0 ? c.tile_table() : nullptr;
   a.h = h;
   a.K = d.K;
   a.ldh = static_cast<int>(p.ldh);
@@ -645,7 +682,8 @@ void fill_backward_common(const Ctx& c, FusedArgs& a, int mode, int n_layers, in
   a.n_layers = n_layers;
   a.n_nodes = static_cast<int>(p.N);
   a.tile_rows = static_cast<int>(tile_rows);
-  a.n_tiles = static_cast<int>(ceil_div64(p.N, tile_rows));
+  a.n_tiles = static_cast<int>(c.n_tiles());
+  a.tile_start = c.n_graphs > 0 ? c.tile_table() : nullptr;
   a.h = d.hidden_dim;
   a.K = d.K;
   a.ldh = static_cast<int>(p.ldh);
@@ -735,7 +773,7 @@ int backward_impl(const Ctx& c, float* const* grads, const float* dout, int64_t 
   FusedArgs ch;
   std::memset(&ch, 0, sizeof(ch));
   int n_chain = 0;
-  const int64_t dwe_stride = 2 * 4 * ((h + 3) / 4) * ceil_div64(N, std::max<int64_t>(tile_rows, 1));  // floats per EA layer
+  const int64_t dwe_stride = 2 * 4 * ((h + 3) / 4) * c.n_tiles();  // floats per EA layer
   float* part = c.scratch + p.off_part;
   const float* x0 = c.act + p.off_x0;
   const float* G = dout;  // gradient w.r.t. the current layer's (pre-activation) output
@@ -1034,17 +1072,19 @@ extern "C" int pfn_graph_tile_status(const void* graph_ws, int32_t* violated, vo
 static int mpn_forward_common(const pfn_mpn_desc* desc, const float* const* params, const float* x,
                               const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
                               void* act_ws, void* scratch_ws, int training, uint64_t seed, const uint64_t* seed_device,
-                              const float* const* inj_masks, float* out, int64_t tile_rows, void* stream);
+                              const float* const* inj_masks, float* out, int64_t tile_rows, const int64_t* graph_ptr,
+                              int64_t n_graphs, void* stream);
 
 extern "C" int pfn_mpn_forward_tiled(const pfn_mpn_desc* desc, const float* const* params, const float* x,
                                      const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
                                      void* act_ws, void* scratch_ws, int training, uint64_t seed,
                                      const uint64_t* seed_device, const float* const* inj_masks, float* out,
-                                     int64_t tile_rows, void* stream) {
+                                     int64_t tile_rows, const int64_t* graph_ptr, int64_t n_graphs, void* stream) {
   PFN_REQUIRE(tile_rows > 0 && pfn_mpn_fused_supported(desc, tile_rows), PFN_E_UNSUPPORTED,
               "pfn_mpn_forward_tiled: configuration outside the graph-resident kernel (use pfn_mpn_forward)");
+  PFN_REQUIRE(graph_ptr == nullptr || (n_graphs > 0 && n_graphs <= n_nodes), PFN_E_INVALID, "pfn_mpn_forward_tiled: bad graph_ptr / n_graphs");
   return mpn_forward_common(desc, params, x, pred_mask, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, seed,
-                            seed_device, inj_masks, out, tile_rows, stream);
+                            seed_device, inj_masks, out, tile_rows, graph_ptr, graph_ptr != nullptr ? n_graphs : 0, stream);
 }
 
 extern "C" int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* params, const float* x,
@@ -1052,13 +1092,14 @@ extern "C" int pfn_mpn_forward(const pfn_mpn_desc* desc, const float* const* par
                                void* act_ws, void* scratch_ws, int training, uint64_t seed, const uint64_t* seed_device,
                                const float* const* inj_masks, float* out, void* stream) {
   return mpn_forward_common(desc, params, x, pred_mask, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, seed,
-                            seed_device, inj_masks, out, 0, stream);
+                            seed_device, inj_masks, out, 0, nullptr, 0, stream);
 }
 
 static int mpn_forward_common(const pfn_mpn_desc* desc, const float* const* params, const float* x,
                               const int64_t* pred_mask, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
                               void* act_ws, void* scratch_ws, int training, uint64_t seed, const uint64_t* seed_device,
-                              const float* const* inj_masks, float* out, int64_t tile_rows, void* stream) {
+                              const float* const* inj_masks, float* out, int64_t tile_rows, const int64_t* graph_ptr,
+                              int64_t n_graphs, void* stream) {
   Plan p;
   PFN_TRY(make_plan(desc, n_nodes, p));
   PFN_TRY(check_tables(p, params, "pfn_mpn_forward(params)"));
@@ -1069,31 +1110,35 @@ static int mpn_forward_common(const pfn_mpn_desc* desc, const float* const* para
         static_cast<cudaStream_t>(stream), training != 0,
         (training != 0 && desc->dropout_rate > 0.f) ? 1.f / (1.f - desc->dropout_rate) : 1.f};
   c.seed_device = seed_device;
+  c.tile_rows = tile_rows;
+  c.graph_ptr = graph_ptr;
+  c.n_graphs = n_graphs;
   return forward_impl(c, x, pred_mask, seed, inj_masks, out, tile_rows);
 }
 
 static int mpn_backward_common(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                                const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws, void* act_ws,
-                               void* scratch_ws, int training, int64_t tile_rows, void* stream);
+                               void* scratch_ws, int training, int64_t tile_rows, int64_t n_graphs, void* stream);
 
 extern "C" int pfn_mpn_backward(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                                 const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws, void* act_ws,
                                 void* scratch_ws, int training, void* stream) {
-  return mpn_backward_common(desc, params, grads, dout, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, 0, stream);
+  return mpn_backward_common(desc, params, grads, dout, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, 0, 0, stream);
 }
 
 extern "C" int pfn_mpn_backward_tiled(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                                       const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws,
-                                      void* act_ws, void* scratch_ws, int training, int64_t tile_rows, void* stream) {
+                                      void* act_ws, void* scratch_ws, int training, int64_t tile_rows, int64_t n_graphs,
+                                      void* stream) {
   PFN_REQUIRE(tile_rows > 0 && pfn_mpn_fused_supported(desc, tile_rows), PFN_E_UNSUPPORTED,
               "pfn_mpn_backward_tiled: configuration outside the graph-resident kernel (use pfn_mpn_backward)");
   return mpn_backward_common(desc, params, grads, dout, n_nodes, e_raw, graph_ws, act_ws, scratch_ws, training, tile_rows,
-                             stream);
+                             n_graphs, stream);
 }
 
 static int mpn_backward_common(const pfn_mpn_desc* desc, const float* const* params, float* const* grads,
                                const float* dout, int64_t n_nodes, int64_t e_raw, const void* graph_ws, void* act_ws,
-                               void* scratch_ws, int training, int64_t tile_rows, void* stream) {
+                               void* scratch_ws, int training, int64_t tile_rows, int64_t n_graphs, void* stream) {
   Plan p;
   PFN_TRY(make_plan(desc, n_nodes, p));
   PFN_TRY(check_tables(p, params, "pfn_mpn_backward(params)"));
@@ -1107,6 +1152,8 @@ static int mpn_backward_common(const pfn_mpn_desc* desc, const float* const* par
   if (n_nodes == 0) {  // gradients of an empty batch are zero
     return 0;
   }
+  c.tile_rows = tile_rows;
+  c.n_graphs = n_graphs;  // > 0: the variable-size tile table the forward left in the activation workspace
   return backward_impl(c, grads, dout, tile_rows);
 }
 

@@ -69,6 +69,10 @@ struct FusedArgs {
   const int* rowptr2;
   const int* nbr2;
   const float2* ea2;
+  // variable-size tiles (batches that mix graph sizes): tile t = rows [tile_start[t], tile_start[t+1]), t < meta[7]; the
+  // grid is the number of graphs (an upper bound known on the host) and the surplus CTAs leave at once.  Null: uniform
+  // tiles of `tile_rows` rows.
+  const int* tile_start;
   long long* timing;  // debug (PFN_FUSED_TIMING): worker 0 of CTA 0 writes clock64() at phase boundaries
 };
 static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");

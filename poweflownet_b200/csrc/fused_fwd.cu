@@ -550,7 +550,25 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = args.h, hm = min(h, 128), ldh = args.ldh;
   const int KT = (hm + 31) / 32;
-  const int r0 = blockIdx.x * args.tile_rows, nr = min(args.tile_rows, args.n_nodes - r0);
+  int r0 = blockIdx.x * args.tile_rows, nr = min(args.tile_rows, args.n_nodes - r0);
+  if (args.tile_start != nullptr) {
+    // variable-size tiles: the table was written by a kernel earlier in the stream (so wait for it first); CTAs beyond the
+    // number of tiles only clear their slots of the per-tile dWe partial sums
+    pdl_wait();
+    if (int(blockIdx.x) >= args.meta[7]) {
+      if (kTwoSlabs) {
+        const int c4 = (h + 3) / 4;
+        for (int li = 0; li < args.n_layers; ++li) {
+          float* part = args.layers[li].dwe_partial;
+          if (part == nullptr) continue;
+          for (int i = threadIdx.x; i < 2 * 4 * c4; i += kFThreads) part[size_t(i) * args.n_tiles + blockIdx.x] = 0.f;
+        }
+      }
+      return;
+    }
+    r0 = args.tile_start[blockIdx.x];
+    nr = args.tile_start[blockIdx.x + 1] - r0;
+  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.wmap)) : "memory");
@@ -595,7 +613,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
   const uint32_t tmem = M->tmem_slot;
   const int e0 = M->rp[0], ne = M->rp[128] - e0;
   {
-    int bad = ne > kFusedEdgeCap ? 1 : 0;
+    int bad = (ne > kFusedEdgeCap || nr > 128 || nr <= 0) ? 1 : 0;  // (nr > 128: a graph too large for the variable-size tiling)
     for (int i = threadIdx.x; i < min(ne, kFusedEdgeCap); i += kFThreads) {
       const int loc = args.nbr[e0 + i] - r0;
       if (loc < 0 || loc >= nr) bad = 1;
@@ -1632,7 +1650,7 @@ int fused_fwd_launch(FusedArgs& a, const float* arena, int64_t arena_rows, cudaS
   }
   PFN_REQUIRE(a.mode >= 0 && a.mode <= 3, PFN_E_INVALID, "fused kernel: bad mode %d", a.mode);
   void (*kernel)(FusedArgs) = kernels[a.h > 128 ? 1 : 0][a.mode];
-  const unsigned tiles = static_cast<unsigned>(ceil_div64(a.n_nodes, a.tile_rows));
+  const unsigned tiles = a.tile_start != nullptr ? static_cast<unsigned>(a.n_tiles) : static_cast<unsigned>(ceil_div64(a.n_nodes, a.tile_rows));
   static const bool timing_on = std::getenv("PFN_FUSED_TIMING") != nullptr;  // debug aid: phase timestamps of CTA 0
   static long long* timing_dev = nullptr;
   if (timing_on) {

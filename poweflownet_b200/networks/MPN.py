@@ -77,9 +77,11 @@ class _MPNFunction(torch.autograd.Function):
     """Whole-model forward/backward through `pfn_mpn_forward` / `pfn_mpn_backward`."""
 
     @staticmethod
-    def forward(ctx, model, tile_rows, x, pred_mask, edge_index, edge_attr, *params):
+    def forward(ctx, model, tiling, x, pred_mask, edge_index, edge_attr, *params):
         dev = ops.require_cuda(x, pred_mask, edge_index, edge_attr, *params)
         n = int(x.size(0))
+        tile_rows, graph_ptr = tiling  # graph_ptr: device int64 [G+1] for batches that mix graph sizes, else None
+        n_graphs = int(graph_ptr.numel()) - 1 if graph_ptr is not None else 0
         training = bool(model.training)
         needs_grad = any(ctx.needs_input_grad)  # (grad mode is off inside Function.forward; this is set by apply)
         with torch.cuda.device(dev):
@@ -106,8 +108,9 @@ class _MPNFunction(torch.autograd.Function):
             stream = torch.cuda.current_stream().cuda_stream
             if tile_rows > 0:
                 # graph-resident kernel: the whole layer stack in one launch, one tile of whole graphs per CTA
-                check(lib().pfn_mpn_forward_tiled(*common, tile_rows, stream), "pfn_mpn_forward_tiled")
-                sig = (n, graph.e_raw, tile_rows)
+                check(lib().pfn_mpn_forward_tiled(*common, tile_rows, None if graph_ptr is None else graph_ptr.data_ptr(),
+                                                  n_graphs, stream), "pfn_mpn_forward_tiled")
+                sig = (n, graph.e_raw, tile_rows, n_graphs)
                 if sig not in model._tiling_checked and not torch.cuda.is_current_stream_capturing():
                     # first batch of this shape: read back the kernel's own validation of the closed-tile promise
                     violated = C.c_int32(0)
@@ -122,6 +125,7 @@ class _MPNFunction(torch.autograd.Function):
         if needs_grad:
             ctx.model, ctx.ws, ctx.params, ctx.n, ctx.e_raw, ctx.training = model, ws, params, n, graph.e_raw, training
             ctx.tile_rows = tile_rows  # > 0: the closed-tile promise held for this batch (validated by the forward kernel)
+            ctx.n_graphs = n_graphs if tile_rows > 0 else 0
             ctx.keep = (x, pred_mask, graph, inj)  # keep inputs alive until backward
         else:
             model._give_workspace(n, graph.e_raw, dev, ws)
@@ -148,7 +152,7 @@ class _MPNFunction(torch.autograd.Function):
                       ws.act.data_ptr(), ws.scratch.data_ptr(), int(ctx.training))
             stream = torch.cuda.current_stream().cuda_stream
             if ctx.tile_rows > 0:
-                check(lib().pfn_mpn_backward_tiled(*common, ctx.tile_rows, stream), "pfn_mpn_backward_tiled")
+                check(lib().pfn_mpn_backward_tiled(*common, ctx.tile_rows, ctx.n_graphs, stream), "pfn_mpn_backward_tiled")
             else:
                 check(lib().pfn_mpn_backward(*common, stream), "pfn_mpn_backward")
             dx = None
@@ -159,7 +163,7 @@ class _MPNFunction(torch.autograd.Function):
                 model._grad_reducer(gflat)  # data parallel: ONE collective over the flat gradient buffer
         model._give_workspace(ctx.n, ctx.e_raw, dev, ws)
         ctx.ws = None
-        return (None, None, dx, None, None, None, *views)
+        return (None, None, dx, None, None, None, *views)  # (model, tiling, x, pred_mask, edge_index, edge_attr, *params)
 
 
 class MaskEmbdMultiMPN(nn.Module):
@@ -243,26 +247,37 @@ class MaskEmbdMultiMPN(nn.Module):
         # scratch layout of engine.cu: dx0 [n, nfeat] comes first
         return ws.scratch.view(torch.float32)[:n * self.nfeature_dim].view(n, self.nfeature_dim)
 
-    def _tile_rows(self, data) -> int:
-        """Rows per closed tile for the graph-resident kernel, or 0 for the layer-wise path.  Uses only host-side
-        shape information (no device read): a batch of `num_graphs` equal-sized graphs of n = N / num_graphs <= 128
-        nodes is tiled as floor(128 / n) whole graphs per tile; the kernel validates that no edge leaves a tile."""
+    def _tiling(self, data):
+        """(tile_rows, graph_ptr) for the graph-resident kernels, or (0, None) for the layer-wise path.  Uses only host-side
+        shape information (no device read):
+        * `num_graphs` equal-sized graphs of n = N / num_graphs <= 128 nodes: floor(128 / n) whole graphs per tile;
+        * otherwise, when the batch carries PyG's `ptr` on the device: graphs of mixed sizes (the reference's
+          `--case mixed`), packed greedily into tiles of <= 128 rows by a device-side pass over `ptr`.
+        Either way the kernel validates the tiling itself (no edge may leave a tile, no graph may exceed 128 nodes)."""
         if not self.fused:
-            return 0
+            return 0, None
         n = int(data.x.size(0))
+        ptr = getattr(data, "ptr", None)
         g = getattr(data, "num_graphs", None)
-        if g is None and getattr(data, "ptr", None) is not None:
-            g = int(data.ptr.numel()) - 1
-        if not g or g <= 0 or n <= 0 or n % g:
-            return 0
-        per = n // g
-        if per > 128:
-            return 0
-        tile = (128 // per) * per
-        if self._tiling_checked.get((n, int(data.edge_index.size(1)), tile), True) is False:
-            return 0
+        if g is None and ptr is not None:
+            g = int(ptr.numel()) - 1
+        if not g or g <= 0 or n <= 0:
+            return 0, None
+        e_raw = int(data.edge_index.size(1))
         desc = self._desc()
-        return tile if lib().pfn_mpn_fused_supported(C.byref(desc), tile) else 0
+        if n % g == 0 and n // g <= 128:
+            tile = (128 // (n // g)) * (n // g)
+            if self._tiling_checked.get((n, e_raw, tile, 0), True) is not False and lib().pfn_mpn_fused_supported(C.byref(desc), tile):
+                return tile, None
+            return 0, None
+        if (ptr is not None and ptr.is_cuda and ptr.dtype == torch.int64 and ptr.numel() == g + 1 and g <= n
+                and self._tiling_checked.get((n, e_raw, 128, g), True) is not False
+                and lib().pfn_mpn_fused_supported(C.byref(desc), 128)):
+            return 128, ptr.contiguous()
+        return 0, None
+
+    def _tile_rows(self, data) -> int:
+        return self._tiling(data)[0]
 
     def forward(self, data):
         """networks/MPN.py:525-559.  `data` is any object with the PyG `Batch` attributes the reference
@@ -275,5 +290,5 @@ class MaskEmbdMultiMPN(nn.Module):
                 "which cannot run unless hidden_dim == output_dim; the sm_100a path implements n_gnn_layers >= 2")
         if self.efeature_dim != 2:
             raise NotImplementedError("the sm_100a path implements efeature_dim == 2 (the dataset's edge width)")
-        return _MPNFunction.apply(self, self._tile_rows(data), data.x, data.pred_mask, data.edge_index, data.edge_attr,
+        return _MPNFunction.apply(self, self._tiling(data), data.x, data.pred_mask, data.edge_index, data.edge_attr,
                                   *self._engine_params())

@@ -153,7 +153,7 @@ def test_tiled_entry_point_rejects_unsupported_configurations():
     assert lib.pfn_mpn_fused_supported(C.byref(MpnDesc(4, 2, 4, 33, 4, 3, 0.2, 0)), 118) == 0
     assert lib.pfn_mpn_fused_supported(C.byref(MpnDesc(4, 2, 4, 64, 2, 3, 0.2, 0)), 126) == 1
     rc = lib.pfn_mpn_forward_tiled(C.byref(MpnDesc(4, 2, 4, 512, 5, 3, 0.2, 0)), None, None, None, 0, 0, None, None, None, 0, 0,
-                                   None, None, None, 118, None)
+                                   None, None, None, 118, None, 0, None)
     assert rc == -2 and b"graph-resident" in lib.pfn_last_error()
 
 
@@ -224,3 +224,51 @@ def test_fused_masked_l2_step_matches_reference(name, regularize):
     assert abs(float(loss) - float(want)) < TOL * abs(float(want))
     for (k, p), (_, q) in zip(m.named_parameters(), oracle.named_parameters()):
         _close(p.grad, q.grad, k)
+
+
+def test_mixed_size_batches_take_variable_tiles():
+    """Batches that mix graph sizes (the reference's --case mixed: 118-bus and 14-bus grids) run on the graph-resident
+    kernels with tiles packed from `ptr` on the device; results equal the layer-wise kernels' and the oracle's."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=129, n_gnn_layers=3, K=3, dropout_rate=0.0)
+    names = ["14", "118v2", "14", "14", "14", "118v2", "118v2", "14", "14", "14", "14", "14", "14", "14", "14", "14", "14", "118v2"]
+    batch = synthetic_batch(cases=names)
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
+    loss_ref, out_ref = O.forward_loss_backward(oracle, batch, "mse")
+    db = batch.to(DEV)
+    grads, outs = {}, {}
+    for fused in (True, False):
+        m = _model(kw, fused).train()
+        tile, ptr = m._tiling(db)
+        assert (tile, ptr is not None) == ((128, True) if fused else (0, False))
+        n0 = _launches()
+        out = m(db)
+        torch.nn.functional.mse_loss(out, db.y).backward()
+        outs[fused] = (out.detach().clone(), _launches() - n0)
+        grads[fused] = {k: p.grad.clone() for k, p in m.named_parameters()}
+        if fused:
+            assert list(m._tiling_checked.values()) == [True]
+    assert outs[True][1] < outs[False][1] / 3
+    _close(outs[True][0], out_ref, "out vs oracle")
+    _close(outs[True][0], outs[False][0], "out vs layer-wise", tol=3e-6)
+    for (k, q) in oracle.named_parameters():
+        _close(grads[True][k], q.grad, k + " vs oracle")
+        _close(grads[True][k], grads[False][k], k + " vs layer-wise", tol=3e-6)
+
+
+def test_variable_tiles_reject_large_graphs():
+    """A batch that mixes a 6470-bus graph with small ones cannot be tiled: the device-side packing flags it and the
+    module falls back to the layer-wise kernels for that shape."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=64, n_gnn_layers=2, K=3, dropout_rate=0.0)
+    batch = synthetic_batch(cases=["14", (300, 420), "14"])
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).eval()
+    with torch.no_grad():
+        want = oracle(batch)
+    m = _model(kw).eval()
+    db = batch.to(DEV)
+    assert m._tiling(db)[0] == 128
+    with torch.no_grad():
+        out = m(db)
+    assert list(m._tiling_checked.values()) == [False] and m._tiling(db)[0] == 0
+    _close(out, want, "fallback result")

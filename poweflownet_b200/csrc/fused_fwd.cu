@@ -1,21 +1,30 @@
-// Graph-resident forward of MaskEmbdMultiMPN (networks/MPN.py:525-559): ONE kernel launch runs mask_embd, every
-// EdgeAggregation and every TAGConv of the stack for a tile of whole graphs, with the activations of the tile living in
-// shared memory / tensor memory between layers.  HBM sees the inputs, the weights (L2-resident) and the activations
-// the backward pass needs -- written once, never read back here.
+// Graph-resident kernels of MaskEmbdMultiMPN (networks/MPN.py:525-559 and the backward autograd would run for it,
+// utils/training.py:74): ONE kernel launch runs mask_embd, every EdgeAggregation and every TAGConv of the stack -- or, in
+// the backward programs, their data gradients in reverse order -- for a tile of whole graphs, with the activations (or
+// gradients) of the tile living in shared memory / tensor memory between layers.  HBM sees the inputs, the weights
+// (L2-resident) and the activations / per-layer gradients that the backward pass / the weight gradients need -- written
+// once, never read back inside the launch that wrote them.
+//
+//   MODE 0  forward                    mask_embd -> [EA, TAG] x (L-1) -> EA
+//   MODE 1  one TAGConv backward       d x_0 = sum_k ((A_hat^T)^k G) W_k, masked by the layer input
+//   MODE 2  one EdgeAggregation backward   dS = G W2 ; dHj (by source), dHi + dWe (by target) ; d cur = dHj Wj + dHi Wi
+//   MODE 3  the whole backward data path   steps of modes 2 / 1 for every layer, the gradient handed on in shared memory
 //
 // Applicability (checked by the launcher / by the kernel itself): the batch is a disjoint union of graphs, so a
 // contiguous range of rows whose edges all stay inside the range ("closed tile") needs no other CTA.  The caller
-// promises closed tiles of `tile_rows` <= 128 rows (118-bus graphs: one per tile; 14-bus graphs: nine per tile); the
-// kernel validates the promise while it stages the tile's CSR slice and, when it is broken, poisons its output rows with
-// NaN and raises meta[6] in the graph workspace.  hidden_dim must be 128..132 or a multiple of 16 in [32, 128]; larger
-// graphs / wider models take the layer-wise kernels (engine.cu).
+// promises closed tiles of <= 128 rows: uniform ones of `tile_rows` rows (118-bus graphs: one per tile; 14-bus graphs:
+// nine per tile) or, for batches that mix sizes, the table a device-side pass packs from PyG's `ptr`.  The kernel validates
+// the promise while it stages the tile's CSR slice and, when it is broken, poisons its output rows with NaN and raises
+// meta[6] in the graph workspace.  hidden_dim must be 129 or a multiple of 16 in [32, 128]; larger graphs / wider models
+// take the layer-wise kernels (engine.cu).
 //
 // CTA = 128 rows.  Roles: warp 0 = TMA producer (weight tiles, pre-split TF32 hi/lo planes of the packed arena),
-// warp 1 = tcgen05.mma issuer + TMEM owner, warps 2..17 = 512 workers (gathers, hops, epilogues).
+// warp 1 = tcgen05.mma issuer + TMEM owner, warps 2..17 = 512 workers (gathers, hops, segmented passes, epilogues).
 // Shared memory: two 64 KB regions R0/R1 that hold EITHER the A operand of the next GEMM as (hi, lo) TF32 planes in the
 // K-major SWIZZLE_128B layout (4 K-tiles of 128 rows x 32 floats each, written by the workers directly in the layout a
-// TMA load would produce) OR two fp32 [128][128] buffers (Hi, Hj of an EdgeAggregation, XOR-swizzled for conflict-free
-// row-per-thread writes and row-per-warp reads); 2 x 32 KB weight stages; ~29 KB of CSR slab / border columns.
+// TMA load would produce) OR two fp32 [128][128] buffers (Hi, Hj of an EdgeAggregation; dS and the other side's H in its
+// backward), XOR-swizzled for conflict-free row-per-thread writes and row-per-warp reads; 2 x 32 KB weight stages;
+// ~34 KB of CSR slices (by target and by source) / border columns / per-layer constants.
 // hidden_dim = 129 = 128 + 1: the tensor core multiplies the 128 x 128 x 128 core; the border row/column of every weight
 // matrix is applied by the workers (rank-1 updates in the epilogue, one dot product per row while the MMA runs).
 // Accuracy: 3xTF32 split (A_lo B_hi + A_hi B_lo in their own accumulator, A_hi B_hi rotating over the remaining ones),

@@ -105,6 +105,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   return v;
 }
+// Eight warp-wide sums at once (p[i] = this lane's contribution to row slot i): a transposing butterfly halves the number
+// of live values at every stage, 10 shuffles instead of 8 x 5.  Returns, in lane l < 8, the total of slot l.
+__device__ __forceinline__ float warp_sum8(const float (&p)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float q[4], r[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b4 ? p[i] : p[i + 4], keep = b4 ? p[i + 4] : p[i];
+    q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);  // slot i + 4 * b4
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b3 ? q[i] : q[i + 2], keep = b3 ? q[i + 2] : q[i];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);  // slot i + 2 * b3 + 4 * b4
+  }
+  const float send = b2 ? r[0] : r[1], keep = b2 ? r[1] : r[0];
+  float s = keep + __shfl_xor_sync(0xffffffffu, send, 4);  // slot b2 + 2 * b3 + 4 * b4 = lane >> 2 (bits 2..4)
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  return __shfl_sync(0xffffffffu, s, 4 * (lane & 7));
+}
+static_assert(kRW == 8, "warp_sum8 serves the eight row slots of a worker warp");
 // border columns live in float4 slots of shared memory; component kb of slot `p`
 __device__ __forceinline__ float& bcol(float4* p, int kb) { return reinterpret_cast<float*>(p)[kb]; }
 __device__ __forceinline__ float bcol(const float4* p, int kb) { return reinterpret_cast<const float*>(p)[kb]; }
@@ -215,19 +237,17 @@ __device__ __forceinline__ void border_dot(const Wk& w, int seg, int w_row, int 
 #pragma unroll
     for (int kb = 0; kb < NB; ++kb) wc[nb][kb] = __ldg(W + size_t(nb) * w.ldh + 128 + kb);
   float mine[NB];
-#pragma unroll
-  for (int nb = 0; nb < NB; ++nb) mine[nb] = 0.f;
+  float part[NB][kRW];
 #pragma unroll
   for (int i = 0; i < kRW; ++i) {
     const int r = rowof(w, i);
     const float4 av = ld_planes(w.R0, w.R1, r, 4 * w.lane);
     if (save != nullptr && r < w.nr) *reinterpret_cast<float4*>(save + size_t(w.r0 + r) * ld_save + 4 * w.lane) = av;
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const float t = warp_sum(dot4(av, wv[nb]));
-      if (w.lane == i) mine[nb] = t;
-    }
+    for (int nb = 0; nb < NB; ++nb) part[nb][i] = dot4(av, wv[nb]);
   }
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) mine[nb] = warp_sum8(part[nb], w.lane);  // lane l < 8: the sum of row slot l
   if (w.lane < kRW) {
     const int r = w.rb;
     const float4* xbp = &w.m->xb[seg][r];
@@ -1046,11 +1066,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
             float4 wv = f4zero();
             if (cl_ok) wv = make_float4(__ldg(L.W1 + (cl + 0) * ldw1 + off + k), __ldg(L.W1 + (cl + 1) * ldw1 + off + k),
                                         __ldg(L.W1 + (cl + 2) * ldw1 + off + k), __ldg(L.W1 + (cl + 3) * ldw1 + off + k));
+            float part[kRW];
 #pragma unroll
-            for (int i = 0; i < kRW; ++i) {
-              const float sres = warp_sum(dot4(D[i], wv));
-              if (lane == i) mine[k] = sres;
-            }
+            for (int i = 0; i < kRW; ++i) part[i] = dot4(D[i], wv);
+            mine[k] = warp_sum8(part, lane);
           }
           if (lane < kRW) {
             if (HB > 0) {
@@ -1200,7 +1219,8 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         mb2 = make_float4(__ldg(args.mb2 + 0), __ldg(args.mb2 + 1), __ldg(args.mb2 + 2), __ldg(args.mb2 + 3));
       }
       float mine[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+      float part[4][kRW];
+#pragma unroll
       for (int i = 0; i < kRW; ++i) {
         const int r = rowof(w, i), m = r0 + r;
         const float4 mk = M->ob[1][r];
@@ -1215,11 +1235,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         }
         if (r < nr && cl_ok) *reinterpret_cast<float4*>(args.t1 + size_t(m) * ldh + cl) = make_float4(t[0], t[1], t[2], t[3]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float s = warp_sum(t[0] * w2m[k][0] + t[1] * w2m[k][1] + t[2] * w2m[k][2] + t[3] * w2m[k][3]);
-          if (lane == i) mine[k] = s;
-        }
+        for (int k = 0; k < 4; ++k) part[k][i] = t[0] * w2m[k][0] + t[1] * w2m[k][1] + t[2] * w2m[k][2] + t[3] * w2m[k][3];
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mine[k] = warp_sum8(part[k], lane);  // lane l < 8: row slot l
       if (lane < kRW) {
         const int r = rb, m = r0 + r;
         const float4 mk = M->ob[1][r];
@@ -1471,11 +1490,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
             if (k < od) {
               float4 wv = f4zero();
               if (cl_ok) wv = make_float4(__ldg(L.W2 + k * h + cl), __ldg(L.W2 + k * h + cl + 1), __ldg(L.W2 + k * h + cl + 2), __ldg(L.W2 + k * h + cl + 3));
+              float part[kRW];
 #pragma unroll
-              for (int i = 0; i < kRW; ++i) {
-                const float s = warp_sum(dot4(S[i], wv));
-                if (lane == i) mine[k] = s;
-              }
+              for (int i = 0; i < kRW; ++i) part[i] = dot4(S[i], wv);
+              mine[k] = warp_sum8(part, lane);
             }
           }
           if (lane < kRW && rb < nr) {

@@ -614,8 +614,10 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&M->tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // zero the operand regions once: K-tile padding is multiplied by zero weights, but must not hold NaN bit patterns
-  for (uint32_t o = threadIdx.x * 16u; o < 2 * kPlaneBytes; o += kFThreads * 16u) sts4(R0 + o, f4zero());
+  // zero the operand regions once when hidden_dim < 128: K-tile padding is multiplied by zero weights, but must not hold
+  // NaN bit patterns (at 128 columns every byte of both regions is written before it is first read)
+  if (hm < 128)
+    for (uint32_t o = threadIdx.x * 16u; o < 2 * kPlaneBytes; o += kFThreads * 16u) sts4(R0 + o, f4zero());
   for (int i = threadIdx.x; i < kFusedMaxSeg * 128; i += kFThreads) (&M->xb[0][0])[i] = f4zero();
   for (int i = threadIdx.x; i < kFusedMaxSeg * 128; i += kFThreads) (&M->wkb[0][0][0])[i] = 0.f;
   pdl_wait();

@@ -217,6 +217,26 @@ PFN_API size_t pfn_masked_l2_scratch_bytes(int64_t count);
 PFN_API int pfn_masked_l2_fwd_bwd(const float* out, const float* y, const int64_t* mask, int64_t count, int regularize,
                           float regcoeff, float* loss, float* dout, void* scratch, void* stream);
 
+/* ---- PowerImbalance loss + gradient: utils/custom_loss_functions.py:99-286 (`PowerImbalance.forward`; selected by
+ *      train.py:95-101, called at utils/training.py:63-68).  x: normalised predictions [N, >=4] (Vm, Va[deg], P, Q),
+ *      row pitch ldx floats (multiple of 4, 16-byte aligned).  graph_ws: a workspace filled by pfn_graph_prep with
+ *      undirect_mode = 1 from the batch's edge_index / edge_attr (the loss doubles the branch list by the same first-edge
+ *      rule as the model, :131-150).  stats: HOST array of 12 floats = xymean[4], xystd[4], edgemean[2], edgestd[2]
+ *      (PowerFlowData.get_data_means_stds, datasets/PowerFlowData.py:115-117).  loss: device scalar = mean over buses
+ *      of dP^2 + dQ^2.  dx: d loss / d x [N, 4] with row pitch lddx, or NULL for the forward value only.
+ *      scratch: at least pfn_power_imbalance_scratch_bytes(N).  No atomics: sums follow the edge order. ------------- */
+PFN_API size_t pfn_power_imbalance_scratch_bytes(int64_t n_nodes);
+PFN_API int pfn_power_imbalance_fwd_bwd(const float* x, int64_t ldx, const void* graph_ws, int64_t n_nodes, int64_t e_raw,
+                                const float* stats, float* loss, float* dx, int64_t lddx, void* scratch, void* stream);
+
+/* ---- AdamW over a list of fp32 tensors in one launch: train.py:123 `torch.optim.AdamW` (torch/optim/adamw.py
+ *      `_single_tensor_adamw`, amsgrad = maximize = False).  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays
+ *      of n_tensors device pointers / element counts; `step` is the 1-based count of this update (bias corrections are
+ *      taken in double precision on the host, like torch's Python scalars).  Updates params and both moments in place. */
+PFN_API int pfn_adamw_step(int64_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

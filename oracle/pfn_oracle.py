@@ -212,6 +212,73 @@ def masked_l2_loss(output, target, mask, regularize=True, regcoeff=1.0):
 
 
 # --------------------------------------------------------------------------------------------
+# utils/custom_loss_functions.py:99-306  PowerImbalance / MixedMSEPoweImbalance  
+# --------------------------------------------------------------------------------------------
+def power_imbalance_message(x_i, x_j, edge_attr):
+    """utils/custom_loss_functions.py:159-227 (`message`), the "another mine" formula that is live at :216-217.
+    `x_*`: de-normalised (Vm, Va[deg], P, Q) of the aggregating / the neighbouring bus, `edge_attr`: de-normalised
+    (r, x) of the branch.  Returns `[E, 2]` = (Pji, Qji)."""
+    r_x = edge_attr[:, 0:2]
+    r, x = r_x[:, 0:1], r_x[:, 1:2]
+    g_ij = r / (r ** 2 + x ** 2)
+    b_ij = -x / (r ** 2 + x ** 2)
+    vm_i = x_i[:, 0:1]
+    va_i = 1 / 180. * math.pi * x_i[:, 1:2]
+    vm_j = x_j[:, 0:1]
+    va_j = 1 / 180. * math.pi * x_j[:, 1:2]
+    e_i = vm_i * torch.cos(va_i)
+    f_i = vm_i * torch.sin(va_i)
+    e_j = vm_j * torch.cos(va_j)
+    f_j = vm_j * torch.sin(va_j)
+    Pji = g_ij * (e_i * e_j - e_i ** 2 + f_i * f_j - f_i ** 2) + b_ij * (f_i * e_j - e_i * f_j)
+    Qji = g_ij * (f_i * e_j - e_i * f_j) + b_ij * (-e_i * e_j + e_i ** 2 - f_i * f_j + f_i ** 2)
+    return torch.cat([Pji, Qji], dim=-1)
+
+
+def power_imbalance(x, edge_index, edge_attr, xymean, xystd, edgemean, edgestd):
+    """utils/custom_loss_functions.py:254-286 (`forward`) with :229-252 (`update`) and :124-129 (`de_normalize`).
+
+    `MessagePassing(aggr='add', flow='target_to_source')` (:118): `i = edge_index[0]` is the aggregating bus and
+    `j = edge_index[1]` its neighbour.  The branch list is doubled when `is_directed` (:131-133: the same
+    first-edge test as the model's, without the empty-list guard).  `dPQ_i = -sum_e msg_e + (P_i, Q_i)`;
+    loss = mean over buses of `dP^2 + dQ^2`.  `xymean/xystd`: `[1, 4]` (rows beyond the first are dropped, :119-122),
+    `edgemean/edgestd`: `[1, 2]`."""
+    xymean, xystd = xymean[0:1].to(x.dtype), xystd[0:1].to(x.dtype)
+    edgemean, edgestd = edgemean.to(x.dtype), edgestd.to(x.dtype)
+    if is_directed(edge_index):
+        edge_index, edge_attr = undirect_graph(edge_index, edge_attr)
+    x = x * xystd + xymean
+    edge_attr = edge_attr * edgestd + edgemean
+    i, j = edge_index[0], edge_index[1]
+    msg = power_imbalance_message(x.index_select(0, i), x.index_select(0, j), edge_attr)
+    agg = scatter_sum(msg, i, x.size(0))
+    dPi = -agg[:, 0:1] + x[:, 2:3]
+    dQi = -agg[:, 1:2] + x[:, 3:4]
+    dPQ = torch.cat([dPi, dQi], dim=-1)
+    return dPQ.square().sum(dim=-1).mean()
+
+
+def mixed_mse_power_imbalance(x, edge_index, edge_attr, y, stats, alpha=0.5):
+    """utils/custom_loss_functions.py:289-306: `alpha * MSE(x, y) + (1 - alpha) * 0.020 * power_imbalance`."""
+    return alpha * F.mse_loss(x, y) + (1 - alpha) * 0.020 * power_imbalance(x, edge_index, edge_attr, *stats)
+
+
+def adamw_step(params, grads, exp_avgs, exp_avg_sqs, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2):
+    """One `torch.optim.AdamW` update (train.py:123; torch/optim/adamw.py `_single_tensor_adamw`, no amsgrad / maximize),
+    in place on lists of tensors: decoupled decay, moment updates, bias corrections taken in Python doubles."""
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    step_size = lr / bc1
+    bc2_sqrt = math.sqrt(bc2)
+    for p, g, m, v in zip(params, grads, exp_avgs, exp_avg_sqs):
+        p.mul_(1 - lr * weight_decay)
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (v.sqrt() / bc2_sqrt).add_(eps)
+        p.addcdiv_(m, denom, value=-step_size)
+
+
+# --------------------------------------------------------------------------------------------
 # utils/training.py:55-77  one optimisation step's model work (forward + loss + backward)
 # --------------------------------------------------------------------------------------------
 def forward_loss_backward(model: MaskEmbdMultiMPN, data, loss: str = "mse", dropout_masks=None):

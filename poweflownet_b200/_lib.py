@@ -73,6 +73,11 @@ SIGNATURES = {
     "pfn_masked_l2_scratch_bytes": (c_sz, [c_i64]),
     "pfn_masked_l2_fwd_bwd": (C.c_int, [c_f32p, c_f32p, C.c_void_p, c_i64, C.c_int, C.c_float, c_f32p, c_f32p, C.c_void_p,
                                         C.c_void_p]),
+    "pfn_power_imbalance_scratch_bytes": (c_sz, [c_i64]),
+    "pfn_power_imbalance_fwd_bwd": (C.c_int, [c_f32p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_f32p, c_f32p, c_i64,
+                                              C.c_void_p, C.c_void_p]),
+    "pfn_adamw_step": (C.c_int, [c_i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, C.c_double, c_i64, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -121,3 +121,42 @@ class EngineEmulation:
         grads["mask_embd.0.bias"] = dt1.sum(0)
         self.dx0 = g
         return grads
+
+
+def power_imbalance_emulation(x, undirected, stats):
+    """The arithmetic of csrc/loss_optim.cu (k_pi_node / k_pi_final / k_pi_grad) in plain torch: the loss and the
+    HAND-DERIVED gradient w.r.t. the normalised predictions.  `undirected` = the (doubled) branch list the loss works
+    on; `stats` = (xymean, xystd, edgemean, edgestd).  Returns (loss, dx [N, 4])."""
+    import math
+    xm, xs, em, es = [s.reshape(-1).to(x.dtype) for s in stats]
+    ei, ea = undirected
+    n = x.size(0)
+    k = 1 / 180. * math.pi
+    vm = x[:, 0] * xs[0] + xm[0]
+    va = k * (x[:, 1] * xs[1] + xm[1])
+    c, s = torch.cos(va), torch.sin(va)
+    e, f = vm * c, vm * s
+    r, xx = ea[:, 0].to(x.dtype) * es[0] + em[0], ea[:, 1].to(x.dtype) * es[1] + em[1]
+    den = r * r + xx * xx
+    g, b = r / den, -xx / den
+    i, j = ei[0], ei[1]
+    ei_, fi_, ej_, fj_ = e[i], f[i], e[j], f[j]
+    cross = fi_ * ej_ - ei_ * fj_
+    P = g * (ei_ * ej_ - ei_ * ei_ + fi_ * fj_ - fi_ * fi_) + b * cross
+    Q = g * cross + b * (-ei_ * ej_ + ei_ * ei_ - fi_ * fj_ + fi_ * fi_)
+    agg = seg_sum(torch.stack([P, Q], dim=1), i, n)
+    dp = -agg[:, 0] + (x[:, 2] * xs[2] + xm[2])
+    dq = -agg[:, 1] + (x[:, 3] * xs[3] + xm[3])
+    loss = (dp * dp + dq * dq).sum() / n
+    # k_pi_grad: a = d loss / d aggregated of the aggregating bus of each branch
+    ap, aq = (-2.0 * dp / n)[i], (-2.0 * dq / n)[i]
+    p_e, p_f = g * (ej_ - 2 * ei_) - b * fj_, g * (fj_ - 2 * fi_) + b * ej_
+    q_e, q_f = -g * fj_ + b * (2 * ei_ - ej_), g * ej_ + b * (2 * fi_ - fj_)
+    own = torch.stack([ap * p_e + aq * q_e, ap * p_f + aq * q_f], dim=1)          # row of the CSR by source
+    pj_e, pj_f = g * ei_ + b * fi_, g * fi_ - b * ei_
+    far = torch.stack([ap * pj_e + aq * pj_f, ap * pj_f - aq * pj_e], dim=1)        # row of the CSR by target
+    d = seg_sum(own, i, n) + seg_sum(far, j, n)
+    de, df = d[:, 0], d[:, 1]
+    dvm, dva = de * c + df * s, -de * f + df * e
+    dx = torch.stack([dvm * xs[0], dva * k * xs[1], 2.0 * dp / n * xs[2], 2.0 * dq / n * xs[3]], dim=1)
+    return loss, dx

@@ -237,6 +237,30 @@ PFN_API int pfn_adamw_step(int64_t n_tensors, float* const* params, const float*
                    float* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, void* stream);
 
+/* ---- mini-batch assembly from a device-resident dataset: datasets/PowerFlowData.py:171-217 (`process`) + :119-140
+ *      (`_normalize_dataset`) + PyG `Batch.from_data_list` (train.py:90, utils/training.py:55-56), in one pass.
+ *      A dataset is the concatenation of up to 8 cases (`--case mixed`, :151-155); each case keeps the reference's RAW
+ *      arrays in device memory: node_features [S, n, 6] = (index, type, Vm, Va, P, Q), edge_features [S, E, 4] =
+ *      (from, to, r, x), fp32.  sample_ids: DEVICE int64 [batch], indices into the concatenation.  n_total / e_total:
+ *      node / branch totals of the batch (the caller sized the outputs with them; checked on the device).
+ *      norm: HOST array of 12 floats = xymean[4], xystd[4] + 1e-7, edgemean[2], edgestd[2] + 1e-7, or NULL for
+ *      normalize=False.  random_bus_type_seed != 0 applies the `random_bus_type` transform (:36-40; bus_type is unused
+ *      by the model).  Outputs (device): x, y [N, 4] f32; bus_type [N], pred_mask [N, 4], batch_vec [N], ptr [batch + 1]
+ *      int64; edge_index [2, E] int64 (node offsets added); edge_attr [E, 2] f32.
+ *      scratch: at least pfn_batch_assemble_scratch_bytes(batch).  pfn_batch_assemble_status reads back (synchronising)
+ *      whether a sample id was out of range or the totals disagreed (flag != 0: outputs were not written). ---------- */
+typedef struct pfn_dataset_case {
+  const float* node_features;
+  const float* edge_features;
+  int64_t n_samples, n_nodes, n_edges;
+} pfn_dataset_case;
+PFN_API size_t pfn_batch_assemble_scratch_bytes(int64_t batch);
+PFN_API int pfn_batch_assemble(const pfn_dataset_case* cases, int n_cases, const int64_t* sample_ids, int64_t batch,
+                       int64_t n_total, int64_t e_total, const float* norm, uint64_t random_bus_type_seed,
+                       float* x, float* y, int64_t* bus_type, int64_t* pred_mask, int64_t* edge_index,
+                       float* edge_attr, int64_t* batch_vec, int64_t* ptr, void* scratch, void* stream);
+PFN_API int pfn_batch_assemble_status(const void* scratch, int64_t batch, int32_t* host_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,6 +279,69 @@ def adamw_step(params, grads, exp_avgs, exp_avg_sqs, step, lr, beta1=0.9, beta2=
 
 
 # --------------------------------------------------------------------------------------------
+# datasets/PowerFlowData.py:119-140,171-217 + PyG collation  
+# --------------------------------------------------------------------------------------------
+BUS_TYPE_MASK = ((0, 0, 1, 1), (0, 1, 0, 1), (1, 1, 0, 0))  # datasets/PowerFlowData.py:71-74
+
+
+def process_split(raw_cases, split, task):
+    """datasets/PowerFlowData.py:171-217 (`process`) for one task: `raw_cases` = [(edge_features [S, E, 4],
+    node_features [S, n, 6]), ...] in `raw_file_names` order; every case is cut with `torch.split` by
+    `[int(S * f) for f in split]` and the per-case sample lists of the task are concatenated (:214).  Returns a list
+    of dicts with the `Data` fields."""
+    idx = {"train": 0, "val": 1, "test": 2}[task]
+    table = torch.tensor(BUS_TYPE_MASK)
+    samples = []
+    for edge_features, node_features in raw_cases:
+        edge_features, node_features = edge_features.float(), node_features.float()
+        split_len = [int(len(node_features) * f) for f in split]
+        e = torch.split(edge_features, split_len, dim=0)[idx]
+        nf = torch.split(node_features, split_len, dim=0)[idx]
+        y = nf[:, :, 2:]
+        bus_type = nf[:, :, 1].type(torch.long)
+        mask = table[bus_type]
+        x = y.clone() * (1. - mask)
+        for i in range(len(x)):
+            samples.append(dict(x=x[i], y=y[i], bus_type=bus_type[i], pred_mask=mask[i],
+                                edge_index=e[i, :, 0:2].T.to(torch.long), edge_attr=e[i, :, 2:]))
+    return samples
+
+
+def dataset_stats(samples):
+    """datasets/PowerFlowData.py:126-138: mean / std (unbiased) over every bus / branch of the split."""
+    y = torch.cat([s["y"] for s in samples], dim=0)
+    ea = torch.cat([s["edge_attr"] for s in samples], dim=0)
+    return (torch.mean(y, dim=0, keepdim=True), torch.std(y, dim=0, keepdim=True),
+            torch.mean(ea, dim=0, keepdim=True), torch.std(ea, dim=0, keepdim=True))
+
+
+def collate_batch(samples, ids, stats=None):
+    """`_normalize_dataset` (:132-139, when `stats` is given) + PyG `Batch.from_data_list` of `samples[ids]`: tensors
+    concatenated on dim 0, `edge_index` on dim 1 with cumulative node offsets, plus `batch` and `ptr`."""
+    out = {k: [] for k in ("x", "y", "bus_type", "pred_mask", "edge_index", "edge_attr", "batch")}
+    ptr = [0]
+    for b, i in enumerate(int(v) for v in ids):
+        s = samples[i]
+        x, y, ea = s["x"], s["y"], s["edge_attr"]
+        if stats is not None:
+            xymean, xystd, edgemean, edgestd = stats
+            x = (x - xymean) / (xystd + 0.0000001)
+            y = (y - xymean) / (xystd + 0.0000001)
+            ea = (ea - edgemean) / (edgestd + 0.0000001)
+        out["x"].append(x)
+        out["y"].append(y)
+        out["edge_attr"].append(ea)
+        out["bus_type"].append(s["bus_type"])
+        out["pred_mask"].append(s["pred_mask"])
+        out["edge_index"].append(s["edge_index"] + ptr[-1])
+        out["batch"].append(torch.full((x.size(0),), b, dtype=torch.long))
+        ptr.append(ptr[-1] + x.size(0))
+    res = {k: torch.cat(v, dim=1 if k == "edge_index" else 0) for k, v in out.items()}
+    res["ptr"] = torch.tensor(ptr, dtype=torch.long)
+    return res
+
+
+# --------------------------------------------------------------------------------------------
 # utils/training.py:55-77  one optimisation step's model work (forward + loss + backward)
 # --------------------------------------------------------------------------------------------
 def forward_loss_backward(model: MaskEmbdMultiMPN, data, loss: str = "mse", dropout_masks=None):

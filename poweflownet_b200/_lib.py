@@ -30,6 +30,11 @@ class MpnDesc(C.Structure):
                 ("dropout_rate", C.c_float), ("reserved", C.c_int32)]
 
 
+class DatasetCase(C.Structure):
+    _fields_ = [("node_features", C.c_void_p), ("edge_features", C.c_void_p), ("n_samples", C.c_int64),
+                ("n_nodes", C.c_int64), ("n_edges", C.c_int64)]
+
+
 # name -> (restype, argtypes); mirrors include/pfn_b200.h one to one
 SIGNATURES = {
     "pfn_version": (C.c_char_p, []),
@@ -76,6 +81,11 @@ SIGNATURES = {
     "pfn_power_imbalance_scratch_bytes": (c_sz, [c_i64]),
     "pfn_power_imbalance_fwd_bwd": (C.c_int, [c_f32p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_f32p, c_f32p, c_i64,
                                               C.c_void_p, C.c_void_p]),
+    "pfn_batch_assemble_scratch_bytes": (c_sz, [c_i64]),
+    "pfn_batch_assemble": (C.c_int, [C.POINTER(DatasetCase), C.c_int, C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, c_u64,
+                                     c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
+    "pfn_batch_assemble_status": (C.c_int, [C.c_void_p, c_i64, C.POINTER(C.c_int32), C.c_void_p]),
     "pfn_adamw_step": (C.c_int, [c_i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                  C.c_double, C.c_double, C.c_double, c_i64, C.c_void_p]),
 }

@@ -1,0 +1,154 @@
+"""Device-resident dataset + on-GPU batch assembly (`poweflownet_b200.datasets.PowerFlowData`, `pfn_batch_assemble`)
+against the fixtures produced by the reference's own datasets/PowerFlowData.py + DataLoader, and against the CPU oracle
+at BASELINE config 2 size.  Every tensor of the batch must be bit-exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import common
+import make_golden_dataset as mgd
+from oracle import pfn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _raws(gold):
+    return [(gold["raw"][tag]["edge_features"], gold["raw"][tag]["node_features"]) for tag in gold["raw"]]
+
+
+def _dataset(gold, task, **kw):
+    from poweflownet_b200.datasets import PowerFlowData
+    return PowerFlowData(case=gold["meta"]["case"], split=mgd.SPLIT, task=task, device=DEV, raw=_raws(gold), **kw)
+
+
+def _same(batch, want):
+    for f in mgd.FIELDS:
+        got = getattr(batch, f).cpu()
+        assert got.dtype == want[f].dtype and got.shape == want[f].shape, f
+        assert torch.equal(got, want[f]), f
+
+
+@pytest.mark.parametrize("name", list(mgd.DATASET_CASES))
+def test_batches_match_the_reference_loader(name):
+    torch.set_num_threads(1)
+    gold = torch.load(mgd.dataset_golden_path(name), weights_only=False)
+    for task, sp in gold["splits"].items():
+        ds = _dataset(gold, task)
+        assert len(ds) == sp["len"] and ds.get_data_dimensions() == tuple(sp["dims"])
+        for a, b in zip(ds.get_data_means_stds(), sp["stats"]):
+            assert a.shape == b.shape and torch.equal(a, b)
+        for bt in sp["batches"]:
+            _same(ds.batch(bt["ids"]), bt)
+        bs = gold["meta"]["batch_size"]
+        loaded = list(ds.loader(batch_size=bs, shuffle=False))
+        assert len(loaded) == len(sp["batches"]) == ds.num_batches(bs)
+        for got, bt in zip(loaded, sp["batches"]):
+            _same(got, bt)
+    tr = gold["splits"]["train"]["stats"]
+    ds = _dataset(gold, "val", xymean=tr[0], xystd=tr[1], edgemean=tr[2], edgestd=tr[3])
+    _same(ds.batch(gold["val_with_train_stats"]["ids"]), gold["val_with_train_stats"])
+
+
+def test_arbitrary_sample_orders_and_repeats_mixed_sizes():
+    gold = torch.load(mgd.dataset_golden_path("ds_mixed"), weights_only=False)
+    ds = _dataset(gold, "train")
+    samples = O.process_split(_raws(gold), mgd.SPLIT, "train")
+    stats = gold["splits"]["train"]["stats"]
+    for ids in ([14, 0, 7, 7, 3, 9, 1], [5], list(range(14, -1, -1))):
+        want = O.collate_batch(samples, ids, stats)
+        _same(ds.batch(ids), want)
+    raw = _dataset(gold, "train", normalize=False)
+    _same(raw.batch([2, 11, 4]), O.collate_batch(samples, [2, 11, 4], None))
+
+
+def test_shuffled_loader_visits_every_sample_once():
+    gold = torch.load(mgd.dataset_golden_path("ds_case14"), weights_only=False)
+    ds = _dataset(gold, "train")
+    g = torch.Generator().manual_seed(0)
+    ys = torch.cat([b.y.cpu() for b in ds.loader(batch_size=6, shuffle=True, generator=g)])
+    everything = ds.batch(list(range(len(ds)))).y.cpu()
+    assert ys.shape == everything.shape and not torch.equal(ys, everything)
+    key = lambda t: sorted(map(tuple, t.reshape(-1, 14 * 4).tolist()))  # noqa: E731 -- one row per graph
+    assert key(ys) == key(everything)
+    assert sum(1 for _ in ds.loader(batch_size=6, drop_last=True)) == len(ds) // 6
+
+
+def test_random_bus_type_transform_touches_only_bus_type():
+    gold = torch.load(mgd.dataset_golden_path("ds_case14"), weights_only=False)
+    plain, rnd = _dataset(gold, "train"), _dataset(gold, "train", random_bus_type=True)
+    ids = list(range(16))
+    a, b, c = plain.batch(ids), rnd.batch(ids, seed=1), rnd.batch(ids, seed=2)
+    for f in mgd.FIELDS:
+        if f != "bus_type":
+            assert torch.equal(getattr(a, f), getattr(b, f)), f
+    assert set(b.bus_type.unique().tolist()) == {0, 1} and not torch.equal(b.bus_type, c.bus_type)
+    assert abs(float(b.bus_type.float().mean()) - 0.5) < 0.15
+    assert torch.equal(b.bus_type, rnd.batch(ids, seed=1).bus_type)
+
+
+def test_bad_sample_ids_are_refused_on_host_and_device():
+    from poweflownet_b200._lib import lib
+    gold = torch.load(mgd.dataset_golden_path("ds_case14"), weights_only=False)
+    ds = _dataset(gold, "train")
+    with pytest.raises(IndexError):
+        ds.batch([0, len(ds)])
+    with pytest.raises(ValueError):
+        ds.batch([])
+    # device-side guard: ids handed over on the GPU that disagree with the host's list leave the outputs untouched
+    lying = torch.tensor([0, 10 ** 6], dtype=torch.int64, device=DEV)
+    out = ds.batch([0, 1], ids_device=lying)
+    torch.cuda.synchronize()
+    flag = C.c_int32(0)
+    scratch = torch.empty(int(lib().pfn_batch_assemble_scratch_bytes(2)), dtype=torch.uint8, device=DEV)
+    rc = lib().pfn_batch_assemble(ds._cases, 1, lying.data_ptr(), 2, 28, 40, ds._norm, 0, out.x.data_ptr(), out.y.data_ptr(),
+                                  out.bus_type.data_ptr(), out.pred_mask.data_ptr(), out.edge_index.data_ptr(),
+                                  out.edge_attr.data_ptr(), out.batch.data_ptr(), out.ptr.data_ptr(), scratch.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert lib().pfn_batch_assemble_status(scratch.data_ptr(), 2, C.byref(flag), torch.cuda.current_stream().cuda_stream) == 0
+    assert flag.value == 1
+
+
+def test_reads_the_reference_file_layout(tmp_path):
+    from poweflownet_b200.datasets import PowerFlowData
+    gold = torch.load(mgd.dataset_golden_path("ds_mixed"), weights_only=False)
+    os.makedirs(tmp_path / "raw")
+    for tag, g in gold["raw"].items():
+        np.save(tmp_path / "raw" / f"case{tag}_edge_features.npy", g["edge_features"].numpy().astype(np.float64))
+        np.save(tmp_path / "raw" / f"case{tag}_node_features.npy", g["node_features"].numpy().astype(np.float64))
+    ds = PowerFlowData(root=str(tmp_path), case="mixed", split=mgd.SPLIT, task="test", device=DEV)
+    sp = gold["splits"]["test"]
+    assert len(ds) == sp["len"]
+    for bt in sp["batches"]:
+        _same(ds.batch(bt["ids"]), bt)
+    with pytest.raises(RuntimeError):
+        PowerFlowData(case="14", split=mgd.SPLIT, device="cpu", raw=_raws(gold))
+
+
+def test_full_size_batch_feeds_the_model():
+    """BASELINE config 2: 128 graphs of case118v2 drawn from a 250-sample split; bit-exact against the oracle's collation,
+    and the tiled forward accepts the assembled batch (its `ptr` marks 118-bus graphs)."""
+    from poweflownet_b200.datasets import PowerFlowData
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    e, nf = mgd.synthetic_raw(118, 186, 500, seed=3)
+    raws = [(torch.from_numpy(e), torch.from_numpy(nf))]
+    ds = PowerFlowData(case="118v2", split=mgd.SPLIT, task="train", device=DEV, raw=raws)
+    assert len(ds) == 250
+    samples = O.process_split(raws, mgd.SPLIT, "train")
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randperm(250, generator=g)[:128]
+    batch = ds.batch(ids)
+    want = O.collate_batch(samples, ids, ds.get_data_means_stds())
+    _same(batch, want)
+    kw = common.model_kwargs("case118_standard")
+    model = common.load_seeded(MaskEmbdMultiMPN(**kw)).to(DEV).eval()
+    with torch.no_grad():
+        out = model(batch)
+    ref = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).eval()
+    with torch.no_grad():
+        want_out = ref(common.GraphBatch(**want))
+    assert max(common.rel_err(out.cpu(), want_out)) < 1e-5

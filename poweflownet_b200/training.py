@@ -208,3 +208,47 @@ def train_step(model: MaskEmbdMultiMPN, host_batch, device, loss: str = "mse", t
     else:
         raise ValueError(f"unknown loss {loss!r}")
     return float(val.item())
+
+
+def train_epoch(model: MaskEmbdMultiMPN, loader, loss_fn, optimizer, device) -> float:
+    """`utils/training.py:30-80` with the same arguments and the same loss dispatch (:61-72), on the library's kernels:
+
+    * `torch.nn.MSELoss()` (train.py:103) and `Masked_L2_loss` (the parser default) take the fused
+      forward + loss + backward steps above (no autograd tape);
+    * `PowerImbalance` gets `out * pred_mask + x * (1 - pred_mask)` (:63-68), `MixedMSEPoweImbalance` gets `out` and `y`
+      (:69-70) -- both through `model(data)` + `loss.backward()`;
+    * any other callable is applied as `loss_fn(out, data.y)` (:72).
+
+    The reference reads `loss.item()` every step (:77, one stream synchronisation per batch); here the running sum stays
+    on the device and is read once per epoch.  The return value is the reference's: sum(loss * len(data)) /
+    sum(len(data)), where `len(data)` is the number of stored attributes of the batch (PyG `BaseData.__len__`), i.e. an
+    unweighted mean over batches.  `loader`: any iterable of batches (`datasets.PowerFlowData.loader`, a PyG DataLoader)."""
+    from .losses import Masked_L2_loss, MixedMSEPoweImbalance, PowerImbalance
+    model = model.to(device)
+    total, num_samples = None, 0
+    model.train()
+    for data in loader:
+        data = data.to(device)
+        optimizer.zero_grad()
+        if isinstance(loss_fn, torch.nn.MSELoss) and loss_fn.reduction == "mean":
+            loss = fused_mse_step(model, data).view(())
+        elif isinstance(loss_fn, Masked_L2_loss):
+            loss = fused_masked_l2_step(model, data, loss_fn.regularize, float(loss_fn.regcoeff)).view(())
+        else:
+            out = model(data)
+            if isinstance(loss_fn, PowerImbalance):
+                # "have to mask out the non-predicted values, otherwise the network can learn to predict full-zeros"
+                masked_out = out * data.pred_mask + data.x * (1 - data.pred_mask)
+                loss = loss_fn(masked_out, data.edge_index, data.edge_attr)
+            elif isinstance(loss_fn, MixedMSEPoweImbalance):
+                loss = loss_fn(out, data.edge_index, data.edge_attr, data.y)
+            else:
+                loss = loss_fn(out, data.y)
+            loss.backward()
+        optimizer.step()
+        num_samples += len(data)
+        weighted = loss.detach() * len(data)
+        total = weighted if total is None else total + weighted
+    if total is None:
+        raise ZeroDivisionError("train_epoch: empty loader")  # the reference divides by num_samples == 0
+    return float(total.item()) / num_samples

@@ -152,3 +152,50 @@ def test_full_size_batch_feeds_the_model():
     with torch.no_grad():
         want_out = ref(common.GraphBatch(**want))
     assert max(common.rel_err(out.cpu(), want_out)) < 1e-5
+
+
+@pytest.mark.parametrize("loss_name", ["mse", "masked_l2", "power_imbalance", "mixed"])
+def test_train_epoch_matches_the_reference_loop(loss_name):
+    """`training.train_epoch` (utils/training.py:30-80) over the device-resident loader with the one-launch AdamW,
+    against the same epoch on the CPU: oracle model, oracle losses, torch.optim.AdamW, the reference's loop."""
+    import torch.nn.functional as F
+    from poweflownet_b200 import losses
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    from poweflownet_b200.optim import FusedAdamW
+    from poweflownet_b200.training import train_epoch
+    torch.set_num_threads(1)
+    gold = torch.load(mgd.dataset_golden_path("ds_case14"), weights_only=False)
+    ds = _dataset(gold, "train")
+    stats = ds.get_data_means_stds()
+    kw = common.model_kwargs("case14_small")
+    kw["dropout_rate"] = 0.0
+    # CPU: the reference's loop, restated
+    ref = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
+    opt = torch.optim.AdamW(ref.parameters(), lr=1e-3, foreach=False)
+    samples = O.process_split(_raws(gold), mgd.SPLIT, "train")
+    ref_losses, n_attr = [], 8
+    for bt in gold["splits"]["train"]["batches"]:
+        data = common.GraphBatch(**O.collate_batch(samples, bt["ids"], gold["splits"]["train"]["stats"]))
+        opt.zero_grad()
+        out = ref(data)
+        if loss_name == "mse":
+            loss = F.mse_loss(out, data.y)
+        elif loss_name == "masked_l2":
+            loss = O.masked_l2_loss(out, data.y, data.pred_mask)
+        elif loss_name == "power_imbalance":
+            loss = O.power_imbalance(out * data.pred_mask + data.x * (1 - data.pred_mask), data.edge_index, data.edge_attr, *stats)
+        else:
+            loss = O.mixed_mse_power_imbalance(out, data.edge_index, data.edge_attr, data.y, stats, alpha=0.9)
+        loss.backward()
+        opt.step()
+        ref_losses.append(float(loss.detach()))
+    want = sum(v * n_attr for v in ref_losses) / (n_attr * len(ref_losses))
+    # GPU
+    model = common.load_seeded(MaskEmbdMultiMPN(**kw))
+    fn = {"mse": torch.nn.MSELoss(), "masked_l2": losses.Masked_L2_loss(),
+          "power_imbalance": losses.PowerImbalance(*stats),
+          "mixed": losses.MixedMSEPoweImbalance(*stats, alpha=0.9)}[loss_name]
+    opt2 = FusedAdamW(model.parameters(), lr=1e-3)
+    got = train_epoch(model, ds.loader(batch_size=16, shuffle=False), fn, opt2, DEV)
+    assert abs(got - want) <= 2e-4 * abs(want), (got, want, ref_losses)
+    assert next(model.parameters()).is_cuda and model.training

@@ -116,6 +116,26 @@ def synthetic_batch(case: str = "118v2", batch_size: int = 128, seed: int = 1234
         edge_attr=torch.cat(eas).contiguous(), batch=torch.cat(bs), ptr=torch.tensor(ptr, dtype=torch.long))
 
 
+def synthetic_raw_case(case: str = "118v2", samples: int = 64, seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(edge_features [S, E, 4] = (from, to, r, x), node_features [S, n, 6] = (index, type, Vm, Va, P, Q)), fp32, in the
+    layout of the reference's raw files (datasets/PowerFlowData.py:58-61,178-204): one fixed topology, per-sample
+    branch parameters and bus states.  Input for `datasets.PowerFlowData(raw=[...])` when no dataset can be downloaded."""
+    n, e_raw = CASES[case]
+    g = torch.Generator().manual_seed(seed)
+    edges = torch.zeros((samples, e_raw, 4))
+    edges[:, :, :2] = synthetic_topology(n, e_raw).T.float()
+    edges[:, :, 2:] = (0.05 + 0.02 * torch.randn((samples, e_raw, 2), generator=g)).abs() + 1e-3
+    nodes = torch.zeros((samples, n, 6))
+    nodes[:, :, 0] = torch.arange(n).float()
+    bt = torch.where(torch.rand(n, generator=g) < 0.45, 1, 2)
+    bt[0] = 0
+    nodes[:, :, 1] = bt.float()
+    nodes[:, :, 2] = 1.0 + 0.02 * torch.randn((samples, n), generator=g)
+    nodes[:, :, 3] = 5.0 * torch.randn((samples, n), generator=g)
+    nodes[:, :, 4:] = 0.5 * torch.randn((samples, n, 2), generator=g)
+    return edges, nodes
+
+
 def shard_batch(batch: GraphBatch, rank: int, world: int) -> GraphBatch:
     """Contiguous block of whole graphs for `rank` (split at `ptr` boundaries, balanced by branch
     count so that a 6470-bus graph is not weighed like a 14-bus one)."""

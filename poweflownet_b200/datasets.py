@@ -100,9 +100,11 @@ class PowerFlowData:
         return self.xymean[:1, :], self.xystd[:1, :], self.edgemean[:1, :], self.edgestd[:1, :]
 
     # -- batches ----------------------------------------------------------------------------------
-    def batch(self, ids, ids_device: Optional[torch.Tensor] = None, seed: Optional[int] = None) -> GraphBatch:
+    def batch(self, ids, ids_device: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+              out: Optional[GraphBatch] = None) -> GraphBatch:
         """The PyG `Batch` of samples `ids` (host sequence / tensor), assembled on the device.  `ids_device`: the same
-        ids already on the GPU (int64), to skip the copy."""
+        ids already on the GPU (int64), to skip the copy.  `out`: a batch of the same shape to overwrite (the static
+        input buffers of a captured CUDA graph, `training.GraphedEpochs`)."""
         ids_host = np.asarray(torch.as_tensor(ids).cpu().numpy() if torch.is_tensor(ids) else ids, dtype=np.int64).reshape(-1)
         b = int(ids_host.size)
         if b == 0:
@@ -116,10 +118,14 @@ class PowerFlowData:
             if ids_device is None:
                 ids_device = torch.from_numpy(ids_host).to(dev, non_blocking=True)
             f32, i64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int64, device=dev)
-            out = GraphBatch(x=torch.empty((n_total, 4), **f32), y=torch.empty((n_total, 4), **f32),
-                             bus_type=torch.empty((n_total,), **i64), pred_mask=torch.empty((n_total, 4), **i64),
-                             edge_index=torch.empty((2, e_total), **i64), edge_attr=torch.empty((e_total, 2), **f32),
-                             batch=torch.empty((n_total,), **i64), ptr=torch.empty((b + 1,), **i64))
+            if out is None:
+                out = GraphBatch(x=torch.empty((n_total, 4), **f32), y=torch.empty((n_total, 4), **f32),
+                                 bus_type=torch.empty((n_total,), **i64), pred_mask=torch.empty((n_total, 4), **i64),
+                                 edge_index=torch.empty((2, e_total), **i64), edge_attr=torch.empty((e_total, 2), **f32),
+                                 batch=torch.empty((n_total,), **i64), ptr=torch.empty((b + 1,), **i64))
+            elif (tuple(out.x.shape) != (n_total, 4) or tuple(out.edge_index.shape) != (2, e_total) or out.ptr.numel() != b + 1
+                  or out.x.device != dev or not all(getattr(out, f).is_contiguous() for f in GraphBatch.__dataclass_fields__)):
+                raise ValueError(f"`out` does not have the shape of this batch (N={n_total}, E={e_total}, graphs={b})")
             scratch = torch.empty(int(lib().pfn_batch_assemble_scratch_bytes(b)), dtype=torch.uint8, device=dev)
             bus_seed = 0
             if self.random_bus_type:

@@ -18,6 +18,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if lr < 0.0 or eps < 0.0 or weight_decay < 0.0 or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
             raise ValueError(f"invalid AdamW hyper-parameters: lr={lr} betas={betas} eps={eps} weight_decay={weight_decay}")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._tables = {}  # param-group index -> (data_ptr key, ctypes pointer tables, element counts)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -25,45 +26,55 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
-            ps, gs, ms, vs = [], [], [], []
-            step = None
+        for gi, group in enumerate(self.param_groups):
+            by_step = {}
             for p in group["params"]:
-                if p.grad is None:
+                g = p.grad
+                if g is None:
                     continue
-                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32:
-                    raise RuntimeError("FusedAdamW: CUDA float32 parameters and gradients only (no CPU fallback)")
-                if p.grad.is_sparse:
-                    raise RuntimeError("FusedAdamW does not support sparse gradients")
-                if not p.is_contiguous():
-                    raise RuntimeError("FusedAdamW: parameters must be contiguous")
                 st = self.state[p]
                 if len(st) == 0:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)  # host scalar tensor, as torch keeps it
+                    self._check(p, g)
+                    st["step"] = 0.0  # a Python number: torch's AdamW converts it on load (`__setstate__`)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                k = int(st["step"].item())
-                if step is None:
-                    step = k
-                elif step != k:  # parameters that joined later: their own launch keeps the bias corrections right
-                    self._launch([p], [p.grad.contiguous()], [st["exp_avg"]], [st["exp_avg_sq"]], group, k)
-                    continue
-                ps.append(p)
-                gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
-                ms.append(st["exp_avg"])
-                vs.append(st["exp_avg_sq"])
-            if ps:
-                self._launch(ps, gs, ms, vs, group, step)
+                k = st["step"] + 1  # stays a tensor when the state came from torch.optim.AdamW
+                st["step"] = k
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                by_step.setdefault(int(k), []).append((p, g, st["exp_avg"], st["exp_avg_sq"]))
+            # parameters that joined later carry their own step count: one launch per distinct count keeps the bias
+            # corrections right (normally there is exactly one)
+            for k, items in by_step.items():
+                self._launch(gi, items, group, k)
         return loss
 
     @staticmethod
-    def _launch(ps, gs, ms, vs, group, step):
-        n = len(ps)
-        ptrs = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
-        numel = (C.c_int64 * n)(*[t.numel() for t in ps])
+    def _check(p, g):
+        if not p.is_cuda or p.dtype != torch.float32 or g.dtype != torch.float32:
+            raise RuntimeError("FusedAdamW: CUDA float32 parameters and gradients only (no CPU fallback)")
+        if g.is_sparse:
+            raise RuntimeError("FusedAdamW does not support sparse gradients")
+        if not p.is_contiguous():
+            raise RuntimeError("FusedAdamW: parameters must be contiguous")
+
+    def _launch(self, gi, items, group, step):
+        n = len(items)
+        key = tuple(t.data_ptr() for it in items for t in it)
+        cached = self._tables.get(gi)
+        if cached is None or cached[0] != key:
+            # pointer tables are rebuilt only when a tensor moved (with static gradient buffers -- CUDA-graph replays,
+            # `zero_grad(set_to_none=False)` -- never)
+            for p, g, _, _ in items:
+                self._check(p, g)
+            cols = list(zip(*items))
+            tabs = [(C.c_void_p * n)(*[t.data_ptr() for t in col]) for col in cols]
+            numel = (C.c_int64 * n)(*[t.numel() for t in cols[0]])
+            cached = (key, tabs, numel)
+            self._tables[gi] = cached
+        _, tabs, numel = cached
         beta1, beta2 = group["betas"]
-        with torch.cuda.device(ps[0].device):
-            check(lib().pfn_adamw_step(n, ptrs(ps), ptrs(gs), ptrs(ms), ptrs(vs), numel, float(group["lr"]), float(beta1),
+        with torch.cuda.device(items[0][0].device):
+            check(lib().pfn_adamw_step(n, tabs[0], tabs[1], tabs[2], tabs[3], numel, float(group["lr"]), float(beta1),
                                        float(beta2), float(group["eps"]), float(group["weight_decay"]), int(step),
                                        torch.cuda.current_stream().cuda_stream), "pfn_adamw_step")

@@ -199,6 +199,40 @@ class PipelinedMSESteps:
         return loss
 
 
+class GraphedEpochs:
+    """Whole optimisation epochs at a fixed mini-batch shape with (almost) no host work per step: the sample ids of an
+    epoch go to the GPU once, `pfn_batch_assemble` writes every mini-batch straight INTO the static input buffers of a
+    captured forward + MSE + backward graph (`GraphedMSEStep`), the graph is replayed, and the optimizer (meant for
+    `optim.FusedAdamW`: one launch, pointer tables cached because the gradient buffers are static) follows.  The loss
+    sum stays on the device; one read-back per epoch.  The `train_epoch` loop of utils/training.py:30-80 for
+    `--train_loss_fn mse_loss` on a single-case dataset (all graphs of one size; incomplete last batches are dropped)."""
+
+    def __init__(self, model: MaskEmbdMultiMPN, dataset, batch_size: int, optimizer, total_count: Optional[int] = None):
+        if batch_size > len(dataset):
+            raise ValueError("batch_size exceeds the dataset")
+        self.model, self.dataset, self.batch_size, self.optimizer = model, dataset, int(batch_size), optimizer
+        model.train()
+        self.step = GraphedMSEStep(model, dataset.batch(list(range(batch_size))), total_count)
+        self.n_attr = len(self.step.static)
+
+    def run_epoch(self, shuffle: bool = True, generator: Optional[torch.Generator] = None) -> float:
+        ds, bs = self.dataset, self.batch_size
+        order = torch.randperm(len(ds), generator=generator) if shuffle else torch.arange(len(ds))
+        order_dev = order.to(self.step.device, non_blocking=True)
+        order_host = order.numpy()
+        total = None
+        steps = len(ds) // bs
+        self.model.train()
+        for k in range(steps):
+            ds.batch(order_host[k * bs:(k + 1) * bs], ids_device=order_dev[k * bs:(k + 1) * bs], out=self.step.static)
+            loss = self.step(None)  # replay; parameter .grads are the graph's static buffers
+            self.optimizer.step()
+            total = loss.clone() if total is None else total + loss  # `loss` is a static tensor of the graph
+        if total is None:
+            raise ZeroDivisionError("GraphedEpochs.run_epoch: no full batch")
+        return float(total.item()) / steps
+
+
 def train_step(model: MaskEmbdMultiMPN, host_batch, device, loss: str = "mse", total_count: Optional[int] = None):
     """End-to-end step from HOST memory: H2D of the batch (pinned -> non_blocking), forward, loss, backward,
     and the device->host read of the loss (utils/training.py:56-77 minus optimizer.step)."""

@@ -199,3 +199,33 @@ def test_train_epoch_matches_the_reference_loop(loss_name):
     got = train_epoch(model, ds.loader(batch_size=16, shuffle=False), fn, opt2, DEV)
     assert abs(got - want) <= 2e-4 * abs(want), (got, want, ref_losses)
     assert next(model.parameters()).is_cuda and model.training
+
+
+def test_graphed_epochs_equal_the_eager_loop():
+    """`training.GraphedEpochs` (assembly into the static buffers of a captured step + replay + AdamW) walks the same
+    trajectory as `training.train_epoch` on the same sample order."""
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    from poweflownet_b200.optim import FusedAdamW
+    from poweflownet_b200.training import GraphedEpochs, train_epoch
+    gold = torch.load(mgd.dataset_golden_path("ds_case14"), weights_only=False)
+    ds = _dataset(gold, "train")  # 20 samples
+    kw = common.model_kwargs("case14_small")
+    kw["dropout_rate"] = 0.0
+    runs = []
+    for graphed in (False, True):
+        model = common.load_seeded(MaskEmbdMultiMPN(**kw)).to(DEV)
+        opt = FusedAdamW(model.parameters(), lr=1e-3)
+        if graphed:
+            runner = GraphedEpochs(model, ds, 10, opt)
+            losses = [runner.run_epoch(shuffle=False) for _ in range(3)]
+        else:
+            losses = [train_epoch(model, ds.loader(10, shuffle=False), torch.nn.MSELoss(), opt, DEV) for _ in range(3)]
+        runs.append((losses, [p.detach().clone() for p in model.parameters()]))
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert abs(a - b) <= 1e-6 * abs(a), runs
+    assert runs[0][0][2] < runs[0][0][0]
+    for p, q in zip(runs[0][1], runs[1][1]):
+        assert torch.allclose(p, q, rtol=0, atol=2e-6)
+    # shuffled epochs still see every sample once: 2 full batches of 10
+    g = torch.Generator().manual_seed(0)
+    assert runner.run_epoch(shuffle=True, generator=g) > 0

@@ -286,3 +286,38 @@ def train_epoch(model: MaskEmbdMultiMPN, loader, loss_fn, optimizer, device) -> 
     if total is None:
         raise ZeroDivisionError("train_epoch: empty loader")  # the reference divides by num_samples == 0
     return float(total.item()) / num_samples
+
+
+@torch.no_grad()
+def evaluate_epoch(model: MaskEmbdMultiMPN, loader, loss_fn, device="cuda", pre_loss_fn=None) -> float:
+    """`utils/evaluation.py:53-104` with the same arguments and dispatch: `model.eval()`, `out = model(data)`, the loss
+    picked by the type of `loss_fn` (including the reference's `out*pred_mask + pred_mask*(1-pred_mask)` for
+    `PowerImbalance`, :85-90 -- the second term is identically zero, kept as written), mean weighted by `len(data)`.
+    The running sum stays on the device; one read-back per epoch instead of one per batch (:101)."""
+    from .losses import Masked_L2_loss, MixedMSEPoweImbalance, PowerImbalance
+    pre_loss_fn = pre_loss_fn or (lambda x: x)
+    model.eval()
+    total, num_samples = None, 0
+    for data in loader:
+        data = data.to(device)
+        out = model(data)
+        if isinstance(loss_fn, Masked_L2_loss):
+            out = pre_loss_fn(out)
+            target = pre_loss_fn(data.y)
+            loss = loss_fn(out, target, data.pred_mask)
+        elif isinstance(loss_fn, PowerImbalance):
+            masked_out = out * data.pred_mask + data.pred_mask * (1 - data.pred_mask)
+            masked_out = pre_loss_fn(masked_out)
+            loss = loss_fn(masked_out, data.edge_index, data.edge_attr)
+        elif isinstance(loss_fn, MixedMSEPoweImbalance):
+            out = pre_loss_fn(out)
+            loss = loss_fn(out, data.edge_index, data.edge_attr, data.y)
+        else:
+            out, target = pre_loss_fn(out), pre_loss_fn(data.y)
+            loss = loss_fn(out, target)
+        num_samples += len(data)
+        weighted = loss.detach().reshape(()) * len(data)
+        total = weighted if total is None else total + weighted
+    if total is None:
+        raise ZeroDivisionError("evaluate_epoch: empty loader")
+    return float(total.item()) / num_samples

@@ -229,3 +229,41 @@ def test_graphed_epochs_equal_the_eager_loop():
     # shuffled epochs still see every sample once: 2 full batches of 10
     g = torch.Generator().manual_seed(0)
     assert runner.run_epoch(shuffle=True, generator=g) > 0
+
+
+@pytest.mark.parametrize("loss_name", ["mse", "masked_l2", "power_imbalance", "mixed"])
+def test_evaluate_epoch_matches_the_reference_loop(loss_name):
+    """`training.evaluate_epoch` (utils/evaluation.py:53-104) on the device loader against the same loop on the CPU
+    oracle, mixed-size dataset (118- and 14-bus graphs in one batch)."""
+    import torch.nn.functional as F
+    from poweflownet_b200 import losses
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    from poweflownet_b200.training import evaluate_epoch
+    torch.set_num_threads(1)
+    gold = torch.load(mgd.dataset_golden_path("ds_mixed"), weights_only=False)
+    ds = _dataset(gold, "test")  # 9 samples, batches of 6 + 3
+    stats = ds.get_data_means_stds()
+    kw = common.model_kwargs("mixed")
+    ref = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).eval()
+    vals = []
+    with torch.no_grad():
+        for bt in gold["splits"]["test"]["batches"]:
+            data = common.GraphBatch(**{f: bt[f] for f in mgd.FIELDS})
+            out = ref(data)
+            if loss_name == "mse":
+                vals.append(float(F.mse_loss(out, data.y)))
+            elif loss_name == "masked_l2":
+                vals.append(float(O.masked_l2_loss(out, data.y, data.pred_mask)))
+            elif loss_name == "power_imbalance":
+                masked = out * data.pred_mask + data.pred_mask * (1 - data.pred_mask)
+                vals.append(float(O.power_imbalance(masked, data.edge_index, data.edge_attr, *stats)))
+            else:
+                vals.append(float(O.mixed_mse_power_imbalance(out, data.edge_index, data.edge_attr, data.y, stats, alpha=0.9)))
+    want = sum(vals) / len(vals)
+    model = common.load_seeded(MaskEmbdMultiMPN(**kw)).to(DEV)
+    fn = {"mse": torch.nn.MSELoss(), "masked_l2": losses.Masked_L2_loss(),
+          "power_imbalance": losses.PowerImbalance(*stats),
+          "mixed": losses.MixedMSEPoweImbalance(*stats, alpha=0.9)}[loss_name]
+    got = evaluate_epoch(model, ds.loader(batch_size=6, shuffle=False), fn, DEV)
+    assert abs(got - want) <= 2e-5 * abs(want), (got, want)
+    assert not model.training

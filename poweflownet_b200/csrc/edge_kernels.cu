@@ -168,6 +168,180 @@ k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_ea_fwd_warp: the same message + aggregate with a WARP owning two consecutive rows at a time (hidden widths of
+// 24..33 float4 columns, i.e. hidden_dim 93..132: standard.json's 129).  k_ea_fwd above moves a CTA in lock step through
+// "stage the CSR slab -> barrier -> one row per thread -> next row" and keeps ~5 row loads per thread in flight; its
+// SMs are busy only two thirds of the kernel's duration (ncu: sm__cycles_active / elapsed = 0.67, 5 barrier-stalled
+// warps per issue).  Here nothing is shared between warps after the first barrier (We in shared memory) and the warps
+// are persistent and software-pipelined: while the neighbour rows of row pair i are in flight, the neighbour ids /
+// edge_attr of pair i+1 and the row pointers of pair i+2 are already being fetched, so the dependent chain
+// rowptr -> neighbour id -> neighbour row is paid once per warp, not once per row.  Lanes 0..2 read the row pointers;
+// the lanes read the pair's neighbour ids / edge_attr in one coalesced load each and broadcast them by shuffle; every
+// lane keeps its float4 column of BOTH rows and up to eight gathered neighbour rows in flight at once.  Column 32
+// (floats 128..131, the odd 129th channel) would cost a second pass with one active lane: instead lane u gathers that
+// chunk for edge u of the pair and the per-row sums are taken in edge order through shuffles.  Per-row results are
+// bit-identical to k_ea_fwd (same FMAs, same ascending-edge summation order).
+constexpr int kEaWarpChunk = 8;
+constexpr int kEaWarpThreads = 128;
+constexpr bool kEaFwdWarpDefault = false;  // measured on the B200: 19.5 us against 12.6 us for k_ea_fwd at case118v2 x 128
+                                           // (profiles/r1_ea_fwd_warp_vs_cta.json) -- opt-in (PFN_EA_FWD=warp) until it wins
+
+__device__ __forceinline__ float4 shfl4(float4 v, int src) {
+  return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
+                     __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+
+struct RowPair {
+  int r0, nrow, e0, deg0, ne;  // first row, rows (1 or 2), first edge, edges of row 0, edges of the pair
+};
+
+// lanes 0..nrow of a live pair read its row pointers; 0 for pairs past the end
+__device__ __forceinline__ int pair_rowptr(const int* __restrict__ rowptr, int pair, int npairs, int n_nodes, int lane) {
+  if (pair >= npairs) return 0;
+  const int r0 = 2 * pair, nrow = min(2, n_nodes - r0);
+  return lane <= nrow ? __ldg(rowptr + r0 + lane) : 0;
+}
+
+__device__ __forceinline__ RowPair pair_derive(int rp, int pair, int n_nodes) {
+  RowPair p;
+  p.r0 = 2 * pair;
+  p.nrow = min(2, n_nodes - p.r0);
+  const int e0 = __shfl_sync(0xffffffffu, rp, 0), e1 = __shfl_sync(0xffffffffu, rp, 1), e2 = __shfl_sync(0xffffffffu, rp, p.nrow);
+  p.e0 = e0;
+  p.deg0 = e1 - e0;
+  p.ne = e2 - e0;
+  return p;
+}
+
+__global__ void __launch_bounds__(kEaWarpThreads)
+k_ea_fwd_warp(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh, const int* __restrict__ rowptr,
+              const int* __restrict__ nbr, const float2* __restrict__ ea, const float* __restrict__ We, int64_t ldwe,
+              float* __restrict__ S, int64_t lds, int n_nodes, int h, int c4) {
+  pdl_wait();
+  __shared__ float4 s_w[33][2];
+  constexpr int kWarps = kEaWarpThreads / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npairs = (n_nodes + 1) >> 1, stride = gridDim.x * kWarps;
+  int pair = blockIdx.x * kWarps + warp;
+  const int rp_cur = pair_rowptr(rowptr, pair, npairs, n_nodes, lane);  // in flight while We is staged
+  int rp_nxt = pair_rowptr(rowptr, pair + stride, npairs, n_nodes, lane);
+  if (threadIdx.x < 2 * c4) {
+    const int q = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float w[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ch = 4 * q + c;
+      w[c] = ch < h ? __ldg(We + ch * ldwe + k) : 0.f;
+    }
+    s_w[q][k] = make_float4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+  if (pair >= npairs) return;  // surplus warp
+  const bool act = lane < min(c4, 32);
+  const bool tail = c4 > 32;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w0 = zero, w1 = zero;
+  if (act) {
+    w0 = s_w[lane][0];
+    w1 = s_w[lane][1];
+  }
+  RowPair cur = pair_derive(rp_cur, pair, n_nodes);
+  int my_nbr = 0;  // neighbour id / edge_attr of edge `lane` of the current pair (its first 32 edges)
+  float2 my_ea = make_float2(0.f, 0.f);
+  if (lane < min(32, cur.ne)) {
+    my_nbr = __ldg(nbr + cur.e0 + lane);
+    my_ea = __ldg(ea + cur.e0 + lane);
+  }
+  while (true) {
+    // ---- prefetch: row pointers two pairs ahead, neighbour ids / edge_attr one pair ahead ----
+    const int nxt_pair = pair + stride;
+    const bool has_next = nxt_pair < npairs;
+    const int rp_nn = pair_rowptr(rowptr, nxt_pair + stride, npairs, n_nodes, lane);
+    RowPair nxt = cur;
+    int nbr_n = 0;
+    float2 ea_n = make_float2(0.f, 0.f);
+    if (has_next) {
+      nxt = pair_derive(rp_nxt, nxt_pair, n_nodes);
+      if (lane < min(32, nxt.ne)) {
+        nbr_n = __ldg(nbr + nxt.e0 + lane);
+        ea_n = __ldg(ea + nxt.e0 + lane);
+      }
+    }
+    // ---- the current pair ----
+    float4 hi0 = zero, hi1 = zero;
+    if (act) {
+      hi0 = ld4(Hi + cur.r0 * ldh + 4 * lane);
+      if (cur.nrow == 2) hi1 = ld4(Hi + (cur.r0 + 1) * ldh + 4 * lane);
+    }
+    float4 acc0 = zero, acc1 = zero, tacc0 = zero, tacc1 = zero;
+    for (int eb = 0; eb < cur.ne; eb += 32) {  // 32 edges of the pair per round (one round unless a hub bus is involved)
+      const int cnt = min(32, cur.ne - eb);
+      int nb = my_nbr;
+      float2 a_l = my_ea;
+      if (eb > 0) {
+        nb = 0;
+        a_l = make_float2(0.f, 0.f);
+        if (lane < cnt) {
+          nb = __ldg(nbr + cur.e0 + eb + lane);
+          a_l = __ldg(ea + cur.e0 + eb + lane);
+        }
+      }
+      float4 tg = zero, ht = zero;  // column 32: lane u works on edge u of the round
+      if (tail && lane < cnt) {
+        ht = ld4(Hi + (cur.r0 + (eb + lane < cur.deg0 ? 0 : 1)) * ldh + 128);
+        tg = ldg4(Hj + nb * ldh + 128);
+      }
+      for (int cb = 0; cb < cnt; cb += kEaWarpChunk) {
+        float4 g[kEaWarpChunk];
+#pragma unroll
+        for (int u = 0; u < kEaWarpChunk; ++u) {
+          const int s = __shfl_sync(0xffffffffu, nb, (cb + u) & 31);
+          g[u] = zero;
+          if (cb + u < cnt && act) g[u] = ldg4(Hj + s * ldh + 4 * lane);
+        }
+#pragma unroll
+        for (int u = 0; u < kEaWarpChunk; ++u) {
+          if (cb + u < cnt) {  // warp-uniform
+            const float2 a = make_float2(__shfl_sync(0xffffffffu, a_l.x, cb + u), __shfl_sync(0xffffffffu, a_l.y, cb + u));
+            if (eb + cb + u < cur.deg0) {  // warp-uniform: which row of the pair the edge belongs to
+              add_relu(acc0, preact(hi0, g[u], a, w0, w1));
+            } else {
+              add_relu(acc1, preact(hi1, g[u], a, w0, w1));
+            }
+          }
+        }
+      }
+      if (tail) {
+        float4 tr = zero;
+        if (lane < cnt) {
+          const float4 p = preact(ht, tg, a_l, s_w[32][0], s_w[32][1]);
+          tr = make_float4(fmaxf(p.x, 0.f), fmaxf(p.y, 0.f), fmaxf(p.z, 0.f), fmaxf(p.w, 0.f));
+        }
+        for (int u = 0; u < cnt; ++u) {  // ascending edge order; every lane keeps a copy
+          const float4 v = shfl4(tr, u);
+          if (eb + u < cur.deg0) {
+            tacc0.x += v.x; tacc0.y += v.y; tacc0.z += v.z; tacc0.w += v.w;
+          } else {
+            tacc1.x += v.x; tacc1.y += v.y; tacc1.z += v.z; tacc1.w += v.w;
+          }
+        }
+      }
+    }
+    if (act) {
+      st4(S + cur.r0 * lds + 4 * lane, acc0);
+      if (cur.nrow == 2) st4(S + (cur.r0 + 1) * lds + 4 * lane, acc1);
+    }
+    if (tail && lane < cur.nrow) st4(S + (cur.r0 + lane) * lds + 128, lane == 0 ? tacc0 : tacc1);
+    if (!has_next) break;
+    pair = nxt_pair;
+    cur = nxt;
+    my_nbr = nbr_n;
+    my_ea = ea_n;
+    rp_nxt = rp_nn;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // blockIdx.y == 0: target-side pass over the CSR by target:  dHi[i] = sum_{e in in(i)} dS[i] * 1[p_e > 0]
 //                  and the per-CTA partial of dWe[c,k] = sum_e g_e[c] * ea_e[k]
 // blockIdx.y == 1: source-side pass over the CSR by source:  dHj[j] = sum_{e in out(j)} dS[tgt e] * 1[p_e > 0]
@@ -346,6 +520,16 @@ k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, 
   }
 }
 
+// which forward kernel: warp-owned row pairs for 24..33 float4 columns (PFN_EA_FWD=cta forces the CTA-slab kernel,
+// PFN_EA_FWD=warp the warp kernel; read per call so that tests can compare the two)
+bool ea_fwd_warp_rows(int c4) {
+  const bool eligible = c4 >= 24 && c4 <= 33;
+  const char* e = std::getenv("PFN_EA_FWD");
+  if (e != nullptr && e[0] == 'c') return false;
+  if (e != nullptr && e[0] == 'w') return eligible;
+  return eligible && kEaFwdWarpDefault;
+}
+
 constexpr int kBlocksPerSm = 4;  // measured: 4 x 231-thread CTAs per SM beat 8 (and 1 x 1024) at case118 sizes
 
 bool rows_ok(const void* p, int64_t ld) { return p != nullptr && aligned16(p) && ld % 4 == 0; }
@@ -360,6 +544,20 @@ int ea_fwd_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView
   if (n_nodes == 0) return 0;
   const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
   ProfScope prof(PFN_PROF_EA_FWD, stream);
+  if (ea_fwd_warp_rows(t.c4) && n_nodes * std::max(ldh, lds) < (int64_t(1) << 31)) {
+    static const int resident = [] {
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ea_fwd_warp, kEaWarpThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+      return per_sm;
+    }();
+    const int64_t warps = kEaWarpThreads / 32, pairs = ceil_div64(n_nodes, 2);
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div64(pairs, warps), int64_t(sm_count()) * resident));
+    PFN_CUDA_OK(launch_kernel(k_ea_fwd_warp, dim3(blocks), dim3(kEaWarpThreads), 0, stream, Hi, Hj, ldh, static_cast<const int*>(g.rowptr_t),
+                              static_cast<const int*>(g.nbr_t), reinterpret_cast<const float2*>(g.ea_t), We, ldwe, S, lds,
+                              static_cast<int>(n_nodes), static_cast<int>(h), t.c4));
+    PFN_LAUNCHED();
+    return 0;
+  }
   PFN_CUDA_OK(launch_kernel(k_ea_fwd, dim3(t.nblocks), dim3(t.threads), 0, stream, Hi, Hj, ldh, g.rowptr_t, g.nbr_t, reinterpret_cast<const float2*>(g.ea_t),
                                                We, ldwe, S, lds, static_cast<int>(n_nodes), static_cast<int>(h), t.c4,
                                                t.cx, t.rows, t.npb));

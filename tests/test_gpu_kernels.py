@@ -166,3 +166,39 @@ def test_fused_mse():
     _assert_close(dout, 2 * (out.double() - y.double()) / out.numel())
     loss2, _ = mse_loss_and_grad(out.to(DEV), y.to(DEV), total_count=2 * out.numel())
     assert abs(float(loss2) - float(ref) / 2) < 1e-6 * float(ref)
+
+
+def _star_batch():
+    """75 buses (odd): a hub with 70 branches (its row pair holds 71 > 32 edges: several rounds of the warp kernel),
+    a short chain and one isolated bus."""
+    n = 75
+    hub = torch.stack([torch.zeros(70, dtype=torch.long), torch.arange(1, 71)])
+    chain = torch.tensor([[71, 72], [72, 73]])
+    ei = torch.cat([hub, chain], dim=1)
+    g = torch.Generator().manual_seed(123)
+    z = torch.zeros(n, 4)
+    return common.GraphBatch(x=z, y=z, bus_type=torch.zeros(n, dtype=torch.long), pred_mask=torch.zeros(n, 4, dtype=torch.long),
+                             edge_index=ei.contiguous(), edge_attr=torch.randn(ei.size(1), 2, generator=g),
+                             batch=torch.zeros(n, dtype=torch.long), ptr=torch.tensor([0, n]))
+
+
+@pytest.mark.parametrize("h", [93, 100, 128, 129, 132])
+@pytest.mark.parametrize("name", ["mixed", "star", "isolated_and_parallel", "case118_h33"])
+def test_ea_forward_warp_kernel_equals_cta_kernel(name, h, monkeypatch):
+    """`k_ea_fwd_warp` (persistent warps, two rows per warp, 24..33 float4 columns) against the double-precision
+    reference and, bit for bit, against the CTA-slab kernel."""
+    from poweflownet_b200 import ops
+    batch = _star_batch() if name == "star" else name
+    n, ei, ea, hi, hj, ds, w1, fin, graph = _edge_case(batch, h, seed=11)
+    src, tgt = ei[0], ei[1]
+    pre = hi.double()[tgt] + hj.double()[src] + ea.double() @ w1[:, 2 * fin:].double().T
+    s_ref = seg_sum(torch.relu(pre), tgt, n)
+    outs = {}
+    for which in ("cta", "warp"):
+        monkeypatch.setenv("PFN_EA_FWD", which)
+        s = ops.new_rows(n, h, DEV)
+        s.fill_(float("nan"))
+        ops.ea_fwd(_rows(hi), _rows(hj), graph, w1.to(DEV), fin, h, s)
+        outs[which] = s
+        _assert_close(s[:, :h], s_ref, what=f"S ({which})")
+    assert torch.equal(outs["cta"][:, :h], outs["warp"][:, :h])

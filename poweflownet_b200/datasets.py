@@ -29,6 +29,23 @@ SPLIT_ORDER = {"train": 0, "val": 1, "test": 2}
 MIXED_CASES = ["118v2", "14v2"]  # datasets/PowerFlowData.py:67-70
 
 
+def epoch_batches(n_samples: int, batch_size: int, shuffle: bool = False, generator: Optional[torch.Generator] = None,
+                  drop_last: bool = False, rank: int = 0, world: int = 1) -> List[torch.Tensor]:
+    """Sample ids of one pass, cut into mini-batches.  With `world > 1` the permutation is cut into groups of `world`
+    consecutive mini-batches and rank r takes the r-th of each group, so the ranks see disjoint samples, the same number
+    of steps (a trailing group that cannot serve every rank is dropped) and, when `drop_last`, the same batch shape --
+    what the per-step gradient all-reduce needs."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside [0, {world})")
+    order = torch.randperm(n_samples, generator=generator) if shuffle else torch.arange(n_samples)
+    batches = [order[lo:lo + batch_size] for lo in range(0, n_samples, batch_size)]
+    if drop_last and batches and batches[-1].numel() < batch_size:
+        batches.pop()
+    if world > 1:
+        batches = batches[:len(batches) // world * world][rank::world]
+    return batches
+
+
 class PowerFlowData:
     def __init__(self, root: Optional[str] = None, case: str = "14", split: Optional[Sequence[float]] = None,
                  task: str = "train", normalize: bool = True, xymean=None, xystd=None, edgemean=None, edgestd=None,
@@ -138,13 +155,11 @@ class PowerFlowData:
         return out
 
     def loader(self, batch_size: int = 1, shuffle: bool = False, generator: Optional[torch.Generator] = None,
-               drop_last: bool = False) -> Iterator[GraphBatch]:
-        """`DataLoader(dataset, batch_size, shuffle)` (train.py:90-92): one permutation per pass, drawn on the host."""
-        order = torch.randperm(self.len(), generator=generator) if shuffle else torch.arange(self.len())
-        for lo in range(0, self.len(), batch_size):
-            ids = order[lo:lo + batch_size]
-            if drop_last and ids.numel() < batch_size:
-                return
+               drop_last: bool = False, rank: int = 0, world: int = 1) -> Iterator[GraphBatch]:
+        """`DataLoader(dataset, batch_size, shuffle)` (train.py:90-92): one permutation per pass, drawn on the host.
+        Data parallel (`world > 1`): every rank draws the SAME permutation (seed the generators alike) and takes every
+        `world`-th mini-batch of it, see `epoch_batches`."""
+        for ids in epoch_batches(self.len(), batch_size, shuffle, generator, drop_last, rank, world):
             yield self.batch(ids)
 
     def num_batches(self, batch_size: int, drop_last: bool = False) -> int:

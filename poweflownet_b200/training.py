@@ -207,21 +207,29 @@ class GraphedEpochs:
     sum stays on the device; one read-back per epoch.  The `train_epoch` loop of utils/training.py:30-80 for
     `--train_loss_fn mse_loss` on a single-case dataset (all graphs of one size; incomplete last batches are dropped)."""
 
-    def __init__(self, model: MaskEmbdMultiMPN, dataset, batch_size: int, optimizer, total_count: Optional[int] = None):
+    def __init__(self, model: MaskEmbdMultiMPN, dataset, batch_size: int, optimizer, total_count: Optional[int] = None,
+                 rank: int = 0, world: int = 1):
+        """Data parallel: pass `rank` / `world` (every rank must seed `run_epoch`'s generator alike) and
+        `total_count = world * batch_size * nodes_per_graph * output_dim`; the model's gradient all-reduce
+        (`parallel.attach_gradient_allreduce`) runs after every replay."""
         if batch_size > len(dataset):
             raise ValueError("batch_size exceeds the dataset")
         self.model, self.dataset, self.batch_size, self.optimizer = model, dataset, int(batch_size), optimizer
+        self.rank, self.world = int(rank), int(world)
         model.train()
         self.step = GraphedMSEStep(model, dataset.batch(list(range(batch_size))), total_count)
         self.n_attr = len(self.step.static)
 
     def run_epoch(self, shuffle: bool = True, generator: Optional[torch.Generator] = None) -> float:
+        from .datasets import epoch_batches
         ds, bs = self.dataset, self.batch_size
-        order = torch.randperm(len(ds), generator=generator) if shuffle else torch.arange(len(ds))
-        order_dev = order.to(self.step.device, non_blocking=True)
-        order_host = order.numpy()
+        batches = epoch_batches(len(ds), bs, shuffle, generator, True, self.rank, self.world)
+        steps = len(batches)
         total = None
-        steps = len(ds) // bs
+        if steps:
+            order = torch.cat(batches)
+            order_dev = order.to(self.step.device, non_blocking=True)  # the ids of the whole epoch travel once
+            order_host = order.numpy()
         self.model.train()
         for k in range(steps):
             ds.batch(order_host[k * bs:(k + 1) * bs], ids_device=order_dev[k * bs:(k + 1) * bs], out=self.step.static)

@@ -62,3 +62,22 @@ def test_fused_supported_matrix():
     assert ok(130, 4, 3, 118) == 0 and ok(48, 4, 3, 118) == 1 and ok(16, 4, 3, 118) == 0
     assert ok(129, 1, 3, 118) == 0            # the reference's single-layer constructor is shape-inconsistent
     assert ok(129, 4, 3, 118, nf=6) == 0 and ok(129, 4, 3, 118, out=5) == 0 and ok(129, 4, 3, 118, ef=4) == 0
+
+
+def test_epoch_batches_partition_samples_across_ranks():
+    """datasets.epoch_batches: the sample-id plan of one pass (pure host logic of the device-resident loader)."""
+    import torch
+    from poweflownet_b200.datasets import epoch_batches
+    plain = epoch_batches(10, 4)
+    assert [b.tolist() for b in plain] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+    assert [b.tolist() for b in epoch_batches(10, 4, drop_last=True)] == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    world = 3
+    per_rank = [epoch_batches(50, 4, True, torch.Generator().manual_seed(7), True, r, world) for r in range(world)]
+    assert len({len(b) for b in per_rank}) == 1 and len(per_rank[0]) == (50 // 4) // world
+    seen = torch.cat([torch.cat(b) for b in per_rank])
+    assert seen.numel() == seen.unique().numel() == world * len(per_rank[0]) * 4  # disjoint, full batches only
+    again = epoch_batches(50, 4, True, torch.Generator().manual_seed(7), True, 1, world)
+    assert all(torch.equal(a, b) for a, b in zip(again, per_rank[1]))
+    import pytest
+    with pytest.raises(ValueError):
+        epoch_batches(10, 4, rank=2, world=2)

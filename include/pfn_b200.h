@@ -212,10 +212,15 @@ PFN_API int pfn_mse_fwd_bwd(const float* out, const float* y, int64_t count, flo
  *      utils/argument_parser.py:36-37; dispatched at utils/training.py:61-62): fused value + gradient.
  *      loss = mean over {mask != 0} of (out-y)^2 + regcoeff * mean over {mask == 0} of (out-y)^2 (second term only when
  *      `regularize`); the element counts stay on the device (the reference's masked_select costs two host syncs).
- *      mask: int64 [count] (data.pred_mask).  scratch: at least pfn_masked_l2_scratch_bytes(count). --------------- */
+ *      mask: int64 [count] (data.pred_mask).  scratch: at least pfn_masked_l2_scratch_bytes(count).
+ *      global_counts: NULL, or a DEVICE array of 2 floats = (number of mask != 0 entries, number of mask == 0 entries)
+ *      over ALL ranks of a data-parallel step: the two means are then taken over the global selections, so that the SUM
+ *      over ranks of `loss` is the loss of the whole batch and the SUM all-reduce of the parameter gradients equals the
+ *      single-process gradient (the reference has no multi-GPU mode; 1-GPU results are the parity oracle). --------- */
 PFN_API size_t pfn_masked_l2_scratch_bytes(int64_t count);
 PFN_API int pfn_masked_l2_fwd_bwd(const float* out, const float* y, const int64_t* mask, int64_t count, int regularize,
-                          float regcoeff, float* loss, float* dout, void* scratch, void* stream);
+                          float regcoeff, const float* global_counts, float* loss, float* dout, void* scratch,
+                          void* stream);
 
 /* ---- PowerImbalance loss + gradient: utils/custom_loss_functions.py:99-286 (`PowerImbalance.forward`; selected by
  *      train.py:95-101, called at utils/training.py:63-68).  x: normalised predictions [N, >=4] (Vm, Va[deg], P, Q),

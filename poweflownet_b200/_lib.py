@@ -76,8 +76,8 @@ SIGNATURES = {
     "pfn_mse_scratch_bytes": (c_sz, [c_i64]),
     "pfn_mse_fwd_bwd": (C.c_int, [c_f32p, c_f32p, c_i64, C.c_float, c_f32p, c_f32p, C.c_void_p, C.c_void_p]),
     "pfn_masked_l2_scratch_bytes": (c_sz, [c_i64]),
-    "pfn_masked_l2_fwd_bwd": (C.c_int, [c_f32p, c_f32p, C.c_void_p, c_i64, C.c_int, C.c_float, c_f32p, c_f32p, C.c_void_p,
-                                        C.c_void_p]),
+    "pfn_masked_l2_fwd_bwd": (C.c_int, [c_f32p, c_f32p, C.c_void_p, c_i64, C.c_int, C.c_float, c_f32p, c_f32p, c_f32p,
+                                        C.c_void_p, C.c_void_p]),
     "pfn_power_imbalance_scratch_bytes": (c_sz, [c_i64]),
     "pfn_power_imbalance_fwd_bwd": (C.c_int, [c_f32p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, c_f32p, c_f32p, c_i64,
                                               C.c_void_p, C.c_void_p]),

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <atomic>
+
 #include "../../include/pfn_b200.h"
 
 namespace pfn {
@@ -68,6 +70,25 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // wait until the preceding kernel(s) in the stream have completed and their writes are visible (no-op without PDL)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
+
+// The opt-in dynamic shared-memory limit (cudaFuncAttributeMaxDynamicSharedMemorySize) is a PER-DEVICE function
+// attribute: a process that drives several GPUs must set it on each of them.  `done` holds one bit per device ordinal;
+// the check is a cudaGetDevice + an atomic load on the hot path.  Thread-safe (setting the attribute twice is harmless).
+struct SmemAttrOnce {
+  std::atomic<uint64_t> done[4] = {};  // device ordinals 0..255
+  bool needs(int dev) const { return (done[(dev >> 6) & 3].load(std::memory_order_acquire) & (1ull << (dev & 63))) == 0; }
+  void mark(int dev) { done[(dev >> 6) & 3].fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+template <typename F>
+inline cudaError_t ensure_dynamic_smem(SmemAttrOnce& once, F set_all) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!once.needs(dev)) return cudaSuccess;
+  e = set_all();
+  if (e == cudaSuccess) once.mark(dev);
+  return e;
+}
 
 // RAII bracket used by the launch sites; a no-op unless pfn_profile_enable(1) was called.
 struct ProfScope {

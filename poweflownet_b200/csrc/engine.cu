@@ -159,8 +159,8 @@ k_ml2_partial(const float* __restrict__ out, const float* __restrict__ y, const 
   if (threadIdx.x < 3) partial[threadIdx.x * gridDim.x + blockIdx.x] = red[threadIdx.x][0];
 }
 __global__ void __launch_bounds__(kMseBlock)
-k_ml2_final(const float* __restrict__ partial, int n, int64_t count, int regularize, float regcoeff, float* __restrict__ loss,
-            float* __restrict__ scales) {
+k_ml2_final(const float* __restrict__ partial, int n, int64_t count, int regularize, float regcoeff,
+            const float* __restrict__ global_counts, float* __restrict__ loss, float* __restrict__ scales) {
   pdl_wait();
   __shared__ float red[3][kMseBlock];
   for (int k = 0; k < 3; ++k) {
@@ -175,7 +175,11 @@ k_ml2_final(const float* __restrict__ partial, int n, int64_t count, int regular
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float n1 = red[2][0], n0 = static_cast<float>(count) - n1;
+    float n1 = red[2][0], n0 = static_cast<float>(count) - n1;
+    if (global_counts != nullptr) {  // data parallel: means over the selections of ALL ranks
+      n1 = global_counts[0];
+      n0 = global_counts[1];
+    }
     float l = red[0][0] / n1;  // mean over an empty selection is NaN, as torch.nn.MSELoss gives
     float sc0 = 0.f;
     if (regularize) {
@@ -1174,7 +1178,8 @@ extern "C" int pfn_mse_fwd_bwd(const float* out, const float* y, int64_t count, 
 extern "C" size_t pfn_masked_l2_scratch_bytes(int64_t count) { return size_t(3 * mse_blocks(count) + 2) * sizeof(float); }
 
 extern "C" int pfn_masked_l2_fwd_bwd(const float* out, const float* y, const int64_t* mask, int64_t count, int regularize,
-                                     float regcoeff, float* loss, float* dout, void* scratch, void* stream_) {
+                                     float regcoeff, const float* global_counts, float* loss, float* dout, void* scratch,
+                                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PFN_REQUIRE(out && y && mask && loss && dout && scratch && count > 0, PFN_E_INVALID, "pfn_masked_l2_fwd_bwd: bad arguments");
   const int blocks = mse_blocks(count);
@@ -1183,7 +1188,7 @@ extern "C" int pfn_masked_l2_fwd_bwd(const float* out, const float* y, const int
   PFN_CUDA_OK(launch_kernel(k_ml2_partial, dim3(blocks), dim3(kMseBlock), 0, stream, out, y, mask, count, partial));
   PFN_LAUNCHED();
   PFN_CUDA_OK(launch_kernel(k_ml2_final, dim3(1), dim3(kMseBlock), 0, stream, static_cast<const float*>(partial), blocks, count, regularize,
-                            regcoeff, loss, scales));
+                            regcoeff, global_counts, loss, scales));
   PFN_LAUNCHED();
   PFN_CUDA_OK(launch_kernel(k_ml2_grad, dim3(blocks), dim3(kMseBlock), 0, stream, out, y, mask, count, static_cast<const float*>(scales), dout));
   PFN_LAUNCHED();

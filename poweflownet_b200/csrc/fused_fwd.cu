@@ -1673,12 +1673,15 @@ int fused_fwd_launch(FusedArgs& a, const float* arena, int64_t arena_rows, cudaS
        k_mpn_fused_fwd<0, kFusedModeBackward>},
       {k_mpn_fused_fwd<1, kFusedModeForward>, k_mpn_fused_fwd<1, kFusedModeTagBackward>, k_mpn_fused_fwd<1, kFusedModeEaBackward>,
        k_mpn_fused_fwd<1, kFusedModeBackward>}};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static SmemAttrOnce attr_once;
+  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [&] {
     for (auto& row : kernels)
-      for (auto* k : row) PFN_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem)));
-    attr_set = true;
-  }
+      for (auto* k : row) {
+        const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmem));
+        if (e != cudaSuccess) return e;
+      }
+    return cudaSuccess;
+  }));
   PFN_REQUIRE(a.mode >= 0 && a.mode <= 3, PFN_E_INVALID, "fused kernel: bad mode %d", a.mode);
   void (*kernel)(FusedArgs) = kernels[a.h > 128 ? 1 : 0][a.mode];
   const unsigned tiles = a.tile_start != nullptr ? static_cast<unsigned>(a.n_tiles) : static_cast<unsigned>(ceil_div64(a.n_nodes, a.tile_rows));

@@ -1118,11 +1118,8 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   a.keep_thresh = g.keep_thresh;
   a.seed_dev = g.seed_dev;
   const uint32_t smem = uint32_t(a.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PFN_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] { return cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)); }));
   dim3 grid(static_cast<unsigned>(ceil_div64(g.M, kTcBM)), static_cast<unsigned>(ceil_div64(g.N, bn)), static_cast<unsigned>(count));
   static const bool timing_on = std::getenv("PFN_TC_TIMING") != nullptr;  // debug aid: phase timestamps of CTA 0
   static long long* timing_dev = nullptr;
@@ -1211,11 +1208,8 @@ int wgrad_tc_launch(GemmArgs& g, cudaStream_t stream) {
   g.splitk = a.splitk;  // the reduction pass must know how many partials were written
   g.kchunk = a.kchunk;
   const uint32_t smem = uint32_t(a.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PFN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] { return cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)); }));
   dim3 grid(static_cast<unsigned>(a.splitk), static_cast<unsigned>(count), static_cast<unsigned>(m_groups));
   PFN_CUDA_OK(launch_kernel(k_wgrad_tc, grid, dim3(kTcThreads), smem, stream, a));
   PFN_LAUNCHED();
@@ -1324,12 +1318,9 @@ static int wgrad_batch_launch(const WgradProblem* probs, int n, int64_t nodes, f
     floats += size_t(a.splitk) * size_t(a.p[i].Mo) * size_t(a.p[i].n_eff);
   }
   if (floats * sizeof(float) > partial_bytes) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    // (the kernel also has 512 bytes of static shared memory: the opt-in maximum is for the sum)
-    PFN_CUDA_OK(cudaFuncSetAttribute(k_wgrad_group, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit - 1024u)));
-    attr_set = true;
-  }
+  static SmemAttrOnce attr_once;
+  // (the kernel also has 512 bytes of static shared memory: the opt-in maximum is for the sum)
+  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] { return cudaFuncSetAttribute(k_wgrad_group, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit - 1024u)); }));
   static const bool timing_on = std::getenv("PFN_WG_TIMING") != nullptr;
   static long long* timing_dev = nullptr;
   if (timing_on) {

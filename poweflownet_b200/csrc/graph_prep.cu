@@ -345,11 +345,8 @@ extern "C" int pfn_graph_prep(const int64_t* edge_index, int64_t ei_row_stride, 
   if (N <= kScanSmemNodes) {
     const int per = (N + kScanThreads - 1) / kScanThreads, n_pad = per * kScanThreads;
     const size_t smem = 2 * size_t(n_pad + n_pad / 32 + 32) * sizeof(int32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-      PFN_CUDA_OK(cudaFuncSetAttribute(k_scan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-      attr_set = true;
-    }
+    static SmemAttrOnce attr_once;
+    PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] { return cudaFuncSetAttribute(k_scan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024); }));
     PFN_CUDA_OK(launch_kernel(k_scan_smem, dim3(2), dim3(kScanThreads), smem, stream, N, cnt_t, cnt_s, g.rowptr_t, g.rowptr_s, g.deg, g.dis));
   } else {
     PFN_CUDA_OK(launch_kernel(k_scan, dim3(2), dim3(kScanThreads), 0, stream, N, cnt_t, cnt_s, g.rowptr_t, g.rowptr_s, g.deg, g.dis));

@@ -77,13 +77,15 @@ class _MPNFunction(torch.autograd.Function):
     """Whole-model forward/backward through `pfn_mpn_forward` / `pfn_mpn_backward`."""
 
     @staticmethod
-    def forward(ctx, model, tiling, x, pred_mask, edge_index, edge_attr, *params):
+    def forward(ctx, model, tiling, needs_grad, x, pred_mask, edge_index, edge_attr, *params):
         dev = ops.require_cuda(x, pred_mask, edge_index, edge_attr, *params)
         n = int(x.size(0))
-        tile_rows, graph_ptr = tiling  # graph_ptr: device int64 [G+1] for batches that mix graph sizes, else None
-        n_graphs = int(graph_ptr.numel()) - 1 if graph_ptr is not None else 0
+        # tiling: (tile_rows, graph_ptr, alt_ptr).  graph_ptr: device int64 [G+1] for batches that mix graph sizes, else
+        # None; alt_ptr: the batch's `ptr` when the uniform tiling was chosen (second attempt if its promise is broken)
+        tile_rows, graph_ptr, alt_ptr = tiling
         training = bool(model.training)
-        needs_grad = any(ctx.needs_input_grad)  # (grad mode is off inside Function.forward; this is set by apply)
+        # `needs_grad` comes from the module (grad mode and requires_grad of the inputs): inside Function.forward grad
+        # mode is off and ctx.needs_input_grad is True for every parameter even under torch.no_grad()
         with torch.cuda.device(dev):
             x = x.contiguous().float()
             pred_mask = pred_mask.contiguous()
@@ -106,20 +108,32 @@ class _MPNFunction(torch.autograd.Function):
                       ws.act.data_ptr(), ws.scratch.data_ptr(), int(training), seed,
                       None if seed_dev is None else seed_dev.data_ptr(), inj_table, out.data_ptr())
             stream = torch.cuda.current_stream().cuda_stream
-            if tile_rows > 0:
+            capturing = torch.cuda.is_current_stream_capturing()
+            attempts = [(tile_rows, graph_ptr)] if tile_rows > 0 else []
+            if tile_rows > 0 and graph_ptr is None and alt_ptr is not None:
+                attempts.append((128, alt_ptr))  # equal-sized tiles refused: whole graphs packed from `ptr` may still fit
+            tile_rows, n_graphs = 0, 0
+            for rows, gptr in attempts:
                 # graph-resident kernel: the whole layer stack in one launch, one tile of whole graphs per CTA
-                check(lib().pfn_mpn_forward_tiled(*common, tile_rows, None if graph_ptr is None else graph_ptr.data_ptr(),
-                                                  n_graphs, stream), "pfn_mpn_forward_tiled")
-                sig = (n, graph.e_raw, tile_rows, n_graphs)
-                if sig not in model._tiling_checked and not torch.cuda.is_current_stream_capturing():
-                    # first batch of this shape: read back the kernel's own validation of the closed-tile promise
+                ng = int(gptr.numel()) - 1 if gptr is not None else 0
+                sig = (n, graph.e_raw, rows, ng)
+                if model._tiling_checked.get(sig, True) is False:
+                    continue
+                check(lib().pfn_mpn_forward_tiled(*common, rows, None if gptr is None else gptr.data_ptr(), ng, stream),
+                      "pfn_mpn_forward_tiled")
+                # the kernel validates the closed-tile promise itself (a violation raises meta[6] and poisons the tile's
+                # rows with NaN); the flag is read back for the first batch of a shape and then every
+                # `_tiling_recheck` batches of it -- never during stream capture
+                calls = model._tiling_calls.get(sig, 0)
+                model._tiling_calls[sig] = calls + 1
+                if not capturing and (sig not in model._tiling_checked or calls % model._tiling_recheck == 0):
                     violated = C.c_int32(0)
                     check(lib().pfn_graph_tile_status(ws.graph.data_ptr(), C.byref(violated), stream), "pfn_graph_tile_status")
                     model._tiling_checked[sig] = not violated.value
                     if violated.value:
-                        tile_rows = 0
-                elif not model._tiling_checked.get(sig, True):
-                    tile_rows = 0
+                        continue
+                tile_rows, n_graphs = rows, ng
+                break
             if tile_rows <= 0:
                 check(lib().pfn_mpn_forward(*common, stream), "pfn_mpn_forward")
         if needs_grad:
@@ -128,14 +142,16 @@ class _MPNFunction(torch.autograd.Function):
             ctx.n_graphs = n_graphs if tile_rows > 0 else 0
             ctx.keep = (x, pred_mask, graph, inj)  # keep inputs alive until backward
         else:
+            ctx.ws = None
             model._give_workspace(n, graph.e_raw, dev, ws)
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        if getattr(ctx, "ws", None) is None:
+            raise RuntimeError("backward on a MaskEmbdMultiMPN forward whose activations were released (called twice, or "
+                               "the forward ran without grad mode)")
         model, ws, params = ctx.model, ctx.ws, ctx.params
-        if ws is None:
-            raise RuntimeError("backward called twice on the same MaskEmbdMultiMPN forward: activations were released")
         dev = dout.device
         with torch.cuda.device(dev):
             dout = dout.contiguous().float()
@@ -156,14 +172,14 @@ class _MPNFunction(torch.autograd.Function):
             else:
                 check(lib().pfn_mpn_backward(*common, stream), "pfn_mpn_backward")
             dx = None
-            if ctx.needs_input_grad[2]:
+            if ctx.needs_input_grad[3]:
                 # x enters as `mask_embd(mask) + x` (MPN.py:537): d loss / d x is the gradient w.r.t. that sum
                 dx = model._dx0_view(ws, ctx.n).clone()
             if model._grad_reducer is not None:
                 model._grad_reducer(gflat)  # data parallel: ONE collective over the flat gradient buffer
         model._give_workspace(ctx.n, ctx.e_raw, dev, ws)
         ctx.ws = None
-        return (None, None, dx, None, None, None, *views)  # (model, tiling, x, pred_mask, edge_index, edge_attr, *params)
+        return (None, None, None, dx, None, None, None, *views)  # (model, tiling, needs_grad, x, pred_mask, edge_index, edge_attr, *params)
 
 
 class MaskEmbdMultiMPN(nn.Module):
@@ -189,7 +205,9 @@ class MaskEmbdMultiMPN(nn.Module):
         self._grad_reducer = None  # set by poweflownet_b200.parallel.attach_gradient_allreduce
         self._seed_device: Optional[torch.Tensor] = None  # int64[1] on the device: dropout seed read by the kernels
         self.fused = True  # use the graph-resident kernel when the batch is made of equal-sized graphs of <= 128 nodes
-        self._tiling_checked = {}  # (N, E_raw, tile_rows) -> did the kernel's closed-tile validation pass
+        self._tiling_checked = {}  # (N, E_raw, tile_rows, n_graphs) -> did the kernel's closed-tile validation pass
+        self._tiling_calls = {}    # same key -> forwards taken on the graph-resident route
+        self._tiling_recheck = 64  # the validation flag is read back (one stream sync) every this many batches of a shape
 
     # ---- reference helper methods (networks/MPN.py:498-523) -------------------------------------
     def is_directed(self, edge_index):
@@ -243,38 +261,50 @@ class MaskEmbdMultiMPN(nn.Module):
         if len(free) < 2:
             free.append(ws)
 
+    def _swap_pool(self, pool: dict) -> dict:
+        """Install `pool` as the workspace pool and return the previous one.  `training.GraphedMSEStep` captures its
+        CUDA graph on a PRIVATE pool that it keeps alive itself: the captured kernels have the workspace addresses baked
+        in, so those buffers must never be handed to (or dropped by) another forward of the same shape."""
+        old, self._pool = self._pool, pool
+        return old
+
     def _dx0_view(self, ws: _Workspace, n: int) -> torch.Tensor:
         # scratch layout of engine.cu: dx0 [n, nfeat] comes first
         return ws.scratch.view(torch.float32)[:n * self.nfeature_dim].view(n, self.nfeature_dim)
 
     def _tiling(self, data):
-        """(tile_rows, graph_ptr) for the graph-resident kernels, or (0, None) for the layer-wise path.  Uses only host-side
-        shape information (no device read):
-        * `num_graphs` equal-sized graphs of n = N / num_graphs <= 128 nodes: floor(128 / n) whole graphs per tile;
+        """(tile_rows, graph_ptr, alt_ptr) for the graph-resident kernels, or (0, None, None) for the layer-wise path.
+        Uses only host-side shape information (no device read):
+        * `num_graphs` equal-sized graphs of n = N / num_graphs <= 128 nodes: floor(128 / n) whole graphs per tile
+          (`alt_ptr` = the batch's device `ptr`, if any: the variable tiling below is tried next when the kernel
+          refuses the uniform one);
         * otherwise, when the batch carries PyG's `ptr` on the device: graphs of mixed sizes (the reference's
           `--case mixed`), packed greedily into tiles of <= 128 rows by a device-side pass over `ptr`.
         Either way the kernel validates the tiling itself (no edge may leave a tile, no graph may exceed 128 nodes)."""
+        none = (0, None, None)
         if not self.fused:
-            return 0, None
+            return none
         n = int(data.x.size(0))
         ptr = getattr(data, "ptr", None)
         g = getattr(data, "num_graphs", None)
         if g is None and ptr is not None:
             g = int(ptr.numel()) - 1
         if not g or g <= 0 or n <= 0:
-            return 0, None
+            return none
         e_raw = int(data.edge_index.size(1))
         desc = self._desc()
+        ptr_ok = (ptr is not None and ptr.is_cuda and ptr.dtype == torch.int64 and ptr.numel() == g + 1 and g <= n
+                  and self._tiling_checked.get((n, e_raw, 128, g), True) is not False
+                  and bool(lib().pfn_mpn_fused_supported(C.byref(desc), 128)))
         if n % g == 0 and n // g <= 128:
             tile = (128 // (n // g)) * (n // g)
             if self._tiling_checked.get((n, e_raw, tile, 0), True) is not False and lib().pfn_mpn_fused_supported(C.byref(desc), tile):
-                return tile, None
-            return 0, None
-        if (ptr is not None and ptr.is_cuda and ptr.dtype == torch.int64 and ptr.numel() == g + 1 and g <= n
-                and self._tiling_checked.get((n, e_raw, 128, g), True) is not False
-                and lib().pfn_mpn_fused_supported(C.byref(desc), 128)):
-            return 128, ptr.contiguous()
-        return 0, None
+                return tile, None, (ptr.contiguous() if ptr_ok else None)
+            if not ptr_ok:
+                return none
+        if ptr_ok:
+            return 128, ptr.contiguous(), None
+        return none
 
     def _tile_rows(self, data) -> int:
         return self._tiling(data)[0]
@@ -290,5 +320,7 @@ class MaskEmbdMultiMPN(nn.Module):
                 "which cannot run unless hidden_dim == output_dim; the sm_100a path implements n_gnn_layers >= 2")
         if self.efeature_dim != 2:
             raise NotImplementedError("the sm_100a path implements efeature_dim == 2 (the dataset's edge width)")
-        return _MPNFunction.apply(self, self._tiling(data), data.x, data.pred_mask, data.edge_index, data.edge_attr,
-                                  *self._engine_params())
+        params = self._engine_params()
+        needs_grad = torch.is_grad_enabled() and (data.x.requires_grad or any(p.requires_grad for p in params))
+        return _MPNFunction.apply(self, self._tiling(data), needs_grad, data.x, data.pred_mask, data.edge_index,
+                                  data.edge_attr, *params)

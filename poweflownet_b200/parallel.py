@@ -57,6 +57,21 @@ def global_count(local_numel: int, device=None, group=None) -> int:
     return int(t.item())
 
 
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def global_mask_counts(pred_mask: torch.Tensor, group=None) -> torch.Tensor:
+    """float32 [2] on `pred_mask`'s device: (number of mask != 0 entries, number of mask == 0 entries) summed over all
+    ranks -- the denominators of the two means of `Masked_L2_loss` (utils/custom_loss_functions.py:29-46) under data
+    parallelism.  No host synchronisation: the counts stay on the device and are read by the loss kernel."""
+    n1 = (pred_mask != 0).sum()
+    counts = torch.stack([n1, pred_mask.numel() - n1]).to(torch.float32)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
 def broadcast_parameters(model, src: int = 0, group=None) -> None:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         for p in model.parameters():

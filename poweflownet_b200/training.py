@@ -36,11 +36,13 @@ def mse_loss_and_grad(out: torch.Tensor, y: torch.Tensor, total_count: Optional[
 
 
 def masked_l2_loss_and_grad(out: torch.Tensor, y: torch.Tensor, mask: torch.Tensor, regularize: bool = True,
-                            regcoeff: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+                            regcoeff: float = 1.0, global_counts: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(loss, d loss / d out) for the reference's `Masked_L2_loss(regularize, regcoeff)(out, y, mask)`
     (utils/custom_loss_functions.py:10-46): mean over the masked entries plus `regcoeff` x mean over the others.
-    Element counts are taken on the device (no masked_select, no host sync).  Single process only: under data
-    parallelism the two means need global counts -- use `model(data)` + torch autograd there."""
+    Element counts are taken on the device (no masked_select, no host sync).  Data parallel: `global_counts` = device
+    float32 [2] = (masked, unmasked) element counts over ALL ranks (`parallel.global_mask_counts`); the two means are
+    then global ones, the SUM over ranks of the returned loss is the whole batch's loss, and the SUM all-reduce of the
+    parameter gradients equals the single-process gradient."""
     dev = ops.require_cuda(out, y, mask)
     with torch.cuda.device(dev):
         out, y = out.contiguous(), y.contiguous().float()
@@ -49,26 +51,36 @@ def masked_l2_loss_and_grad(out: torch.Tensor, y: torch.Tensor, mask: torch.Tens
             mask = mask.long()
         if mask.shape != out.shape:
             raise ValueError(f"mask shape {tuple(mask.shape)} != output shape {tuple(out.shape)}")
+        if global_counts is not None:
+            ops.require_cuda(global_counts)
+            if global_counts.dtype != torch.float32 or global_counts.numel() != 2 or not global_counts.is_contiguous():
+                raise ValueError("global_counts must be a contiguous float32 tensor of 2 elements (masked, unmasked)")
         count = out.numel()
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         dout = torch.empty_like(out)
         scratch = torch.empty(int(lib().pfn_masked_l2_scratch_bytes(count)), dtype=torch.uint8, device=dev)
         check(lib().pfn_masked_l2_fwd_bwd(out.data_ptr(), y.data_ptr(), mask.data_ptr(), count, int(bool(regularize)),
-                                          float(regcoeff), loss.data_ptr(), dout.data_ptr(), scratch.data_ptr(),
+                                          float(regcoeff), None if global_counts is None else global_counts.data_ptr(),
+                                          loss.data_ptr(), dout.data_ptr(), scratch.data_ptr(),
                                           torch.cuda.current_stream().cuda_stream), "pfn_masked_l2_fwd_bwd")
     return loss, dout
 
 
-def fused_masked_l2_step(model: MaskEmbdMultiMPN, data, regularize: bool = True, regcoeff: float = 1.0) -> torch.Tensor:
-    """forward + Masked_L2_loss + backward (the parser-default training loss, utils/training.py:61-62); parameter
-    `.grad`s are SET.  Returns the loss as a 1-element device tensor."""
-    with torch.enable_grad():
-        out = model(data)
-    loss, dout = masked_l2_loss_and_grad(out.detach(), data.y, data.pred_mask, regularize, regcoeff)
+def _set_grads(model: MaskEmbdMultiMPN, out: torch.Tensor, dout: torch.Tensor) -> None:
     params = model._engine_params()
     grads = torch.autograd.grad(out, params, grad_outputs=dout, allow_unused=False)
     for p, g in zip(params, grads):
         p.grad = g
+
+
+def fused_masked_l2_step(model: MaskEmbdMultiMPN, data, regularize: bool = True, regcoeff: float = 1.0,
+                         global_counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """forward + Masked_L2_loss + backward (the parser-default training loss, utils/training.py:61-62); parameter
+    `.grad`s are SET.  Returns the loss as a 1-element device tensor (this rank's share when `global_counts` is given)."""
+    with torch.enable_grad():
+        out = model(data)
+    loss, dout = masked_l2_loss_and_grad(out.detach(), data.y, data.pred_mask, regularize, regcoeff, global_counts)
+    _set_grads(model, out, dout)
     return loss
 
 
@@ -78,35 +90,77 @@ def fused_mse_step(model: MaskEmbdMultiMPN, data, total_count: Optional[int] = N
     with torch.enable_grad():
         out = model(data)
     loss, dout = mse_loss_and_grad(out.detach(), data.y, total_count)
-    params = model._engine_params()
-    grads = torch.autograd.grad(out, params, grad_outputs=dout, allow_unused=False)
-    for p, g in zip(params, grads):
-        p.grad = g
+    _set_grads(model, out, dout)
     return loss
 
 
-class GraphedMSEStep:
-    """forward + MSE + backward of one mini-batch SHAPE captured once as a CUDA graph and replayed per step.
+class _SeedRing:
+    """Dropout seeds for CUDA-graph replays: the captured kernels read ONE device-resident int64; every replay is
+    preceded by an asynchronous copy of a fresh host-drawn seed into it.  The host runs many steps ahead of the device
+    (`GraphedEpochs`, `PipelinedMSESteps`), so each queued copy gets its own pinned slot -- a single slot would be
+    overwritten by a later `random_()` before the copy engine reads it, and consecutive replays would share masks.  A
+    slot is reused only after the copy that read it has completed (event per slot).  Seeds come from torch's global CPU
+    generator, so runs are reproducible under `torch.manual_seed`."""
+
+    SLOTS = 64
+
+    def __init__(self, device):
+        self.host = torch.zeros(self.SLOTS, dtype=torch.int64).pin_memory()
+        self.dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self.events = [None] * self.SLOTS
+        self.k = 0
+
+    def refresh(self) -> None:
+        k = self.k
+        self.k = (k + 1) % self.SLOTS
+        if self.events[k] is not None:
+            self.events[k].synchronize()  # the copy issued SLOTS refreshes ago (long done in practice)
+        else:
+            self.events[k] = torch.cuda.Event()
+        self.host[k:k + 1].random_()
+        self.dev.copy_(self.host[k:k + 1], non_blocking=True)
+        self.events[k].record(torch.cuda.current_stream(self.dev.device))
+
+
+class GraphedStep:
+    """forward + loss + backward of one mini-batch SHAPE captured once as a CUDA graph and replayed per step.
+
+    `loss`: "mse" (`torch.nn.MSELoss()`, train.py:103) or "masked_l2" (`Masked_L2_loss`, the parser default,
+    utils/argument_parser.py:36-37 -- `regularize` / `regcoeff` as its constructor takes them).
 
     The kernel launches of a step (13 on the graph-resident route, ~90 on the layer-wise one) and the host-side
-    tensor-map encodes of the tensor-core GEMMs cost more
-    CPU time than the kernels take on a B200, so the step is recorded once on static buffers; every call copies
-    the new batch into those buffers, refreshes the device-resident dropout seed and replays.  Parameter `.grad`s
-    are static tensors owned by the graph (as after `zero_grad(); loss.backward()`), so an optimizer step can
-    follow directly.  The data-parallel gradient all-reduce runs right after the replay, outside the graph.
-    Mini-batches of a different shape (other N / E_raw) need their own instance.
+    tensor-map encodes of the tensor-core GEMMs cost more CPU time than the kernels take on a B200, so the step is
+    recorded once on static buffers; every call copies the new batch into those buffers, refreshes the device-resident
+    dropout seed and replays.  Parameter `.grad`s are static tensors owned by the graph (as after `zero_grad();
+    loss.backward()`), so an optimizer step can follow directly.  Data parallel: `total_count` = global number of output
+    elements for "mse"; for "masked_l2" the global (masked, unmasked) counts are all-reduced right before every replay
+    (2 floats) into a static buffer the captured loss kernel reads; the gradient all-reduce runs right after the
+    replay, outside the graph.  Mini-batches of a different shape (other N / E_raw) need their own instance.
+
+    The activation / scratch workspaces the captured kernels address are held in a pool PRIVATE to this object: no other
+    forward of the same shape (an `evaluate_epoch` between replays) can take, overwrite-and-free or drop them.
     """
 
     FIELDS = ("x", "y", "bus_type", "pred_mask", "edge_index", "edge_attr", "batch", "ptr")
 
-    def __init__(self, model: MaskEmbdMultiMPN, example_batch, total_count: Optional[int] = None, warmup: int = 3):
+    def __init__(self, model: MaskEmbdMultiMPN, example_batch, total_count: Optional[int] = None, warmup: int = 3,
+                 loss: str = "mse", regularize: bool = True, regcoeff: float = 1.0, group=None):
+        if loss not in ("mse", "masked_l2"):
+            raise ValueError(f"GraphedStep captures 'mse' or 'masked_l2' steps, not {loss!r}")
         dev = ops.require_cuda(*[p for p in model.parameters()])
         self.model, self.device, self.total_count = model, dev, total_count
+        self.loss_kind, self.regularize, self.regcoeff, self.group = loss, bool(regularize), float(regcoeff), group
         self.static = example_batch.to(dev)
         self.static = type(self.static)(*[getattr(self.static, f).clone() for f in self.FIELDS])
-        self.seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
-        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.seeds = _SeedRing(dev)
+        self.seed_dev = self.seeds.dev
         self.reducer, model._grad_reducer = model._grad_reducer, None  # the collective stays outside the graph
+        self.counts = None
+        if loss == "masked_l2" and self.reducer is not None:
+            self.counts = torch.zeros(2, dtype=torch.float32, device=dev)
+            self._refresh_counts()
+        self._pool = {}  # private workspace pool (see the class docstring)
+        outer_pool = model._swap_pool(self._pool)
         model._seed_device = self.seed_dev
         try:
             side = torch.cuda.Stream(device=dev)
@@ -114,21 +168,30 @@ class GraphedMSEStep:
             with torch.cuda.stream(side):
                 for _ in range(max(warmup, 1)):  # also runs every one-time cudaFuncSetAttribute / workspace allocation
                     self._refresh_seed()
-                    fused_mse_step(model, self.static, total_count)
+                    self._step()
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.loss = fused_mse_step(model, self.static, total_count)
+                self.loss = self._step()
             self.params = model._engine_params()
             self.grads = [p.grad for p in self.params]
         finally:
             model._seed_device = None
             model._grad_reducer = self.reducer
+            model._swap_pool(outer_pool)
+
+    def _step(self) -> torch.Tensor:
+        if self.loss_kind == "mse":
+            return fused_mse_step(self.model, self.static, self.total_count)
+        return fused_masked_l2_step(self.model, self.static, self.regularize, self.regcoeff, self.counts)
 
     def _refresh_seed(self):
-        self.seed_host.random_()
-        self.seed_dev.copy_(self.seed_host, non_blocking=True)
+        self.seeds.refresh()
+
+    def _refresh_counts(self):
+        from .parallel import global_mask_counts
+        self.counts.copy_(global_mask_counts(self.static.pred_mask, self.group))
 
     def load(self, batch) -> None:
         """Copy a batch of the captured shape (host pinned or device) into the static input buffers."""
@@ -143,6 +206,8 @@ class GraphedMSEStep:
         if batch is not None:
             self.load(batch)
         self._refresh_seed()
+        if self.counts is not None:
+            self._refresh_counts()
         self.graph.replay()
         for p, g in zip(self.params, self.grads):
             p.grad = g
@@ -154,6 +219,13 @@ class GraphedMSEStep:
                 for g in self.grads:
                     self.reducer(g)
         return self.loss
+
+
+class GraphedMSEStep(GraphedStep):
+    """`GraphedStep(loss="mse")` under its round-1 name."""
+
+    def __init__(self, model: MaskEmbdMultiMPN, example_batch, total_count: Optional[int] = None, warmup: int = 3):
+        super().__init__(model, example_batch, total_count, warmup, loss="mse")
 
 
 class PipelinedMSESteps:
@@ -200,25 +272,56 @@ class PipelinedMSESteps:
 
 
 class GraphedEpochs:
-    """Whole optimisation epochs at a fixed mini-batch shape with (almost) no host work per step: the sample ids of an
-    epoch go to the GPU once, `pfn_batch_assemble` writes every mini-batch straight INTO the static input buffers of a
-    captured forward + MSE + backward graph (`GraphedMSEStep`), the graph is replayed, and the optimizer (meant for
-    `optim.FusedAdamW`: one launch, pointer tables cached because the gradient buffers are static) follows.  The loss
-    sum stays on the device; one read-back per epoch.  The `train_epoch` loop of utils/training.py:30-80 for
-    `--train_loss_fn mse_loss` on a single-case dataset (all graphs of one size; incomplete last batches are dropped)."""
+    """Whole optimisation epochs with (almost) no host work per step: the sample ids of an epoch go to the GPU once,
+    `pfn_batch_assemble` writes every mini-batch straight INTO the static input buffers of a captured forward + loss +
+    backward graph (`GraphedStep`), the graph is replayed, and the optimizer (meant for `optim.FusedAdamW`: one launch,
+    pointer tables cached because the gradient buffers are static) follows.  The loss sum stays on the device; one
+    read-back per epoch.  The `train_epoch` loop of utils/training.py:30-80 for `--train_loss_fn mse_loss` or the parser
+    default `masked_l2` (incomplete last batches are dropped).
+
+    Datasets that mix graph sizes (`--case mixed`, datasets/PowerFlowData.py:67-70): the shape of a mini-batch is set by
+    how many samples of each case it drew, so steps are BUCKETED BY BATCH SHAPE -- the first batch of a shape captures
+    its own graph (at most `max_graphs` are kept; further shapes run the same step eagerly), later ones replay it.
+    """
 
     def __init__(self, model: MaskEmbdMultiMPN, dataset, batch_size: int, optimizer, total_count: Optional[int] = None,
-                 rank: int = 0, world: int = 1):
-        """Data parallel: pass `rank` / `world` (every rank must seed `run_epoch`'s generator alike) and
-        `total_count = world * batch_size * nodes_per_graph * output_dim`; the model's gradient all-reduce
+                 rank: int = 0, world: int = 1, loss: str = "mse", regularize: bool = True, regcoeff: float = 1.0,
+                 max_graphs: int = 64):
+        """Data parallel: pass `rank` / `world` (every rank must seed `run_epoch`'s generator alike); single-case
+        datasets with loss "mse" also need `total_count = world * batch_size * nodes_per_graph * output_dim` (for mixed
+        datasets the global count is all-reduced per step).  The model's gradient all-reduce
         (`parallel.attach_gradient_allreduce`) runs after every replay."""
         if batch_size > len(dataset):
             raise ValueError("batch_size exceeds the dataset")
         self.model, self.dataset, self.batch_size, self.optimizer = model, dataset, int(batch_size), optimizer
-        self.rank, self.world = int(rank), int(world)
+        self.rank, self.world, self.total_count = int(rank), int(world), total_count
+        self.loss_kind, self.regularize, self.regcoeff, self.max_graphs = loss, regularize, regcoeff, int(max_graphs)
+        self.uniform = len(set(int(v) for v in dataset._n)) == 1 and len(set(int(v) for v in dataset._e)) == 1
         model.train()
-        self.step = GraphedMSEStep(model, dataset.batch(list(range(batch_size))), total_count)
-        self.n_attr = len(self.step.static)
+        self.steps = {}
+        self.eager_steps = 0
+        if self.uniform:
+            self.step = self._step_for(dataset.batch(list(range(batch_size))))
+            self.n_attr = len(self.step.static)
+
+    def _shape_key(self, ids_host):
+        ds = self.dataset
+        import numpy as np
+        case_of = np.searchsorted(ds._first, ids_host, side="right") - 1
+        return int(ds._n[case_of].sum()), int(ds._e[case_of].sum())
+
+    def _step_for(self, example) -> "GraphedStep":
+        key = (int(example.x.size(0)), int(example.edge_index.size(1)))
+        step = self.steps.get(key)
+        if step is None:
+            total = self.total_count
+            if not self.uniform and self.loss_kind == "mse" and self.world > 1:
+                raise NotImplementedError("mixed-size datasets under data parallelism: use loss='masked_l2' (global counts "
+                                          "are all-reduced per step) or the eager `train_epoch`")
+            step = GraphedStep(self.model, example, total, loss=self.loss_kind, regularize=self.regularize,
+                               regcoeff=self.regcoeff)
+            self.steps[key] = step
+        return step
 
     def run_epoch(self, shuffle: bool = True, generator: Optional[torch.Generator] = None) -> float:
         from .datasets import epoch_batches
@@ -228,12 +331,27 @@ class GraphedEpochs:
         total = None
         if steps:
             order = torch.cat(batches)
-            order_dev = order.to(self.step.device, non_blocking=True)  # the ids of the whole epoch travel once
+            dev = next(self.model.parameters()).device
+            order_dev = order.to(dev, non_blocking=True)  # the ids of the whole epoch travel once
             order_host = order.numpy()
         self.model.train()
         for k in range(steps):
-            ds.batch(order_host[k * bs:(k + 1) * bs], ids_device=order_dev[k * bs:(k + 1) * bs], out=self.step.static)
-            loss = self.step(None)  # replay; parameter .grads are the graph's static buffers
+            ids_h, ids_d = order_host[k * bs:(k + 1) * bs], order_dev[k * bs:(k + 1) * bs]
+            if self.uniform:
+                step = self.step
+            else:
+                key = self._shape_key(ids_h)
+                step = self.steps.get(key)
+                if step is None and len(self.steps) < self.max_graphs:
+                    step = self._step_for(ds.batch(ids_h, ids_device=ids_d))
+            if step is not None:
+                ds.batch(ids_h, ids_device=ids_d, out=step.static)
+                loss = step(None)  # replay; parameter .grads are the graph's static buffers
+            else:  # more distinct shapes than `max_graphs`: the same step, launched eagerly
+                self.eager_steps += 1
+                data = ds.batch(ids_h, ids_device=ids_d)
+                loss = (fused_mse_step(self.model, data, self.total_count) if self.loss_kind == "mse" else
+                        fused_masked_l2_step(self.model, data, self.regularize, self.regcoeff))
             self.optimizer.step()
             total = loss.clone() if total is None else total + loss  # `loss` is a static tensor of the graph
         if total is None:
@@ -266,17 +384,29 @@ def train_epoch(model: MaskEmbdMultiMPN, loader, loss_fn, optimizer, device) -> 
     sum(len(data)), where `len(data)` is the number of stored attributes of the batch (PyG `BaseData.__len__`), i.e. an
     unweighted mean over batches.  `loader`: any iterable of batches (`datasets.PowerFlowData.loader`, a PyG DataLoader)."""
     from .losses import Masked_L2_loss, MixedMSEPoweImbalance, PowerImbalance
+    from . import parallel
     model = model.to(device)
     total, num_samples = None, 0
     model.train()
+    # data parallel (`parallel.attach_gradient_allreduce` + `loader(rank=, world=)`): the means of the fused losses are
+    # taken over the GLOBAL element counts, so the SUM all-reduce of the gradients equals the single-process gradient
+    # (also when ranks hold unequal last batches) and the returned loss is this rank's share of the global one.  Losses
+    # that go through autograd below keep per-rank means: their reduced gradient is divided by the world size instead.
+    dp = model._grad_reducer is not None and parallel.world_size() > 1
     for data in loader:
         data = data.to(device)
         optimizer.zero_grad()
         if isinstance(loss_fn, torch.nn.MSELoss) and loss_fn.reduction == "mean":
-            loss = fused_mse_step(model, data).view(())
+            count = parallel.global_count(data.y.numel(), device) if dp else None
+            loss = fused_mse_step(model, data, count).view(())
         elif isinstance(loss_fn, Masked_L2_loss):
-            loss = fused_masked_l2_step(model, data, loss_fn.regularize, float(loss_fn.regcoeff)).view(())
+            counts = parallel.global_mask_counts(data.pred_mask) if dp else None
+            loss = fused_masked_l2_step(model, data, loss_fn.regularize, float(loss_fn.regcoeff), counts).view(())
         else:
+            if dp:
+                raise NotImplementedError(
+                    "data-parallel train_epoch supports MSELoss and Masked_L2_loss (global element counts); other losses "
+                    "normalise per rank -- divide the reduced gradient by the world size in your own loop")
             out = model(data)
             if isinstance(loss_fn, PowerImbalance):
                 # "have to mask out the non-predicted values, otherwise the network can learn to predict full-zeros"

@@ -134,12 +134,74 @@ def test_broken_tile_promise_is_detected_and_falls_back():
     assert m._tile_rows(db) == 126
     with torch.no_grad():
         out = m(db)
-    assert list(m._tiling_checked.values()) == [False]
+    # both tilings were tried (equal tiles, then whole graphs packed from `ptr`: the same boundary) and refused
+    assert len(m._tiling_checked) == 2 and not any(m._tiling_checked.values())
     assert m._tile_rows(db) == 0  # the shape is remembered as not tileable
     assert not torch.isnan(out).any()
     _close(out, want, "fallback result")
     with torch.no_grad():
         _close(m(db), want, "second call (layer-wise from the start)")
+
+
+def test_uniform_tiling_refused_then_variable_tiles_accepted():
+    """N divisible by num_graphs although the graphs differ in size (10- and 18-bus grids alternating): the equal-tile
+    guess cuts a graph in two, the kernel refuses it, and the module retries with whole graphs packed from `ptr` on the
+    graph-resident route instead of dropping to the layer-wise kernels."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=64, n_gnn_layers=2, K=3, dropout_rate=0.0)
+    batch = synthetic_batch(cases=[(10, 13), (18, 25)] * 6)  # 168 nodes, 12 graphs: N / G = 14 -> tiles of 126 rows guessed
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).eval()
+    with torch.no_grad():
+        want = oracle(batch)
+    m = _model(kw).eval()
+    db = batch.to(DEV)
+    assert m._tiling(db)[0] == 126 and m._tiling(db)[2] is not None
+    n0 = _launches()
+    with torch.no_grad():
+        out = m(db)
+    first = _launches() - n0
+    assert m._tiling_checked == {(168, int(db.edge_index.size(1)), 126, 0): False, (168, int(db.edge_index.size(1)), 128, 12): True}
+    _close(out, want, "variable tiles after a refused uniform tiling")
+    assert m._tiling(db)[:1] == (128,) and m._tiling(db)[1] is not None
+    n0 = _launches()
+    with torch.no_grad():
+        _close(m(db), want, "second call (variable tiles from the start)")
+    assert _launches() - n0 < first
+
+
+def test_tile_validation_is_repeated_periodically():
+    """The closed-tile flag is read back for the first batch of a shape and then every `_tiling_recheck` batches: a later
+    batch of the same shape that breaks the promise is caught at the next re-check (its own output rows are NaN-poisoned
+    by the kernel in the meantime, never silently wrong)."""
+    from poweflownet_b200.data import synthetic_batch
+    kw = dict(common.MODEL_DIMS, hidden_dim=64, n_gnn_layers=2, K=3, dropout_rate=0.0)
+    import types
+    good = synthetic_batch("14", 18)
+    ei = good.edge_index.clone()
+    ei[:, -1] = torch.tensor([125, 126])
+    bad = common.GraphBatch(**{f: (ei if f == "edge_index" else getattr(good, f)) for f in
+                               ("x", "y", "bus_type", "pred_mask", "edge_index", "edge_attr", "batch", "ptr")})
+    oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).eval()
+    with torch.no_grad():
+        want_bad = oracle(bad)
+    m = _model(kw).eval()
+    m._tiling_recheck = 3
+
+    def no_ptr(b):  # a batch object without `ptr` (only num_graphs): no variable-tile second attempt
+        d = b.to(DEV)
+        return types.SimpleNamespace(x=d.x, y=d.y, pred_mask=d.pred_mask, edge_index=d.edge_index, edge_attr=d.edge_attr,
+                                     num_graphs=b.num_graphs)
+    dg, dbad = no_ptr(good), no_ptr(bad)
+    sig = (good.num_nodes, int(good.edge_index.size(1)), 126, 0)
+    with torch.no_grad():
+        m(dg)                      # call 0: validated
+        assert m._tiling_checked == {sig: True}
+        out1 = m(dbad)             # call 1: not re-validated -> the broken tiles come back NaN, never silently wrong
+        assert torch.isnan(out1).any()
+        m(dg)                      # call 2
+        out3 = m(dbad)             # call 3: re-validated -> refused -> layer-wise result
+    assert m._tiling_checked[sig] is False
+    _close(out3, want_bad, "layer-wise result after the periodic re-check")
 
 
 def test_tiled_entry_point_rejects_unsupported_configurations():
@@ -239,7 +301,7 @@ def test_mixed_size_batches_take_variable_tiles():
     grads, outs = {}, {}
     for fused in (True, False):
         m = _model(kw, fused).train()
-        tile, ptr = m._tiling(db)
+        tile, ptr, _ = m._tiling(db)
         assert (tile, ptr is not None) == ((128, True) if fused else (0, False))
         n0 = _launches()
         out = m(db)

@@ -16,11 +16,11 @@ def _model(**cfg):
 def test_uniform_batches_get_whole_graph_tiles():
     from poweflownet_b200.data import synthetic_batch
     m = _model(hidden_dim=129, n_gnn_layers=4, K=3)
-    assert m._tiling(synthetic_batch("118v2", 5)) == (118, None)      # one 118-bus graph per 128-row tile
-    assert m._tiling(synthetic_batch("14", 20)) == (126, None)        # nine 14-bus graphs per tile
-    assert m._tiling(synthetic_batch("6470rte", 1)) == (0, None)      # too large: layer-wise kernels
+    assert m._tiling(synthetic_batch("118v2", 5)) == (118, None, None)      # one 118-bus graph per 128-row tile
+    assert m._tiling(synthetic_batch("14", 20)) == (126, None, None)        # nine 14-bus graphs per tile
+    assert m._tiling(synthetic_batch("6470rte", 1)) == (0, None, None)      # too large: layer-wise kernels
     m.fused = False
-    assert m._tiling(synthetic_batch("118v2", 5)) == (0, None)
+    assert m._tiling(synthetic_batch("118v2", 5)) == (0, None, None)
 
 
 def test_unsupported_widths_and_depths_take_the_layerwise_route():
@@ -37,9 +37,9 @@ def test_mixed_sizes_need_ptr_on_the_device():
     from poweflownet_b200.data import synthetic_batch
     m = _model(hidden_dim=129, n_gnn_layers=4, K=3)
     mixed = synthetic_batch(cases=["14", "118v2", "14"])
-    assert m._tiling(mixed) == (0, None)  # ptr is a CPU tensor here: the variable-size tiling is a device-side pass
+    assert m._tiling(mixed) == (0, None, None)  # ptr is a CPU tensor here: the variable-size tiling is a device-side pass
     m._tiling_checked[(mixed.num_nodes, int(mixed.edge_index.size(1)), 128, 3)] = False
-    assert m._tiling(mixed) == (0, None)
+    assert m._tiling(mixed) == (0, None, None)
 
 
 def test_a_failed_validation_is_remembered_per_shape():
@@ -48,7 +48,7 @@ def test_a_failed_validation_is_remembered_per_shape():
     b = synthetic_batch("118v2", 4)
     assert m._tiling(b)[0] == 118
     m._tiling_checked[(b.num_nodes, int(b.edge_index.size(1)), 118, 0)] = False
-    assert m._tiling(b) == (0, None)
+    assert m._tiling(b) == (0, None, None)
     assert m._tiling(synthetic_batch("118v2", 5))[0] == 118  # another shape is unaffected
 
 

@@ -168,176 +168,286 @@ k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_ea_fwd_warp: the same message + aggregate with a WARP owning two consecutive rows at a time (hidden widths of
-// 24..33 float4 columns, i.e. hidden_dim 93..132: standard.json's 129).  k_ea_fwd above moves a CTA in lock step through
-// "stage the CSR slab -> barrier -> one row per thread -> next row" and keeps ~5 row loads per thread in flight; its
-// SMs are busy only two thirds of the kernel's duration (ncu: sm__cycles_active / elapsed = 0.67, 5 barrier-stalled
-// warps per issue).  Here nothing is shared between warps after the first barrier (We in shared memory) and the warps
-// are persistent and software-pipelined: while the neighbour rows of row pair i are in flight, the neighbour ids /
-// edge_attr of pair i+1 and the row pointers of pair i+2 are already being fetched, so the dependent chain
-// rowptr -> neighbour id -> neighbour row is paid once per warp, not once per row.  Lanes 0..2 read the row pointers;
-// the lanes read the pair's neighbour ids / edge_attr in one coalesced load each and broadcast them by shuffle; every
-// lane keeps its float4 column of BOTH rows and up to eight gathered neighbour rows in flight at once.  Column 32
-// (floats 128..131, the odd 129th channel) would cost a second pass with one active lane: instead lane u gathers that
-// chunk for edge u of the pair and the per-row sums are taken in edge order through shuffles.  Per-row results are
-// bit-identical to k_ea_fwd (same FMAs, same ascending-edge summation order).
-constexpr int kEaWarpChunk = 8;
-constexpr int kEaWarpThreads = 128;
-constexpr bool kEaFwdWarpDefault = false;  // measured on the B200: 19.5 us against 12.6 us for k_ea_fwd at case118v2 x 128
-                                           // (profiles/r1_ea_fwd_warp_vs_cta.json) -- opt-in (PFN_EA_FWD=warp) until it wins
+// k_ea_fwd_pipe: the same message + aggregate as k_ea_fwd, restructured around ASYNCHRONOUS COPIES INTO SHARED MEMORY so
+// that the bytes in flight are bounded by shared memory (~200 KB per SM) instead of by registers (k_ea_fwd: 61 registers
+// x 924 threads, five 16-byte row loads per thread; ncu: long_scoreboard 50 %, barrier 23 %, SMs busy 0.67 of the time).
+//
+//  * One persistent CTA per SM, W autonomous warps.  A warp owns a contiguous range of rows and runs its own software
+//    pipeline: no CTA-wide barrier after the prologue, no producer/consumer hand-off between warps.
+//  * The warp's slice of the CSR (row pointers, neighbour ids, edge_attr) is staged in shared memory in chunks of up to
+//    kPipeRows rows / kPipeEdges edges, so the dependent chain rowptr -> neighbour id -> neighbour row is paid once per
+//    chunk, not once per row.
+//  * Rows travel in BATCHES of whole rows: R consecutive Hi rows -- ONE bulk copy (cp.async.bulk, SASS UBLKCP; the rows
+//    of a node matrix are contiguous) -- followed by the gathered Hj row of every incoming edge, into a ring of
+//    n_stages buffers per warp.  Gathered rows of >= 1 KB go as one bulk copy per row issued by one lane each (32 rows
+//    per instruction round); shorter rows (hidden 129: 528 B) go as 16-byte cp.async (LDGSTS) chunks, whose issue
+//    cost is known and small (the TMA unit's rate for sub-kilobyte copies is not).  Either way completion lands on the
+//    batch's mbarrier (complete_tx bytes / cp.async.mbarrier.arrive), and the warp computes batch i while batches
+//    i+1 .. i+n_stages-1 are in flight.
+//  * Compute: the (row, 16-byte column chunk) pairs of a batch are dealt to the lanes round-robin (pair t -> lane t mod
+//    32), so widths that are not a multiple of 32 chunks (hidden 129 = 33 chunks) leave no lane idle; the pair's Hi chunk
+//    sits at byte 16 t of the batch buffer.  Per pair the edges are summed in ascending edge id with the same FMAs as
+//    k_ea_fwd: the two kernels are BIT-IDENTICAL (tests/test_gpu_kernels.py).  S rows leave as 16-byte stores at
+//    consecutive addresses.
+//  * Small problems (both node matrices within a fraction of L2): before griddepcontrol.wait every warp asks the L2 to
+//    prefetch its slice of Hi, Hj and the CSR arrays (cp.async.bulk.prefetch.L2): the HBM reads start at once instead
+//    of trickling in behind the two dependent metadata loads, and the gathers become L2 hits.
+//  A row whose degree exceeds a batch buffer (a hub bus) is summed straight from global memory by the same warp.
+constexpr int kPipeRows = 64;     // rows of CSR metadata staged per chunk and warp
+constexpr int kPipeEdges = 256;   // edges of CSR metadata staged per chunk and warp
+constexpr int kPipeMaxStages = 4;
+constexpr int kPipeMaxWarps = 8;
 
-__device__ __forceinline__ float4 shfl4(float4 v, int src) {
-  return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
-                     __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
-}
-
-struct RowPair {
-  int r0, nrow, e0, deg0, ne;  // first row, rows (1 or 2), first edge, edges of row 0, edges of the pair
+struct PipeWarpMeta {
+  int rp[kPipeRows + 4];
+  int nb[kPipeEdges];
+  float2 ea[kPipeEdges];
 };
 
-// lanes 0..nrow of a live pair read its row pointers; 0 for pairs past the end
-__device__ __forceinline__ int pair_rowptr(const int* __restrict__ rowptr, int pair, int npairs, int n_nodes, int lane) {
-  if (pair >= npairs) return 0;
-  const int r0 = 2 * pair, nrow = min(2, n_nodes - r0);
-  return lane <= nrow ? __ldg(rowptr + r0 + lane) : 0;
+struct PipeArgs {
+  const float* Hi;
+  const float* Hj;
+  const int* rowptr;
+  const int* nbr;
+  const float2* ea;
+  const float* We;
+  float* S;
+  long long ldh, lds, ldwe;
+  int n_nodes, h, c4, warps, n_stages, cap_slots, rows_per_warp, prefetch_l2, early_trigger, contiguous;
+  unsigned stage_bytes;
+  long long e_cap;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t pipe_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void pipe_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pipe_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pipe_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 
-__device__ __forceinline__ RowPair pair_derive(int rp, int pair, int n_nodes) {
-  RowPair p;
-  p.r0 = 2 * pair;
-  p.nrow = min(2, n_nodes - p.r0);
-  const int e0 = __shfl_sync(0xffffffffu, rp, 0), e1 = __shfl_sync(0xffffffffu, rp, 1), e2 = __shfl_sync(0xffffffffu, rp, p.nrow);
-  p.e0 = e0;
-  p.deg0 = e1 - e0;
-  p.ne = e2 - e0;
-  return p;
+// prefetch this warp's 1/total share of [base, base + bytes) into L2 (one lane; 16-byte granules, pieces of <= 64 KB)
+__device__ __forceinline__ void prefetch_share(const void* base, long long bytes, int part, int parts) {
+  const long long gran = (bytes + 15) >> 4;  // 16-byte granules (the arrays are padded to 16 bytes)
+  const long long per = (gran + parts - 1) / parts;
+  long long lo = per * part, hi = min(gran, lo + per);
+  const char* p = static_cast<const char*>(base);
+  for (; lo < hi; lo += 4096) bulk_prefetch_l2(p + (lo << 4), static_cast<uint32_t>(min((long long)4096, hi - lo) << 4));
 }
 
-__global__ void __launch_bounds__(kEaWarpThreads)
-k_ea_fwd_warp(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh, const int* __restrict__ rowptr,
-              const int* __restrict__ nbr, const float2* __restrict__ ea, const float* __restrict__ We, int64_t ldwe,
-              float* __restrict__ S, int64_t lds, int n_nodes, int h, int c4) {
-  pdl_wait();
-  __shared__ float4 s_w[33][2];
-  constexpr int kWarps = kEaWarpThreads / 32;
+template <bool BULK>
+__global__ void __launch_bounds__(32 * kPipeMaxWarps, 1) k_ea_fwd_pipe(const __grid_constant__ PipeArgs a) {
+  extern __shared__ __align__(128) uint8_t pipe_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int npairs = (n_nodes + 1) >> 1, stride = gridDim.x * kWarps;
-  int pair = blockIdx.x * kWarps + warp;
-  const int rp_cur = pair_rowptr(rowptr, pair, npairs, n_nodes, lane);  // in flight while We is staged
-  int rp_nxt = pair_rowptr(rowptr, pair + stride, npairs, n_nodes, lane);
-  if (threadIdx.x < 2 * c4) {
-    const int q = threadIdx.x >> 1, k = threadIdx.x & 1;
+  const int c4 = a.c4, W = a.warps, NS = a.n_stages, cap = a.cap_slots;
+  const uint32_t rowbytes = uint32_t(c4) * 16u;
+  // shared-memory map: We table [c4][2] float4 | barriers [W][kPipeMaxStages] | per-warp metadata | per-warp stage ring
+  float4* s_w = reinterpret_cast<float4*>(pipe_smem);
+  const uint32_t off_bar = (uint32_t(c4) * 32u + 127u) & ~127u;
+  const uint32_t off_meta = off_bar + ((uint32_t(W) * kPipeMaxStages * 8u + 127u) & ~127u);
+  const uint32_t meta_bytes = (uint32_t(sizeof(PipeWarpMeta)) + 127u) & ~127u;
+  const uint32_t off_data = off_meta + uint32_t(W) * meta_bytes;
+  PipeWarpMeta& m = *reinterpret_cast<PipeWarpMeta*>(pipe_smem + off_meta + uint32_t(warp) * meta_bytes);
+  const uint32_t smem0 = pipe_smem_u32(pipe_smem);
+  const uint32_t bar0 = smem0 + off_bar + uint32_t(warp) * kPipeMaxStages * 8u;
+  const uint32_t data0 = smem0 + off_data + uint32_t(warp) * uint32_t(NS) * a.stage_bytes;
+
+  const int gw = blockIdx.x * W + warp, n_warps = gridDim.x * W;
+  const int w_start = min(a.n_nodes, gw * a.rows_per_warp), w_end = min(a.n_nodes, w_start + a.rows_per_warp);
+
+  // ---- prologue that may overlap the previous kernel's tail (nothing here reads data as a value) ----
+  if (lane == 0) {
+    for (int s = 0; s < NS; ++s) pipe_mbar_init(bar0 + 8u * s, BULK ? 1u : 33u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (a.prefetch_l2) {
+      if (a.contiguous && w_end > w_start) {
+        // the warp's own Hi rows; its 1/n_warps share of Hj (some warp gathers every row of it exactly once from HBM)
+        const long long lo = (long long)w_start * a.ldh * 4, hi = (long long)w_end * a.ldh * 4;
+        for (long long o = lo; o < hi; o += 65536)
+          bulk_prefetch_l2(reinterpret_cast<const char*>(a.Hi) + o, static_cast<uint32_t>(min((long long)65536, hi - o)));
+      }
+      if (a.contiguous) prefetch_share(a.Hj, (long long)a.n_nodes * a.ldh * 4, gw, n_warps);
+      prefetch_share(a.nbr, a.e_cap * 4, gw, n_warps);
+      prefetch_share(a.ea, a.e_cap * 8, gw, n_warps);
+      prefetch_share(a.rowptr, ((long long)a.n_nodes + 1) * 4, gw, n_warps);
+    }
+  }
+  pdl_wait();
+  if (a.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int i = threadIdx.x; i < 2 * c4; i += blockDim.x) {
+    const int q = i >> 1, k = i & 1;
     float w[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int ch = 4 * q + c;
-      w[c] = ch < h ? __ldg(We + ch * ldwe + k) : 0.f;
+      w[c] = ch < a.h ? __ldg(a.We + ch * a.ldwe + k) : 0.f;
     }
-    s_w[q][k] = make_float4(w[0], w[1], w[2], w[3]);
+    s_w[2 * q + k] = make_float4(w[0], w[1], w[2], w[3]);
   }
-  __syncthreads();
-  if (pair >= npairs) return;  // surplus warp
-  const bool act = lane < min(c4, 32);
-  const bool tail = c4 > 32;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 w0 = zero, w1 = zero;
-  if (act) {
-    w0 = s_w[lane][0];
-    w1 = s_w[lane][1];
-  }
-  RowPair cur = pair_derive(rp_cur, pair, n_nodes);
-  int my_nbr = 0;  // neighbour id / edge_attr of edge `lane` of the current pair (its first 32 edges)
-  float2 my_ea = make_float2(0.f, 0.f);
-  if (lane < min(32, cur.ne)) {
-    my_nbr = __ldg(nbr + cur.e0 + lane);
-    my_ea = __ldg(ea + cur.e0 + lane);
-  }
-  while (true) {
-    // ---- prefetch: row pointers two pairs ahead, neighbour ids / edge_attr one pair ahead ----
-    const int nxt_pair = pair + stride;
-    const bool has_next = nxt_pair < npairs;
-    const int rp_nn = pair_rowptr(rowptr, nxt_pair + stride, npairs, n_nodes, lane);
-    RowPair nxt = cur;
-    int nbr_n = 0;
-    float2 ea_n = make_float2(0.f, 0.f);
-    if (has_next) {
-      nxt = pair_derive(rp_nxt, nxt_pair, n_nodes);
-      if (lane < min(32, nxt.ne)) {
-        nbr_n = __ldg(nbr + nxt.e0 + lane);
-        ea_n = __ldg(ea + nxt.e0 + lane);
+  __syncthreads();  // the only CTA-wide barrier: We table + barrier initialisation
+  if (warp >= W) return;
+
+  // largest R in [0, min(32, n - r0)] with R + (edges of rows [r0, r0 + R)) <= cap slots; 0 = row r0 alone does not fit
+  auto greedy = [&](int r0, int n) {
+    const int c = lane + 1;
+    bool ok = false;
+    if (r0 + c <= n) ok = c + (m.rp[r0 + c] - m.rp[r0]) <= cap;
+    return __popc(__ballot_sync(0xffffffffu, ok));
+  };
+
+  unsigned issued = 0, consumed = 0;  // batches over the whole kernel: stage = idx % NS, mbarrier parity = (idx / NS) & 1
+  int row = w_start;
+  while (row < w_end) {  // ---- one chunk of CSR metadata ----
+    const int nr_try = min(kPipeRows, w_end - row);
+    for (int i = lane; i <= nr_try; i += 32) m.rp[i] = a.rowptr[row + i];
+    __syncwarp();
+    const int e_base = m.rp[0];
+    int n;
+    {
+      const int c1 = lane + 1, c2 = lane + 33;
+      const bool ok1 = c1 <= nr_try && m.rp[c1] - e_base <= kPipeEdges;
+      const bool ok2 = c2 <= nr_try && m.rp[c2] - e_base <= kPipeEdges;
+      n = __popc(__ballot_sync(0xffffffffu, ok1)) + __popc(__ballot_sync(0xffffffffu, ok2));
+    }
+    const int ne = n > 0 ? m.rp[n] - e_base : 0;
+    for (int i = lane; i < ne; i += 32) {
+      m.nb[i] = a.nbr[e_base + i];
+      m.ea[i] = a.ea[e_base + i];
+    }
+    __syncwarp();
+
+    // a row summed straight from global memory (hub bus: more incident edges than a batch buffer / a metadata chunk holds)
+    auto slow_row = [&](int node) {
+      const int beg = a.rowptr[node], fin = a.rowptr[node + 1];
+      for (int q = lane; q < c4; q += 32) {
+        const float4 w0 = s_w[2 * q], w1 = s_w[2 * q + 1];
+        const float4 hi = ld4(a.Hi + (size_t)node * a.ldh + 4 * q);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = beg; e < fin; ++e)
+          add_relu(acc, preact(hi, ldg4(a.Hj + (size_t)a.nbr[e] * a.ldh + 4 * q), a.ea[e], w0, w1));
+        st4(a.S + (size_t)node * a.lds + 4 * q, acc);
       }
+    };
+    if (n == 0) {  // the first row alone has more than kPipeEdges edges
+      slow_row(row);
+      ++row;
+      __syncwarp();
+      continue;
     }
-    // ---- the current pair ----
-    float4 hi0 = zero, hi1 = zero;
-    if (act) {
-      hi0 = ld4(Hi + cur.r0 * ldh + 4 * lane);
-      if (cur.nrow == 2) hi1 = ld4(Hi + (cur.r0 + 1) * ldh + 4 * lane);
-    }
-    float4 acc0 = zero, acc1 = zero, tacc0 = zero, tacc1 = zero;
-    for (int eb = 0; eb < cur.ne; eb += 32) {  // 32 edges of the pair per round (one round unless a hub bus is involved)
-      const int cnt = min(32, cur.ne - eb);
-      int nb = my_nbr;
-      float2 a_l = my_ea;
-      if (eb > 0) {
-        nb = 0;
-        a_l = make_float2(0.f, 0.f);
-        if (lane < cnt) {
-          nb = __ldg(nbr + cur.e0 + eb + lane);
-          a_l = __ldg(ea + cur.e0 + eb + lane);
+
+    int issue_ptr = 0, cons_ptr = 0;  // local row indices inside the chunk
+    while (true) {
+      // ---- issue as many batches as the ring holds ----
+      while (issued - consumed < unsigned(NS) && issue_ptr < n) {
+        const int R = greedy(issue_ptr, n);
+        if (R == 0) break;  // hub row: handled below once the ring has drained
+        const uint32_t bar = bar0 + 8u * (issued % NS), buf = data0 + (issued % NS) * a.stage_bytes;
+        const int e0 = m.rp[issue_ptr] - e_base, nE = m.rp[issue_ptr + R] - e_base - e0;
+        const float* hi_src = a.Hi + (size_t)(row + issue_ptr) * a.ldh;
+        __syncwarp();  // every lane has finished reading the buffer's previous contents
+        if (lane == 0) {
+          const uint32_t tx = (a.contiguous || BULK ? uint32_t(R) * rowbytes : 0u) + (BULK ? uint32_t(nE) * rowbytes : 0u);
+          pipe_mbar_expect_tx(bar, tx);
+          if (a.contiguous) bulk_g2s(buf, hi_src, uint32_t(R) * rowbytes, bar);  // R consecutive Hi rows: one bulk copy
         }
-      }
-      float4 tg = zero, ht = zero;  // column 32: lane u works on edge u of the round
-      if (tail && lane < cnt) {
-        ht = ld4(Hi + (cur.r0 + (eb + lane < cur.deg0 ? 0 : 1)) * ldh + 128);
-        tg = ldg4(Hj + nb * ldh + 128);
-      }
-      for (int cb = 0; cb < cnt; cb += kEaWarpChunk) {
-        float4 g[kEaWarpChunk];
-#pragma unroll
-        for (int u = 0; u < kEaWarpChunk; ++u) {
-          const int s = __shfl_sync(0xffffffffu, nb, (cb + u) & 31);
-          g[u] = zero;
-          if (cb + u < cnt && act) g[u] = ldg4(Hj + s * ldh + 4 * lane);
-        }
-#pragma unroll
-        for (int u = 0; u < kEaWarpChunk; ++u) {
-          if (cb + u < cnt) {  // warp-uniform
-            const float2 a = make_float2(__shfl_sync(0xffffffffu, a_l.x, cb + u), __shfl_sync(0xffffffffu, a_l.y, cb + u));
-            if (eb + cb + u < cur.deg0) {  // warp-uniform: which row of the pair the edge belongs to
-              add_relu(acc0, preact(hi0, g[u], a, w0, w1));
-            } else {
-              add_relu(acc1, preact(hi1, g[u], a, w0, w1));
-            }
+        __syncwarp();
+        if (BULK) {
+          if (!a.contiguous && lane < R) bulk_g2s(buf + uint32_t(lane) * rowbytes, hi_src + (size_t)lane * a.ldh, rowbytes, bar);
+          for (int i = lane; i < nE; i += 32)
+            bulk_g2s(buf + uint32_t(R + i) * rowbytes, a.Hj + (size_t)m.nb[e0 + i] * a.ldh, rowbytes, bar);
+        } else {
+          // 16-byte chunks, dealt to the lanes round-robin over the (row, chunk) pairs of the batch
+          const int first = a.contiguous ? R : 0, total = (R + nE) * c4;
+          int k = first, q = lane;
+          while (q >= c4) { q -= c4; ++k; }
+          for (int t = first * c4 + lane; t < total; t += 32) {
+            const float* src = k < R ? a.Hi + (size_t)(row + issue_ptr + k) * a.ldh : a.Hj + (size_t)m.nb[e0 + k - R] * a.ldh;
+            cp_async16(buf + uint32_t(t) * 16u, src + 4 * q);
+            q += 32;
+            while (q >= c4) { q -= c4; ++k; }
           }
+          cp_async_arrive_noinc(bar);
         }
+        ++issued;
+        issue_ptr += R;
       }
-      if (tail) {
-        float4 tr = zero;
-        if (lane < cnt) {
-          const float4 p = preact(ht, tg, a_l, s_w[32][0], s_w[32][1]);
-          tr = make_float4(fmaxf(p.x, 0.f), fmaxf(p.y, 0.f), fmaxf(p.z, 0.f), fmaxf(p.w, 0.f));
-        }
-        for (int u = 0; u < cnt; ++u) {  // ascending edge order; every lane keeps a copy
-          const float4 v = shfl4(tr, u);
-          if (eb + u < cur.deg0) {
-            tacc0.x += v.x; tacc0.y += v.y; tacc0.z += v.z; tacc0.w += v.w;
-          } else {
-            tacc1.x += v.x; tacc1.y += v.y; tacc1.z += v.z; tacc1.w += v.w;
-          }
-        }
+      if (consumed == issued) {
+        if (issue_ptr >= n) break;
+        slow_row(row + issue_ptr);  // nothing in flight and the next row does not fit a batch
+        ++issue_ptr;
+        cons_ptr = issue_ptr;
+        __syncwarp();
+        continue;
       }
+      // ---- consume the oldest batch ----
+      const int R = greedy(cons_ptr, n);  // the same value as when the batch was issued
+      const uint32_t bar = bar0 + 8u * (consumed % NS), buf = data0 + (consumed % NS) * a.stage_bytes;
+      pipe_mbar_wait(bar, (consumed / NS) & 1u);
+      const int e0 = m.rp[cons_ptr] - e_base;
+      const uint32_t gat = buf + uint32_t(R) * rowbytes;  // gathered rows: edge e of the chunk at slot e - e0
+      float* s_dst = a.S + (size_t)(row + cons_ptr) * a.lds;
+      const int total = R * c4;
+      int k = 0, q = lane;
+      while (q >= c4) { q -= c4; ++k; }
+      for (int t = lane; t < total; t += 32) {
+        const float4 hi = lds4(buf + uint32_t(t) * 16u);
+        const float4 w0 = s_w[2 * q], w1 = s_w[2 * q + 1];
+        const int beg = m.rp[cons_ptr + k] - e_base, fin = m.rp[cons_ptr + k + 1] - e_base;
+        const uint32_t col = gat + uint32_t(q) * 16u;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int e = beg;
+        for (; e + 3 < fin; e += 4) {  // four shared-memory row reads in flight
+          const float4 h0 = lds4(col + uint32_t(e - e0) * rowbytes), h1 = lds4(col + uint32_t(e + 1 - e0) * rowbytes);
+          const float4 h2 = lds4(col + uint32_t(e + 2 - e0) * rowbytes), h3 = lds4(col + uint32_t(e + 3 - e0) * rowbytes);
+          add_relu(acc, preact(hi, h0, m.ea[e], w0, w1));
+          add_relu(acc, preact(hi, h1, m.ea[e + 1], w0, w1));
+          add_relu(acc, preact(hi, h2, m.ea[e + 2], w0, w1));
+          add_relu(acc, preact(hi, h3, m.ea[e + 3], w0, w1));
+        }
+        if (e + 1 < fin) {
+          const float4 h0 = lds4(col + uint32_t(e - e0) * rowbytes), h1 = lds4(col + uint32_t(e + 1 - e0) * rowbytes);
+          add_relu(acc, preact(hi, h0, m.ea[e], w0, w1));
+          add_relu(acc, preact(hi, h1, m.ea[e + 1], w0, w1));
+          e += 2;
+        }
+        if (e < fin) add_relu(acc, preact(hi, lds4(col + uint32_t(e - e0) * rowbytes), m.ea[e], w0, w1));
+        st4(s_dst + (size_t)k * a.lds + 4 * q, acc);
+        q += 32;
+        while (q >= c4) { q -= c4; ++k; }
+      }
+      ++consumed;
+      cons_ptr += R;
     }
-    if (act) {
-      st4(S + cur.r0 * lds + 4 * lane, acc0);
-      if (cur.nrow == 2) st4(S + (cur.r0 + 1) * lds + 4 * lane, acc1);
-    }
-    if (tail && lane < cur.nrow) st4(S + (cur.r0 + lane) * lds + 128, lane == 0 ? tacc0 : tacc1);
-    if (!has_next) break;
-    pair = nxt_pair;
-    cur = nxt;
-    my_nbr = nbr_n;
-    my_ea = ea_n;
-    rp_nxt = rp_nn;
+    row += n;
+    __syncwarp();  // the metadata of this chunk is overwritten next
   }
 }
 
@@ -520,14 +630,80 @@ k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, 
   }
 }
 
-// which forward kernel: warp-owned row pairs for 24..33 float4 columns (PFN_EA_FWD=cta forces the CTA-slab kernel,
-// PFN_EA_FWD=warp the warp kernel; read per call so that tests can compare the two)
-bool ea_fwd_warp_rows(int c4) {
-  const bool eligible = c4 >= 24 && c4 <= 33;
+// ---- host side of k_ea_fwd_pipe --------------------------------------------------------------------------------------
+// PFN_EA_FWD=cta forces the CTA-slab kernel (k_ea_fwd), PFN_EA_FWD=pipe / unset takes the pipelined kernel whenever the
+// width fits; read per call so that tests can compare the two.  Tuning knobs (experiments): PFN_EA_STAGES (2..4),
+// PFN_EA_WARPS (1..8), PFN_EA_PREFETCH (0/1), PFN_EA_TRIGGER (0/1), PFN_EA_BULK (0/1: gathered rows as bulk copies).
+constexpr uint32_t kPipeSmemLimit = 227 * 1024;
+constexpr long long kPipePrefetchMaxBytes = 48ll << 20;  // L2-prefetch both node matrices only when they fit well inside L2
+
+bool ea_fwd_use_pipe() {
   const char* e = std::getenv("PFN_EA_FWD");
-  if (e != nullptr && e[0] == 'c') return false;
-  if (e != nullptr && e[0] == 'w') return eligible;
-  return eligible && kEaFwdWarpDefault;
+  return !(e != nullptr && e[0] == 'c');
+}
+
+// 0 = launched, 1 = shape outside this kernel (caller uses k_ea_fwd)
+int ea_fwd_pipe_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView& g, int64_t n_nodes, const float* We,
+                       int64_t ldwe, float* S, int64_t lds, int64_t h, cudaStream_t stream) {
+  const int c4 = static_cast<int>((h + 3) / 4);
+  const uint32_t rowbytes = uint32_t(c4) * 16u;
+  if (n_nodes >= (int64_t(1) << 31) - 64 || rowbytes > 16384u) return 1;
+  PipeArgs a{};
+  const int env_bulk = env_int("PFN_EA_BULK", -1);
+  const bool bulk = env_bulk >= 0 ? env_bulk != 0 : rowbytes >= 1024u;
+  int warps = rowbytes <= 1024u ? 8 : rowbytes <= 4096u ? 4 : 2;
+  warps = std::max(1, std::min(kPipeMaxWarps, env_int("PFN_EA_WARPS", warps)));
+  int stages = std::max(2, std::min(kPipeMaxStages, env_int("PFN_EA_STAGES", 3)));
+  const uint32_t meta_bytes = (uint32_t(sizeof(PipeWarpMeta)) + 127u) & ~127u;
+  auto fixed_bytes = [&](int w) {
+    return ((uint32_t(c4) * 32u + 127u) & ~127u) + ((uint32_t(w) * kPipeMaxStages * 8u + 127u) & ~127u) + uint32_t(w) * meta_bytes;
+  };
+  // at least 8 slots (a row and seven incident edges) per batch buffer: fewer warps, then fewer stages
+  uint32_t stage_bytes = 0;
+  int cap = 0;
+  for (;;) {
+    const uint32_t per_warp = (kPipeSmemLimit - 128u - fixed_bytes(warps)) / uint32_t(warps);
+    stage_bytes = (per_warp / uint32_t(stages)) & ~127u;
+    cap = static_cast<int>(stage_bytes / rowbytes);
+    if (cap >= 8) break;
+    if (stages > 2) --stages;
+    else if (warps > 1) warps = std::max(1, warps / 2);
+    else break;
+  }
+  if (cap < 2) return 1;
+  cap = std::min(cap, 32 + kPipeEdges);
+  a.Hi = Hi;
+  a.Hj = Hj;
+  a.rowptr = g.rowptr_t;
+  a.nbr = g.nbr_t;
+  a.ea = reinterpret_cast<const float2*>(g.ea_t);
+  a.We = We;
+  a.S = S;
+  a.ldh = ldh;
+  a.lds = lds;
+  a.ldwe = ldwe;
+  a.n_nodes = static_cast<int>(n_nodes);
+  a.h = static_cast<int>(h);
+  a.c4 = c4;
+  a.warps = warps;
+  a.n_stages = stages;
+  a.cap_slots = cap;
+  a.stage_bytes = stage_bytes;
+  a.contiguous = (ldh * 4 == int64_t(rowbytes)) ? 1 : 0;
+  a.e_cap = g.e_cap;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), ceil_div64(n_nodes, warps))));
+  a.rows_per_warp = static_cast<int>(ceil_div64(n_nodes, int64_t(grid) * warps));
+  a.prefetch_l2 = env_int("PFN_EA_PREFETCH", 2 * n_nodes * int64_t(rowbytes) <= kPipePrefetchMaxBytes ? 1 : 0) != 0 ? 1 : 0;
+  a.early_trigger = env_int("PFN_EA_TRIGGER", 0) != 0 ? 1 : 0;
+  const uint32_t smem = fixed_bytes(warps) + uint32_t(warps) * uint32_t(stages) * stage_bytes + 128u;
+  static SmemAttrOnce attr_once;
+  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] {
+    const cudaError_t e = cudaFuncSetAttribute(k_ea_fwd_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPipeSmemLimit));
+    return e != cudaSuccess ? e : cudaFuncSetAttribute(k_ea_fwd_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPipeSmemLimit));
+  }));
+  PFN_CUDA_OK(launch_kernel(bulk ? k_ea_fwd_pipe<true> : k_ea_fwd_pipe<false>, dim3(grid), dim3(32 * warps), smem, stream, a));
+  PFN_LAUNCHED();
+  return 0;
 }
 
 constexpr int kBlocksPerSm = 4;  // measured: 4 x 231-thread CTAs per SM beat 8 (and 1 x 1024) at case118 sizes
@@ -544,19 +720,9 @@ int ea_fwd_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView
   if (n_nodes == 0) return 0;
   const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
   ProfScope prof(PFN_PROF_EA_FWD, stream);
-  if (ea_fwd_warp_rows(t.c4) && n_nodes * std::max(ldh, lds) < (int64_t(1) << 31)) {
-    static const int resident = [] {
-      int per_sm = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ea_fwd_warp, kEaWarpThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-      return per_sm;
-    }();
-    const int64_t warps = kEaWarpThreads / 32, pairs = ceil_div64(n_nodes, 2);
-    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div64(pairs, warps), int64_t(sm_count()) * resident));
-    PFN_CUDA_OK(launch_kernel(k_ea_fwd_warp, dim3(blocks), dim3(kEaWarpThreads), 0, stream, Hi, Hj, ldh, static_cast<const int*>(g.rowptr_t),
-                              static_cast<const int*>(g.nbr_t), reinterpret_cast<const float2*>(g.ea_t), We, ldwe, S, lds,
-                              static_cast<int>(n_nodes), static_cast<int>(h), t.c4));
-    PFN_LAUNCHED();
-    return 0;
+  if (ea_fwd_use_pipe()) {
+    const int rc = ea_fwd_pipe_launch(Hi, Hj, ldh, g, n_nodes, We, ldwe, S, lds, h, stream);
+    if (rc != 1) return rc;
   }
   PFN_CUDA_OK(launch_kernel(k_ea_fwd, dim3(t.nblocks), dim3(t.threads), 0, stream, Hi, Hj, ldh, g.rowptr_t, g.nbr_t, reinterpret_cast<const float2*>(g.ea_t),
                                                We, ldwe, S, lds, static_cast<int>(n_nodes), static_cast<int>(h), t.c4,

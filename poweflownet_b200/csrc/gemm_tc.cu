@@ -210,6 +210,19 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& args, const EpiCtx& 
       args.timing[slot] = clock64();                                                       \
   } while (0)
 
+// DRAIN = true (reductions longer than kTcDrainMinTiles K tiles: hidden 512, the K-segmented TAGConv GEMMs): the hi*hi
+// accumulator is FLUSHED every kTcDrainTiles K tiles.  The tensor core adds into its fp32 TMEM accumulator with truncation,
+// so a sum that stays in TMEM for c accumulating instructions is off by ~c * 2^-25 relative -- and always towards zero,
+// a BIAS that compounds through a 10-19 layer forward + backward instead of averaging out (measured: gradients of the
+// hidden-512 configurations 1.5e-5 from the fp64 twin).  Here phase p (kTcDrainTiles tiles) accumulates into TMEM slot
+// p mod n_hi starting from zero; when its MMAs have completed the worker warps read the slot (tcgen05.ld) and add it to
+// per-thread fp32 REGISTER accumulators in round-to-nearest, while the tensor core is already filling the next slot.
+// No TMEM sum is ever longer than 4 * kTcDrainTiles instructions, whatever K is.
+constexpr int kTcDrainTiles = 2;
+constexpr int kTcDrainMinTiles = 6;
+constexpr int kTcDrainChunks = 5;  // 16-column chunks per worker thread: ceil(160 / 32)
+
+template <bool DRAIN>
 __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant__ TcArgs args) {
   extern __shared__ uint8_t smem_dyn[];
   if (threadIdx.x == 0) PFN_TSTAMP(0);
@@ -223,11 +236,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kTcMaxStages + s); };
   const uint32_t accum_bar = bar_base + 8u * (3 * kTcMaxStages);
   const uint32_t tmem_slot = accum_bar + 8u;
+  auto ready_bar = [&](int a) { return accum_bar + 16u + 8u * a; };         // DRAIN: MMAs of a phase complete -> workers
+  auto drained_bar = [&](int a) { return accum_bar + 16u + 8u * (3 + a); };  // DRAIN: slot read out -> MMA issuer
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * BN;
   const int prob = blockIdx.z;
   const int seg_begin = args.batched ? prob : 0, seg_end = args.batched ? prob + 1 : args.n_items;
+  int n_tiles_total = 0;
+  for (int seg = seg_begin; seg < seg_end; ++seg) n_tiles_total += (args.it[seg].K + kTcBK - 1) / kTcBK;
 
   // TMA producer state (warp 0, lane 0): the first S tiles are requested BEFORE the CTA-wide setup barrier so the
   // first load's latency (~2 us: descriptor fetch + 272 row segments from L2/HBM) overlaps TMEM allocation
@@ -264,6 +281,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accum_bar, 1);
+    if (DRAIN) {
+      for (int a = 0; a < 3; ++a) {
+        mbar_init(ready_bar(a), 1);
+        mbar_init(drained_bar(a), kTcWorkers / 32);
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     pdl_wait();  // everything above overlaps the previous kernel's tail; the operands may only be read from here on
     produce(S);
@@ -299,6 +322,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(conv_bar(s), ph);
+        const int phase = it / kTcDrainTiles, slot = phase % n_hi;  // DRAIN only
+        const bool phase_first = it % kTcDrainTiles == 0;
+        if (DRAIN && phase_first && phase >= n_hi) mbar_wait(drained_bar(slot), uint32_t(phase / n_hi - 1) & 1u);
         tc_fence_after();
         const int nk = min(kTcBK / 8, (K - k0 + 7) / 8);  // 8 TF32 elements (32 bytes) per UMMA K step
         if (lane == 0 && it < 8) PFN_TSTAMP(18 + it);
@@ -309,12 +335,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
           for (int j = 0; j < nk; ++j) {
             const uint64_t adv = uint64_t(j * 2);  // +32 bytes in the 16-byte-granular start-address field
             const int k_idx = kk + j;
-            const uint32_t d_hi = tmem_base + uint32_t((k_idx % n_hi) * BN);
+            uint32_t d_hi, acc_hi;
+            if (DRAIN) {
+              d_hi = tmem_base + uint32_t(slot * BN);
+              acc_hi = (phase_first && j == 0) ? 0u : 1u;
+            } else {
+              d_hi = tmem_base + uint32_t((k_idx % n_hi) * BN);
+              acc_hi = k_idx >= n_hi ? 1u : 0u;
+            }
             umma_tf32(d_lo, a_lo + adv, b_hi + adv, idesc, k_idx > 0 ? 1u : 0u);
             umma_tf32(d_lo, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, k_idx >= n_hi ? 1u : 0u);
+            umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, acc_hi);
           }
           umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
+          if (DRAIN && (it % kTcDrainTiles == kTcDrainTiles - 1 || it == n_tiles_total - 1)) umma_commit(ready_bar(slot));
         }
         kk += nk;
         __syncwarp();
@@ -326,6 +360,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
   } else {
     // ===== converters (hi/lo split in shared memory), then epilogue =====
     const int tid_c = threadIdx.x - 64;
+    const int wk = warp - 2;                 // 0..7
+    const int q = warp & 3, half = wk >> 2;  // TMEM lane quarter this warp may read / which 16-column chunks it drains
+    const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
+    // DRAIN: this thread's share of the output tile (row 32 q + lane, columns 16 half + 32 i + [0, 16)) lives in registers
+    float racc[DRAIN ? kTcDrainChunks : 1][16];
+#pragma unroll
+    for (int i = 0; i < (DRAIN ? kTcDrainChunks : 1); ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) racc[i][j] = 0.f;
+    auto drain_slot = [&](uint32_t col0) {  // racc += TMEM columns [col0, col0 + BN) of this thread's row
+#pragma unroll
+      for (int i = 0; i < (DRAIN ? kTcDrainChunks : 1); ++i) {
+        const int c0 = 16 * half + 32 * i;
+        if (c0 < BN) {  // warp-uniform
+          uint32_t r[16];
+          tmem_ld16(lane_base + col0 + uint32_t(c0), r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) racc[i][j] += __uint_as_float(r[j]);
+        }
+      }
+    };
+    int next_drain = 0;  // first phase whose slot has not been read out yet
     int it = 0;
     for (int seg = seg_begin; seg < seg_end; ++seg) {
       const int K = args.it[seg].K;
@@ -341,6 +397,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         if (tid_c == 0 && it < 8) PFN_TSTAMP(10 + it);
         __syncwarp();
         if (lane == 0) mbar_arrive(conv_bar(s));
+        if (DRAIN && it % kTcDrainTiles == kTcDrainTiles - 1 && it >= 2 * kTcDrainTiles - 1) {
+          // every tile of phase p has been handed to the tensor core: read out phase p - 1 (issued two tiles ago, so its
+          // MMAs have normally completed) while phase p is being multiplied
+          const int pd = it / kTcDrainTiles - 1, slot = pd % args.n_hi;
+          mbar_wait(ready_bar(slot), uint32_t(pd / args.n_hi) & 1u);
+          tc_fence_after();
+          drain_slot(uint32_t(slot * BN));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(drained_bar(slot));
+          next_drain = pd + 1;
+        }
       }
     }
     mbar_wait(accum_bar, 0);
@@ -350,16 +418,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     // shared memory: phase 1, each warp drains its TMEM lane quarter (two warps per quarter, alternating 16-column
     // chunks) and adds the accumulators in fp32; phase 2, the eight warps take 16 rows each and stream them out as
     // float4 with all global loads of a row batch in flight together.
-    const int wk = warp - 2;                 // 0..7
-    const int q = warp & 3, half = wk >> 2;  // TMEM lane quarter this warp may read / which 16-column chunks it drains
     const uint32_t tile_ld = uint32_t(BN) + 4u;  // floats; +4 keeps the 16-byte row-chunk stores conflict-free
     const int ncols = min(BN, args.N - n0);
-    {
+    if (DRAIN) {
+      // the phases not read out yet (every MMA has completed), then the lo terms; registers -> staging tile
+      const int n_phases = (n_tiles_total + kTcDrainTiles - 1) / kTcDrainTiles;
+      for (int pd = next_drain; pd < n_phases; ++pd) drain_slot(uint32_t((pd % args.n_hi) * BN));
+      drain_slot(uint32_t(args.n_hi * BN));
+      const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
+#pragma unroll
+      for (int i = 0; i < kTcDrainChunks; ++i) {
+        const int c0 = 16 * half + 32 * i;
+        if (c0 < ncols) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + 4u * (c0 + j)), "f"(racc[DRAIN ? i : 0][j]),
+                         "f"(racc[DRAIN ? i : 0][j + 1]), "f"(racc[DRAIN ? i : 0][j + 2]), "f"(racc[DRAIN ? i : 0][j + 3]) : "memory");
+        }
+      }
+    } else {
       int total_k = 0;
       for (int seg = seg_begin; seg < seg_end; ++seg) total_k += (args.it[seg].K + 7) / 8;
       const int n_act = min(args.n_hi, total_k);  // hi accumulators that were actually written
       const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
-      const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
       for (int c0 = 16 * half; c0 < ncols; c0 += 32) {
         uint32_t r[4][16];  // lo terms + up to three hi accumulators, all loads in flight before one wait
         tmem_ld16_issue(lane_base + uint32_t(args.n_hi * BN + c0), r[0]);
@@ -639,6 +720,7 @@ struct WgGroupProb {
   int Mo, N, n_eff, BN, mt, nb, extra_col, lddw, m_groups, tmem_cols, stages, item0;
   int acc_hi[2], acc_lo[2];
   int odd, oddn;
+  int n_hi;  // mt == 1: hi*hi products rotate over n_hi accumulators at columns 0, BN, ... (lo terms at n_hi * BN)
 };
 struct WgGroupArgs {
   WgGroupProb p[kWgMaxProb];
@@ -737,14 +819,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         for (int j = 0; j < kTcBK / 8; ++j) {  // 8 nodes per UMMA K step = one 1024-byte K group
           const uint32_t koff = uint32_t(j) * kstep;
           const uint64_t dbh = umma_desc_mn128(b_hi + koff, lbo, sbo), dbl = umma_desc_mn128(b_lo + koff, lbo, sbo);
+          const int k_idx = it * (kTcBK / 8) + j;
           for (int t = 0; t < mt; ++t) {
             const uint32_t a_hi = st + uint32_t(t) * 16384u, a_lo = a_hi + a_bytes;
             const uint64_t dah = umma_desc_mn128(a_hi + koff, lbo, sbo), dal = umma_desc_mn128(a_lo + koff, lbo, sbo);
-            const uint32_t d_hi = tmem_base + uint32_t(P.acc_hi[t]), d_lo = tmem_base + uint32_t(P.acc_lo[t]);
-            const uint32_t first = (it > 0 || j > 0) ? 1u : 0u;
+            const uint32_t d_lo = tmem_base + uint32_t(P.acc_lo[t]);
+            const uint32_t first = k_idx > 0 ? 1u : 0u;
+            // one M tile per CTA: the hi*hi products rotate over P.n_hi accumulators, so each one takes 1/n_hi of the
+            // truncating fp32 adds (the tensor core's accumulate is not round-to-nearest; see kWgMaxChunkDefault)
+            const uint32_t d_hi = tmem_base + uint32_t(mt == 1 ? (k_idx % P.n_hi) * BN : P.acc_hi[t]);
+            const uint32_t acc_hi = mt == 1 ? (k_idx >= P.n_hi ? 1u : 0u) : ((d_hi == d_lo) ? 1u : first);
             umma_tf32(d_lo, dal, dbh, idesc, first);
             umma_tf32(d_lo, dah, dbl, idesc, 1u);
-            umma_tf32(d_hi, dah, dbh, idesc, (d_hi == d_lo) ? 1u : first);
+            umma_tf32(d_hi, dah, dbh, idesc, acc_hi);
           }
         }
         umma_commit(empty_bar(s));
@@ -874,13 +961,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       if (n_tiles > 0) {
         const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
         const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
+        const int n_rot = mt == 1 ? min(P.n_hi, n_tiles * (kTcBK / 8)) : 0;  // rotating accumulators actually written
         for (int c0 = 16 * half; c0 < n_main; c0 += 32) {
           uint32_t r[16];
           float acc[16];
           tmem_ld16(lane_base + uint32_t(P.acc_lo[t] + c0), r);
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
-          if (P.acc_hi[t] != P.acc_lo[t]) {
+          if (mt == 1) {
+            for (int a = 0; a < n_rot; ++a) {  // round-to-nearest fp32 adds of the partial sums
+              tmem_ld16(lane_base + uint32_t(a * BN + c0), r);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
+            }
+          } else if (P.acc_hi[t] != P.acc_lo[t]) {
             tmem_ld16(lane_base + uint32_t(P.acc_hi[t] + c0), r);
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(r[i]);
@@ -1117,9 +1211,25 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   a.seed_hi = g.seed_hi;
   a.keep_thresh = g.keep_thresh;
   a.seed_dev = g.seed_dev;
-  const uint32_t smem = uint32_t(a.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2);
+  const uint32_t smem = uint32_t(a.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2 + 6);
+  // long reductions flush the TMEM accumulators into registers every kTcDrainTiles K tiles (see the kernel);
+  // PFN_TC_DRAIN=0 / 1 forces the choice (accuracy experiments)
+  int max_tiles = 0;
+  for (int z = 0; z < count; ++z) {
+    int tiles = 0;
+    for (int i = (g.batched ? z : 0); i < (g.batched ? z + 1 : g.n_items); ++i) tiles += (g.it[i].K + kTcBK - 1) / kTcBK;
+    max_tiles = std::max(max_tiles, tiles);
+  }
+  static const int drain_env = [] {
+    const char* e = std::getenv("PFN_TC_DRAIN");
+    return e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
+  }();
+  const bool drain = a.n_hi >= 2 && bn <= 32 * kTcDrainChunks && (drain_env >= 0 ? drain_env == 1 : max_tiles >= kTcDrainMinTiles);
   static SmemAttrOnce attr_once;
-  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] { return cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)); }));
+  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] {
+    const cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
+    return e != cudaSuccess ? e : cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
+  }));
   dim3 grid(static_cast<unsigned>(ceil_div64(g.M, kTcBM)), static_cast<unsigned>(ceil_div64(g.N, bn)), static_cast<unsigned>(count));
   static const bool timing_on = std::getenv("PFN_TC_TIMING") != nullptr;  // debug aid: phase timestamps of CTA 0
   static long long* timing_dev = nullptr;
@@ -1128,7 +1238,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     cudaMemsetAsync(timing_dev, 0, 64 * sizeof(long long), stream);
     a.timing = timing_dev;
   }
-  PFN_CUDA_OK(launch_kernel(k_gemm_tc, grid, dim3(kTcThreads), smem, stream, a));
+  PFN_CUDA_OK(launch_kernel(drain ? k_gemm_tc<true> : k_gemm_tc<false>, grid, dim3(kTcThreads), smem, stream, a));
   PFN_LAUNCHED();
   if (timing_on) {
     long long t[64];
@@ -1278,8 +1388,10 @@ static int wgrad_batch_launch(const WgradProblem* probs, int n, int64_t nodes, f
     P.mt = (m_tiles == 2 && 2 * P.BN <= 512) ? 2 : 1;
     P.m_groups = static_cast<int>(ceil_div64(m_tiles, P.mt));
     int used;
+    P.n_hi = 1;
     if (P.mt == 1) {
-      P.acc_hi[0] = 0; P.acc_lo[0] = P.BN; used = 2 * P.BN;
+      P.n_hi = std::max(1, std::min(3, 512 / P.BN - 1));
+      P.acc_hi[0] = 0; P.acc_lo[0] = P.n_hi * P.BN; used = (P.n_hi + 1) * P.BN;
     } else if (3 * P.BN <= 512) {
       P.acc_hi[0] = 0; P.acc_lo[0] = P.BN; P.acc_hi[1] = P.acc_lo[1] = 2 * P.BN; used = 3 * P.BN;
     } else {

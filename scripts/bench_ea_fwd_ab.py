@@ -1,5 +1,11 @@
-"""A/B timing of the two EdgeAggregation forward kernels (PFN_EA_FWD=cta|warp) on the bench workload, one process,
-same routine as bench.py's roofline figure.  Prints one JSON object."""
+"""A/B timing of the EdgeAggregation forward kernels on the two roofline workloads:
+case118v2 x 128 at hidden 129 (24.0 MB algorithmic) and case6470rte x 32 at hidden 512 (1.28 GB).  Variants = the CTA-slab
+kernel (PFN_EA_FWD=cta) and the pipelined kernel with its tuning knobs.  Two timing modes per variant: `iters` eager
+back-to-back launches between one pair of CUDA events, and the same launches captured once into a CUDA graph and replayed
+(no host launch cost).  Operand sets rotate so that no launch finds its operands in L2.  Prints one JSON object per line.
+
+    python scripts/bench_ea_fwd_ab.py [small|large|both]
+"""
 import json
 import os
 import sys
@@ -9,19 +15,80 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from poweflownet_b200 import _lib  # noqa: E402
+from poweflownet_b200 import _lib, ops  # noqa: E402
 from poweflownet_b200.data import synthetic_batch  # noqa: E402
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 lib = _lib.lib()
-batch = synthetic_batch("118v2", 128).to(dev)
-by = bench.ea_algorithmic_bytes(batch.num_nodes, 2 * int(batch.edge_index.size(1)), 129)
 peak, _ = bench.load_peaks()
-out = {"algorithmic_bytes": by, "hbm_peak_gbs": peak}
-for rep in range(2):
-    for which in ("cta", "warp"):
-        os.environ["PFN_EA_FWD"] = which
-        us, n = bench.time_ea_fwd_alone(lib, dev, batch, 129)
-        out[f"{which}_{rep}"] = {"us_per_launch": us, "gbs": by / us / 1e3, "frac": by / us / 1e3 / peak}
-print(json.dumps(out))
+KNOBS = ("PFN_EA_FWD", "PFN_EA_STAGES", "PFN_EA_WARPS", "PFN_EA_PREFETCH", "PFN_EA_TRIGGER", "PFN_EA_BULK")
+
+
+def run(case, b, h, variants, iters, n_sets):
+    batch = synthetic_batch(case, b).to(dev)
+    n, ld = batch.num_nodes, (h + 3) // 4 * 4
+    g = ops.PreparedGraph(batch.edge_index, batch.edge_attr, n, mode=1)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    sets = [(torch.randn(n, ld, device=dev, generator=gen), torch.randn(n, ld, device=dev, generator=gen),
+             torch.empty(n, ld, device=dev)) for _ in range(n_sets)]
+    we = torch.randn(h, 2, device=dev, generator=gen)
+    by = bench.ea_algorithmic_bytes(n, 2 * int(batch.edge_index.size(1)), h)
+
+    def launch(i, stream):
+        hi, hj, s = sets[i % n_sets]
+        _lib.check(lib.pfn_ea_fwd(hi.data_ptr(), hj.data_ptr(), ld, g.ws.data_ptr(), n, g.e_raw, we.data_ptr(), 2,
+                                  s.data_ptr(), ld, h, stream), "pfn_ea_fwd")
+
+    ref = None
+    for name, env in variants:
+        for k in KNOBS:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        cur = torch.cuda.current_stream().cuda_stream
+        for i in range(n_sets):
+            launch(i, cur)
+        torch.cuda.synchronize()
+        out = sets[0][2].clone()
+        if ref is None:
+            ref = out
+        same = bool(torch.equal(ref, out))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            launch(i, cur)
+        e1.record()
+        torch.cuda.synchronize()
+        us_eager = 1e3 * e0.elapsed_time(e1) / iters
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(iters):
+                    launch(i, side.cuda_stream)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us_graph = 1e3 * e0.elapsed_time(e1) / (3 * iters)
+        print(json.dumps({"workload": f"{case} x {b}, hidden {h}", "variant": name, "env": env, "bit_identical_to_first": same,
+                          "us_eager": round(us_eager, 3), "us_graph": round(us_graph, 3), "algorithmic_bytes": by,
+                          "frac_eager": round(by / us_eager / 1e3 / peak, 4), "frac_graph": round(by / us_graph / 1e3 / peak, 4)}), flush=True)
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+P = {"PFN_EA_FWD": "pipe"}
+small = [("cta", {"PFN_EA_FWD": "cta"}), ("pipe", P), ("pipe_noprefetch", {**P, "PFN_EA_PREFETCH": "0"}),
+         ("pipe_trigger", {**P, "PFN_EA_TRIGGER": "1"}), ("pipe_s2", {**P, "PFN_EA_STAGES": "2"}), ("pipe_s4", {**P, "PFN_EA_STAGES": "4"}),
+         ("pipe_w4", {**P, "PFN_EA_WARPS": "4"}), ("pipe_bulkrows", {**P, "PFN_EA_BULK": "1"}),
+         ("pipe_bulkrows_trigger", {**P, "PFN_EA_BULK": "1", "PFN_EA_TRIGGER": "1"})]
+large = [("cta", {"PFN_EA_FWD": "cta"}), ("pipe", P), ("pipe_s2", {**P, "PFN_EA_STAGES": "2"}), ("pipe_s4", {**P, "PFN_EA_STAGES": "4"}),
+         ("pipe_w8", {**P, "PFN_EA_WARPS": "8"}), ("pipe_w2", {**P, "PFN_EA_WARPS": "2"}), ("pipe_cpasync", {**P, "PFN_EA_BULK": "0"}),
+         ("pipe_trigger", {**P, "PFN_EA_TRIGGER": "1"})]
+if which in ("small", "both"):
+    run("118v2", 128, 129, small, iters=240, n_sets=12)
+if which in ("large", "both"):
+    run("6470rte", 32, 512, large, iters=12, n_sets=2)

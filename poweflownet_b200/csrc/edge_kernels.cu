@@ -168,43 +168,40 @@ k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_ea_fwd_pipe: the same message + aggregate as k_ea_fwd, restructured around ASYNCHRONOUS COPIES INTO SHARED MEMORY so
-// that the bytes in flight are bounded by shared memory (~200 KB per SM) instead of by registers (k_ea_fwd: 61 registers
-// x 924 threads, five 16-byte row loads per thread; ncu: long_scoreboard 50 %, barrier 23 %, SMs busy 0.67 of the time).
+// k_ea_fwd_tma: the same message + aggregate as k_ea_fwd, fed by ASYNCHRONOUS BULK COPIES INTO SHARED MEMORY, so that
+// the bytes in flight are bounded by shared memory (~200 KB per SM) instead of by registers.  k_ea_fwd keeps five 16-byte
+// row loads per thread in flight and walks "stage the CSR slab -> barrier -> one row per thread -> next row" in lock
+// step (ncu: long_scoreboard 9.5 + barrier 5.0 stalled warps per issue, DRAM 13 % of peak); a first attempt with
+// autonomous warps (each warp its own copy ring, 8 warps per SM) moved the bytes but was issue-bound: 7.0 M warp
+// instructions at 0.4 eligible warps per cycle (profiles/r2_ea_fwd_ncu.md).  This kernel separates the two jobs:
 //
-//  * One persistent CTA per SM, W autonomous warps.  A warp owns a contiguous range of rows and runs its own software
-//    pipeline: no CTA-wide barrier after the prologue, no producer/consumer hand-off between warps.
-//  * The warp's slice of the CSR (row pointers, neighbour ids, edge_attr) is staged in shared memory in chunks of up to
-//    kPipeRows rows / kPipeEdges edges, so the dependent chain rowptr -> neighbour id -> neighbour row is paid once per
-//    chunk, not once per row.
-//  * Rows travel in BATCHES of whole rows: R consecutive Hi rows -- ONE bulk copy (cp.async.bulk, SASS UBLKCP; the rows
-//    of a node matrix are contiguous) -- followed by the gathered Hj row of every incoming edge, into a ring of
-//    n_stages buffers per warp.  Gathered rows of >= 1 KB go as one bulk copy per row issued by one lane each (32 rows
-//    per instruction round); shorter rows (hidden 129: 528 B) go as 16-byte cp.async (LDGSTS) chunks, whose issue
-//    cost is known and small (the TMA unit's rate for sub-kilobyte copies is not).  Either way completion lands on the
-//    batch's mbarrier (complete_tx bytes / cp.async.mbarrier.arrive), and the warp computes batch i while batches
-//    i+1 .. i+n_stages-1 are in flight.
-//  * Compute: the (row, 16-byte column chunk) pairs of a batch are dealt to the lanes round-robin (pair t -> lane t mod
-//    32), so widths that are not a multiple of 32 chunks (hidden 129 = 33 chunks) leave no lane idle; the pair's Hi chunk
-//    sits at byte 16 t of the batch buffer.  Per pair the edges are summed in ascending edge id with the same FMAs as
-//    k_ea_fwd: the two kernels are BIT-IDENTICAL (tests/test_gpu_kernels.py).  S rows leave as 16-byte stores at
-//    consecutive addresses.
-//  * Small problems (both node matrices within a fraction of L2): before griddepcontrol.wait every warp asks the L2 to
-//    prefetch its slice of Hi, Hj and the CSR arrays (cp.async.bulk.prefetch.L2): the HBM reads start at once instead
-//    of trickling in behind the two dependent metadata loads, and the gathers become L2 hits.
-//  A row whose degree exceeds a batch buffer (a hub bus) is summed straight from global memory by the same warp.
-constexpr int kPipeRows = 64;     // rows of CSR metadata staged per chunk and warp
-constexpr int kPipeEdges = 256;   // edges of CSR metadata staged per chunk and warp
-constexpr int kPipeMaxStages = 4;
-constexpr int kPipeMaxWarps = 8;
+//  * ONE PRODUCER WARP per CTA (one persistent CTA per SM, a contiguous range of rows) walks the CSR and issues, per
+//    batch of R whole rows: one bulk copy (cp.async.bulk, SASS UBLKCP) for the R consecutive Hi rows and one bulk copy
+//    per gathered Hj row -- each lane issues a row, so 32 rows per instruction round -- into a ring of n_stages batch
+//    buffers; completion is counted in bytes on the batch's mbarrier.  The producer also writes the batch header (row
+//    pointers relative to the batch, edge_attr in edge order), so the consumers never touch the CSR arrays.
+//  * ~24 CONSUMER WARPS run k_ea_fwd's inner loop unchanged -- thread (x, y) owns 16-byte column chunk x (its slice of We
+//    stays in registers) and sums rows y, y + rows, ... of the batch in ascending edge id -- but every operand comes from
+//    shared memory (~30 cycles) instead of L2/HBM (~600+): the two kernels are BIT-IDENTICAL (tests/test_gpu_kernels.py).
+//    A consumer warp releases the buffer through the batch's second mbarrier.
+//  * The row pointers of the CTA's whole range and the first window of neighbour ids / edge_attr are fetched by ALL
+//    threads before the roles split (two wide coalesced round trips instead of two narrow ones).
+//  * Small problems (both node matrices within a fraction of L2): before griddepcontrol.wait every thread asks the L2 to
+//    prefetch a piece of the CTA's share of Hi, Hj and the CSR arrays (cp.async.bulk.prefetch.L2): the HBM reads start
+//    at once instead of trickling in behind the dependent metadata loads, and the gathers become L2 hits.
+//  A row with more incident edges than a batch buffer holds (a hub bus) is summed from global memory by the consumers.
+constexpr int kTmaMaxStages = 4;
+constexpr int kTmaMetaRows = 2048;   // row pointers staged at once (a CTA's whole range unless the batch is huge)
+constexpr int kTmaMetaEdges = 1024;  // producer-private window of neighbour ids / edge_attr
+constexpr int kTmaMaxBatchRows = 64;
 
-struct PipeWarpMeta {
-  int rp[kPipeRows + 4];
-  int nb[kPipeEdges];
-  float2 ea[kPipeEdges];
+struct TmaBatchHeader {
+  int R, row0, direct, pad;
+  int rp[kTmaMaxBatchRows + 4];  // edge offsets relative to the batch's first edge; rp[R] = edges of the batch
+  // float2 ea[cap_slots] follows
 };
 
-struct PipeArgs {
+struct TmaArgs {
   const float* Hi;
   const float* Hj;
   const int* rowptr;
@@ -212,10 +209,9 @@ struct PipeArgs {
   const float2* ea;
   const float* We;
   float* S;
-  long long ldh, lds, ldwe;
-  int n_nodes, h, c4, warps, n_stages, cap_slots, rows_per_warp, prefetch_l2, early_trigger, contiguous;
-  unsigned stage_bytes;
-  long long e_cap;
+  long long ldh, lds, ldwe, e_cap;
+  int n_nodes, h, c4, rows, n_stages, cap_slots, rows_per_cta, prefetch_l2, contiguous, cons_warps, prod_warps, bulk_rows;
+  unsigned stage_bytes, hdr_bytes;
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -231,14 +227,17 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ uint32_t pipe_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void pipe_mbar_init(uint32_t bar, uint32_t count) {
+__device__ __forceinline__ uint32_t tma_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void tma_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void pipe_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+__device__ __forceinline__ void tma_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void pipe_mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void tma_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
@@ -253,201 +252,213 @@ __device__ __forceinline__ float4 lds4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-
-// prefetch this warp's 1/total share of [base, base + bytes) into L2 (one lane; 16-byte granules, pieces of <= 64 KB)
-__device__ __forceinline__ void prefetch_share(const void* base, long long bytes, int part, int parts) {
-  const long long gran = (bytes + 15) >> 4;  // 16-byte granules (the arrays are padded to 16 bytes)
-  const long long per = (gran + parts - 1) / parts;
-  long long lo = per * part, hi = min(gran, lo + per);
-  const char* p = static_cast<const char*>(base);
-  for (; lo < hi; lo += 4096) bulk_prefetch_l2(p + (lo << 4), static_cast<uint32_t>(min((long long)4096, hi - lo) << 4));
+__device__ __forceinline__ float2 lds2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
 }
 
-template <bool BULK>
-__global__ void __launch_bounds__(32 * kPipeMaxWarps, 1) k_ea_fwd_pipe(const __grid_constant__ PipeArgs a) {
-  extern __shared__ __align__(128) uint8_t pipe_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c4 = a.c4, W = a.warps, NS = a.n_stages, cap = a.cap_slots;
-  const uint32_t rowbytes = uint32_t(c4) * 16u;
-  // shared-memory map: We table [c4][2] float4 | barriers [W][kPipeMaxStages] | per-warp metadata | per-warp stage ring
-  float4* s_w = reinterpret_cast<float4*>(pipe_smem);
-  const uint32_t off_bar = (uint32_t(c4) * 32u + 127u) & ~127u;
-  const uint32_t off_meta = off_bar + ((uint32_t(W) * kPipeMaxStages * 8u + 127u) & ~127u);
-  const uint32_t meta_bytes = (uint32_t(sizeof(PipeWarpMeta)) + 127u) & ~127u;
-  const uint32_t off_data = off_meta + uint32_t(W) * meta_bytes;
-  PipeWarpMeta& m = *reinterpret_cast<PipeWarpMeta*>(pipe_smem + off_meta + uint32_t(warp) * meta_bytes);
-  const uint32_t smem0 = pipe_smem_u32(pipe_smem);
-  const uint32_t bar0 = smem0 + off_bar + uint32_t(warp) * kPipeMaxStages * 8u;
-  const uint32_t data0 = smem0 + off_data + uint32_t(warp) * uint32_t(NS) * a.stage_bytes;
+// the CTA's 1/gridDim share of [base, base + bytes) -> L2, in pieces of 4 KB dealt to the threads (16-byte granules)
+__device__ __forceinline__ void prefetch_share(const void* base, unsigned bytes) {
+  const unsigned gran = (bytes + 15u) >> 4, per = (gran + gridDim.x - 1) / gridDim.x;
+  const unsigned lo = min(gran, per * blockIdx.x), hi = min(gran, lo + per);
+  const char* p = static_cast<const char*>(base);
+  for (unsigned g = lo + 256u * threadIdx.x; g < hi; g += 256u * blockDim.x)
+    bulk_prefetch_l2(p + (size_t(g) << 4), min(256u, hi - g) << 4);
+}
 
-  const int gw = blockIdx.x * W + warp, n_warps = gridDim.x * W;
-  const int w_start = min(a.n_nodes, gw * a.rows_per_warp), w_end = min(a.n_nodes, w_start + a.rows_per_warp);
+__global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ TmaArgs a) {
+  extern __shared__ __align__(128) uint8_t tma_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c4 = a.c4, NS = a.n_stages, cap = a.cap_slots;
+  const uint32_t rowbytes = uint32_t(c4) * 16u;
+  // shared-memory map: barriers full[4] empty[4] | rp [kTmaMetaRows + 4] | nb [kTmaMetaEdges] | ea [kTmaMetaEdges] | stages
+  int* m_rp = reinterpret_cast<int*>(tma_smem + 128);
+  int* m_nb = m_rp + kTmaMetaRows + 4;
+  float2* m_ea = reinterpret_cast<float2*>(m_nb + kTmaMetaEdges);
+  const uint32_t smem0 = tma_smem_u32(tma_smem);
+  const uint32_t off_stage = (128u + uint32_t(kTmaMetaRows + 4) * 4u + uint32_t(kTmaMetaEdges) * 12u + 127u) & ~127u;
+  auto full_bar = [&](int s) { return smem0 + 8u * s; };
+  auto empty_bar = [&](int s) { return smem0 + 8u * (kTmaMaxStages + s); };
+  const int row_start = min(a.n_nodes, int(blockIdx.x) * a.rows_per_cta), row_end = min(a.n_nodes, row_start + a.rows_per_cta);
 
   // ---- prologue that may overlap the previous kernel's tail (nothing here reads data as a value) ----
-  if (lane == 0) {
-    for (int s = 0; s < NS; ++s) pipe_mbar_init(bar0 + 8u * s, BULK ? 1u : 33u);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (a.prefetch_l2) {
-      if (a.contiguous && w_end > w_start) {
-        // the warp's own Hi rows; its 1/n_warps share of Hj (some warp gathers every row of it exactly once from HBM)
-        const long long lo = (long long)w_start * a.ldh * 4, hi = (long long)w_end * a.ldh * 4;
-        for (long long o = lo; o < hi; o += 65536)
-          bulk_prefetch_l2(reinterpret_cast<const char*>(a.Hi) + o, static_cast<uint32_t>(min((long long)65536, hi - o)));
-      }
-      if (a.contiguous) prefetch_share(a.Hj, (long long)a.n_nodes * a.ldh * 4, gw, n_warps);
-      prefetch_share(a.nbr, a.e_cap * 4, gw, n_warps);
-      prefetch_share(a.ea, a.e_cap * 8, gw, n_warps);
-      prefetch_share(a.rowptr, ((long long)a.n_nodes + 1) * 4, gw, n_warps);
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      tma_mbar_init(full_bar(s), 1u + (a.bulk_rows ? 0u : 32u * uint32_t(a.prod_warps)));  // expect_tx + one arrival per cp.async lane
+      tma_mbar_init(empty_bar(s), uint32_t(a.cons_warps));
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (a.prefetch_l2) {
+    if (a.contiguous) {
+      // the CTA's own Hi rows; its share of Hj (every row of it is fetched from HBM exactly once, by whoever comes first)
+      const char* hi0 = reinterpret_cast<const char*>(a.Hi) + size_t(row_start) * rowbytes;
+      const unsigned own = unsigned(row_end - row_start) * rowbytes;
+      for (unsigned o = 4096u * tid; o < own; o += 4096u * blockDim.x) bulk_prefetch_l2(hi0 + o, min(4096u, own - o));
+      prefetch_share(a.Hj, unsigned(a.n_nodes) * rowbytes);
+    }
+    prefetch_share(a.nbr, unsigned(a.e_cap) * 4u);
+    prefetch_share(a.ea, unsigned(a.e_cap) * 8u);
+    prefetch_share(a.rowptr, (unsigned(a.n_nodes) + 1u) * 4u);
   }
   pdl_wait();
-  if (a.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  for (int i = threadIdx.x; i < 2 * c4; i += blockDim.x) {
-    const int q = i >> 1, k = i & 1;
-    float w[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int ch = 4 * q + c;
-      w[c] = ch < a.h ? __ldg(a.We + ch * a.ldwe + k) : 0.f;
-    }
-    s_w[2 * q + k] = make_float4(w[0], w[1], w[2], w[3]);
+  // ---- all threads: row pointers of the CTA's range, then the first window of neighbour ids / edge_attr ----
+  int meta_row0 = row_start, meta_rows = min(kTmaMetaRows, row_end - row_start);
+  for (int i = tid; i <= meta_rows; i += blockDim.x) m_rp[i] = a.rowptr[row_start + i];
+  __syncthreads();
+  int ew_lo = m_rp[0];
+  long long ew_hi = min((long long)a.e_cap, (long long)ew_lo + kTmaMetaEdges);
+  for (int i = tid; i < int(ew_hi - ew_lo); i += blockDim.x) {
+    m_nb[i] = a.nbr[ew_lo + i];
+    m_ea[i] = a.ea[ew_lo + i];
   }
-  __syncthreads();  // the only CTA-wide barrier: We table + barrier initialisation
-  if (warp >= W) return;
+  __syncthreads();
 
-  // largest R in [0, min(32, n - r0)] with R + (edges of rows [r0, r0 + R)) <= cap slots; 0 = row r0 alone does not fit
-  auto greedy = [&](int r0, int n) {
-    const int c = lane + 1;
-    bool ok = false;
-    if (r0 + c <= n) ok = c + (m.rp[r0 + c] - m.rp[r0]) <= cap;
-    return __popc(__ballot_sync(0xffffffffu, ok));
-  };
-
-  unsigned issued = 0, consumed = 0;  // batches over the whole kernel: stage = idx % NS, mbarrier parity = (idx / NS) & 1
-  int row = w_start;
-  while (row < w_end) {  // ---- one chunk of CSR metadata ----
-    const int nr_try = min(kPipeRows, w_end - row);
-    for (int i = lane; i <= nr_try; i += 32) m.rp[i] = a.rowptr[row + i];
-    __syncwarp();
-    const int e_base = m.rp[0];
-    int n;
-    {
-      const int c1 = lane + 1, c2 = lane + 33;
-      const bool ok1 = c1 <= nr_try && m.rp[c1] - e_base <= kPipeEdges;
-      const bool ok2 = c2 <= nr_try && m.rp[c2] - e_base <= kPipeEdges;
-      n = __popc(__ballot_sync(0xffffffffu, ok1)) + __popc(__ballot_sync(0xffffffffu, ok2));
-    }
-    const int ne = n > 0 ? m.rp[n] - e_base : 0;
-    for (int i = lane; i < ne; i += 32) {
-      m.nb[i] = a.nbr[e_base + i];
-      m.ea[i] = a.ea[e_base + i];
-    }
-    __syncwarp();
-
-    // a row summed straight from global memory (hub bus: more incident edges than a batch buffer / a metadata chunk holds)
-    auto slow_row = [&](int node) {
-      const int beg = a.rowptr[node], fin = a.rowptr[node + 1];
-      for (int q = lane; q < c4; q += 32) {
-        const float4 w0 = s_w[2 * q], w1 = s_w[2 * q + 1];
-        const float4 hi = ld4(a.Hi + (size_t)node * a.ldh + 4 * q);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = beg; e < fin; ++e)
-          add_relu(acc, preact(hi, ldg4(a.Hj + (size_t)a.nbr[e] * a.ldh + 4 * q), a.ea[e], w0, w1));
-        st4(a.S + (size_t)node * a.lds + 4 * q, acc);
+  if (warp >= a.cons_warps) {
+    // =================================== producer warps ===================================
+    // All `P` producer warps walk the same batch sequence (the greedy row count is recomputed by each: a ballot over
+    // shared row pointers).  Producer 0 writes the batch header and issues the Hi bulk copy; the gathered rows are
+    // dealt to the 32 P producer lanes in 16-byte chunks (consecutive lanes = consecutive chunks of a row: coalesced)
+    // or, for rows of >= kTmaBulkRowBytes, as one bulk copy per row.
+    const int P = a.prod_warps, pw = warp - a.cons_warps, pt = pw * 32 + lane, stride = 32 * P;
+    const int step_slot = stride / c4, step_q = stride % c4;
+    auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(stride) : "memory"); };
+    int r = row_start;
+    unsigned batch = 0;
+    while (r < row_end) {
+      if (r >= meta_row0 + meta_rows) {  // next slice of row pointers (only ranges longer than kTmaMetaRows rows)
+        meta_row0 = r;
+        meta_rows = min(kTmaMetaRows, row_end - r);
+        producers_sync();
+        for (int i = pt; i <= meta_rows; i += stride) m_rp[i] = a.rowptr[r + i];
+        producers_sync();
       }
-    };
-    if (n == 0) {  // the first row alone has more than kPipeEdges edges
-      slow_row(row);
-      ++row;
-      __syncwarp();
-      continue;
-    }
-
-    int issue_ptr = 0, cons_ptr = 0;  // local row indices inside the chunk
-    while (true) {
-      // ---- issue as many batches as the ring holds ----
-      while (issued - consumed < unsigned(NS) && issue_ptr < n) {
-        const int R = greedy(issue_ptr, n);
-        if (R == 0) break;  // hub row: handled below once the ring has drained
-        const uint32_t bar = bar0 + 8u * (issued % NS), buf = data0 + (issued % NS) * a.stage_bytes;
-        const int e0 = m.rp[issue_ptr] - e_base, nE = m.rp[issue_ptr + R] - e_base - e0;
-        const float* hi_src = a.Hi + (size_t)(row + issue_ptr) * a.ldh;
-        __syncwarp();  // every lane has finished reading the buffer's previous contents
+      const int lr = r - meta_row0;
+      // largest R <= 64 with R + (edges of rows [r, r + R)) <= cap slots; 0 = row r alone does not fit (hub bus)
+      int R;
+      {
+        const int avail = meta_rows - lr, c1 = lane + 1, c2 = lane + 33;
+        const bool ok1 = c1 <= avail && c1 + (m_rp[lr + c1] - m_rp[lr]) <= cap;
+        const bool ok2 = c2 <= avail && c2 + (m_rp[lr + c2] - m_rp[lr]) <= cap;
+        R = __popc(__ballot_sync(0xffffffffu, ok1)) + __popc(__ballot_sync(0xffffffffu, ok2));
+      }
+      if (R > a.rows) R = R / a.rows * a.rows;  // whole passes of the consumers' row lanes
+      const bool direct = R == 0;
+      if (direct) R = 1;
+      const int e0 = m_rp[lr], nE = direct ? 0 : m_rp[lr + R] - e0;
+      if (!direct && (long long)e0 + nE > ew_hi) {  // slide the producers' window of neighbour ids / edge_attr
+        ew_lo = e0;
+        ew_hi = min((long long)a.e_cap, (long long)ew_lo + kTmaMetaEdges);
+        producers_sync();
+        for (int i = pt; i < int(ew_hi - ew_lo); i += stride) {
+          m_nb[i] = a.nbr[ew_lo + i];
+          m_ea[i] = a.ea[ew_lo + i];
+        }
+        producers_sync();
+      }
+      const int s = int(batch % unsigned(NS));
+      tma_mbar_wait(empty_bar(s), ((batch / unsigned(NS)) & 1u) ^ 1u);  // the consumers have released this buffer
+      const uint32_t buf = smem0 + off_stage + uint32_t(s) * a.stage_bytes + a.hdr_bytes;
+      const float* hi_src = a.Hi + (size_t)r * a.ldh;
+      const bool bulk_rows = a.bulk_rows != 0;
+      if (pw == 0) {
+        uint8_t* stage = tma_smem + off_stage + size_t(s) * a.stage_bytes;
+        TmaBatchHeader* hdr = reinterpret_cast<TmaBatchHeader*>(stage);
+        float2* hdr_ea = reinterpret_cast<float2*>(stage + sizeof(TmaBatchHeader));
         if (lane == 0) {
-          const uint32_t tx = (a.contiguous || BULK ? uint32_t(R) * rowbytes : 0u) + (BULK ? uint32_t(nE) * rowbytes : 0u);
-          pipe_mbar_expect_tx(bar, tx);
-          if (a.contiguous) bulk_g2s(buf, hi_src, uint32_t(R) * rowbytes, bar);  // R consecutive Hi rows: one bulk copy
+          hdr->R = R;
+          hdr->row0 = r;
+          hdr->direct = direct ? 1 : 0;
+        }
+        for (int i = lane; i <= R; i += 32) hdr->rp[i] = direct ? 0 : m_rp[lr + i] - e0;
+        for (int j = lane; j < nE; j += 32) hdr_ea[j] = m_ea[e0 - ew_lo + j];
+        __syncwarp();
+        if (lane == 0) {
+          // bytes that arrive by bulk copy: the Hi rows (always), the gathered rows when they are wide
+          tma_mbar_expect_tx(full_bar(s), direct ? 0u : uint32_t(R + (bulk_rows ? nE : 0)) * rowbytes);
+          if (!direct && a.contiguous) bulk_g2s(buf, hi_src, uint32_t(R) * rowbytes, full_bar(s));  // R consecutive rows: one copy
         }
         __syncwarp();
-        if (BULK) {
-          if (!a.contiguous && lane < R) bulk_g2s(buf + uint32_t(lane) * rowbytes, hi_src + (size_t)lane * a.ldh, rowbytes, bar);
-          for (int i = lane; i < nE; i += 32)
-            bulk_g2s(buf + uint32_t(R + i) * rowbytes, a.Hj + (size_t)m.nb[e0 + i] * a.ldh, rowbytes, bar);
+        if (!direct && !a.contiguous)
+          for (int i = lane; i < R; i += 32) bulk_g2s(buf + uint32_t(i) * rowbytes, hi_src + (size_t)i * a.ldh, rowbytes, full_bar(s));
+      }
+      if (!direct) {
+        const uint32_t gat = buf + uint32_t(R) * rowbytes;
+        const int* nb = m_nb + (e0 - ew_lo);
+        if (bulk_rows) {
+          for (int j = pt; j < nE; j += stride) bulk_g2s(gat + uint32_t(j) * rowbytes, a.Hj + (size_t)nb[j] * a.ldh, rowbytes, full_bar(s));
         } else {
-          // 16-byte chunks, dealt to the lanes round-robin over the (row, chunk) pairs of the batch
-          const int first = a.contiguous ? R : 0, total = (R + nE) * c4;
-          int k = first, q = lane;
-          while (q >= c4) { q -= c4; ++k; }
-          for (int t = first * c4 + lane; t < total; t += 32) {
-            const float* src = k < R ? a.Hi + (size_t)(row + issue_ptr + k) * a.ldh : a.Hj + (size_t)m.nb[e0 + k - R] * a.ldh;
-            cp_async16(buf + uint32_t(t) * 16u, src + 4 * q);
-            q += 32;
-            while (q >= c4) { q -= c4; ++k; }
+          int slot = pt / c4, q = pt % c4;
+          for (; slot < nE; ) {
+            cp_async16(gat + uint32_t(slot) * rowbytes + uint32_t(q) * 16u, a.Hj + (size_t)nb[slot] * a.ldh + 4 * q);
+            slot += step_slot;
+            q += step_q;
+            if (q >= c4) {
+              q -= c4;
+              ++slot;
+            }
           }
-          cp_async_arrive_noinc(bar);
         }
-        ++issued;
-        issue_ptr += R;
       }
-      if (consumed == issued) {
-        if (issue_ptr >= n) break;
-        slow_row(row + issue_ptr);  // nothing in flight and the next row does not fit a batch
-        ++issue_ptr;
-        cons_ptr = issue_ptr;
-        __syncwarp();
-        continue;
-      }
-      // ---- consume the oldest batch ----
-      const int R = greedy(cons_ptr, n);  // the same value as when the batch was issued
-      const uint32_t bar = bar0 + 8u * (consumed % NS), buf = data0 + (consumed % NS) * a.stage_bytes;
-      pipe_mbar_wait(bar, (consumed / NS) & 1u);
-      const int e0 = m.rp[cons_ptr] - e_base;
-      const uint32_t gat = buf + uint32_t(R) * rowbytes;  // gathered rows: edge e of the chunk at slot e - e0
-      float* s_dst = a.S + (size_t)(row + cons_ptr) * a.lds;
-      const int total = R * c4;
-      int k = 0, q = lane;
-      while (q >= c4) { q -= c4; ++k; }
-      for (int t = lane; t < total; t += 32) {
-        const float4 hi = lds4(buf + uint32_t(t) * 16u);
-        const float4 w0 = s_w[2 * q], w1 = s_w[2 * q + 1];
-        const int beg = m.rp[cons_ptr + k] - e_base, fin = m.rp[cons_ptr + k + 1] - e_base;
-        const uint32_t col = gat + uint32_t(q) * 16u;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int e = beg;
-        for (; e + 3 < fin; e += 4) {  // four shared-memory row reads in flight
-          const float4 h0 = lds4(col + uint32_t(e - e0) * rowbytes), h1 = lds4(col + uint32_t(e + 1 - e0) * rowbytes);
-          const float4 h2 = lds4(col + uint32_t(e + 2 - e0) * rowbytes), h3 = lds4(col + uint32_t(e + 3 - e0) * rowbytes);
-          add_relu(acc, preact(hi, h0, m.ea[e], w0, w1));
-          add_relu(acc, preact(hi, h1, m.ea[e + 1], w0, w1));
-          add_relu(acc, preact(hi, h2, m.ea[e + 2], w0, w1));
-          add_relu(acc, preact(hi, h3, m.ea[e + 3], w0, w1));
-        }
-        if (e + 1 < fin) {
-          const float4 h0 = lds4(col + uint32_t(e - e0) * rowbytes), h1 = lds4(col + uint32_t(e + 1 - e0) * rowbytes);
-          add_relu(acc, preact(hi, h0, m.ea[e], w0, w1));
-          add_relu(acc, preact(hi, h1, m.ea[e + 1], w0, w1));
-          e += 2;
-        }
-        if (e < fin) add_relu(acc, preact(hi, lds4(col + uint32_t(e - e0) * rowbytes), m.ea[e], w0, w1));
-        st4(s_dst + (size_t)k * a.lds + 4 * q, acc);
-        q += 32;
-        while (q >= c4) { q -= c4; ++k; }
-      }
-      ++consumed;
-      cons_ptr += R;
+      if (!bulk_rows) cp_async_arrive_noinc(full_bar(s));  // fires when this lane's copies of the batch have landed
+      r += R;
+      ++batch;
     }
-    row += n;
-    __syncwarp();  // the metadata of this chunk is overwritten next
+  } else if (warp < a.cons_warps) {
+    // =================================== consumer warps ===================================
+    const int x = tid % c4, y = tid / c4;
+    const bool active = y < a.rows;
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+    if (active) load_we(a.We, a.ldwe, x, a.h, w0, w1);
+    int r = row_start;
+    unsigned batch = 0;
+    while (r < row_end) {
+      const int s = int(batch % unsigned(NS));
+      tma_mbar_wait(full_bar(s), (batch / unsigned(NS)) & 1u);
+      const uint32_t stage = smem0 + off_stage + uint32_t(s) * a.stage_bytes;
+      const TmaBatchHeader* hdr = reinterpret_cast<const TmaBatchHeader*>(tma_smem + off_stage + size_t(s) * a.stage_bytes);
+      const int R = hdr->R;
+      if (hdr->direct) {
+        if (active && y == 0) {  // hub bus: the row's operands straight from global memory, same order of operations
+          const int beg = a.rowptr[r], fin = a.rowptr[r + 1];
+          const float4 hi = ld4(a.Hi + (size_t)r * a.ldh + 4 * x);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int e = beg; e < fin; ++e)
+            add_relu(acc, preact(hi, ldg4(a.Hj + (size_t)a.nbr[e] * a.ldh + 4 * x), a.ea[e], w0, w1));
+          st4(a.S + (size_t)r * a.lds + 4 * x, acc);
+        }
+      } else if (active) {
+        const uint32_t ea_s = stage + uint32_t(sizeof(TmaBatchHeader));
+        const uint32_t hi_s = stage + a.hdr_bytes + uint32_t(x) * 16u, gat = hi_s + uint32_t(R) * rowbytes;
+        for (int lr = y; lr < R; lr += a.rows) {
+          const float4 hi = lds4(hi_s + uint32_t(lr) * rowbytes);
+          const int beg = hdr->rp[lr], fin = hdr->rp[lr + 1];
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          int e = beg;
+          for (; e + 3 < fin; e += 4) {  // four shared-memory row reads in flight per thread
+            const float4 h0 = lds4(gat + uint32_t(e) * rowbytes), h1 = lds4(gat + uint32_t(e + 1) * rowbytes);
+            const float4 h2 = lds4(gat + uint32_t(e + 2) * rowbytes), h3 = lds4(gat + uint32_t(e + 3) * rowbytes);
+            add_relu(acc, preact(hi, h0, lds2(ea_s + 8u * e), w0, w1));
+            add_relu(acc, preact(hi, h1, lds2(ea_s + 8u * (e + 1)), w0, w1));
+            add_relu(acc, preact(hi, h2, lds2(ea_s + 8u * (e + 2)), w0, w1));
+            add_relu(acc, preact(hi, h3, lds2(ea_s + 8u * (e + 3)), w0, w1));
+          }
+          if (e + 1 < fin) {
+            const float4 h0 = lds4(gat + uint32_t(e) * rowbytes), h1 = lds4(gat + uint32_t(e + 1) * rowbytes);
+            add_relu(acc, preact(hi, h0, lds2(ea_s + 8u * e), w0, w1));
+            add_relu(acc, preact(hi, h1, lds2(ea_s + 8u * (e + 1)), w0, w1));
+            e += 2;
+          }
+          if (e < fin) add_relu(acc, preact(hi, lds4(gat + uint32_t(e) * rowbytes), lds2(ea_s + 8u * e), w0, w1));
+          st4(a.S + (size_t)(r + lr) * a.lds + 4 * x, acc);
+        }
+      }
+      __syncwarp();  // every lane has finished reading the buffer
+      if (lane == 0) tma_mbar_arrive(empty_bar(s));
+      r += R;
+      ++batch;
+    }
   }
 }
 
@@ -630,48 +641,50 @@ k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, 
   }
 }
 
-// ---- host side of k_ea_fwd_pipe --------------------------------------------------------------------------------------
-// PFN_EA_FWD=cta forces the CTA-slab kernel (k_ea_fwd), PFN_EA_FWD=pipe / unset takes the pipelined kernel whenever the
-// width fits; read per call so that tests can compare the two.  Tuning knobs (experiments): PFN_EA_STAGES (2..4),
-// PFN_EA_WARPS (1..8), PFN_EA_PREFETCH (0/1), PFN_EA_TRIGGER (0/1), PFN_EA_BULK (0/1: gathered rows as bulk copies).
-constexpr uint32_t kPipeSmemLimit = 227 * 1024;
-constexpr long long kPipePrefetchMaxBytes = 48ll << 20;  // L2-prefetch both node matrices only when they fit well inside L2
+// ---- host side of k_ea_fwd_tma ----------------------------------------------------------------------------------------
+// PFN_EA_FWD=cta forces the CTA-slab kernel (k_ea_fwd); unset / anything else takes the bulk-copy kernel whenever the
+// width fits.  Read per call so that tests can compare the two.  Tuning knobs (experiments): PFN_EA_STAGES (2..4),
+// PFN_EA_THREADS (consumer threads, default 768), PFN_EA_PRODUCERS (1..8), PFN_EA_BULK (0/1), PFN_EA_PREFETCH (0/1).
+constexpr uint32_t kTmaSmemLimit = 227 * 1024;
+constexpr long long kTmaPrefetchMaxBytes = 48ll << 20;  // L2-prefetch both node matrices only when they fit well inside L2
 
-bool ea_fwd_use_pipe() {
+bool ea_fwd_use_tma() {
   const char* e = std::getenv("PFN_EA_FWD");
   return !(e != nullptr && e[0] == 'c');
 }
 
 // 0 = launched, 1 = shape outside this kernel (caller uses k_ea_fwd)
-int ea_fwd_pipe_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView& g, int64_t n_nodes, const float* We,
-                       int64_t ldwe, float* S, int64_t lds, int64_t h, cudaStream_t stream) {
+int ea_fwd_tma_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView& g, int64_t n_nodes, const float* We,
+                      int64_t ldwe, float* S, int64_t lds, int64_t h, cudaStream_t stream) {
   const int c4 = static_cast<int>((h + 3) / 4);
   const uint32_t rowbytes = uint32_t(c4) * 16u;
-  if (n_nodes >= (int64_t(1) << 31) - 64 || rowbytes > 16384u) return 1;
-  PipeArgs a{};
+  if (n_nodes >= (int64_t(1) << 31) - 64 || c4 > 31 * 32 || g.e_cap >= (int64_t(1) << 28)) return 1;
+  constexpr uint32_t kTmaBulkRowBytes = 8192;
+  TmaArgs a{};
+  // gathered rows: one bulk copy per row when rows are wide (the TMA unit needs ~35 ns per copy whatever its size --
+  // measured: 528-byte rows 14.8 us per 424 copies and SM --, so narrow rows go as 16-byte cp.async chunks, LDGSTS)
   const int env_bulk = env_int("PFN_EA_BULK", -1);
-  const bool bulk = env_bulk >= 0 ? env_bulk != 0 : rowbytes >= 1024u;
-  int warps = rowbytes <= 1024u ? 8 : rowbytes <= 4096u ? 4 : 2;
-  warps = std::max(1, std::min(kPipeMaxWarps, env_int("PFN_EA_WARPS", warps)));
-  int stages = std::max(2, std::min(kPipeMaxStages, env_int("PFN_EA_STAGES", 3)));
-  const uint32_t meta_bytes = (uint32_t(sizeof(PipeWarpMeta)) + 127u) & ~127u;
-  auto fixed_bytes = [&](int w) {
-    return ((uint32_t(c4) * 32u + 127u) & ~127u) + ((uint32_t(w) * kPipeMaxStages * 8u + 127u) & ~127u) + uint32_t(w) * meta_bytes;
-  };
-  // at least 8 slots (a row and seven incident edges) per batch buffer: fewer warps, then fewer stages
-  uint32_t stage_bytes = 0;
+  a.bulk_rows = (env_bulk >= 0 ? env_bulk != 0 : rowbytes >= kTmaBulkRowBytes) ? 1 : 0;
+  a.prod_warps = std::max(1, std::min(8, env_int("PFN_EA_PRODUCERS", a.bulk_rows ? 1 : 4)));
+  const int max_cons = (32 - a.prod_warps) * 32;
+  if (c4 > max_cons) return 1;
+  const int want_threads = std::max(c4, std::min(max_cons, env_int("PFN_EA_THREADS", 768)));
+  a.rows = std::max(1, std::min(kTmaMaxBatchRows, want_threads / c4));
+  a.cons_warps = (c4 * a.rows + 31) / 32;
+  int stages = std::max(2, std::min(kTmaMaxStages, env_int("PFN_EA_STAGES", 4)));
+  const uint32_t off_stage = (128u + uint32_t(kTmaMetaRows + 4) * 4u + uint32_t(kTmaMetaEdges) * 12u + 127u) & ~127u;
+  uint32_t stage_bytes = 0, hdr_bytes = 0;
   int cap = 0;
-  for (;;) {
-    const uint32_t per_warp = (kPipeSmemLimit - 128u - fixed_bytes(warps)) / uint32_t(warps);
-    stage_bytes = (per_warp / uint32_t(stages)) & ~127u;
-    cap = static_cast<int>(stage_bytes / rowbytes);
-    if (cap >= 8) break;
-    if (stages > 2) --stages;
-    else if (warps > 1) warps = std::max(1, warps / 2);
-    else break;
+  for (;; --stages) {
+    stage_bytes = ((kTmaSmemLimit - 128u - off_stage) / uint32_t(stages)) & ~127u;
+    // header: fixed part + one float2 per slot (an upper bound of the edges of a batch), rounded to 128 bytes
+    cap = static_cast<int>((stage_bytes - sizeof(TmaBatchHeader) - 128u) / (rowbytes + 8u));
+    cap = std::min(cap, kTmaMetaEdges);
+    hdr_bytes = (uint32_t(sizeof(TmaBatchHeader)) + 8u * uint32_t(std::max(cap, 0)) + 127u) & ~127u;
+    // a batch buffer should hold at least one pass of the consumers' row lanes with their edges (~4 slots per row)
+    if (cap >= std::min(4 * a.rows, 64) || stages == 2) break;
   }
   if (cap < 2) return 1;
-  cap = std::min(cap, 32 + kPipeEdges);
   a.Hi = Hi;
   a.Hj = Hj;
   a.rowptr = g.rowptr_t;
@@ -682,26 +695,23 @@ int ea_fwd_pipe_launch(const float* Hi, const float* Hj, int64_t ldh, const Grap
   a.ldh = ldh;
   a.lds = lds;
   a.ldwe = ldwe;
+  a.e_cap = g.e_cap;
   a.n_nodes = static_cast<int>(n_nodes);
   a.h = static_cast<int>(h);
   a.c4 = c4;
-  a.warps = warps;
   a.n_stages = stages;
   a.cap_slots = cap;
   a.stage_bytes = stage_bytes;
+  a.hdr_bytes = hdr_bytes;
   a.contiguous = (ldh * 4 == int64_t(rowbytes)) ? 1 : 0;
-  a.e_cap = g.e_cap;
-  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), ceil_div64(n_nodes, warps))));
-  a.rows_per_warp = static_cast<int>(ceil_div64(n_nodes, int64_t(grid) * warps));
-  a.prefetch_l2 = env_int("PFN_EA_PREFETCH", 2 * n_nodes * int64_t(rowbytes) <= kPipePrefetchMaxBytes ? 1 : 0) != 0 ? 1 : 0;
-  a.early_trigger = env_int("PFN_EA_TRIGGER", 0) != 0 ? 1 : 0;
-  const uint32_t smem = fixed_bytes(warps) + uint32_t(warps) * uint32_t(stages) * stage_bytes + 128u;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), ceil_div64(n_nodes, a.rows))));
+  a.rows_per_cta = static_cast<int>(ceil_div64(n_nodes, grid));
+  // (measured at case118v2 x 128: the prefetch makes the kernel ~10 % SLOWER -- it stays an opt-in experiment)
+  a.prefetch_l2 = (env_int("PFN_EA_PREFETCH", 0) != 0 && 2 * n_nodes * int64_t(rowbytes) <= kTmaPrefetchMaxBytes) ? 1 : 0;
+  const uint32_t smem = off_stage + uint32_t(stages) * stage_bytes + 128u;
   static SmemAttrOnce attr_once;
-  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] {
-    const cudaError_t e = cudaFuncSetAttribute(k_ea_fwd_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPipeSmemLimit));
-    return e != cudaSuccess ? e : cudaFuncSetAttribute(k_ea_fwd_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPipeSmemLimit));
-  }));
-  PFN_CUDA_OK(launch_kernel(bulk ? k_ea_fwd_pipe<true> : k_ea_fwd_pipe<false>, dim3(grid), dim3(32 * warps), smem, stream, a));
+  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] { return cudaFuncSetAttribute(k_ea_fwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTmaSmemLimit)); }));
+  PFN_CUDA_OK(launch_kernel(k_ea_fwd_tma, dim3(grid), dim3(32 * (a.cons_warps + a.prod_warps)), smem, stream, a));
   PFN_LAUNCHED();
   return 0;
 }
@@ -720,8 +730,8 @@ int ea_fwd_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView
   if (n_nodes == 0) return 0;
   const RowTiling t = make_tiling(n_nodes, h, kBlocksPerSm);
   ProfScope prof(PFN_PROF_EA_FWD, stream);
-  if (ea_fwd_use_pipe()) {
-    const int rc = ea_fwd_pipe_launch(Hi, Hj, ldh, g, n_nodes, We, ldwe, S, lds, h, stream);
+  if (ea_fwd_use_tma()) {
+    const int rc = ea_fwd_tma_launch(Hi, Hj, ldh, g, n_nodes, We, ldwe, S, lds, h, stream);
     if (rc != 1) return rc;
   }
   PFN_CUDA_OK(launch_kernel(k_ea_fwd, dim3(t.nblocks), dim3(t.threads), 0, stream, Hi, Hj, ldh, g.rowptr_t, g.nbr_t, reinterpret_cast<const float2*>(g.ea_t),

@@ -54,7 +54,7 @@ struct TcArgs {
   TcItem it[kGemmMaxItems];
   float* C[kGemmMaxItems];
   const float* bias[kGemmMaxItems];
-  int n_items, batched, M, N, BN, ldc, stages, tmem_cols, n_hi, pad0_;
+  int n_items, batched, M, N, BN, ldc, stages, tmem_cols, n_hi, drain_tiles;
   const float* rowscale;
   const float* addend;
   const float* ymask;
@@ -211,14 +211,14 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& args, const EpiCtx& 
   } while (0)
 
 // DRAIN = true (reductions longer than kTcDrainMinTiles K tiles: hidden 512, the K-segmented TAGConv GEMMs): the hi*hi
-// accumulator is FLUSHED every kTcDrainTiles K tiles.  The tensor core adds into its fp32 TMEM accumulator with truncation,
+// accumulator is FLUSHED every drain_tiles K tiles.  The tensor core adds into its fp32 TMEM accumulator with truncation,
 // so a sum that stays in TMEM for c accumulating instructions is off by ~c * 2^-25 relative -- and always towards zero,
 // a BIAS that compounds through a 10-19 layer forward + backward instead of averaging out (measured: gradients of the
 // hidden-512 configurations 1.5e-5 from the fp64 twin).  Here phase p (kTcDrainTiles tiles) accumulates into TMEM slot
 // p mod n_hi starting from zero; when its MMAs have completed the worker warps read the slot (tcgen05.ld) and add it to
 // per-thread fp32 REGISTER accumulators in round-to-nearest, while the tensor core is already filling the next slot.
-// No TMEM sum is ever longer than 4 * kTcDrainTiles instructions, whatever K is.
-constexpr int kTcDrainTiles = 2;
+// No TMEM sum is ever longer than 4 * drain_tiles instructions, whatever K is (drain_tiles = 1 or 2 K tiles per phase).
+constexpr int kTcDrainTilesDefault = 1;  // measured (case6470rte x 2, hidden 512, 5 layers): gradients 1.0-1.3x the fp32 reference's own distance to fp64 (2 tiles: 2-3x), forward GEMMs +8 %
 constexpr int kTcDrainMinTiles = 6;
 constexpr int kTcDrainChunks = 5;  // 16-column chunks per worker thread: ceil(160 / 32)
 
@@ -322,8 +322,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(conv_bar(s), ph);
-        const int phase = it / kTcDrainTiles, slot = phase % n_hi;  // DRAIN only
-        const bool phase_first = it % kTcDrainTiles == 0;
+        const int dt = args.drain_tiles;
+        const int phase = it / dt, slot = phase % n_hi;  // DRAIN only
+        const bool phase_first = it % dt == 0;
         if (DRAIN && phase_first && phase >= n_hi) mbar_wait(drained_bar(slot), uint32_t(phase / n_hi - 1) & 1u);
         tc_fence_after();
         const int nk = min(kTcBK / 8, (K - k0 + 7) / 8);  // 8 TF32 elements (32 bytes) per UMMA K step
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
             umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, acc_hi);
           }
           umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
-          if (DRAIN && (it % kTcDrainTiles == kTcDrainTiles - 1 || it == n_tiles_total - 1)) umma_commit(ready_bar(slot));
+          if (DRAIN && (it % dt == dt - 1 || it == n_tiles_total - 1)) umma_commit(ready_bar(slot));
         }
         kk += nk;
         __syncwarp();
@@ -397,10 +398,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         if (tid_c == 0 && it < 8) PFN_TSTAMP(10 + it);
         __syncwarp();
         if (lane == 0) mbar_arrive(conv_bar(s));
-        if (DRAIN && it % kTcDrainTiles == kTcDrainTiles - 1 && it >= 2 * kTcDrainTiles - 1) {
-          // every tile of phase p has been handed to the tensor core: read out phase p - 1 (issued two tiles ago, so its
+        if (DRAIN && (it + 1) % args.drain_tiles == 0 && it + 1 >= 2 * args.drain_tiles) {
+          // every tile of phase p has been handed to the tensor core: read out phase p - 1 (issued a phase ago, so its
           // MMAs have normally completed) while phase p is being multiplied
-          const int pd = it / kTcDrainTiles - 1, slot = pd % args.n_hi;
+          const int pd = (it + 1) / args.drain_tiles - 2, slot = pd % args.n_hi;
           mbar_wait(ready_bar(slot), uint32_t(pd / args.n_hi) & 1u);
           tc_fence_after();
           drain_slot(uint32_t(slot * BN));
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     const int ncols = min(BN, args.N - n0);
     if (DRAIN) {
       // the phases not read out yet (every MMA has completed), then the lo terms; registers -> staging tile
-      const int n_phases = (n_tiles_total + kTcDrainTiles - 1) / kTcDrainTiles;
+      const int n_phases = (n_tiles_total + args.drain_tiles - 1) / args.drain_tiles;
       for (int pd = next_drain; pd < n_phases; ++pd) drain_slot(uint32_t((pd % args.n_hi) * BN));
       drain_slot(uint32_t(args.n_hi * BN));
       const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
@@ -1212,7 +1213,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   a.keep_thresh = g.keep_thresh;
   a.seed_dev = g.seed_dev;
   const uint32_t smem = uint32_t(a.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2 + 6);
-  // long reductions flush the TMEM accumulators into registers every kTcDrainTiles K tiles (see the kernel);
+  // long reductions flush the TMEM accumulators into registers every drain_tiles K tiles (see the kernel);
   // PFN_TC_DRAIN=0 / 1 forces the choice (accuracy experiments)
   int max_tiles = 0;
   for (int z = 0; z < count; ++z) {
@@ -1224,6 +1225,11 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     const char* e = std::getenv("PFN_TC_DRAIN");
     return e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
   }();
+  static const int drain_tiles_env = [] {
+    const char* e = std::getenv("PFN_TC_DRAIN_TILES");
+    return e != nullptr && e[0] == '1' ? 1 : (e != nullptr && e[0] == '2' ? 2 : kTcDrainTilesDefault);
+  }();
+  a.drain_tiles = drain_tiles_env;
   const bool drain = a.n_hi >= 2 && bn <= 32 * kTcDrainChunks && (drain_env >= 0 ? drain_env == 1 : max_tiles >= kTcDrainMinTiles);
   static SmemAttrOnce attr_once;
   PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] {

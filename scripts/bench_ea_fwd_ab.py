@@ -1,6 +1,6 @@
 """A/B timing of the EdgeAggregation forward kernels on the two roofline workloads:
 case118v2 x 128 at hidden 129 (24.0 MB algorithmic) and case6470rte x 32 at hidden 512 (1.28 GB).  Variants = the CTA-slab
-kernel (PFN_EA_FWD=cta) and the pipelined kernel with its tuning knobs.  Two timing modes per variant: `iters` eager
+kernel (PFN_EA_FWD=cta) and the bulk-copy kernel with its tuning knobs.  Two timing modes per variant: `iters` eager
 back-to-back launches between one pair of CUDA events, and the same launches captured once into a CUDA graph and replayed
 (no host launch cost).  Operand sets rotate so that no launch finds its operands in L2.  Prints one JSON object per line.
 
@@ -22,7 +22,7 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 lib = _lib.lib()
 peak, _ = bench.load_peaks()
-KNOBS = ("PFN_EA_FWD", "PFN_EA_STAGES", "PFN_EA_WARPS", "PFN_EA_PREFETCH", "PFN_EA_TRIGGER", "PFN_EA_BULK")
+KNOBS = ("PFN_EA_FWD", "PFN_EA_STAGES", "PFN_EA_THREADS", "PFN_EA_PREFETCH", "PFN_EA_PRODUCERS", "PFN_EA_BULK")
 
 
 def run(case, b, h, variants, iters, n_sets):
@@ -80,15 +80,21 @@ def run(case, b, h, variants, iters, n_sets):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
-P = {"PFN_EA_FWD": "pipe"}
-small = [("cta", {"PFN_EA_FWD": "cta"}), ("pipe", P), ("pipe_noprefetch", {**P, "PFN_EA_PREFETCH": "0"}),
-         ("pipe_trigger", {**P, "PFN_EA_TRIGGER": "1"}), ("pipe_s2", {**P, "PFN_EA_STAGES": "2"}), ("pipe_s4", {**P, "PFN_EA_STAGES": "4"}),
-         ("pipe_w4", {**P, "PFN_EA_WARPS": "4"}), ("pipe_bulkrows", {**P, "PFN_EA_BULK": "1"}),
-         ("pipe_bulkrows_trigger", {**P, "PFN_EA_BULK": "1", "PFN_EA_TRIGGER": "1"})]
-large = [("cta", {"PFN_EA_FWD": "cta"}), ("pipe", P), ("pipe_s2", {**P, "PFN_EA_STAGES": "2"}), ("pipe_s4", {**P, "PFN_EA_STAGES": "4"}),
-         ("pipe_w8", {**P, "PFN_EA_WARPS": "8"}), ("pipe_w2", {**P, "PFN_EA_WARPS": "2"}), ("pipe_cpasync", {**P, "PFN_EA_BULK": "0"}),
-         ("pipe_trigger", {**P, "PFN_EA_TRIGGER": "1"})]
-if which in ("small", "both"):
-    run("118v2", 128, 129, small, iters=240, n_sets=12)
-if which in ("large", "both"):
+only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None  # optional: comma-separated variant names
+P = {"PFN_EA_FWD": "tma"}
+small = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_prefetch", {**P, "PFN_EA_PREFETCH": "1"}),
+         ("tma_p2", {**P, "PFN_EA_PRODUCERS": "2"}), ("tma_p8", {**P, "PFN_EA_PRODUCERS": "8"}),
+         ("tma_s2", {**P, "PFN_EA_STAGES": "2"}), ("tma_s3", {**P, "PFN_EA_STAGES": "3"}),
+         ("tma_t512", {**P, "PFN_EA_THREADS": "512"}), ("tma_t896", {**P, "PFN_EA_THREADS": "896"}),
+         ("tma_bulk", {**P, "PFN_EA_BULK": "1"})]
+large = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_s2", {**P, "PFN_EA_STAGES": "2"}), ("tma_s3", {**P, "PFN_EA_STAGES": "3"}),
+         ("tma_p2", {**P, "PFN_EA_PRODUCERS": "2"}), ("tma_p8", {**P, "PFN_EA_PRODUCERS": "8"}), ("tma_p1", {**P, "PFN_EA_PRODUCERS": "1"}),
+         ("tma_t512", {**P, "PFN_EA_THREADS": "512"}), ("tma_t896", {**P, "PFN_EA_THREADS": "896"}),
+         ("tma_bulk_s2", {**P, "PFN_EA_BULK": "1", "PFN_EA_STAGES": "2"})]
+if only is not None:
+    small = [v for v in small if v[0] in only]
+    large = [v for v in large if v[0] in only]
+if which in ("small", "both") and small:
+    run("118v2", 128, 129, small, iters=int(os.environ.get("AB_ITERS", "240")), n_sets=12)
+if which in ("large", "both") and large:
     run("6470rte", 32, 512, large, iters=12, n_sets=2)

@@ -11,11 +11,14 @@ for step in "$@"; do
     ab_large)  timeout 600 python scripts/bench_ea_fwd_ab.py large > gpurun_out/${tag}_ab_large.jsonl 2> gpurun_out/${tag}_ab_large.err; echo "rc=$?"; cat gpurun_out/${tag}_ab_large.jsonl | cut -c1-260 ;;
     t_kernels) timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu > gpurun_out/${tag}_t_kernels.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/${tag}_t_kernels.log ;;
     t_all)     timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/${tag}_t_all.log 2>&1; echo "rc=$?"; tail -40 gpurun_out/${tag}_t_all.log ;;
-    gemm_acc)  for d in 0 1; do PFN_TC_DRAIN=$d timeout 300 python scripts/debug_gemm_acc.py > gpurun_out/${tag}_gemm_acc_drain$d.log 2>&1; echo "rc=$?"; cat gpurun_out/${tag}_gemm_acc_drain$d.log; done ;;
-    parity_large) for d in 0 1; do PFN_TC_DRAIN=$d timeout 900 python scripts/debug_parity.py 2 6470rte 512 5 > gpurun_out/${tag}_parity_large_drain$d.log 2>&1; echo "rc=$?"; cat gpurun_out/${tag}_parity_large_drain$d.log | cut -c1-200; done ;;
+    gemm_acc)  for d in 1 2; do PFN_TC_DRAIN_TILES=$d timeout 300 python scripts/debug_gemm_acc.py > gpurun_out/${tag}_gemm_acc_dt$d.log 2>&1; echo "rc=$?"; grep abs gpurun_out/${tag}_gemm_acc_dt$d.log; done ;;
+    parity_large) for d in 1 2; do PFN_TC_DRAIN_TILES=$d timeout 900 python scripts/debug_parity.py 2 6470rte 512 5 > gpurun_out/${tag}_parity_large_dt$d.log 2>&1; echo "rc=$?"; cat gpurun_out/${tag}_parity_large_dt$d.log | cut -c1-200; done ;;
+    large_step) for d in 0 1 2; do PFN_TC_DRAIN=$([ $d = 0 ] && echo 0 || echo 1) PFN_TC_DRAIN_TILES=$([ $d = 0 ] && echo 2 || echo $d) timeout 900 python scripts/bench_large.py > gpurun_out/${tag}_large_step_dt$d.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/${tag}_large_step_dt$d.log | cut -c1-250; done ;;
     parity_std) timeout 600 python scripts/debug_parity.py 128 118v2 129 4 > gpurun_out/${tag}_parity_std.log 2>&1; echo "rc=$?"; tail -40 gpurun_out/${tag}_parity_std.log | cut -c1-200 ;;
     bench)     timeout 900 python bench.py --steps 100 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "rc=$?"; cat gpurun_out/${tag}_bench.json | cut -c1-3000 ;;
     smoke)     timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/${tag}_smoke.log ;;
+    ncu_pipe)  for v in tma cta; do AB_ITERS=24 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 30 -c 1 -o gpurun_out/${tag}_ncu_$v -f python scripts/bench_ea_fwd_ab.py small $v > gpurun_out/${tag}_ncu_$v.log 2>&1; echo "rc=$?"; done ;;
+    ncu_pipe_large)  for v in tma cta; do timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 3 -c 1 -o gpurun_out/${tag}_ncu_large_$v -f python scripts/bench_ea_fwd_ab.py large $v > gpurun_out/${tag}_ncu_large_$v.log 2>&1; echo "rc=$?"; done ;;
     *) echo "unknown step $step" ;;
   esac
 done

@@ -169,8 +169,9 @@ def test_fused_mse():
 
 
 def _star_batch(spokes=70):
-    """A hub bus with `spokes` branches (70: more than a batch buffer of the pipelined kernel holds at hidden 129, so the
-    hub row is summed from global memory; 300: more than a whole metadata chunk), a short chain and one isolated bus."""
+    """A hub bus with `spokes` branches (70: several rounds of gathered rows in one batch; 300 / 1200: more than a batch
+    buffer of the bulk-copy kernel holds, so the hub row is summed from global memory -- 1200 also exceeds the producer's
+    window of neighbour ids), a short chain and one isolated bus."""
     n = spokes + 5
     hub = torch.stack([torch.zeros(spokes, dtype=torch.long), torch.arange(1, spokes + 1)])
     chain = torch.tensor([[spokes + 1, spokes + 2], [spokes + 2, spokes + 3]])
@@ -182,14 +183,14 @@ def _star_batch(spokes=70):
                              batch=torch.zeros(n, dtype=torch.long), ptr=torch.tensor([0, n]))
 
 
-def _pipe_vs_cta(batch, h, monkeypatch, env=None, seed=11):
+def _tma_vs_cta(batch, h, monkeypatch, env=None, seed=11):
     from poweflownet_b200 import ops
     n, ei, ea, hi, hj, ds, w1, fin, graph = _edge_case(batch, h, seed=seed)
     src, tgt = ei[0], ei[1]
     pre = hi.double()[tgt] + hj.double()[src] + ea.double() @ w1[:, 2 * fin:].double().T
     s_ref = seg_sum(torch.relu(pre), tgt, n)
     outs = {}
-    for which in ("cta", "pipe"):
+    for which in ("cta", "tma"):
         monkeypatch.setenv("PFN_EA_FWD", which)
         for k, v in (env or {}).items():
             monkeypatch.setenv(k, v)
@@ -198,51 +199,51 @@ def _pipe_vs_cta(batch, h, monkeypatch, env=None, seed=11):
         ops.ea_fwd(_rows(hi), _rows(hj), graph, w1.to(DEV), fin, h, s)
         outs[which] = s
         _assert_close(s[:, :h], s_ref, what=f"S ({which})")
-    assert torch.equal(outs["cta"][:, :h], outs["pipe"][:, :h])  # same FMAs, same ascending-edge summation order
+    assert torch.equal(outs["cta"][:, :h], outs["tma"][:, :h])  # same FMAs, same ascending-edge summation order
 
 
-@pytest.mark.parametrize("h", [8, 33, 64, 93, 128, 129, 132, 256, 512, 1100])
-@pytest.mark.parametrize("name", ["mixed", "star", "bigstar", "isolated_and_parallel", "case118_h33", "no_edges"])
-def test_ea_forward_pipelined_kernel_equals_cta_kernel(name, h, monkeypatch):
-    """`k_ea_fwd_pipe` (asynchronous copies into per-warp shared-memory rings: bulk copies for row runs and wide rows,
-    16-byte cp.async for narrow gathered rows) against the double-precision reference and, bit for bit, against the
-    CTA-slab kernel -- narrow and wide rows, hub buses beyond a batch buffer (star) and beyond a metadata chunk
-    (bigstar), isolated buses, parallel branches, an empty edge list."""
-    batch = _star_batch() if name == "star" else _star_batch(300) if name == "bigstar" else name
-    _pipe_vs_cta(batch, h, monkeypatch)
+@pytest.mark.parametrize("h", [8, 33, 64, 93, 128, 129, 132, 256, 512, 1100, 3300])
+@pytest.mark.parametrize("name", ["mixed", "star", "bigstar", "hugestar", "isolated_and_parallel", "case118_h33", "no_edges"])
+def test_ea_forward_bulk_copy_kernel_equals_cta_kernel(name, h, monkeypatch):
+    """`k_ea_fwd_tma` (a producer warp feeding shared-memory batch buffers with bulk copies, ~24 consumer warps) against
+    the double-precision reference and, bit for bit, against the CTA-slab kernel -- narrow and wide rows, hub buses
+    inside a batch (star) and beyond a batch buffer / the neighbour window (bigstar, hugestar), isolated buses, parallel
+    branches, an empty edge list."""
+    batch = {"star": lambda: _star_batch(), "bigstar": lambda: _star_batch(300), "hugestar": lambda: _star_batch(1200)}.get(name, lambda: name)()
+    _tma_vs_cta(batch, h, monkeypatch)
 
 
-@pytest.mark.parametrize("env", [{"PFN_EA_BULK": "1"}, {"PFN_EA_BULK": "0"}, {"PFN_EA_STAGES": "2", "PFN_EA_WARPS": "3"},
-                                 {"PFN_EA_STAGES": "4", "PFN_EA_WARPS": "1"}, {"PFN_EA_PREFETCH": "0", "PFN_EA_TRIGGER": "1"},
-                                 {"PFN_EA_PREFETCH": "1"}])
+@pytest.mark.parametrize("env", [{"PFN_EA_STAGES": "2"}, {"PFN_EA_STAGES": "3", "PFN_EA_THREADS": "256"}, {"PFN_EA_THREADS": "992"},
+                                 {"PFN_EA_THREADS": "64", "PFN_EA_PRODUCERS": "1"}, {"PFN_EA_PRODUCERS": "7", "PFN_EA_THREADS": "800"},
+                                 {"PFN_EA_BULK": "1"}, {"PFN_EA_BULK": "0", "PFN_EA_PRODUCERS": "2"}, {"PFN_EA_PREFETCH": "1"}])
 @pytest.mark.parametrize("name,h", [("mixed", 129), ("star", 64), ("case118_h33", 512)])
-def test_ea_forward_pipelined_kernel_knobs(name, h, env, monkeypatch):
-    """Every copy mechanism / ring geometry the host can pick gives the same bits (bulk copies forced on narrow rows,
-    cp.async forced on wide ones, 2-4 stages, odd warp counts, L2 prefetch and early dependent launch on and off)."""
-    _pipe_vs_cta(_star_batch() if name == "star" else name, h, monkeypatch, env)
+def test_ea_forward_bulk_copy_kernel_knobs(name, h, env, monkeypatch):
+    """Every ring geometry / copy mechanism the host can pick gives the same bits (2-4 stages, 2 to 31 consumer warps, 1 to
+    7 producer warps, gathered rows as bulk copies or as cp.async chunks, L2 prefetch)."""
+    _tma_vs_cta(_star_batch() if name == "star" else name, h, monkeypatch, env)
 
 
-def test_ea_forward_pipelined_full_size_and_strided(monkeypatch):
-    """Bench size (case118v2 x 128, hidden 129: 13 rows per warp) and a 6470-bus graph at hidden 512 (several metadata
-    chunks per warp), plus operands that are column blocks of wider matrices (rows not contiguous: per-row copies)."""
+def test_ea_forward_bulk_copy_full_size_and_strided(monkeypatch):
+    """Bench size (case118v2 x 128, hidden 129), 6470-bus graphs at hidden 512 and a batch whose CTA row ranges exceed the
+    staged row-pointer slice, plus operands that are column blocks of wider matrices (rows not contiguous: per-row copies)."""
     from poweflownet_b200 import ops
     from poweflownet_b200.data import synthetic_batch
-    _pipe_vs_cta(synthetic_batch("118v2", 128), 129, monkeypatch, seed=5)
-    _pipe_vs_cta(synthetic_batch("6470rte", 2), 512, monkeypatch, seed=6)
-    for h, bulk in ((129, "0"), (256, "1")):
+    _tma_vs_cta(synthetic_batch("118v2", 128), 129, monkeypatch, seed=5)
+    _tma_vs_cta(synthetic_batch("6470rte", 2), 512, monkeypatch, seed=6)
+    _tma_vs_cta(synthetic_batch("6470rte", 50), 8, monkeypatch, seed=7)  # 323,500 rows: 2,186 per CTA > 2,048 staged row pointers
+    for h in (129, 256):
         n, ei, ea, hi, hj, ds, w1, fin, graph = _edge_case("mixed", h, seed=12)
         ld = ops.round_up4(h)
         wide_i, wide_j = torch.zeros(n, 3 * ld, device=DEV), torch.zeros(n, 3 * ld, device=DEV)
         wide_i[:, ld:ld + h].copy_(hi)
         wide_j[:, 2 * ld:2 * ld + h].copy_(hj)
         outs = {}
-        for which in ("cta", "pipe"):
+        for which in ("cta", "tma"):
             monkeypatch.setenv("PFN_EA_FWD", which)
-            monkeypatch.setenv("PFN_EA_BULK", bulk)
             s = torch.zeros(n, 2 * ld, device=DEV)
             from poweflownet_b200._lib import check, lib
             check(lib().pfn_ea_fwd(wide_i[:, ld:].data_ptr(), wide_j[:, ld:].data_ptr() + 4 * ld, 3 * ld, graph.ws.data_ptr(), n, graph.e_raw,
                                    w1.to(DEV).data_ptr() + 4 * 2 * fin, 2 * fin + 2, s[:, ld:].data_ptr(), 2 * ld, h,
                                    torch.cuda.current_stream().cuda_stream), "pfn_ea_fwd")
             outs[which] = s
-        assert torch.equal(outs["cta"], outs["pipe"]) and float(outs["pipe"][:, :ld].abs().max()) == 0.0
+        assert torch.equal(outs["cta"], outs["tma"]) and float(outs["tma"][:, :ld].abs().max()) == 0.0

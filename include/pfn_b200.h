@@ -57,7 +57,8 @@ PFN_API uint64_t pfn_launch_count(void);
 #define PFN_PROF_GEMM_WGRAD 5 /* dense Linear weight gradient (incl. split-K reduction)  */
 #define PFN_PROF_PREP 6       /* graph preparation (all passes)                          */
 #define PFN_PROF_FUSED_FWD 7 /* graph-resident whole-forward kernel (pfn_mpn_forward_tiled)   */
-#define PFN_PROF_CATEGORIES 8
+#define PFN_PROF_FUSED_BWD 8 /* graph-resident backward kernel(s) (pfn_mpn_backward_tiled)     */
+#define PFN_PROF_CATEGORIES 9
 PFN_API int pfn_profile_enable(int on);
 PFN_API int pfn_profile_read(int category, double* total_ms, int64_t* launches);
 

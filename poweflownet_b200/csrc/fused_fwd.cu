@@ -1693,7 +1693,7 @@ int fused_fwd_launch(FusedArgs& a, const float* arena, int64_t arena_rows, cudaS
     a.timing = timing_dev;
   }
   {
-    ProfScope prof(a.mode == kFusedModeForward ? PFN_PROF_FUSED_FWD : PFN_PROF_GEMM_DGRAD, stream);
+    ProfScope prof(a.mode == kFusedModeForward ? PFN_PROF_FUSED_FWD : PFN_PROF_FUSED_BWD, stream);
     PFN_CUDA_OK(launch_kernel(kernel, dim3(tiles), dim3(kFThreads), kFusedSmem, stream, a));
     PFN_LAUNCHED();
   }

@@ -21,7 +21,7 @@ from poweflownet_b200.data import synthetic_batch  # noqa: E402
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 lib = _lib.lib()
-peak, _ = bench.load_peaks()
+peak = bench.load_peaks()["hbm_gbs"]
 KNOBS = ("PFN_EA_FWD", "PFN_EA_STAGES", "PFN_EA_THREADS", "PFN_EA_PREFETCH", "PFN_EA_PRODUCERS", "PFN_EA_BULK")
 
 

@@ -21,7 +21,7 @@ ap.add_argument("--hidden", type=int, default=129)
 ap.add_argument("--iters", type=int, default=50)
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
-peak, _ = bench.load_peaks()
+peak = bench.load_peaks()["hbm_gbs"]
 b = synthetic_batch(args.case, args.batch).to(dev)
 n, h = b.num_nodes, args.hidden
 g = ops.PreparedGraph(b.edge_index, b.edge_attr, n, mode=1)

@@ -86,6 +86,7 @@ SIGNATURES = {
                                      c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "pfn_batch_assemble_status": (C.c_int, [C.c_void_p, c_i64, C.POINTER(C.c_int32), C.c_void_p]),
+    "pfn_allreduce_oneshot": (C.c_int, [c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_i64, C.c_int, C.c_void_p]),
     "pfn_adamw_step": (C.c_int, [c_i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                  C.c_double, C.c_double, C.c_double, c_i64, C.c_void_p]),
 }

@@ -18,7 +18,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libpfn_b200.so")
-SOURCES = ["graph_prep.cu", "edge_kernels.cu", "gemm.cu", "gemm_tc.cu", "fused_fwd.cu", "loss_optim.cu", "batch_assemble.cu", "engine.cu"]
+SOURCES = ["graph_prep.cu", "edge_kernels.cu", "gemm.cu", "gemm_tc.cu", "fused_fwd.cu", "loss_optim.cu", "batch_assemble.cu", "allreduce.cu", "engine.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -414,6 +414,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    // The staging tile written below overlays pipeline stage 0, last written by split_tile.  The mbarrier chain (conv_bar
+    // arrivals of ALL converter warps -> MMA -> accum_bar) already orders the two; this named barrier restates the
+    // ordering among the worker warps in a form compute-sanitizer's racecheck models (once per CTA: free).
+    asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");
     if (threadIdx.x == 64) PFN_TSTAMP(27);
     // Epilogue.  The pipeline stages are free now (every MMA has completed), so the accumulator tile is staged through
     // shared memory: phase 1, each warp drains its TMEM lane quarter (two warps per quarter, alternating 16-column
@@ -647,6 +651,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
+    asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");  // (see k_gemm_tc: orders split_tile's stores before the staging tile's)
     for (int t = 0; t < mt; ++t) {
       if (row0 + t * kTcBM >= Mo) break;  // CTA-uniform
       if (n_tiles > 0) {
@@ -956,6 +961,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
+    asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");  // (see k_gemm_tc: orders split_tile's stores before the staging tile's)
     if (tid_c == 0) WSTAMP(45);
     for (int t = 0; t < mt; ++t) {
       if (row0 + t * kTcBM >= Mo) break;  // CTA-uniform

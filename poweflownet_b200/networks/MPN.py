@@ -156,7 +156,9 @@ class _MPNFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             dout = dout.contiguous().float()
             sizes = [p.numel() for p in params]
-            gflat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            gflat = torch.empty((sum(sizes) + 3) // 4 * 4, dtype=torch.float32, device=dev)  # (whole float4s: the one-shot all-reduce)
+            if gflat.numel() != sum(sizes):
+                gflat[sum(sizes):].zero_()
             views, off = [], 0
             for p, s in zip(params, sizes):
                 views.append(gflat[off:off + s].view(p.shape))

@@ -41,10 +41,83 @@ def allreduce_flat_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
-def attach_gradient_allreduce(model, group=None) -> None:
+class OneShotAllReduce:
+    """In-place SUM all-reduce of one flat fp32 CUDA buffer as ONE kernel of libpfn_b200.so over NVLink peer memory
+    (`pfn_allreduce_oneshot`, csrc/allreduce.cu): every rank pushes its buffer into a per-source slot of every peer's
+    symmetric receive buffer, exchanges one flag per CTA, and sums the slots locally in rank order.  No host
+    synchronisation and no host-side state per call, so the kernel can be CAPTURED inside the CUDA graph of a training
+    step (`graph_safe`), unlike an NCCL call issued after the replay.  Meant for the latency-bound case (the 1.4 MB
+    gradient of configs/standard.json); traffic grows with world x n, so large buffers should stay on NCCL
+    (`attach_gradient_allreduce` picks by size).  Construction is collective (symmetric-memory rendezvous)."""
+
+    graph_safe = True
+    CTAS = 64
+
+    def __init__(self, n_floats: int, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import lib
+        lib()  # fail early if the library is missing
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n = (int(n_floats) + 3) // 4 * 4
+        self.device = torch.device(device)
+        self.recv = symm.empty(2 * self.world * self.n, dtype=torch.float32, device=self.device)
+        self.sig = symm.empty(self.CTAS * self.world, dtype=torch.int32, device=self.device)
+        self.recv.zero_()
+        self.sig.zero_()
+        h_recv = symm.rendezvous(self.recv, self.group)
+        h_sig = symm.rendezvous(self.sig, self.group)
+        self._handles = (h_recv, h_sig)  # keep the mappings alive
+        self.peer_recv = torch.tensor([int(p) for p in h_recv.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.peer_sig = torch.tensor([int(p) for p in h_sig.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.epochs = torch.zeros(self.CTAS, dtype=torch.int32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)  # every rank has zeroed its flags before anyone signals
+        self._C = C
+
+    def __call__(self, flat: torch.Tensor) -> torch.Tensor:
+        from ._lib import check, lib
+        if not (flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.data_ptr() % 16 == 0):
+            raise ValueError("OneShotAllReduce: contiguous 16-byte-aligned float32 CUDA buffer expected")
+        n = flat.numel()
+        if n % 4 != 0 or n > self.n:
+            raise ValueError(f"OneShotAllReduce: buffer of {n} floats (must be a multiple of 4 and <= {self.n})")
+        check(lib().pfn_allreduce_oneshot(flat.data_ptr(), self.peer_recv.data_ptr(), self.peer_sig.data_ptr(), self.epochs.data_ptr(),
+                                          self.rank, self.world, n if n == self.n else n, self.CTAS,
+                                          torch.cuda.current_stream(flat.device).cuda_stream), "pfn_allreduce_oneshot")
+        return flat
+
+
+ONE_SHOT_MAX_BYTES = 4 << 20  # beyond this the (world - 1) x traffic of the one-shot exchange loses to NCCL's ring
+
+
+def attach_gradient_allreduce(model, group=None, one_shot: Optional[bool] = None) -> None:
     """Make `model`'s backward all-reduce its flat gradient buffer (all parameter gradients are views of it)
     before autograd hands them to the optimizer: one collective per step, stream-ordered after the last
-    weight-gradient kernel."""
+    weight-gradient kernel.  Small gradients (<= ONE_SHOT_MAX_BYTES, CUDA, NCCL world > 1) take the library's own
+    one-shot NVLink kernel (`OneShotAllReduce`; `one_shot=False` forces NCCL, `True` insists); anything else NCCL / gloo.
+    If the symmetric-memory rendezvous is not available on the system the NCCL path is kept (a warning says so)."""
+    params = list(model.parameters())
+    n = sum(p.numel() for p in params)
+    dev = params[0].device if params else torch.device("cpu")
+    want = one_shot if one_shot is not None else (4 * n <= ONE_SHOT_MAX_BYTES and os.environ.get("PFN_ONE_SHOT_ALLREDUCE", "1") != "0")
+    if want and dev.type == "cuda" and dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl":
+        try:
+            reducer = OneShotAllReduce(n, dev, group)
+            # every rank must take the same path: agree on success
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                model._grad_reducer = reducer
+                return
+        except Exception as exc:  # noqa: BLE001 -- symmetric memory unsupported here: fall back, loudly
+            import warnings
+            warnings.warn(f"one-shot NVLink all-reduce unavailable ({type(exc).__name__}: {exc}); using NCCL")
+            if one_shot:
+                raise
+            bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MIN, group=group)
     model._grad_reducer = lambda flat: allreduce_flat_(flat, group)
 
 

@@ -154,7 +154,12 @@ class GraphedStep:
         self.static = type(self.static)(*[getattr(self.static, f).clone() for f in self.FIELDS])
         self.seeds = _SeedRing(dev)
         self.seed_dev = self.seeds.dev
-        self.reducer, model._grad_reducer = model._grad_reducer, None  # the collective stays outside the graph
+        # an NCCL collective stays outside the graph (issued after every replay); the library's own one-shot NVLink
+        # all-reduce is a plain kernel without host-side state and is captured with the step
+        self.reducer = model._grad_reducer
+        self.reducer_in_graph = bool(getattr(self.reducer, "graph_safe", False))
+        if not self.reducer_in_graph:
+            model._grad_reducer = None
         self.counts = None
         if loss == "masked_l2" and self.reducer is not None:
             self.counts = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -211,9 +216,9 @@ class GraphedStep:
         self.graph.replay()
         for p, g in zip(self.params, self.grads):
             p.grad = g
-        if self.reducer is not None:
+        if self.reducer is not None and not self.reducer_in_graph:
             flat = self.grads[0]._base if self.grads[0]._base is not None else None
-            if flat is not None and flat.numel() == sum(g.numel() for g in self.grads):
+            if flat is not None and flat.numel() >= sum(g.numel() for g in self.grads):
                 self.reducer(flat)
             else:
                 for g in self.grads:

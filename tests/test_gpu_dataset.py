@@ -267,3 +267,118 @@ def test_evaluate_epoch_matches_the_reference_loop(loss_name):
     got = evaluate_epoch(model, ds.loader(batch_size=6, shuffle=False), fn, DEV)
     assert abs(got - want) <= 2e-5 * abs(want), (got, want)
     assert not model.training
+
+
+def test_graphed_epochs_with_the_parser_default_loss():
+    """`GraphedEpochs(loss="masked_l2")` (Masked_L2_loss, the reference's default --train_loss_fn,
+    utils/argument_parser.py:36-37) walks the same trajectory as the eager `train_epoch` with the loss module."""
+    from poweflownet_b200.losses import Masked_L2_loss
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    from poweflownet_b200.optim import FusedAdamW
+    from poweflownet_b200.training import GraphedEpochs, train_epoch
+    gold = torch.load(mgd.dataset_golden_path("ds_case14"), weights_only=False)
+    ds = _dataset(gold, "train")  # 20 samples
+    kw = common.model_kwargs("case14_small")
+    kw["dropout_rate"] = 0.0
+    runs = []
+    for graphed in (False, True):
+        model = common.load_seeded(MaskEmbdMultiMPN(**kw)).to(DEV)
+        opt = FusedAdamW(model.parameters(), lr=1e-3)
+        if graphed:
+            runner = GraphedEpochs(model, ds, 10, opt, loss="masked_l2", regularize=True, regcoeff=0.5)
+            losses = [runner.run_epoch(shuffle=False) for _ in range(3)]
+        else:
+            losses = [train_epoch(model, ds.loader(10, shuffle=False), Masked_L2_loss(regularize=True, regcoeff=0.5), opt, DEV) for _ in range(3)]
+        runs.append((losses, [p.detach().clone() for p in model.parameters()]))
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert abs(a - b) <= 1e-6 * abs(a), runs
+    assert runs[0][0][2] < runs[0][0][0]
+    for p, q in zip(runs[0][1], runs[1][1]):
+        assert torch.allclose(p, q, rtol=0, atol=2e-6)
+
+
+def test_graphed_epochs_on_a_mixed_size_dataset_bucket_by_batch_shape():
+    """`--case mixed` (118- and 14-bus samples in one dataset, datasets/PowerFlowData.py:67-70): the shape of a mini-batch
+    depends on how many samples of each case it drew; `GraphedEpochs` captures one graph per shape on first sight and
+    replays it afterwards, and the trajectory equals the eager loop's on the same sample order."""
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    from poweflownet_b200.optim import FusedAdamW
+    from poweflownet_b200.training import GraphedEpochs, train_epoch
+    gold = torch.load(mgd.dataset_golden_path("ds_mixed"), weights_only=False)
+    ds = _dataset(gold, "train")
+    assert len(set(int(v) for v in ds._n)) == 2  # two graph sizes
+    kw = common.model_kwargs("mixed")
+    kw["dropout_rate"] = 0.0
+    bs = 4
+    runs = []
+    for graphed in (False, True):
+        model = common.load_seeded(MaskEmbdMultiMPN(**kw)).to(DEV)
+        opt = FusedAdamW(model.parameters(), lr=1e-3)
+        losses = []
+        for ep in range(3):
+            g = torch.Generator().manual_seed(100 + ep)
+            if graphed:
+                if ep == 0:
+                    runner = GraphedEpochs(model, ds, bs, opt, loss="mse", max_graphs=2)
+                losses.append(runner.run_epoch(shuffle=True, generator=g))
+            else:
+                losses.append(train_epoch(model, ds.loader(bs, shuffle=True, generator=g, drop_last=True), torch.nn.MSELoss(), opt, DEV))
+        runs.append((losses, [p.detach().clone() for p in model.parameters()]))
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert abs(a - b) <= 2e-6 * abs(a), runs
+    for p, q in zip(runs[0][1], runs[1][1]):
+        assert torch.allclose(p, q, rtol=0, atol=5e-6)
+    assert 1 <= len(runner.steps) <= 2  # at most `max_graphs` captured shapes; any further shape ran eagerly
+
+
+def test_evaluation_between_graph_replays_does_not_touch_the_captured_workspace():
+    """a captured step has its activation / scratch workspace addresses baked in.  An eval forward of
+    the SAME (N, E_raw) shape between replays (train, validate, train: the reference's epoch loop) must neither take nor
+    free that workspace: replays before and after the evaluation produce the same gradients for the same batch, also after
+    the caching allocator has been emptied and refilled."""
+    from poweflownet_b200.data import synthetic_batch
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    from poweflownet_b200.training import GraphedMSEStep
+    kw = dict(common.MODEL_DIMS, hidden_dim=64, n_gnn_layers=2, K=3, dropout_rate=0.0)
+    model = common.load_seeded(MaskEmbdMultiMPN(**kw)).to(DEV).train()
+    batch = synthetic_batch("14", 18, seed=3).to(DEV)
+    other = synthetic_batch("14", 18, seed=4).to(DEV)
+    step = GraphedMSEStep(model, batch)
+    assert not model._pool  # the capture ran on a pool private to the step; nothing of it is reachable from the model
+    loss0 = float(step(batch))
+    g0 = [p.grad.clone() for p in model.parameters()]
+    model.eval()
+    with torch.no_grad():
+        for _ in range(3):
+            model(other)  # same shape: must run on workspaces of its own
+    n_ws = sum(len(v) for v in model._pool.values())
+    assert n_ws == 1  # ... which it hands back even under no_grad (it used to keep and drop them)
+    torch.cuda.empty_cache()
+    junk = [torch.full((1 << 22,), float("nan"), device=DEV) for _ in range(8)]  # reuse whatever the allocator freed
+    model.train()
+    loss1 = float(step(batch))
+    assert loss1 == loss0
+    for a, b in zip(g0, [p.grad for p in model.parameters()]):
+        assert torch.equal(a, b)
+    del junk
+
+
+def test_graph_replays_draw_a_fresh_dropout_seed_each():
+    """consecutive replays queued back to back (the host runs ahead of the device) must not share a dropout
+    seed; under a fixed torch seed the sequence is reproducible."""
+    from poweflownet_b200.data import synthetic_batch
+    from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
+    from poweflownet_b200.training import GraphedMSEStep
+    kw = dict(common.MODEL_DIMS, hidden_dim=64, n_gnn_layers=2, K=3, dropout_rate=0.5)
+    batch = synthetic_batch("14", 18, seed=3).to(DEV)
+    seqs = []
+    for _ in range(2):
+        model = common.load_seeded(MaskEmbdMultiMPN(**kw)).to(DEV).train()
+        step = GraphedMSEStep(model, batch)
+        torch.manual_seed(99)
+        total = torch.zeros(200, device=DEV)
+        for i in range(200):  # queued without any synchronisation
+            total[i:i + 1] = step(batch)
+        seqs.append(total.cpu())
+    assert torch.equal(seqs[0], seqs[1])  # reproducible
+    assert len(set(seqs[0].tolist())) > 190  # and (almost surely) all different: no two replays shared a mask

@@ -51,8 +51,23 @@ def _worker(rank, world, port, out_path):
     parallel.allreduce_flat_(flat)
     loss_sum = loss.detach().clone()
     dist.all_reduce(loss_sum)
+    # Masked_L2_loss (the reference's default loss) under data parallelism: the two means run over the GLOBAL masked /
+    # unmasked selections (`parallel.global_mask_counts`: one 2-element all-reduce), which is what the CUDA loss kernel
+    # reads through its `global_counts` argument
+    model.zero_grad()
+    counts = parallel.global_mask_counts(mine.pred_mask)
+    out = model(mine)
+    d2 = (out - mine.y) ** 2
+    m = mine.pred_mask != 0
+    loss_m = d2[m].sum() / counts[0] + 0.5 * d2[~m].sum() / counts[1]
+    loss_m.backward()
+    flat_m = _flat_grad(model)
+    parallel.allreduce_flat_(flat_m)
+    loss_m_sum = loss_m.detach().clone()
+    dist.all_reduce(loss_m_sum)
     if rank == 0:
-        torch.save({"flat": flat, "loss": loss_sum, "total": total, "nodes": mine.num_nodes}, out_path)
+        torch.save({"flat": flat, "loss": loss_sum, "total": total, "nodes": mine.num_nodes, "flat_masked": flat_m,
+                    "loss_masked": loss_m_sum, "counts": counts}, out_path)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -69,6 +84,15 @@ def test_two_rank_gradient_equals_single_process(tmp_path):
     assert 0 < got["nodes"] < full.num_nodes
     assert abs(float(got["loss"]) - float(loss_ref)) < 1e-6 * float(loss_ref)
     e = common.rel_err(got["flat"], _flat_grad(ref))
+    assert max(e) < 1e-5, e
+    # masked loss: global counts, summed loss and reduced gradient equal the single-process Masked_L2_loss(regcoeff=0.5)
+    ref.zero_grad()
+    loss_m = O.masked_l2_loss(ref(full), full.y, full.pred_mask, True, 0.5)
+    loss_m.backward()
+    n1 = int((full.pred_mask != 0).sum())
+    assert got["counts"].tolist() == [float(n1), float(full.pred_mask.numel() - n1)]
+    assert abs(float(got["loss_masked"]) - float(loss_m)) < 1e-6 * float(loss_m)
+    e = common.rel_err(got["flat_masked"], _flat_grad(ref))
     assert max(e) < 1e-5, e
 
 

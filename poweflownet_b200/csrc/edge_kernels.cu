@@ -258,13 +258,12 @@ __device__ __forceinline__ float2 lds2(uint32_t addr) {
   return v;
 }
 
-// the CTA's 1/gridDim share of [base, base + bytes) -> L2, in pieces of 4 KB dealt to the threads (16-byte granules)
+// the CTA's 1/gridDim share of [base, base + bytes) -> L2 as ONE bulk prefetch (16-byte granules).  One operation, not many
+// small ones: the TMA unit needs ~35 ns per operation whatever its size, and the batch copies queue behind these.
 __device__ __forceinline__ void prefetch_share(const void* base, unsigned bytes) {
   const unsigned gran = (bytes + 15u) >> 4, per = (gran + gridDim.x - 1) / gridDim.x;
   const unsigned lo = min(gran, per * blockIdx.x), hi = min(gran, lo + per);
-  const char* p = static_cast<const char*>(base);
-  for (unsigned g = lo + 256u * threadIdx.x; g < hi; g += 256u * blockDim.x)
-    bulk_prefetch_l2(p + (size_t(g) << 4), min(256u, hi - g) << 4);
+  if (hi > lo) bulk_prefetch_l2(static_cast<const char*>(base) + (size_t(lo) << 4), (hi - lo) << 4);
 }
 
 __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ TmaArgs a) {
@@ -290,17 +289,15 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (a.prefetch_l2) {
-    if (a.contiguous) {
-      // the CTA's own Hi rows; its share of Hj (every row of it is fetched from HBM exactly once, by whoever comes first)
-      const char* hi0 = reinterpret_cast<const char*>(a.Hi) + size_t(row_start) * rowbytes;
-      const unsigned own = unsigned(row_end - row_start) * rowbytes;
-      for (unsigned o = 4096u * tid; o < own; o += 4096u * blockDim.x) bulk_prefetch_l2(hi0 + o, min(4096u, own - o));
-      prefetch_share(a.Hj, unsigned(a.n_nodes) * rowbytes);
-    }
-    prefetch_share(a.nbr, unsigned(a.e_cap) * 4u);
-    prefetch_share(a.ea, unsigned(a.e_cap) * 8u);
-    prefetch_share(a.rowptr, (unsigned(a.n_nodes) + 1u) * 4u);
+  if (a.prefetch_l2 && tid < 5) {
+    // thread 0: the CTA's share of Hj (every row of it is fetched from HBM exactly once, by whoever comes first);
+    // thread 1: its own Hi rows; threads 2..4: its shares of the CSR arrays
+    if (tid == 0 && a.contiguous) prefetch_share(a.Hj, unsigned(a.n_nodes) * rowbytes);
+    if (tid == 1 && a.contiguous && row_end > row_start)
+      bulk_prefetch_l2(reinterpret_cast<const char*>(a.Hi) + size_t(row_start) * rowbytes, unsigned(row_end - row_start) * rowbytes);
+    if (tid == 2) prefetch_share(a.nbr, unsigned(a.e_cap) * 4u);
+    if (tid == 3) prefetch_share(a.ea, unsigned(a.e_cap) * 8u);
+    if (tid == 4) prefetch_share(a.rowptr, (unsigned(a.n_nodes) + 1u) * 4u);
   }
   pdl_wait();
   // ---- all threads: row pointers of the CTA's range, then the first window of neighbour ids / edge_attr ----
@@ -389,15 +386,29 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
         if (bulk_rows) {
           for (int j = pt; j < nE; j += stride) bulk_g2s(gat + uint32_t(j) * rowbytes, a.Hj + (size_t)nb[j] * a.ldh, rowbytes, full_bar(s));
         } else {
+          // four chunks per lane and trip: the neighbour-id reads and the address arithmetic of a trip are independent,
+          // so the shared-memory latency is paid once per four copies (one chunk per trip measured 88 cycles per copy and
+          // made the whole kernel producer-bound: 10.5 us + 15 us / P at case118v2 x 128)
           int slot = pt / c4, q = pt % c4;
-          for (; slot < nE; ) {
-            cp_async16(gat + uint32_t(slot) * rowbytes + uint32_t(q) * 16u, a.Hj + (size_t)nb[slot] * a.ldh + 4 * q);
-            slot += step_slot;
-            q += step_q;
-            if (q >= c4) {
-              q -= c4;
-              ++slot;
+          while (slot < nE) {
+            int sl[4], qq[4], nbv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              sl[u] = slot;
+              qq[u] = q;
+              slot += step_slot;
+              q += step_q;
+              if (q >= c4) {
+                q -= c4;
+                ++slot;
+              }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nbv[u] = nb[min(sl[u], nE - 1)];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (sl[u] < nE)
+                cp_async16(gat + uint32_t(sl[u]) * rowbytes + uint32_t(qq[u]) * 16u, a.Hj + (size_t)nbv[u] * a.ldh + 4 * qq[u]);
           }
         }
       }
@@ -665,7 +676,7 @@ int ea_fwd_tma_launch(const float* Hi, const float* Hj, int64_t ldh, const Graph
   // measured: 528-byte rows 14.8 us per 424 copies and SM --, so narrow rows go as 16-byte cp.async chunks, LDGSTS)
   const int env_bulk = env_int("PFN_EA_BULK", -1);
   a.bulk_rows = (env_bulk >= 0 ? env_bulk != 0 : rowbytes >= kTmaBulkRowBytes) ? 1 : 0;
-  a.prod_warps = std::max(1, std::min(8, env_int("PFN_EA_PRODUCERS", a.bulk_rows ? 1 : 4)));
+  a.prod_warps = std::max(1, std::min(8, env_int("PFN_EA_PRODUCERS", a.bulk_rows ? 1 : 8)));
   const int max_cons = (32 - a.prod_warps) * 32;
   if (c4 > max_cons) return 1;
   const int want_threads = std::max(c4, std::min(max_cons, env_int("PFN_EA_THREADS", 768)));

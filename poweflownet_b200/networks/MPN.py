@@ -95,7 +95,7 @@ class _MPNFunction(torch.autograd.Function):
             graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph)
             ws.graph = graph.ws
             seed_dev = model._seed_device if training else None  # device-resident seed (CUDA-graph replays)
-            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if (training and seed_dev is None) else 0
+            seed = model._next_seed() if (training and seed_dev is None and model.dropout.p > 0) else 0
             inj = model._inject_dropout_masks if training else None
             inj_table = None
             if inj is not None:
@@ -113,12 +113,14 @@ class _MPNFunction(torch.autograd.Function):
             if tile_rows > 0 and graph_ptr is None and alt_ptr is not None:
                 attempts.append((128, alt_ptr))  # equal-sized tiles refused: whole graphs packed from `ptr` may still fit
             tile_rows, n_graphs = 0, 0
-            for rows, gptr in attempts:
+            for attempt, (rows, gptr) in enumerate(attempts):
                 # graph-resident kernel: the whole layer stack in one launch, one tile of whole graphs per CTA
                 ng = int(gptr.numel()) - 1 if gptr is not None else 0
                 sig = (n, graph.e_raw, rows, ng)
                 if model._tiling_checked.get(sig, True) is False:
                     continue
+                if attempt > 0:  # the refused attempt left its violation flag in the graph workspace: rebuild it
+                    graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph)
                 check(lib().pfn_mpn_forward_tiled(*common, rows, None if gptr is None else gptr.data_ptr(), ng, stream),
                       "pfn_mpn_forward_tiled")
                 # the kernel validates the closed-tile promise itself (a violation raises meta[6] and poisons the tile's
@@ -232,6 +234,14 @@ class MaskEmbdMultiMPN(nn.Module):
             return ops.PreparedGraph(edge_index, edge_attr.float(), n, mode=1).export()
 
     # ---- plumbing ---------------------------------------------------------------------------------
+    def _next_seed(self) -> int:
+        """Dropout seed of one training forward, drawn from torch's global CPU generator (reproducible under
+        `torch.manual_seed`, re-seeding replays the same masks).  Only called when dropout_rate > 0: with dropout off
+        the module consumes no random numbers at all, exactly like `nn.Dropout(p=0)` in the reference, so a
+        `DataLoader(shuffle=True)` fed from the same global stream shuffles identically for both
+        (tests/test_gpu_dropin_train.py compares the two trajectories batch for batch)."""
+        return int(torch.empty((), dtype=torch.int64).random_().item())
+
     def _desc(self) -> MpnDesc:
         return MpnDesc(self.nfeature_dim, self.efeature_dim, self.output_dim, self.hidden_dim, self.n_gnn_layers,
                        self.K, float(self.dropout.p), 0)

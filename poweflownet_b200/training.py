@@ -100,17 +100,22 @@ class _SeedRing:
     (`GraphedEpochs`, `PipelinedMSESteps`), so each queued copy gets its own pinned slot -- a single slot would be
     overwritten by a later `random_()` before the copy engine reads it, and consecutive replays would share masks.  A
     slot is reused only after the copy that read it has completed (event per slot).  Seeds come from torch's global CPU
-    generator, so runs are reproducible under `torch.manual_seed`."""
+    generator, so runs are reproducible under `torch.manual_seed`; nothing is drawn when the model's dropout rate is 0
+    (as `nn.Dropout(p=0)` draws nothing in the reference)."""
 
     SLOTS = 64
 
-    def __init__(self, device):
+    def __init__(self, device, model=None):
+        self.model = model
+        self.active = model is None or float(model.dropout.p) > 0.0
         self.host = torch.zeros(self.SLOTS, dtype=torch.int64).pin_memory()
         self.dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.events = [None] * self.SLOTS
         self.k = 0
 
     def refresh(self) -> None:
+        if not self.active:
+            return
         k = self.k
         self.k = (k + 1) % self.SLOTS
         if self.events[k] is not None:
@@ -152,7 +157,7 @@ class GraphedStep:
         self.loss_kind, self.regularize, self.regcoeff, self.group = loss, bool(regularize), float(regcoeff), group
         self.static = example_batch.to(dev)
         self.static = type(self.static)(*[getattr(self.static, f).clone() for f in self.FIELDS])
-        self.seeds = _SeedRing(dev)
+        self.seeds = _SeedRing(dev, model)
         self.seed_dev = self.seeds.dev
         # an NCCL collective stays outside the graph (issued after every replay); the library's own one-shot NVLink
         # all-reduce is a plain kernel without host-side state and is captured with the step

@@ -11,7 +11,9 @@ b = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 case = sys.argv[2] if len(sys.argv) > 2 else "118v2"
 hid = int(sys.argv[3]) if len(sys.argv) > 3 else 129
 nl = int(sys.argv[4]) if len(sys.argv) > 4 else 4
-kw = dict(common.MODEL_DIMS, hidden_dim=hid, n_gnn_layers=nl, K=3, dropout_rate=0.0)
+K = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+fused = (sys.argv[6] != "0") if len(sys.argv) > 6 else True
+kw = dict(common.MODEL_DIMS, hidden_dim=hid, n_gnn_layers=nl, K=K, dropout_rate=0.0)
 batch = synthetic_batch(case, b)
 oracle = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).train()
 loss_ref, out_ref = O.forward_loss_backward(oracle, batch, "mse")
@@ -19,6 +21,8 @@ o64 = common.load_seeded(O.MaskEmbdMultiMPN(**kw)).double().train()
 b64 = common.GraphBatch(**{k: (getattr(batch, k).double() if getattr(batch, k).is_floating_point() else getattr(batch, k)) for k in ("x","y","bus_type","pred_mask","edge_index","edge_attr","batch","ptr")})
 O.forward_loss_backward(o64, b64, "mse")
 m = MaskEmbdMultiMPN(**kw); m.load_state_dict(oracle.state_dict()); m = m.cuda().train()
+m.fused = fused
+print("env", {k: v for k, v in os.environ.items() if k.startswith("PFN_")}, "case", case, "b", b, "hidden", hid, "L", nl, "K", K, "fused", fused)
 db = batch.to("cuda")
 out = m(db); loss = torch.nn.functional.mse_loss(out, db.y); loss.backward()
 print("out", common.rel_err(out.detach().cpu(), out_ref))

@@ -17,7 +17,7 @@ for step in "$@"; do
     parity_std) timeout 600 python scripts/debug_parity.py 128 118v2 129 4 > gpurun_out/${tag}_parity_std.log 2>&1; echo "rc=$?"; tail -40 gpurun_out/${tag}_parity_std.log | cut -c1-200 ;;
     bench)     timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "rc=$?"; cat gpurun_out/${tag}_bench.json | cut -c1-6000; tail -5 gpurun_out/${tag}_bench.err ;;
     smoke)     timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/${tag}_smoke.log ;;
-    ncu_pipe)  for v in tma cta; do AB_ITERS=24 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 30 -c 1 -o gpurun_out/${tag}_ncu_$v -f python scripts/bench_ea_fwd_ab.py small $v > gpurun_out/${tag}_ncu_$v.log 2>&1; echo "rc=$?"; done ;;
+    ncu_pipe)  for v in tma_s2 cta; do AB_ITERS=24 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 30 -c 1 -o gpurun_out/${tag}_ncu_$v -f python scripts/bench_ea_fwd_ab.py small $v > gpurun_out/${tag}_ncu_$v.log 2>&1; echo "rc=$?"; done ;;
     ncu_pipe_large)  for v in tma cta; do timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 3 -c 1 -o gpurun_out/${tag}_ncu_large_$v -f python scripts/bench_ea_fwd_ab.py large $v > gpurun_out/${tag}_ncu_large_$v.log 2>&1; echo "rc=$?"; done ;;
     racecheck) timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python scripts/sanitize_fused.py > gpurun_out/${tag}_racecheck.log 2>&1; echo "rc=$?"; grep -E "RACECHECK SUMMARY|fused|layer-wise|Error" gpurun_out/${tag}_racecheck.log | sort | uniq -c | head -30 ;;
     memcheck)  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python scripts/sanitize_fused.py > gpurun_out/${tag}_memcheck.log 2>&1; echo "rc=$?"; grep -E "ERROR SUMMARY|fused|layer-wise|Invalid" gpurun_out/${tag}_memcheck.log | sort | uniq -c | head -30 ;;
@@ -25,6 +25,12 @@ for step in "$@"; do
     bench_large) timeout 900 python bench.py --config large --steps 5 --warmup 3 > gpurun_out/${tag}_bench_large.json 2> gpurun_out/${tag}_bench_large.err; echo "rc=$?"; cat gpurun_out/${tag}_bench_large.json | cut -c1-3000; tail -5 gpurun_out/${tag}_bench_large.err ;;
     bench_mixed) timeout 900 python bench.py --config mixed --steps 5 --warmup 3 > gpurun_out/${tag}_bench_mixed.json 2> gpurun_out/${tag}_bench_mixed.err; echo "rc=$?"; cat gpurun_out/${tag}_bench_mixed.json | cut -c1-3000; tail -5 gpurun_out/${tag}_bench_mixed.err ;;
     bench_ref) timeout 900 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "rc=$?"; cat gpurun_out/${tag}_bench_ref.json | cut -c1-1500 ;;
+    parity_wide) for v in "" "PFN_TC_DRAIN=0" "PFN_GEMM=ffma" "PFN_WGRAD_GROUP=0" "PFN_EA_FWD=cta"; do env $v timeout 600 python scripts/debug_parity.py 16 118v2 129 6 6 > gpurun_out/${tag}_parity_wide_$(echo $v | tr '=' '_').log 2>&1; echo "rc=$? [$v]"; grep -E "env|<<<" gpurun_out/${tag}_parity_wide_$(echo $v | tr '=' '_').log | cut -c1-200 | head -12; done
+               env timeout 600 python scripts/debug_parity.py 16 118v2 129 4 3 0 > gpurun_out/${tag}_parity_std_layerwise.log 2>&1; grep -E "env|<<<" gpurun_out/${tag}_parity_std_layerwise.log | cut -c1-200 | head ;;
+    host_prof) timeout 600 python scripts/profile_host.py > gpurun_out/${tag}_host_prof.log 2>&1; echo "rc=$?"; head -60 gpurun_out/${tag}_host_prof.log | cut -c1-200 ;;
+    debias)    for v in "PFN_TC_DEBIAS=0" "PFN_TC_DEBIAS=1" "PFN_TC_DEBIAS=2"; do env $v timeout 300 python scripts/debug_gemm_acc.py > gpurun_out/${tag}_gemm_acc_$(echo $v | tr '=' '_').log 2>&1; echo "rc=$? [$v]"; cut -c1-200 gpurun_out/${tag}_gemm_acc_$(echo $v | tr '=' '_').log | grep -v "^M=4096 K=32"; 
+                 env $v timeout 600 python scripts/debug_parity.py 16 118v2 129 6 6 > gpurun_out/${tag}_parity_wide_$(echo $v | tr '=' '_').log 2>&1; python scripts/parity_worst.py gpurun_out/${tag}_parity_wide_$(echo $v | tr '=' '_').log
+                 env $v timeout 600 python scripts/debug_parity.py 2 6470rte 512 5 > gpurun_out/${tag}_parity_large_$(echo $v | tr '=' '_').log 2>&1; python scripts/parity_worst.py gpurun_out/${tag}_parity_large_$(echo $v | tr '=' '_').log; done ;;
     *) echo "unknown step $step" ;;
   esac
 done

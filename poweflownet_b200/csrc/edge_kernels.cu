@@ -29,6 +29,9 @@ int env_int(const char* name, int dflt) {
   return e != nullptr ? std::atoi(e) : dflt;
 }
 
+constexpr int kSlabRows = 64;    // rows of CSR metadata a CTA stages at once (see stage_slab)
+constexpr int kSlabEdges = 768;
+
 RowTiling make_tiling(int64_t n_nodes, int64_t h, int blocks_per_sm) {
   static const int max_threads = std::min(1024, std::max(32, env_int("PFN_EDGE_THREADS", 256)));
   static const int bps_override = env_int("PFN_EDGE_BPS", 0);
@@ -41,6 +44,10 @@ RowTiling make_tiling(int64_t n_nodes, int64_t h, int blocks_per_sm) {
   int64_t want = ceil_div64(std::max<int64_t>(n_nodes, 1), t.rows);
   t.nblocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sm_count()) * blocks_per_sm)));
   t.npb = static_cast<int>(ceil_div64(std::max<int64_t>(n_nodes, 1), t.nblocks));
+  // large batches: cyclic slabs (npb = 0, see SlabWalk) once every CTA gets at least four of them
+  static const int cyclic_env = env_int("PFN_EDGE_CYCLIC", -1);
+  const bool cyclic = cyclic_env >= 0 ? cyclic_env != 0 : ceil_div64(n_nodes, kSlabRows) >= int64_t(4) * t.nblocks;
+  if (cyclic) t.npb = 0;
   return t;
 }
 
@@ -78,14 +85,47 @@ __device__ __forceinline__ void add_relu(float4& acc, float4 p) {
   acc.w += fmaxf(p.w, 0.f);
 }
 
+// ---- the same message arithmetic on packed pairs (Blackwell FADD2 / FFMA2: two IEEE fp32 operations per instruction,
+// identical results): 12 instructions per 16-byte chunk and edge instead of 20 -- the bulk-copy kernel below is bound by
+// instruction issue once its copies flow (5.4 bytes per warp instruction measured), not by arithmetic throughput.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+struct Pair4 {
+  uint64_t lo, hi;  // (x, y), (z, w)
+};
+__device__ __forceinline__ Pair4 pair4(float4 v) { return Pair4{pack2(v.x, v.y), pack2(v.z, v.w)}; }
+// acc += ReLU(hi + hj + a.x * w0 + a.y * w1), the operation order of preact() / add_relu()
+__device__ __forceinline__ void add_relu_preact2(Pair4& acc, const Pair4& hi, float4 hj, float2 a, const Pair4& w0, const Pair4& w1) {
+  const uint64_t ax = pack2(a.x, a.x), ay = pack2(a.y, a.y);
+  const uint64_t p01 = fma2(ay, w1.lo, fma2(ax, w0.lo, add2(hi.lo, pack2(hj.x, hj.y))));
+  const uint64_t p23 = fma2(ay, w1.hi, fma2(ax, w0.hi, add2(hi.hi, pack2(hj.z, hj.w))));
+  float p0, p1, p2, p3;
+  unpack2(p01, p0, p1);
+  unpack2(p23, p2, p3);
+  acc.lo = add2(acc.lo, pack2(fmaxf(p0, 0.f), fmaxf(p1, 0.f)));
+  acc.hi = add2(acc.hi, pack2(fmaxf(p2, 0.f), fmaxf(p3, 0.f)));
+}
+
 // ---- CSR slab staging ---------------------------------------------------------------------------------
 // A CTA owns a contiguous slab of rows, so its CSR entries (rowptr slice, neighbour ids, edge_attr) are one contiguous
 // range: they are copied into shared memory once, cooperatively and coalesced.  Without this every thread walks a
 // chain of three dependent global loads per row (rowptr -> neighbour id -> neighbour row); with it the per-row work
 // is a single round of independent gathers.  Slabs larger than the staging buffers are walked in pieces; a piece
 // whose edge count exceeds the buffer (a hub bus) falls back to reading the CSR arrays from global memory.
-constexpr int kSlabRows = 64;
-constexpr int kSlabEdges = 768;
 
 struct SlabSmem {
   int rowptr[kSlabRows + 1];
@@ -98,6 +138,29 @@ struct SlabView {
   const float2* ea;
   int e0;
 };
+
+// How a CTA walks its slabs of kSlabRows rows.  npb > 0: one contiguous range of npb rows per CTA (small batches: every
+// CTA gets work).  npb == 0: slab s belongs to CTA s mod gridDim (large batches).  With contiguous ranges the CTAs of a
+// large batch work in ~150 distant regions at once, i.e. on every graph of the batch simultaneously, and the gathered
+// neighbour rows -- each needed ~3 times, always from the same graph -- fall out of L2 between uses: measured at
+// case6470rte x 32, hidden 512: 1.47 GB read from DRAM for 0.86 GB of operands, L2 hit rate 4.6 %.  Cyclic slabs keep the
+// whole grid inside a window of gridDim x 64 rows (a graph or two), whose neighbour rows stay L2-resident.
+struct SlabWalk {
+  int start, end, step;
+};
+__device__ __forceinline__ SlabWalk slab_walk(int npb, int n_nodes) {
+  SlabWalk w;
+  if (npb > 0) {
+    w.start = blockIdx.x * npb;
+    w.end = min(n_nodes, w.start + npb);
+    w.step = kSlabRows;
+  } else {
+    w.start = blockIdx.x * kSlabRows;
+    w.end = n_nodes;
+    w.step = gridDim.x * kSlabRows;
+  }
+  return w;
+}
 
 __device__ __forceinline__ SlabView stage_slab(SlabSmem& sm, const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                const float2* __restrict__ ea, int r0, int nr) {
@@ -130,9 +193,9 @@ k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh
   pdl_wait();
   __shared__ SlabSmem sm;
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
-  const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
-  for (int r0 = start; r0 < end; r0 += kSlabRows) {  // CTA-uniform
-    const int nr = min(kSlabRows, end - r0);
+  const SlabWalk walk = slab_walk(npb, n_nodes);
+  for (int r0 = walk.start; r0 < walk.end; r0 += walk.step) {  // CTA-uniform
+    const int nr = min(kSlabRows, walk.end - r0);
     const SlabView sv = stage_slab(sm, rowptr, nbr, ea, r0, nr);
     for (int q = x; q < c4; q += cx) {
       float4 w0, w1;
@@ -194,6 +257,7 @@ constexpr int kTmaMaxStages = 4;
 constexpr int kTmaMetaRows = 2048;   // row pointers staged at once (a CTA's whole range unless the batch is huge)
 constexpr int kTmaMetaEdges = 1024;  // producer-private window of neighbour ids / edge_attr
 constexpr int kTmaMaxBatchRows = 64;
+constexpr int kTmaChunkRows = 128;   // rows per cyclic chunk of a large batch
 
 struct TmaBatchHeader {
   int R, row0, direct, pad;
@@ -210,7 +274,7 @@ struct TmaArgs {
   const float* We;
   float* S;
   long long ldh, lds, ldwe, e_cap;
-  int n_nodes, h, c4, rows, n_stages, cap_slots, rows_per_cta, prefetch_l2, contiguous, cons_warps, prod_warps, bulk_rows;
+  int n_nodes, h, c4, rows, n_stages, cap_slots, rows_per_cta, cyclic, prefetch_l2, contiguous, cons_warps, prod_warps, bulk_eighths, round_rows;
   unsigned stage_bytes, hdr_bytes;
 };
 
@@ -242,9 +306,9 @@ __device__ __forceinline__ void tma_mbar_wait(uint32_t bar, uint32_t parity) {
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"  // suspend-time hint: sleep in hardware, do not spin
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
   }
 }
 __device__ __forceinline__ float4 lds4(uint32_t addr) {
@@ -279,12 +343,16 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
   const uint32_t off_stage = (128u + uint32_t(kTmaMetaRows + 4) * 4u + uint32_t(kTmaMetaEdges) * 12u + 127u) & ~127u;
   auto full_bar = [&](int s) { return smem0 + 8u * s; };
   auto empty_bar = [&](int s) { return smem0 + 8u * (kTmaMaxStages + s); };
+  // Row ranges of this CTA: ONE contiguous range of rows_per_cta rows (small batches), or, cyclic, every gridDim-th chunk of
+  // rows_per_cta rows (large batches: the whole grid then works inside a window of a graph or two whose neighbour rows
+  // stay L2-resident -- see SlabWalk).
   const int row_start = min(a.n_nodes, int(blockIdx.x) * a.rows_per_cta), row_end = min(a.n_nodes, row_start + a.rows_per_cta);
+  const long long range_step = a.cyclic ? (long long)gridDim.x * a.rows_per_cta : (long long)a.n_nodes + 1;
 
   // ---- prologue that may overlap the previous kernel's tail (nothing here reads data as a value) ----
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      tma_mbar_init(full_bar(s), 1u + (a.bulk_rows ? 0u : 32u * uint32_t(a.prod_warps)));  // expect_tx + one arrival per cp.async lane
+      tma_mbar_init(full_bar(s), 1u + (a.bulk_eighths >= 8 ? 0u : 32u * uint32_t(a.prod_warps)));  // expect_tx + one arrival per cp.async lane
       tma_mbar_init(empty_bar(s), uint32_t(a.cons_warps));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -321,12 +389,15 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
     const int P = a.prod_warps, pw = warp - a.cons_warps, pt = pw * 32 + lane, stride = 32 * P;
     const int step_slot = stride / c4, step_q = stride % c4;
     auto producers_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(stride) : "memory"); };
-    int r = row_start;
     unsigned batch = 0;
-    while (r < row_end) {
-      if (r >= meta_row0 + meta_rows) {  // next slice of row pointers (only ranges longer than kTmaMetaRows rows)
+    for (long long rs = row_start; rs < a.n_nodes; rs += range_step) {
+    const int range_end = min(a.n_nodes, int(rs) + a.rows_per_cta);
+    int r = int(rs);
+    if (r != row_start) meta_rows = 0;  // a later range: its row pointers are fetched by the producers (first trip below)
+    while (r < range_end) {
+      if (r >= meta_row0 + meta_rows) {  // next slice of row pointers (later ranges; ranges longer than kTmaMetaRows rows)
         meta_row0 = r;
-        meta_rows = min(kTmaMetaRows, row_end - r);
+        meta_rows = min(kTmaMetaRows, range_end - r);
         producers_sync();
         for (int i = pt; i <= meta_rows; i += stride) m_rp[i] = a.rowptr[r + i];
         producers_sync();
@@ -340,7 +411,7 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
         const bool ok2 = c2 <= avail && c2 + (m_rp[lr + c2] - m_rp[lr]) <= cap;
         R = __popc(__ballot_sync(0xffffffffu, ok1)) + __popc(__ballot_sync(0xffffffffu, ok2));
       }
-      if (R > a.rows) R = R / a.rows * a.rows;  // whole passes of the consumers' row lanes
+      if (a.round_rows && R > a.rows) R = R / a.rows * a.rows;  // whole passes of the consumers' row lanes
       const bool direct = R == 0;
       if (direct) R = 1;
       const int e0 = m_rp[lr], nE = direct ? 0 : m_rp[lr + R] - e0;
@@ -358,7 +429,11 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
       tma_mbar_wait(empty_bar(s), ((batch / unsigned(NS)) & 1u) ^ 1u);  // the consumers have released this buffer
       const uint32_t buf = smem0 + off_stage + uint32_t(s) * a.stage_bytes + a.hdr_bytes;
       const float* hi_src = a.Hi + (size_t)r * a.ldh;
-      const bool bulk_rows = a.bulk_rows != 0;
+      // Gathered rows travel through BOTH copy engines at once: the first b8/8 of a batch's slots go as one bulk copy each
+      // (TMA unit: ~35-77 ns per copy whatever its size), the rest as 16-byte cp.async chunks (LSU / L1 miss queue:
+      // bounded number of lines in flight).  Each engine alone topped out near 25 KB/us per SM on 2 KB rows.
+      const int b8 = a.bulk_eighths;
+      const int n_bulk = (nE * b8 + 4) >> 3, n_async = nE - n_bulk;
       if (pw == 0) {
         uint8_t* stage = tma_smem + off_stage + size_t(s) * a.stage_bytes;
         TmaBatchHeader* hdr = reinterpret_cast<TmaBatchHeader*>(stage);
@@ -372,8 +447,8 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
         for (int j = lane; j < nE; j += 32) hdr_ea[j] = m_ea[e0 - ew_lo + j];
         __syncwarp();
         if (lane == 0) {
-          // bytes that arrive by bulk copy: the Hi rows (always), the gathered rows when they are wide
-          tma_mbar_expect_tx(full_bar(s), direct ? 0u : uint32_t(R + (bulk_rows ? nE : 0)) * rowbytes);
+          // bytes that arrive by bulk copy: the Hi rows (always) and the bulk share of the gathered rows
+          tma_mbar_expect_tx(full_bar(s), direct ? 0u : uint32_t(R + n_bulk) * rowbytes);
           if (!direct && a.contiguous) bulk_g2s(buf, hi_src, uint32_t(R) * rowbytes, full_bar(s));  // R consecutive rows: one copy
         }
         __syncwarp();
@@ -383,24 +458,41 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
       if (!direct) {
         const uint32_t gat = buf + uint32_t(R) * rowbytes;
         const int* nb = m_nb + (e0 - ew_lo);
-        if (bulk_rows) {
-          for (int j = pt; j < nE; j += stride) bulk_g2s(gat + uint32_t(j) * rowbytes, a.Hj + (size_t)nb[j] * a.ldh, rowbytes, full_bar(s));
-        } else {
-          // four chunks per lane and trip: the neighbour-id reads and the address arithmetic of a trip are independent,
-          // so the shared-memory latency is paid once per four copies (one chunk per trip measured 88 cycles per copy and
-          // made the whole kernel producer-bound: 10.5 us + 15 us / P at case118v2 x 128)
-          int slot = pt / c4, q = pt % c4;
-          while (slot < nE) {
+        // bulk share: slots [0, n_bulk), dealt to all producer lanes
+        for (int j = pt; j < n_bulk; j += stride)
+          bulk_g2s(gat + uint32_t(j) * rowbytes, a.Hj + (size_t)nb[j] * a.ldh, rowbytes, full_bar(s));
+        if (n_async > 0) {
+          // cp.async share: slots [n_bulk, nE).  Four chunks per lane and trip: the neighbour-id reads and the address
+          // arithmetic of a trip are independent, so the shared-memory latency is paid once per four copies (one chunk per
+          // trip measured 88 cycles per copy and made the kernel producer-bound; so did a division in this loop)
+          int k = n_bulk + pt / c4, q = pt % c4;
+          if (step_q == 0) {
+            // every lane keeps its chunk column (the producer lanes cover whole rows): one neighbour-id read, one 64-bit
+            // multiply-add and the copy per chunk -- ~6 instructions instead of ~26 for the general walk below
+            const char* col = reinterpret_cast<const char*>(a.Hj) + size_t(q) * 16u;
+            const size_t pitch = size_t(a.ldh) * 4u;
+            uint32_t dst = gat + uint32_t(k) * rowbytes + uint32_t(q) * 16u;
+            const uint32_t dst_step = uint32_t(step_slot) * rowbytes;
+            for (; k + 3 * step_slot < nE; k += 4 * step_slot, dst += 4u * dst_step) {
+              const int n0 = nb[k], n1 = nb[k + step_slot], n2 = nb[k + 2 * step_slot], n3 = nb[k + 3 * step_slot];
+              cp_async16(dst, col + size_t(n0) * pitch);
+              cp_async16(dst + dst_step, col + size_t(n1) * pitch);
+              cp_async16(dst + 2u * dst_step, col + size_t(n2) * pitch);
+              cp_async16(dst + 3u * dst_step, col + size_t(n3) * pitch);
+            }
+            for (; k < nE; k += step_slot, dst += dst_step) cp_async16(dst, col + size_t(nb[k]) * pitch);
+          }
+          while (k < nE) {
             int sl[4], qq[4], nbv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              sl[u] = slot;
+              sl[u] = k;
               qq[u] = q;
-              slot += step_slot;
+              k += step_slot;
               q += step_q;
               if (q >= c4) {
                 q -= c4;
-                ++slot;
+                ++k;
               }
             }
 #pragma unroll
@@ -412,9 +504,10 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
           }
         }
       }
-      if (!bulk_rows) cp_async_arrive_noinc(full_bar(s));  // fires when this lane's copies of the batch have landed
+      if (b8 < 8) cp_async_arrive_noinc(full_bar(s));  // fires when this lane's cp.async copies of the batch have landed
       r += R;
       ++batch;
+    }
     }
   } else if (warp < a.cons_warps) {
     // =================================== consumer warps ===================================
@@ -422,9 +515,12 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
     const bool active = y < a.rows;
     float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
     if (active) load_we(a.We, a.ldwe, x, a.h, w0, w1);
-    int r = row_start;
+    const Pair4 w0p = pair4(w0), w1p = pair4(w1);
     unsigned batch = 0;
-    while (r < row_end) {
+    for (long long rs = row_start; rs < a.n_nodes; rs += range_step) {
+    const int range_end = min(a.n_nodes, int(rs) + a.rows_per_cta);
+    int r = int(rs);
+    while (r < range_end) {
       const int s = int(batch % unsigned(NS));
       tma_mbar_wait(full_bar(s), (batch / unsigned(NS)) & 1u);
       const uint32_t stage = smem0 + off_stage + uint32_t(s) * a.stage_bytes;
@@ -443,32 +539,36 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
         const uint32_t ea_s = stage + uint32_t(sizeof(TmaBatchHeader));
         const uint32_t hi_s = stage + a.hdr_bytes + uint32_t(x) * 16u, gat = hi_s + uint32_t(R) * rowbytes;
         for (int lr = y; lr < R; lr += a.rows) {
-          const float4 hi = lds4(hi_s + uint32_t(lr) * rowbytes);
+          const Pair4 hi = pair4(lds4(hi_s + uint32_t(lr) * rowbytes));
           const int beg = hdr->rp[lr], fin = hdr->rp[lr + 1];
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          Pair4 acc{0ull, 0ull};
           int e = beg;
           for (; e + 3 < fin; e += 4) {  // four shared-memory row reads in flight per thread
             const float4 h0 = lds4(gat + uint32_t(e) * rowbytes), h1 = lds4(gat + uint32_t(e + 1) * rowbytes);
             const float4 h2 = lds4(gat + uint32_t(e + 2) * rowbytes), h3 = lds4(gat + uint32_t(e + 3) * rowbytes);
-            add_relu(acc, preact(hi, h0, lds2(ea_s + 8u * e), w0, w1));
-            add_relu(acc, preact(hi, h1, lds2(ea_s + 8u * (e + 1)), w0, w1));
-            add_relu(acc, preact(hi, h2, lds2(ea_s + 8u * (e + 2)), w0, w1));
-            add_relu(acc, preact(hi, h3, lds2(ea_s + 8u * (e + 3)), w0, w1));
+            add_relu_preact2(acc, hi, h0, lds2(ea_s + 8u * e), w0p, w1p);
+            add_relu_preact2(acc, hi, h1, lds2(ea_s + 8u * (e + 1)), w0p, w1p);
+            add_relu_preact2(acc, hi, h2, lds2(ea_s + 8u * (e + 2)), w0p, w1p);
+            add_relu_preact2(acc, hi, h3, lds2(ea_s + 8u * (e + 3)), w0p, w1p);
           }
           if (e + 1 < fin) {
             const float4 h0 = lds4(gat + uint32_t(e) * rowbytes), h1 = lds4(gat + uint32_t(e + 1) * rowbytes);
-            add_relu(acc, preact(hi, h0, lds2(ea_s + 8u * e), w0, w1));
-            add_relu(acc, preact(hi, h1, lds2(ea_s + 8u * (e + 1)), w0, w1));
+            add_relu_preact2(acc, hi, h0, lds2(ea_s + 8u * e), w0p, w1p);
+            add_relu_preact2(acc, hi, h1, lds2(ea_s + 8u * (e + 1)), w0p, w1p);
             e += 2;
           }
-          if (e < fin) add_relu(acc, preact(hi, lds4(gat + uint32_t(e) * rowbytes), lds2(ea_s + 8u * e), w0, w1));
-          st4(a.S + (size_t)(r + lr) * a.lds + 4 * x, acc);
+          if (e < fin) add_relu_preact2(acc, hi, lds4(gat + uint32_t(e) * rowbytes), lds2(ea_s + 8u * e), w0p, w1p);
+          float4 o;
+          unpack2(acc.lo, o.x, o.y);
+          unpack2(acc.hi, o.z, o.w);
+          st4(a.S + (size_t)(r + lr) * a.lds + 4 * x, o);
         }
       }
       __syncwarp();  // every lane has finished reading the buffer
       if (lane == 0) tma_mbar_arrive(empty_bar(s));
       r += R;
       ++batch;
+    }
     }
   }
 }
@@ -488,7 +588,7 @@ k_ea_bwd(const float* __restrict__ dS, int64_t ldds, const float* __restrict__ H
   __shared__ SlabSmem sm;
   __shared__ float red[8][1024];
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
-  const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
+  const SlabWalk walk = slab_walk(npb, n_nodes);
   const bool target_side = blockIdx.y == 0;
   const int nq = (c4 + cx - 1) / cx;  // column passes (1 unless hidden_dim > 1024)
   float4 g0[1] = {make_float4(0.f, 0.f, 0.f, 0.f)}, g1[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
@@ -498,8 +598,8 @@ k_ea_bwd(const float* __restrict__ dS, int64_t ldds, const float* __restrict__ H
     float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
     if (active) load_we(We, ldwe, q, h, w0, w1);
     g0[0] = g1[0] = make_float4(0.f, 0.f, 0.f, 0.f);  // dWe[:,0], dWe[:,1] partial sums of this chunk
-    for (int r0 = start; r0 < end; r0 += kSlabRows) {
-      const int nr = min(kSlabRows, end - r0);
+    for (int r0 = walk.start; r0 < walk.end; r0 += walk.step) {
+      const int nr = min(kSlabRows, walk.end - r0);
       const SlabView sv = target_side ? stage_slab(sm, rowptr_t, nbr_t, ea_t, r0, nr) : stage_slab(sm, rowptr_s, nbr_s, ea_s, r0, nr);
       if (active) {
         for (int lr = y; lr < nr; lr += rows) {
@@ -608,9 +708,9 @@ k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, 
   pdl_wait();
   __shared__ SlabSmem sm;
   const int x = threadIdx.x % cx, y = threadIdx.x / cx;
-  const int start = blockIdx.x * npb, end = min(n_nodes, start + npb);
-  for (int r0 = start; r0 < end; r0 += kSlabRows) {
-    const int nr = min(kSlabRows, end - r0);
+  const SlabWalk walk = slab_walk(npb, n_nodes);
+  for (int r0 = walk.start; r0 < walk.end; r0 += walk.step) {
+    const int nr = min(kSlabRows, walk.end - r0);
     const SlabView sv = stage_slab(sm, rowptr, nbr, nullptr, r0, nr);
     for (int q = x; q < c4; q += cx) {
       for (int lr = y; lr < nr; lr += rows) {
@@ -655,7 +755,7 @@ k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, 
 // ---- host side of k_ea_fwd_tma ----------------------------------------------------------------------------------------
 // PFN_EA_FWD=cta forces the CTA-slab kernel (k_ea_fwd); unset / anything else takes the bulk-copy kernel whenever the
 // width fits.  Read per call so that tests can compare the two.  Tuning knobs (experiments): PFN_EA_STAGES (2..4),
-// PFN_EA_THREADS (consumer threads, default 768), PFN_EA_PRODUCERS (1..8), PFN_EA_BULK (0/1), PFN_EA_PREFETCH (0/1).
+// PFN_EA_THREADS (consumer threads, default 512), PFN_EA_PRODUCERS (1..8), PFN_EA_BULK (0/1), PFN_EA_PREFETCH (0/1).
 constexpr uint32_t kTmaSmemLimit = 227 * 1024;
 constexpr long long kTmaPrefetchMaxBytes = 48ll << 20;  // L2-prefetch both node matrices only when they fit well inside L2
 
@@ -672,17 +772,19 @@ int ea_fwd_tma_launch(const float* Hi, const float* Hj, int64_t ldh, const Graph
   if (n_nodes >= (int64_t(1) << 31) - 64 || c4 > 31 * 32 || g.e_cap >= (int64_t(1) << 28)) return 1;
   constexpr uint32_t kTmaBulkRowBytes = 8192;
   TmaArgs a{};
-  // gathered rows: one bulk copy per row when rows are wide (the TMA unit needs ~35 ns per copy whatever its size --
-  // measured: 528-byte rows 14.8 us per 424 copies and SM --, so narrow rows go as 16-byte cp.async chunks, LDGSTS)
+  // gathered rows: how many of every eight go as one bulk copy each, the rest as 16-byte cp.async chunks (both engines run
+  // concurrently; PFN_EA_BULK8 = 0..8 overrides, PFN_EA_BULK = 0/1 means 0/8)
   const int env_bulk = env_int("PFN_EA_BULK", -1);
-  a.bulk_rows = (env_bulk >= 0 ? env_bulk != 0 : rowbytes >= kTmaBulkRowBytes) ? 1 : 0;
-  a.prod_warps = std::max(1, std::min(8, env_int("PFN_EA_PRODUCERS", a.bulk_rows ? 1 : 8)));
+  int b8 = rowbytes >= kTmaBulkRowBytes ? 8 : 0;  // (measured at 2 KB rows: 0/8 258 us, 2/8 269 us, 4/8 276 us, 8/8 357 us)
+  if (env_bulk >= 0) b8 = env_bulk != 0 ? 8 : 0;
+  a.bulk_eighths = std::max(0, std::min(8, env_int("PFN_EA_BULK8", b8)));
+  a.prod_warps = std::max(1, std::min(8, env_int("PFN_EA_PRODUCERS", a.bulk_eighths >= 8 ? 1 : 8)));
   const int max_cons = (32 - a.prod_warps) * 32;
   if (c4 > max_cons) return 1;
-  const int want_threads = std::max(c4, std::min(max_cons, env_int("PFN_EA_THREADS", 768)));
+  const int want_threads = std::max(c4, std::min(max_cons, env_int("PFN_EA_THREADS", 512)));
   a.rows = std::max(1, std::min(kTmaMaxBatchRows, want_threads / c4));
   a.cons_warps = (c4 * a.rows + 31) / 32;
-  int stages = std::max(2, std::min(kTmaMaxStages, env_int("PFN_EA_STAGES", 4)));
+  int stages = std::max(2, std::min(kTmaMaxStages, env_int("PFN_EA_STAGES", 2)));  // measured: two large batch buffers beat three or four
   const uint32_t off_stage = (128u + uint32_t(kTmaMetaRows + 4) * 4u + uint32_t(kTmaMetaEdges) * 12u + 127u) & ~127u;
   uint32_t stage_bytes = 0, hdr_bytes = 0;
   int cap = 0;
@@ -717,7 +819,15 @@ int ea_fwd_tma_launch(const float* Hi, const float* Hj, int64_t ldh, const Graph
   a.contiguous = (ldh * 4 == int64_t(rowbytes)) ? 1 : 0;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), ceil_div64(n_nodes, a.rows))));
   a.rows_per_cta = static_cast<int>(ceil_div64(n_nodes, grid));
+  // large batches: cyclic chunks of kTmaChunkRows rows once every CTA gets at least four of them (L2 residency of the
+  // gathered rows, see SlabWalk); PFN_EA_CHUNK = rows per chunk (0 = contiguous ranges)
+  const int chunk = env_int("PFN_EA_CHUNK", n_nodes >= int64_t(8) * grid * kTmaChunkRows ? kTmaChunkRows : 0);
+  if (chunk > 0) {
+    a.rows_per_cta = chunk;
+    a.cyclic = 1;
+  }
   // (measured at case118v2 x 128: the prefetch makes the kernel ~10 % SLOWER -- it stays an opt-in experiment)
+  a.round_rows = env_int("PFN_EA_ROUND", 0) != 0 ? 1 : 0;
   a.prefetch_l2 = (env_int("PFN_EA_PREFETCH", 0) != 0 && 2 * n_nodes * int64_t(rowbytes) <= kTmaPrefetchMaxBytes) ? 1 : 0;
   const uint32_t smem = off_stage + uint32_t(stages) * stage_bytes + 128u;
   static SmemAttrOnce attr_once;

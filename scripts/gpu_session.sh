@@ -17,8 +17,8 @@ for step in "$@"; do
     parity_std) timeout 600 python scripts/debug_parity.py 128 118v2 129 4 > gpurun_out/${tag}_parity_std.log 2>&1; echo "rc=$?"; tail -40 gpurun_out/${tag}_parity_std.log | cut -c1-200 ;;
     bench)     timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "rc=$?"; cat gpurun_out/${tag}_bench.json | cut -c1-6000; tail -5 gpurun_out/${tag}_bench.err ;;
     smoke)     timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/${tag}_smoke.log ;;
-    ncu_pipe)  for v in tma_s2 cta; do AB_ITERS=24 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 30 -c 1 -o gpurun_out/${tag}_ncu_$v -f python scripts/bench_ea_fwd_ab.py small $v > gpurun_out/${tag}_ncu_$v.log 2>&1; echo "rc=$?"; done ;;
-    ncu_pipe_large)  for v in tma cta; do timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 3 -c 1 -o gpurun_out/${tag}_ncu_large_$v -f python scripts/bench_ea_fwd_ab.py large $v > gpurun_out/${tag}_ncu_large_$v.log 2>&1; echo "rc=$?"; done ;;
+    ncu_pipe)  for v in tma cta; do AB_ITERS=24 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 30 -c 1 -o gpurun_out/${tag}_ncu_$v -f python scripts/bench_ea_fwd_ab.py small $v > gpurun_out/${tag}_ncu_$v.log 2>&1; echo "rc=$?"; done ;;
+    ncu_pipe_large)  for v in tma; do timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ea_fwd -s 3 -c 1 -o gpurun_out/${tag}_ncu_large_$v -f python scripts/bench_ea_fwd_ab.py large $v > gpurun_out/${tag}_ncu_large_$v.log 2>&1; echo "rc=$?"; done ;;
     racecheck) timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python scripts/sanitize_fused.py > gpurun_out/${tag}_racecheck.log 2>&1; echo "rc=$?"; grep -E "RACECHECK SUMMARY|fused|layer-wise|Error" gpurun_out/${tag}_racecheck.log | sort | uniq -c | head -30 ;;
     memcheck)  timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python scripts/sanitize_fused.py > gpurun_out/${tag}_memcheck.log 2>&1; echo "rc=$?"; grep -E "ERROR SUMMARY|fused|layer-wise|Invalid" gpurun_out/${tag}_memcheck.log | sort | uniq -c | head -30 ;;
     t_new)     timeout 1500 python -m pytest tests/test_gpu_model.py tests/test_gpu_dataset.py tests/test_gpu_dropin_train.py tests/test_gpu_fused.py -q -m gpu > gpurun_out/${tag}_t_new.log 2>&1; echo "rc=$?"; tail -60 gpurun_out/${tag}_t_new.log | cut -c1-300 ;;

@@ -267,15 +267,20 @@ PFN_API int pfn_batch_assemble(const pfn_dataset_case* cases, int n_cases, const
                        float* edge_attr, int64_t* batch_vec, int64_t* ptr, void* scratch, void* stream);
 PFN_API int pfn_batch_assemble_status(const void* scratch, int64_t batch, int32_t* host_flag, void* stream);
 
-/* ---- one-shot all-reduce (SUM, fp32, in place) of the flat gradient buffer over NVLink peer memory: the data-parallel
- *      exchange of SURVEY.md section 8e as ONE kernel that can be captured inside the step's CUDA graph (the reference has
- *      no multi-GPU mode; nothing to mirror).  grad: n floats (n % 4 == 0, 16-byte aligned), replaced by the sum over ranks.
- *      peer_recv: DEVICE array of `world` pointers -- rank r's symmetric receive buffer of 2 * world * n floats as mapped
- *      into this process; peer_sig: DEVICE array of `world` pointers to the ranks' symmetric flag arrays (ctas * world
- *      uint32, zero-initialised once); epochs: device array of `ctas` uint32 (zero-initialised once, local).  Every rank
- *      must call with the same n / ctas.  poweflownet_b200.parallel.OneShotAllReduce owns the buffers. ------------------- */
-PFN_API int pfn_allreduce_oneshot(float* grad, void* const* peer_recv, void* const* peer_sig, void* epochs, int rank, int world,
-                          int64_t n, int ctas, void* stream);
+/* ---- all-reduce (SUM, fp32, in place) of the flat gradient buffer over NVLink peer memory: the data-parallel exchange of
+ *      SURVEY.md section 8e as ONE kernel that can be captured inside the step's CUDA graph (the reference has no multi-GPU
+ *      mode; nothing to mirror).  grad: n floats (n % (4 * world) == 0, 16-byte aligned), replaced by the sum over ranks.
+ *      peer_recv / peer_res / peer_sig: DEVICE arrays of `world` pointers -- rank r's symmetric buffers as mapped into this
+ *      process: recv = 2 * world * n floats (one-shot) or 2 * n floats (two-shot), res = 2 * n floats, sig = 2 * ctas * world
+ *      uint32 (zero-initialised once); epochs: device array of `ctas` uint32 (zero-initialised once, local).  two_shot = 0:
+ *      every rank pushes its whole buffer to every peer and sums locally; 1: reduce-scatter + all-gather (world > 4).
+ *      Every rank must call with the same n / ctas / two_shot.  poweflownet_b200.parallel.OneShotAllReduce owns the buffers. */
+PFN_API int pfn_allreduce_peer(float* grad, void* const* peer_recv, void* const* peer_res, void* const* peer_sig, void* epochs, int rank,
+                       int world, int64_t n, int ctas, int two_shot, void* stream);
+/* debug aid (PFN_AR_TIMING=1 in the environment): %globaltimer stamps (ns) CTA 0 of the LAST pfn_allreduce_peer call left at
+ * its phase boundaries: start, after griddepcontrol.wait, after the pushes, after exchange 1, after sum + second pushes,
+ * after exchange 2, end.  Synchronises the device. */
+PFN_API int pfn_allreduce_debug_stamps(unsigned long long* host8);
 
 #ifdef __cplusplus
 }

@@ -86,7 +86,9 @@ SIGNATURES = {
                                      c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "pfn_batch_assemble_status": (C.c_int, [C.c_void_p, c_i64, C.POINTER(C.c_int32), C.c_void_p]),
-    "pfn_allreduce_oneshot": (C.c_int, [c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_i64, C.c_int, C.c_void_p]),
+    "pfn_allreduce_peer": (C.c_int, [c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_i64, C.c_int, C.c_int,
+                                     C.c_void_p]),
+    "pfn_allreduce_debug_stamps": (C.c_int, [C.POINTER(C.c_ulonglong)]),
     "pfn_adamw_step": (C.c_int, [c_i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                  C.c_double, C.c_double, C.c_double, c_i64, C.c_void_p]),
 }

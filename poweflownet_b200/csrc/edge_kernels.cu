@@ -274,7 +274,8 @@ struct TmaArgs {
   const float* We;
   float* S;
   long long ldh, lds, ldwe, e_cap;
-  int n_nodes, h, c4, rows, n_stages, cap_slots, rows_per_cta, cyclic, prefetch_l2, contiguous, cons_warps, prod_warps, bulk_eighths, round_rows;
+  int n_nodes, h, c4, rows, n_stages, cap_slots, rows_per_cta, cyclic, prefetch_l2, contiguous, cons_warps, prod_warps, bulk_eighths, round_rows,
+      meta_rows, meta_edges;  // capacity of the staged row-pointer slice / neighbour window
   unsigned stage_bytes, hdr_bytes;
 };
 
@@ -335,12 +336,13 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c4 = a.c4, NS = a.n_stages, cap = a.cap_slots;
   const uint32_t rowbytes = uint32_t(c4) * 16u;
-  // shared-memory map: barriers full[4] empty[4] | rp [kTmaMetaRows + 4] | nb [kTmaMetaEdges] | ea [kTmaMetaEdges] | stages
+  // shared-memory map: barriers full[4] empty[4] | rp [meta_rows + 4] | nb [meta_edges] | ea [meta_edges] | stages
+  const int kMetaRows = a.meta_rows, kMetaEdges = a.meta_edges;
   int* m_rp = reinterpret_cast<int*>(tma_smem + 128);
-  int* m_nb = m_rp + kTmaMetaRows + 4;
-  float2* m_ea = reinterpret_cast<float2*>(m_nb + kTmaMetaEdges);
+  int* m_nb = m_rp + kMetaRows + 4;
+  float2* m_ea = reinterpret_cast<float2*>(m_nb + kMetaEdges);
   const uint32_t smem0 = tma_smem_u32(tma_smem);
-  const uint32_t off_stage = (128u + uint32_t(kTmaMetaRows + 4) * 4u + uint32_t(kTmaMetaEdges) * 12u + 127u) & ~127u;
+  const uint32_t off_stage = (128u + uint32_t(kMetaRows + 4) * 4u + uint32_t(kMetaEdges) * 12u + 127u) & ~127u;
   auto full_bar = [&](int s) { return smem0 + 8u * s; };
   auto empty_bar = [&](int s) { return smem0 + 8u * (kTmaMaxStages + s); };
   // Row ranges of this CTA: ONE contiguous range of rows_per_cta rows (small batches), or, cyclic, every gridDim-th chunk of
@@ -369,11 +371,11 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
   }
   pdl_wait();
   // ---- all threads: row pointers of the CTA's range, then the first window of neighbour ids / edge_attr ----
-  int meta_row0 = row_start, meta_rows = min(kTmaMetaRows, row_end - row_start);
+  int meta_row0 = row_start, meta_rows = min(kMetaRows, row_end - row_start);
   for (int i = tid; i <= meta_rows; i += blockDim.x) m_rp[i] = a.rowptr[row_start + i];
   __syncthreads();
   int ew_lo = m_rp[0];
-  long long ew_hi = min((long long)a.e_cap, (long long)ew_lo + kTmaMetaEdges);
+  long long ew_hi = min((long long)a.e_cap, (long long)ew_lo + kMetaEdges);
   for (int i = tid; i < int(ew_hi - ew_lo); i += blockDim.x) {
     m_nb[i] = a.nbr[ew_lo + i];
     m_ea[i] = a.ea[ew_lo + i];
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
     while (r < range_end) {
       if (r >= meta_row0 + meta_rows) {  // next slice of row pointers (later ranges; ranges longer than kTmaMetaRows rows)
         meta_row0 = r;
-        meta_rows = min(kTmaMetaRows, range_end - r);
+        meta_rows = min(kMetaRows, range_end - r);
         producers_sync();
         for (int i = pt; i <= meta_rows; i += stride) m_rp[i] = a.rowptr[r + i];
         producers_sync();
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(1024, 1) k_ea_fwd_tma(const __grid_constant__ 
       const int e0 = m_rp[lr], nE = direct ? 0 : m_rp[lr + R] - e0;
       if (!direct && (long long)e0 + nE > ew_hi) {  // slide the producers' window of neighbour ids / edge_attr
         ew_lo = e0;
-        ew_hi = min((long long)a.e_cap, (long long)ew_lo + kTmaMetaEdges);
+        ew_hi = min((long long)a.e_cap, (long long)ew_lo + kMetaEdges);
         producers_sync();
         for (int i = pt; i < int(ew_hi - ew_lo); i += stride) {
           m_nb[i] = a.nbr[ew_lo + i];
@@ -778,24 +780,31 @@ int ea_fwd_tma_launch(const float* Hi, const float* Hj, int64_t ldh, const Graph
   int b8 = rowbytes >= kTmaBulkRowBytes ? 8 : 0;  // (measured at 2 KB rows: 0/8 258 us, 2/8 269 us, 4/8 276 us, 8/8 357 us)
   if (env_bulk >= 0) b8 = env_bulk != 0 ? 8 : 0;
   a.bulk_eighths = std::max(0, std::min(8, env_int("PFN_EA_BULK8", b8)));
-  a.prod_warps = std::max(1, std::min(8, env_int("PFN_EA_PRODUCERS", a.bulk_eighths >= 8 ? 1 : 8)));
-  const int max_cons = (32 - a.prod_warps) * 32;
+  // CTAs per SM: one CTA owning all of the SM's shared memory (default), or two half-sized CTAs per SM whose latency chains
+  // (row pointers -> neighbour ids -> rows) overlap each other (PFN_EA_CTAS_PER_SM=2; measured at case118v2 x 128: 10.4 us
+  // against 10.1 us -- no gain, it stays an experiment knob).
+  const int per_sm = std::max(1, std::min(2, env_int("PFN_EA_CTAS_PER_SM", 1)));
+  a.prod_warps = std::max(1, std::min(8, env_int("PFN_EA_PRODUCERS", a.bulk_eighths >= 8 ? 1 : (per_sm == 2 ? 4 : 8))));
+  const int max_cons = (32 / per_sm - a.prod_warps) * 32;
   if (c4 > max_cons) return 1;
-  const int want_threads = std::max(c4, std::min(max_cons, env_int("PFN_EA_THREADS", 512)));
+  const int want_threads = std::max(c4, std::min(max_cons, env_int("PFN_EA_THREADS", per_sm == 2 ? 256 : 512)));
   a.rows = std::max(1, std::min(kTmaMaxBatchRows, want_threads / c4));
   a.cons_warps = (c4 * a.rows + 31) / 32;
-  int stages = std::max(2, std::min(kTmaMaxStages, env_int("PFN_EA_STAGES", 2)));  // measured: two large batch buffers beat three or four
-  const uint32_t off_stage = (128u + uint32_t(kTmaMetaRows + 4) * 4u + uint32_t(kTmaMetaEdges) * 12u + 127u) & ~127u;
+  a.meta_rows = per_sm == 2 ? 512 : kTmaMetaRows;
+  a.meta_edges = per_sm == 2 ? 512 : kTmaMetaEdges;
+  const uint32_t smem_limit = per_sm == 2 ? 113u * 1024u : kTmaSmemLimit;  // 2 x (113 KB + 1 KB reserved) <= 228 KB per SM
+  int stages = std::max(1, std::min(kTmaMaxStages, env_int("PFN_EA_STAGES", 2)));  // measured: two large batch buffers beat three or four
+  const uint32_t off_stage = (128u + uint32_t(a.meta_rows + 4) * 4u + uint32_t(a.meta_edges) * 12u + 127u) & ~127u;
   uint32_t stage_bytes = 0, hdr_bytes = 0;
   int cap = 0;
   for (;; --stages) {
-    stage_bytes = ((kTmaSmemLimit - 128u - off_stage) / uint32_t(stages)) & ~127u;
+    stage_bytes = ((smem_limit - 128u - off_stage) / uint32_t(stages)) & ~127u;
     // header: fixed part + one float2 per slot (an upper bound of the edges of a batch), rounded to 128 bytes
     cap = static_cast<int>((stage_bytes - sizeof(TmaBatchHeader) - 128u) / (rowbytes + 8u));
-    cap = std::min(cap, kTmaMetaEdges);
+    cap = std::min(cap, a.meta_edges);
     hdr_bytes = (uint32_t(sizeof(TmaBatchHeader)) + 8u * uint32_t(std::max(cap, 0)) + 127u) & ~127u;
     // a batch buffer should hold at least one pass of the consumers' row lanes with their edges (~4 slots per row)
-    if (cap >= std::min(4 * a.rows, 64) || stages == 2) break;
+    if (cap >= std::min(4 * a.rows, 64) || stages <= 2) break;
   }
   if (cap < 2) return 1;
   a.Hi = Hi;
@@ -817,7 +826,7 @@ int ea_fwd_tma_launch(const float* Hi, const float* Hj, int64_t ldh, const Graph
   a.stage_bytes = stage_bytes;
   a.hdr_bytes = hdr_bytes;
   a.contiguous = (ldh * 4 == int64_t(rowbytes)) ? 1 : 0;
-  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sm_count(), ceil_div64(n_nodes, a.rows))));
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(int64_t(sm_count()) * per_sm, ceil_div64(n_nodes, a.rows))));
   a.rows_per_cta = static_cast<int>(ceil_div64(n_nodes, grid));
   // large batches: cyclic chunks of kTmaChunkRows rows once every CTA gets at least four of them (L2 residency of the
   // gathered rows, see SlabWalk); PFN_EA_CHUNK = rows per chunk (0 = contiguous ranges)

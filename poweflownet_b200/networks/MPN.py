@@ -158,7 +158,8 @@ class _MPNFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             dout = dout.contiguous().float()
             sizes = [p.numel() for p in params]
-            gflat = torch.empty((sum(sizes) + 3) // 4 * 4, dtype=torch.float32, device=dev)  # (whole float4s: the one-shot all-reduce)
+            mult = int(getattr(model._grad_reducer, "pad_multiple", 4))  # whole float4s (per rank slice) for the peer all-reduce
+            gflat = torch.empty((sum(sizes) + mult - 1) // mult * mult, dtype=torch.float32, device=dev)
             if gflat.numel() != sum(sizes):
                 gflat[sum(sizes):].zero_()
             views, off = [], 0

@@ -43,49 +43,53 @@ def allreduce_flat_(flat: torch.Tensor, group=None) -> torch.Tensor:
 
 class OneShotAllReduce:
     """In-place SUM all-reduce of one flat fp32 CUDA buffer as ONE kernel of libpfn_b200.so over NVLink peer memory
-    (`pfn_allreduce_oneshot`, csrc/allreduce.cu): every rank pushes its buffer into a per-source slot of every peer's
-    symmetric receive buffer, exchanges one flag per CTA, and sums the slots locally in rank order.  No host
-    synchronisation and no host-side state per call, so the kernel can be CAPTURED inside the CUDA graph of a training
-    step (`graph_safe`), unlike an NCCL call issued after the replay.  Meant for the latency-bound case (the 1.4 MB
-    gradient of configs/standard.json); traffic grows with world x n, so large buffers should stay on NCCL
+    (`pfn_allreduce_peer`, csrc/allreduce.cu).  Up to `TWO_SHOT_FROM - 1` ranks: every rank pushes its buffer into a
+    per-source slot of every peer's symmetric receive buffer, one flag exchange, local sum in rank order.  More ranks:
+    reduce-scatter + all-gather through the same symmetric buffers (two flag exchanges, (world-1)/world x 2n floats out per
+    rank instead of (world-1) x n).  No host synchronisation and no host-side state per call, so the kernel can be CAPTURED
+    inside the CUDA graph of a training step (`graph_safe`), unlike an NCCL call issued after the replay.  Meant for the
+    latency-bound case (the 1.4 MB gradient of configs/standard.json); large buffers stay on NCCL
     (`attach_gradient_allreduce` picks by size).  Construction is collective (symmetric-memory rendezvous)."""
 
     graph_safe = True
     CTAS = 64
+    TWO_SHOT_FROM = 5
 
-    def __init__(self, n_floats: int, device, group=None):
-        import ctypes as C
+    def __init__(self, n_floats: int, device, group=None, two_shot: Optional[bool] = None):
         import torch.distributed._symmetric_memory as symm
         from ._lib import lib
         lib()  # fail early if the library is missing
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        self.n = (int(n_floats) + 3) // 4 * 4
+        self.two_shot = bool(two_shot) if two_shot is not None else self.world >= self.TWO_SHOT_FROM
+        self.pad_multiple = 4 * self.world
+        self.n = (int(n_floats) + self.pad_multiple - 1) // self.pad_multiple * self.pad_multiple
         self.device = torch.device(device)
-        self.recv = symm.empty(2 * self.world * self.n, dtype=torch.float32, device=self.device)
-        self.sig = symm.empty(self.CTAS * self.world, dtype=torch.int32, device=self.device)
+        recv_floats = 2 * self.n if self.two_shot else 2 * self.world * self.n
+        self.recv = symm.empty(recv_floats, dtype=torch.float32, device=self.device)
+        self.res = symm.empty(2 * self.n, dtype=torch.float32, device=self.device)
+        self.sig = symm.empty(2 * self.CTAS * self.world, dtype=torch.int32, device=self.device)
         self.recv.zero_()
+        self.res.zero_()
         self.sig.zero_()
-        h_recv = symm.rendezvous(self.recv, self.group)
-        h_sig = symm.rendezvous(self.sig, self.group)
-        self._handles = (h_recv, h_sig)  # keep the mappings alive
-        self.peer_recv = torch.tensor([int(p) for p in h_recv.buffer_ptrs], dtype=torch.int64, device=self.device)
-        self.peer_sig = torch.tensor([int(p) for p in h_sig.buffer_ptrs], dtype=torch.int64, device=self.device)
+        handles = [symm.rendezvous(t, self.group) for t in (self.recv, self.res, self.sig)]
+        self._handles = handles  # keep the mappings alive
+        ptrs = lambda h: torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=self.device)  # noqa: E731
+        self.peer_recv, self.peer_res, self.peer_sig = (ptrs(h) for h in handles)
         self.epochs = torch.zeros(self.CTAS, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)  # every rank has zeroed its flags before anyone signals
-        self._C = C
 
     def __call__(self, flat: torch.Tensor) -> torch.Tensor:
         from ._lib import check, lib
         if not (flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.data_ptr() % 16 == 0):
             raise ValueError("OneShotAllReduce: contiguous 16-byte-aligned float32 CUDA buffer expected")
         n = flat.numel()
-        if n % 4 != 0 or n > self.n:
-            raise ValueError(f"OneShotAllReduce: buffer of {n} floats (must be a multiple of 4 and <= {self.n})")
-        check(lib().pfn_allreduce_oneshot(flat.data_ptr(), self.peer_recv.data_ptr(), self.peer_sig.data_ptr(), self.epochs.data_ptr(),
-                                          self.rank, self.world, n if n == self.n else n, self.CTAS,
-                                          torch.cuda.current_stream(flat.device).cuda_stream), "pfn_allreduce_oneshot")
+        if n != self.n:
+            raise ValueError(f"OneShotAllReduce: buffer of {n} floats, built for {self.n} (pad to a multiple of {self.pad_multiple})")
+        check(lib().pfn_allreduce_peer(flat.data_ptr(), self.peer_recv.data_ptr(), self.peer_res.data_ptr(), self.peer_sig.data_ptr(),
+                                       self.epochs.data_ptr(), self.rank, self.world, n, self.CTAS, int(self.two_shot),
+                                       torch.cuda.current_stream(flat.device).cuda_stream), "pfn_allreduce_peer")
         return flat
 
 

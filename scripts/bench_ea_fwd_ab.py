@@ -22,7 +22,7 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 lib = _lib.lib()
 peak = bench.load_peaks()["hbm_gbs"]
-KNOBS = ("PFN_EA_FWD", "PFN_EA_STAGES", "PFN_EA_THREADS", "PFN_EA_PREFETCH", "PFN_EA_PRODUCERS", "PFN_EA_BULK", "PFN_EA_CHUNK", "PFN_EDGE_CYCLIC", "PFN_EA_ROUND", "PFN_EA_BULK8")
+KNOBS = ("PFN_EA_FWD", "PFN_EA_STAGES", "PFN_EA_THREADS", "PFN_EA_PREFETCH", "PFN_EA_PRODUCERS", "PFN_EA_BULK", "PFN_EA_CHUNK", "PFN_EDGE_CYCLIC", "PFN_EA_ROUND", "PFN_EA_BULK8", "PFN_EA_CTAS_PER_SM")
 
 
 def run(case, b, h, variants, iters, n_sets):
@@ -115,12 +115,10 @@ def run(case, b, h, variants, iters, n_sets):
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None  # optional: comma-separated variant names
 P = {"PFN_EA_FWD": "tma"}
-small = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_t384", {**P, "PFN_EA_THREADS": "384"}), ("tma_t768", {**P, "PFN_EA_THREADS": "768"}),
-         ("tma_p6", {**P, "PFN_EA_PRODUCERS": "6"})]
-large = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_t384", {**P, "PFN_EA_THREADS": "384"}), ("tma_t256", {**P, "PFN_EA_THREADS": "256"}),
-         ("tma_t640", {**P, "PFN_EA_THREADS": "640"}), ("tma_chunk64", {**P, "PFN_EA_CHUNK": "64"}), ("tma_chunk96", {**P, "PFN_EA_CHUNK": "96"}),
-         ("tma_chunk192", {**P, "PFN_EA_CHUNK": "192"}), ("tma_t384_chunk96", {**P, "PFN_EA_THREADS": "384", "PFN_EA_CHUNK": "96"}),
-         ("tma_p6", {**P, "PFN_EA_PRODUCERS": "6"}), ("tma_t384_p6", {**P, "PFN_EA_THREADS": "384", "PFN_EA_PRODUCERS": "6"})]
+small = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_1sm", {**P, "PFN_EA_CTAS_PER_SM": "1"}), ("tma_2sm_t128", {**P, "PFN_EA_THREADS": "128"}),
+         ("tma_2sm_t384_p4", {**P, "PFN_EA_THREADS": "384"}), ("tma_2sm_p2", {**P, "PFN_EA_PRODUCERS": "2"}), ("tma_2sm_p6", {**P, "PFN_EA_PRODUCERS": "6"}),
+         ("tma_2sm_s1", {**P, "PFN_EA_STAGES": "1"}), ("tma_2sm_s3", {**P, "PFN_EA_STAGES": "3"}), ("tma_2sm_prefetch", {**P, "PFN_EA_PREFETCH": "1"})]
+large = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_2sm", {**P, "PFN_EA_CTAS_PER_SM": "2"})]
 if only is not None:
     small = [v for v in small if v[0] in only]
     large = [v for v in large if v[0] in only]

@@ -31,6 +31,10 @@ for step in "$@"; do
     debias)    for v in "PFN_TC_DEBIAS=0" "PFN_TC_DEBIAS=1" "PFN_TC_DEBIAS=2"; do env $v timeout 300 python scripts/debug_gemm_acc.py > gpurun_out/${tag}_gemm_acc_$(echo $v | tr '=' '_').log 2>&1; echo "rc=$? [$v]"; cut -c1-200 gpurun_out/${tag}_gemm_acc_$(echo $v | tr '=' '_').log | grep -v "^M=4096 K=32"; 
                  env $v timeout 600 python scripts/debug_parity.py 16 118v2 129 6 6 > gpurun_out/${tag}_parity_wide_$(echo $v | tr '=' '_').log 2>&1; python scripts/parity_worst.py gpurun_out/${tag}_parity_wide_$(echo $v | tr '=' '_').log
                  env $v timeout 600 python scripts/debug_parity.py 2 6470rte 512 5 > gpurun_out/${tag}_parity_large_$(echo $v | tr '=' '_').log 2>&1; python scripts/parity_worst.py gpurun_out/${tag}_parity_large_$(echo $v | tr '=' '_').log; done ;;
+    ar_test)   N=$(nvidia-smi -L | wc -l); for m in one two; do PFN_AR_TIMING=1 AR_MODE=$m timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/test_oneshot_allreduce.py > gpurun_out/${tag}_ar_test_${N}_$m.log 2>&1; echo "rc=$?"; grep "^{\|mismatch\|Error" gpurun_out/${tag}_ar_test_${N}_$m.log | cut -c1-400; done ;;
+    bench_mg)  N=$(nvidia-smi -L | wc -l); for impl in ours; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/${tag}_bench_${N}gpu.json 2> gpurun_out/${tag}_bench_${N}gpu.err; echo "rc=$?"; python scripts/bench_brief.py gpurun_out/${tag}_bench_${N}gpu.json; tail -3 gpurun_out/${tag}_bench_${N}gpu.err | cut -c1-300; done
+               PFN_ONE_SHOT_ALLREDUCE=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/${tag}_bench_${N}gpu_nccl.json 2> gpurun_out/${tag}_bench_${N}gpu_nccl.err; echo "rc=$?"; python scripts/bench_brief.py gpurun_out/${tag}_bench_${N}gpu_nccl.json ;;
+    bench_mixed_mg) N=$(nvidia-smi -L | wc -l); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $N --config mixed --steps 5 --warmup 3 > gpurun_out/${tag}_bench_mixed_${N}gpu.json 2> gpurun_out/${tag}_bench_mixed_${N}gpu.err; echo "rc=$?"; python scripts/bench_brief.py gpurun_out/${tag}_bench_mixed_${N}gpu.json; tail -3 gpurun_out/${tag}_bench_mixed_${N}gpu.err | cut -c1-300 ;;
     *) echo "unknown step $step" ;;
   esac
 done

@@ -1,4 +1,4 @@
-"""Multi-GPU check + timing of the one-shot NVLink all-reduce (pfn_allreduce_oneshot) against NCCL.
+"""Multi-GPU check + timing of the one-shot NVLink all-reduce (pfn_allreduce_peer) against NCCL.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 scripts/test_oneshot_allreduce.py
 
@@ -19,8 +19,9 @@ rank, world, local = parallel.init_from_env("nccl")
 dev = torch.device("cuda", local)
 torch.cuda.set_device(dev)
 n = int(os.environ.get("AR_N", "354500"))
-n4 = (n + 3) // 4 * 4
-red = parallel.OneShotAllReduce(n, dev)
+mode = os.environ.get("AR_MODE", "auto")  # auto | one | two
+red = parallel.OneShotAllReduce(n, dev, two_shot=None if mode == "auto" else mode == "two")
+n4 = red.n
 gen = torch.Generator(device=dev).manual_seed(100 + rank)
 ok = True
 for it in range(300):
@@ -80,8 +81,18 @@ buf = torch.randn(n4, device=dev)
 us_one = timed(lambda: red(buf))
 us_graph = timed(lambda: g.replay())
 us_nccl = timed(lambda: dist.all_reduce(buf))
+stamps = None
+if os.environ.get("PFN_AR_TIMING") == "1":
+    import ctypes as C
+    from poweflownet_b200 import _lib
+    torch.cuda.synchronize()
+    buf = (C.c_ulonglong * 8)()
+    if _lib.lib().pfn_allreduce_debug_stamps(buf) == 0:
+        t = list(buf)
+        stamps = {"launch_to_wait_done": t[1] - t[0], "push": t[2] - t[1], "exchange1": t[3] - t[2], "sum_and_push2": t[4] - t[3] if t[4] else None,
+                  "exchange2": t[5] - t[4] if t[5] else None, "tail": t[6] - (t[5] if t[5] else t[3]), "total_ns": t[6] - t[0]}
 if rank == 0:
-    print(json.dumps({"world": world, "floats": n4, "bytes": 4 * n4, "exact": bool(flag.item()), "us_one_shot": us_one,
+    print(json.dumps({"phase_ns_last_call_cta0": stamps, "world": world, "two_shot": red.two_shot, "floats": n4, "bytes": 4 * n4, "exact": bool(flag.item()), "us_one_shot": us_one,
                       "us_one_shot_graph_replay": us_graph, "us_nccl_all_reduce": us_nccl}), flush=True)
 dist.barrier()
 dist.destroy_process_group()

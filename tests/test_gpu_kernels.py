@@ -217,7 +217,8 @@ def test_ea_forward_bulk_copy_kernel_equals_cta_kernel(name, h, monkeypatch):
                                  {"PFN_EA_THREADS": "64", "PFN_EA_PRODUCERS": "1"}, {"PFN_EA_PRODUCERS": "7", "PFN_EA_THREADS": "800"},
                                  {"PFN_EA_BULK": "1"}, {"PFN_EA_BULK": "0", "PFN_EA_PRODUCERS": "2"}, {"PFN_EA_PREFETCH": "1"},
                                  {"PFN_EA_BULK8": "3"}, {"PFN_EA_BULK8": "5", "PFN_EA_STAGES": "4"}, {"PFN_EA_BULK8": "7", "PFN_EA_PRODUCERS": "3"},
-                                 {"PFN_EA_CHUNK": "8", "PFN_EA_BULK8": "4"}, {"PFN_EA_ROUND": "1"}])
+                                 {"PFN_EA_CHUNK": "8", "PFN_EA_BULK8": "4"}, {"PFN_EA_ROUND": "1"}, {"PFN_EA_CTAS_PER_SM": "1"},
+                                 {"PFN_EA_CTAS_PER_SM": "2", "PFN_EA_STAGES": "1"}, {"PFN_EA_CTAS_PER_SM": "2", "PFN_EA_THREADS": "64", "PFN_EA_PRODUCERS": "1"}])
 @pytest.mark.parametrize("name,h", [("mixed", 129), ("star", 64), ("case118_h33", 512)])
 def test_ea_forward_bulk_copy_kernel_knobs(name, h, env, monkeypatch):
     """Every ring geometry / copy mechanism the host can pick gives the same bits (2-4 stages, 2 to 31 consumer warps, 1 to

@@ -32,7 +32,7 @@ def _nvcc() -> str:
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(PKG, "..", "include", "pfn_b200.h")]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if os.path.isfile(os.path.join(CSRC, f))] + [os.path.join(PKG, "..", "include", "pfn_b200.h")]
     for f in files:
         with open(f, "rb") as fh:
             h.update(fh.read())

@@ -90,6 +90,19 @@ PFN_API int pfn_graph_layout_get(int64_t n_nodes, int64_t e_raw, pfn_graph_layou
  * edge_index: int64 [2, e_raw] with row stride `ei_row_stride` elements; edge_attr: float [e_raw, 2]. */
 PFN_API int pfn_graph_prep(const int64_t* edge_index, int64_t ei_row_stride, const float* edge_attr,
                    int64_t n_nodes, int64_t e_raw, int undirect_mode, void* graph_ws, void* stream);
+
+/* One-launch variant of pfn_graph_prep for batches laid out TILE BY TILE, the shape PyG's loader gives a batch of
+ * equal-sized small graphs (utils/training.py:55-58 iterating a DataLoader over datasets/PowerFlowData.py): rows
+ * [t*tile_rows, (t+1)*tile_rows) are closed under edge_index AND their edges are columns [t*P, (t+1)*P) of edge_index,
+ * P = e_raw / n_tiles.  Fills the workspace with exactly the bytes pfn_graph_prep writes.  The layout is validated on
+ * the device: a column whose endpoints leave its tile raises the same flag pfn_graph_tile_status reports (and the
+ * graph-resident kernels then return NaN for that tile); call pfn_graph_prep instead for such batches.
+ * pfn_graph_prep_tiled_supported: 1 when the shape qualifies (tile_rows <= 128, n_tiles divides e_raw, P <= 768);
+ * pfn_graph_prep_tiled returns PFN_E_UNSUPPORTED otherwise. */
+PFN_API int pfn_graph_prep_tiled_supported(int64_t n_nodes, int64_t e_raw, int64_t tile_rows);
+PFN_API int pfn_graph_prep_tiled(const int64_t* edge_index, int64_t ei_row_stride, const float* edge_attr,
+                                 int64_t n_nodes, int64_t e_raw, int undirect_mode, int64_t tile_rows, void* graph_ws,
+                                 void* stream);
 /* host_meta[0]=directed, [1]=E, [2]=error flag.  Synchronises `stream`. */
 PFN_API int pfn_graph_meta(const void* graph_ws, int32_t* host_meta, void* stream);
 /* materialise the undirected lists (what `undirect_graph` returns): ei_out int64 [2, E], ea_out float [E, 2] */

@@ -44,6 +44,8 @@ SIGNATURES = {
     "pfn_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(c_i64)]),
     "pfn_graph_layout_get": (C.c_int, [c_i64, c_i64, C.POINTER(GraphLayout)]),
     "pfn_graph_prep": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, C.c_void_p, C.c_void_p]),
+    "pfn_graph_prep_tiled": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_int, c_i64, C.c_void_p, C.c_void_p]),
+    "pfn_graph_prep_tiled_supported": (C.c_int, [c_i64, c_i64, c_i64]),
     "pfn_graph_meta": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "pfn_graph_export": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfn_ea_fwd": (C.c_int, [c_f32p, c_f32p, c_i64, C.c_void_p, c_i64, c_i64, c_f32p, c_i64, c_f32p, c_i64, c_i64,

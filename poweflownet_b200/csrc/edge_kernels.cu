@@ -236,22 +236,25 @@ k_ea_fwd(const float* __restrict__ Hi, const float* __restrict__ Hj, int64_t ldh
 // row loads per thread in flight and walks "stage the CSR slab -> barrier -> one row per thread -> next row" in lock
 // step (ncu: long_scoreboard 9.5 + barrier 5.0 stalled warps per issue, DRAM 13 % of peak); a first attempt with
 // autonomous warps (each warp its own copy ring, 8 warps per SM) moved the bytes but was issue-bound: 7.0 M warp
-// instructions at 0.4 eligible warps per cycle (profiles/r2_ea_fwd_ncu.md).  This kernel separates the two jobs:
+// instructions at 0.4 eligible warps per cycle (profiles/r2/ncu_ea_fwd_earlier_designs.txt, profiles/r2_summary.md).  This kernel separates the two jobs:
 //
-//  * ONE PRODUCER WARP per CTA (one persistent CTA per SM, a contiguous range of rows) walks the CSR and issues, per
-//    batch of R whole rows: one bulk copy (cp.async.bulk, SASS UBLKCP) for the R consecutive Hi rows and one bulk copy
-//    per gathered Hj row -- each lane issues a row, so 32 rows per instruction round -- into a ring of n_stages batch
-//    buffers; completion is counted in bytes on the batch's mbarrier.  The producer also writes the batch header (row
+//  * PRODUCER WARPS (8 by default; one persistent CTA per SM) walk the CSR and issue, per batch of R whole rows: ONE bulk
+//    copy (cp.async.bulk, SASS UBLKCP) for the R consecutive Hi rows, and the gathered Hj rows as 16-byte cp.async chunks
+//    (LDGSTS; every lane a fixed column chunk, four copies per trip) into a ring of n_stages batch buffers; completion is
+//    counted on the batch's "full" mbarrier (complete_tx bytes for the bulk copy, cp.async.mbarrier.arrive.noinc for the
+//    chunk copies).  A bulk copy per gathered row -- the first version -- is bound by the TMA unit's ~35-77 ns per
+//    operation whatever its size (14.8 us of copies at case118v2 x 128); it is used for rows of >= 8 KB only
+//    (PFN_EA_BULK8 = how many of every eight gathered rows go that way).  Producer 0 also writes the batch header (row
 //    pointers relative to the batch, edge_attr in edge order), so the consumers never touch the CSR arrays.
-//  * ~24 CONSUMER WARPS run k_ea_fwd's inner loop unchanged -- thread (x, y) owns 16-byte column chunk x (its slice of We
-//    stays in registers) and sums rows y, y + rows, ... of the batch in ascending edge id -- but every operand comes from
-//    shared memory (~30 cycles) instead of L2/HBM (~600+): the two kernels are BIT-IDENTICAL (tests/test_gpu_kernels.py).
-//    A consumer warp releases the buffer through the batch's second mbarrier.
-//  * The row pointers of the CTA's whole range and the first window of neighbour ids / edge_attr are fetched by ALL
-//    threads before the roles split (two wide coalesced round trips instead of two narrow ones).
-//  * Small problems (both node matrices within a fraction of L2): before griddepcontrol.wait every thread asks the L2 to
-//    prefetch a piece of the CTA's share of Hi, Hj and the CSR arrays (cp.async.bulk.prefetch.L2): the HBM reads start
-//    at once instead of trickling in behind the dependent metadata loads, and the gathers become L2 hits.
+//  * CONSUMER WARPS (16) run k_ea_fwd's inner loop -- thread (x, y) owns 16-byte column chunk x (its slice of We stays in
+//    registers) and sums rows y, y + rows, ... of the batch in ascending edge id -- on packed pairs (fma.rn.f32x2 /
+//    add.rn.f32x2, half the issue slots, same rounding), every operand from shared memory: the two kernels are
+//    BIT-IDENTICAL (tests/test_gpu_kernels.py).  A consumer warp releases the buffer through the batch's "empty" mbarrier.
+//  * The row pointers of the CTA's range and the first window of neighbour ids / edge_attr are fetched by ALL threads
+//    before the roles split (two wide coalesced round trips instead of two narrow ones).
+//  * Large problems: CTA c takes the row chunks c, c + grid, ... (kTmaChunkRows rows each), so that all CTAs work inside
+//    one moving window whose gathered rows stay in L2 (DRAM reads 1.47 -> 0.93 GB at case6470rte x 32 x h512).
+//  * Optional (PFN_EA_PREFETCH=1; measured ~10 % slower, off): L2 prefetch of the CTA's share of Hi, Hj and the CSR.
 //  A row with more incident edges than a batch buffer holds (a hub bus) is summed from global memory by the consumers.
 constexpr int kTmaMaxStages = 4;
 constexpr int kTmaMetaRows = 2048;   // row pointers staged at once (a CTA's whole range unless the batch is huge)

@@ -266,6 +266,150 @@ __global__ void k_finalize(const int64_t* __restrict__ ei, int64_t stride, const
   }
 }
 
+// ---- one-launch preparation for batches of small graphs laid out tile by tile ------------------------------------------
+// The five passes above cost ~39 us per step at case118v2 x 128 (two of them are one- or two-CTA kernels), 5 % of the
+// training step.  A PyG batch of equal-sized graphs is block diagonal: the nodes of tile t are rows [t R, (t+1) R) and --
+// because the loader concatenates the graphs' edge lists in order -- its edges are columns [t P, (t+1) P) of edge_index
+// with P = e_raw / n_tiles.  One CTA per tile then builds the tile's slice of BOTH stable CSRs in shared memory (<= 768
+// directed edges, <= 128 rows) and writes it to the same workspace arrays, bit for bit what the general passes write:
+//   * is_directed (MPN.py:504): the reverse of edge 0 can only sit among tile 0's edges, every CTA looks there itself;
+//   * row pointers: the directed edges of the tiles before this one are t * (P or 2 P), no grid-wide scan;
+//   * stable order: one warp per CSR walks the directed list 32 edges at a time, __match_any_sync ranks the lanes that
+//     hit the same row (lane order = edge id order) behind the row's cursor.
+// "Columns [t P, (t+1) P) belong to tile t" is a GUESS that the kernel VALIDATES: an edge of the range with an endpoint
+// outside the tile raises meta[6] (the broken-tile flag) and makes the tile's neighbour ids -1, so that the graph-resident
+// kernels poison the tile with NaN exactly as for any other broken promise; the caller then falls back to pfn_graph_prep.
+// The ranges partition [0, e_raw) by construction, so if every tile validates, every edge has been placed.
+constexpr int kTileThreads = 256;
+constexpr int kTileEdgeCap = 768;  // = kFusedEdgeCap: directed edges of one tile
+constexpr int kTileRows = 128;
+
+__global__ void __launch_bounds__(kTileThreads) k_prep_tiled(const int64_t* __restrict__ ei, int64_t stride,
+                                                             const float2* __restrict__ ea, int e_raw, int mode, int n_nodes,
+                                                             int tile_rows, int per, GraphView g) {
+  __shared__ int16_t s_src[kTileEdgeCap], s_dst[kTileEdgeCap];  // local endpoints of the ORIGINAL edges of the tile
+  __shared__ float2 s_ea[kTileEdgeCap];
+  __shared__ int s_cnt[2][kTileRows], s_ptr[2][kTileRows + 1], s_cur[2][kTileRows];
+  __shared__ int16_t o_nbr[2][kTileEdgeCap];
+  __shared__ int16_t o_loc[2][kTileEdgeCap];  // position in the tile's directed list
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = blockIdx.x, n_tiles = gridDim.x;
+  const int n0 = t * tile_rows, n1 = min(n_nodes, n0 + tile_rows), nr = n1 - n0;
+  const int lo = t * per;
+  if (tid < kTileRows) s_cnt[0][tid] = s_cnt[1][tid] = 0;
+  if (tid == 0) s_bad = 0;
+  pdl_wait();
+  // one round trip: this tile's edges, and the first-edge test over tile 0's edges
+  const int64_t a0 = ei[0], b0 = ei[stride];
+  int found = 0, bad = 0, oob = 0;
+  for (int i = tid; i < per; i += kTileThreads) {
+    const int64_t s = ei[lo + i], d = ei[stride + lo + i];
+    const int64_t fs = ei[i], fd = ei[stride + i];
+    found |= (fs == b0 && fd == a0);
+    if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes) oob = 1;
+    const bool ok = s >= n0 && s < n1 && d >= n0 && d < n1;
+    if (!ok) bad = 1;
+    s_src[i] = static_cast<int16_t>(ok ? s - n0 : 0);
+    s_dst[i] = static_cast<int16_t>(ok ? d - n0 : 0);
+    s_ea[i] = ea[lo + i];
+  }
+  found = __syncthreads_or(found);
+  const bool directed = mode == 1 && e_raw > 0 && found == 0;
+  const int ne = directed ? 2 * per : per;  // directed edges of the tile; host guarantees per <= kTileEdgeCap
+  if (ne > kTileEdgeCap || nr <= 0 || nr > kTileRows) bad = 1;
+  if (bad) s_bad = 1;
+  const int base = t * ne;
+  const int ne_c = min(ne, kTileEdgeCap);
+  // directed edge d of the tile: d < per -> original (src -> dst), else the reversed copy of original d - per
+  auto row_of = [&](int which, int d) {  // which 0: CSR by target, 1: by source
+    const bool rev = d >= per;
+    const int o = rev ? d - per : d;
+    return int((which == 0) != rev ? s_dst[o] : s_src[o]);
+  };
+  auto nbr_of = [&](int which, int d) {
+    const bool rev = d >= per;
+    const int o = rev ? d - per : d;
+    return int((which == 0) != rev ? s_src[o] : s_dst[o]);
+  };
+  for (int d = tid; d < ne_c; d += kTileThreads) {
+    atomicAdd(&s_cnt[0][row_of(0, d)], 1);
+    atomicAdd(&s_cnt[1][row_of(1, d)], 1);
+  }
+  __syncthreads();
+  if (warp < 2) {
+    // exclusive scan of 128 counts: four per lane
+    int c[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      c[j] = s_cnt[warp][4 * lane + j];
+      sum += c[j];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, dlt);
+      if (lane >= dlt) incl += v;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s_ptr[warp][4 * lane + j] = run;
+      s_cur[warp][4 * lane + j] = run;
+      run += c[j];
+    }
+    if (lane == 31) s_ptr[warp][kTileRows] = run;
+    __syncwarp();
+    // stable placement: lanes of a chunk that hit the same row take consecutive slots in lane (= edge id) order
+    for (int d0 = 0; d0 < ne_c; d0 += 32) {
+      const int d = d0 + lane;
+      const bool valid = d < ne_c;
+      const int row = valid ? row_of(warp, d) : kTileRows + lane;  // idle lanes: private keys
+      const unsigned peers = __match_any_sync(0xffffffffu, row);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      const int pos = valid ? s_cur[warp][row] + rank : 0;
+      __syncwarp();
+      if (valid) {
+        o_nbr[warp][pos] = static_cast<int16_t>(nbr_of(warp, d));
+        o_loc[warp][pos] = static_cast<int16_t>(d);
+        if ((peers >> lane) == 1u) s_cur[warp][row] = pos + 1;  // the last peer leaves the cursor behind the group
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const bool tile_bad = s_bad != 0;
+  for (int w = 0; w < 2; ++w) {
+    int32_t* rowptr = w == 0 ? g.rowptr_t : g.rowptr_s;
+    int32_t* nbr = w == 0 ? g.nbr_t : g.nbr_s;
+    int32_t* eid = w == 0 ? g.eid_t : g.eid_s;
+    float2* eao = reinterpret_cast<float2*>(w == 0 ? g.ea_t : g.ea_s);
+    for (int p = tid; p < ne_c; p += kTileThreads) {
+      const int d = o_loc[w][p];
+      const int o = d >= per ? d - per : d;
+      nbr[base + p] = tile_bad ? -1 : n0 + o_nbr[w][p];
+      eid[base + p] = d >= per ? e_raw + lo + o : lo + o;
+      eao[base + p] = s_ea[o];
+    }
+    for (int i = tid; i < nr; i += kTileThreads) rowptr[n0 + i] = base + s_ptr[w][i];
+    if (t == n_tiles - 1 && tid == 0) rowptr[n_nodes] = n_tiles * ne;
+  }
+  for (int i = tid; i < nr; i += kTileThreads) {
+    const int c = s_cnt[0][i];
+    g.deg[n0 + i] = static_cast<float>(c);
+    g.dis[n0 + i] = c > 0 ? 1.0f / sqrtf(static_cast<float>(c)) : 0.0f;
+  }
+  if (t == 0 && tid == 0) {
+    g.meta[0] = (mode == 1 && found) ? 1 : 0;
+    g.meta[1] = directed;
+    g.meta[2] = n_tiles * ne;
+    g.meta[4] = e_raw;
+    g.meta[5] = n_nodes;
+  }
+  if (tid == 0 && tile_bad) g.meta[6] = 1;
+  if (__syncthreads_or(oob) && tid == 0) g.meta[3] = 1;
+}
+
 __global__ void k_export(const int64_t* __restrict__ ei, int64_t stride, const float2* __restrict__ ea,
                          int e_raw, int e_out, int64_t* ei_out, float2* ea_out) {
   pdl_wait();
@@ -364,6 +508,35 @@ extern "C" int pfn_graph_prep(const int64_t* edge_index, int64_t ei_row_stride, 
     }
   }
   return 0;
+}
+
+extern "C" int pfn_graph_prep_tiled(const int64_t* edge_index, int64_t ei_row_stride, const float* edge_attr,
+                                    int64_t n_nodes, int64_t e_raw, int undirect_mode, int64_t tile_rows, void* graph_ws,
+                                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PFN_REQUIRE(graph_ws != nullptr && aligned16(graph_ws), PFN_E_INVALID, "pfn_graph_prep_tiled: graph_ws null or misaligned");
+  PFN_REQUIRE(edge_index != nullptr && edge_attr != nullptr && (reinterpret_cast<uintptr_t>(edge_attr) & 7u) == 0, PFN_E_INVALID,
+              "pfn_graph_prep_tiled: null or misaligned edge arrays");
+  PFN_REQUIRE(ei_row_stride >= e_raw, PFN_E_INVALID, "pfn_graph_prep_tiled: row stride < e_raw");
+  if (pfn_graph_prep_tiled_supported(n_nodes, e_raw, tile_rows) == 0) return PFN_E_UNSUPPORTED;
+  pfn_graph_layout lay;
+  PFN_TRY(pfn_graph_layout_get(n_nodes, e_raw, &lay));
+  GraphView g = graph_view(graph_ws, n_nodes, e_raw);
+  const int64_t n_tiles = ceil_div64(n_nodes, tile_rows);
+  ProfScope prof(PFN_PROF_PREP, stream);
+  PFN_CUDA_OK(cudaMemsetAsync(g.meta, 0, 8 * sizeof(int32_t), stream));
+  PFN_CUDA_OK(launch_kernel(k_prep_tiled, dim3(static_cast<unsigned>(n_tiles)), dim3(kTileThreads), 0, stream, edge_index, ei_row_stride,
+                            reinterpret_cast<const float2*>(edge_attr), static_cast<int>(e_raw), undirect_mode, static_cast<int>(n_nodes),
+                            static_cast<int>(tile_rows), static_cast<int>(e_raw / n_tiles), g));
+  PFN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int pfn_graph_prep_tiled_supported(int64_t n_nodes, int64_t e_raw, int64_t tile_rows) {
+  if (n_nodes <= 0 || e_raw <= 0 || tile_rows <= 0 || tile_rows > kTileRows) return 0;
+  const int64_t n_tiles = ceil_div64(n_nodes, tile_rows);
+  if (e_raw % n_tiles != 0) return 0;
+  return e_raw / n_tiles <= kTileEdgeCap ? 1 : 0;
 }
 
 extern "C" int pfn_graph_meta(const void* graph_ws, int32_t* host_meta, void* stream_) {

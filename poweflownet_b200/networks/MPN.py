@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -92,7 +93,29 @@ class _MPNFunction(torch.autograd.Function):
             if pred_mask.dtype != torch.int64:
                 pred_mask = pred_mask.long()
             ws = model._take_workspace(n, int(edge_index.size(1)), dev)
-            graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph)
+            e_raw = int(edge_index.size(1))
+            # attempts at the graph-resident route, cheapest first: (tile rows, graph_ptr, one-launch preparation?)
+            # * equal-sized tiles with the one-launch preparation (it validates its own guess about the edge layout;
+            #   PFN_PREP_TILED=0 keeps the general five-pass preparation);
+            # * the same tiles on the general preparation;
+            # * whole graphs packed from `ptr` (equal-sized tiles refused, or a batch that mixes graph sizes).
+            attempts = []
+            if tile_rows > 0:
+                if (graph_ptr is None and os.environ.get("PFN_PREP_TILED", "1") != "0"
+                        and lib().pfn_graph_prep_tiled_supported(n, e_raw, tile_rows)):
+                    attempts.append((tile_rows, None, True))
+                attempts.append((tile_rows, graph_ptr, False))
+                if graph_ptr is None and alt_ptr is not None:
+                    attempts.append((128, alt_ptr, False))
+
+            def sig_of(att):  # key of `_tiling_checked`: what was promised about this batch shape
+                if att[2]:
+                    return ("prep_tiled", n, e_raw, att[0])
+                return (n, e_raw, att[0], int(att[1].numel()) - 1 if att[1] is not None else 0)
+
+            attempts = [att for att in attempts if model._tiling_checked.get(sig_of(att), True) is not False]
+            fast = bool(attempts) and attempts[0][2]
+            graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph, tile_rows=attempts[0][0] if fast else 0)
             ws.graph = graph.ws
             seed_dev = model._seed_device if training else None  # device-resident seed (CUDA-graph replays)
             seed = model._next_seed() if (training and seed_dev is None and model.dropout.p > 0) else 0
@@ -104,28 +127,24 @@ class _MPNFunction(torch.autograd.Function):
             out = torch.empty((n, model.output_dim), dtype=torch.float32, device=dev)
             ptable = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
             desc = model._desc()
-            common = (C.byref(desc), ptable, x.data_ptr(), pred_mask.data_ptr(), n, graph.e_raw, ws.graph.data_ptr(),
+            common = (C.byref(desc), ptable, x.data_ptr(), pred_mask.data_ptr(), n, e_raw, ws.graph.data_ptr(),
                       ws.act.data_ptr(), ws.scratch.data_ptr(), int(training), seed,
                       None if seed_dev is None else seed_dev.data_ptr(), inj_table, out.data_ptr())
             stream = torch.cuda.current_stream().cuda_stream
             capturing = torch.cuda.is_current_stream_capturing()
-            attempts = [(tile_rows, graph_ptr)] if tile_rows > 0 else []
-            if tile_rows > 0 and graph_ptr is None and alt_ptr is not None:
-                attempts.append((128, alt_ptr))  # equal-sized tiles refused: whole graphs packed from `ptr` may still fit
-            tile_rows, n_graphs = 0, 0
-            for attempt, (rows, gptr) in enumerate(attempts):
+            tile_rows, n_graphs, refused = 0, 0, False
+            for att in attempts:
                 # graph-resident kernel: the whole layer stack in one launch, one tile of whole graphs per CTA
-                ng = int(gptr.numel()) - 1 if gptr is not None else 0
-                sig = (n, graph.e_raw, rows, ng)
-                if model._tiling_checked.get(sig, True) is False:
-                    continue
-                if attempt > 0:  # the refused attempt left its violation flag in the graph workspace: rebuild it
-                    graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph)
+                rows, gptr, fast = att
+                sig, ng = sig_of(att), (int(gptr.numel()) - 1 if gptr is not None else 0)
+                if refused or graph.tiled != fast:  # a refused attempt leaves its violation flag in the graph workspace
+                    graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph, tile_rows=rows if fast else 0)
+                    refused = False
                 check(lib().pfn_mpn_forward_tiled(*common, rows, None if gptr is None else gptr.data_ptr(), ng, stream),
                       "pfn_mpn_forward_tiled")
-                # the kernel validates the closed-tile promise itself (a violation raises meta[6] and poisons the tile's
-                # rows with NaN); the flag is read back for the first batch of a shape and then every
-                # `_tiling_recheck` batches of it -- never during stream capture
+                # the kernels validate the promises themselves (a violation raises meta[6] and poisons the tile's rows
+                # with NaN); the flag is read back for the first batch of a shape and then every `_tiling_recheck`
+                # batches of it -- never during stream capture
                 calls = model._tiling_calls.get(sig, 0)
                 model._tiling_calls[sig] = calls + 1
                 if not capturing and (sig not in model._tiling_checked or calls % model._tiling_recheck == 0):
@@ -133,9 +152,12 @@ class _MPNFunction(torch.autograd.Function):
                     check(lib().pfn_graph_tile_status(ws.graph.data_ptr(), C.byref(violated), stream), "pfn_graph_tile_status")
                     model._tiling_checked[sig] = not violated.value
                     if violated.value:
+                        refused = True
                         continue
                 tile_rows, n_graphs = rows, ng
                 break
+            if tile_rows <= 0 and graph.tiled:  # the layer-wise route needs the general preparation's arrays
+                graph = ops.PreparedGraph(edge_index, edge_attr, n, mode=1, workspace=ws.graph)
             if tile_rows <= 0:
                 check(lib().pfn_mpn_forward(*common, stream), "pfn_mpn_forward")
         if needs_grad:

@@ -50,10 +50,13 @@ def new_rows(n: int, width: int, device) -> torch.Tensor:
 class PreparedGraph:
     """Device-side CSR (by target and by source), degrees and deg^-1/2 of one mini-batch, built by
     `pfn_graph_prep` without a host round trip (replaces networks/MPN.py:498-523 + PyG gather/scatter
-    bookkeeping).  `mode=1` applies the reference's undirect rule, `mode=0` takes the edges as given."""
+    bookkeeping).  `mode=1` applies the reference's undirect rule, `mode=0` takes the edges as given.
+    `tile_rows > 0`: the batch is promised to be laid out tile by tile (equal-sized small graphs as PyG's loader
+    collates them) and ONE launch (`pfn_graph_prep_tiled`) builds the same arrays; `self.tiled` tells whether that path
+    ran (the shape may not qualify).  The promise is validated on the device and reported by `pfn_graph_tile_status`."""
 
     def __init__(self, edge_index: torch.Tensor, edge_attr: torch.Tensor, n_nodes: int, mode: int,
-                 workspace: Optional[torch.Tensor] = None):
+                 workspace: Optional[torch.Tensor] = None, tile_rows: int = 0):
         dev = require_cuda(edge_index, edge_attr)
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise ValueError("edge_index must be int64 [2, E]")
@@ -72,8 +75,13 @@ class PreparedGraph:
             workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         self.ws = workspace
         stride = int(self.edge_index.stride(0)) if e_raw > 0 else 0
-        check(lib().pfn_graph_prep(_ptr(self.edge_index), max(stride, e_raw), _ptr(self.edge_attr), self.n_nodes, e_raw,
-                                   mode, self.ws.data_ptr(), _stream()), "pfn_graph_prep")
+        self.tiled = tile_rows > 0 and bool(lib().pfn_graph_prep_tiled_supported(self.n_nodes, e_raw, int(tile_rows)))
+        if self.tiled:
+            check(lib().pfn_graph_prep_tiled(_ptr(self.edge_index), max(stride, e_raw), _ptr(self.edge_attr), self.n_nodes,
+                                             e_raw, mode, int(tile_rows), self.ws.data_ptr(), _stream()), "pfn_graph_prep_tiled")
+        else:
+            check(lib().pfn_graph_prep(_ptr(self.edge_index), max(stride, e_raw), _ptr(self.edge_attr), self.n_nodes, e_raw,
+                                       mode, self.ws.data_ptr(), _stream()), "pfn_graph_prep")
 
     # -- views (tests / export) -------------------------------------------------------------------
     def _view(self, off: int, count: int, dtype) -> torch.Tensor:

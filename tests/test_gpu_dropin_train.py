@@ -101,12 +101,12 @@ def _run(model, sets, device, train_loss, eval_loss, masked, epochs, tmp_path, t
 @pytest.mark.parametrize("loss_name", ["mse_loss", "masked_l2"])
 def test_reference_training_loop_with_the_swapped_module_tracks_the_cpu_oracle(tmp_path, loss_name):
     """Dropout off (the two arms draw different random streams otherwise): the B200 arm's per-epoch train / validation
-    losses track the CPU oracle's -- the first epoch (4 AdamW steps) to 1e-4 relative, later epochs to 5 % -- and the saved
+    losses track the CPU oracle's to 1e-4 relative in the first epoch (4 AdamW steps) and 1e-3 afterwards, and the saved
     best-validation checkpoint loads into the ORACLE model (same state_dict keys and shapes) giving the same test loss.
-    Why not tighter after the first epoch: AdamW divides every gradient entry by sqrt(v) + 1e-8, so an entry whose
-    magnitude is at rounding level moves its weight by a full +-lr whatever its value; measured on this test the two
-    trajectories agree to 1e-6 after epoch 1, 3e-3 after epoch 2 and 1e-2 after epoch 3 while the loss falls 6x (the same
-    happens between two fp32 CPU runs with different thread counts)."""
+    Both arms see the same shuffled batches: with dropout off the module draws nothing from torch's global generator
+    (networks/MPN.py `_next_seed`), so the DataLoader's permutations are those of the reference run.  (An earlier
+    version drew a dropout seed per forward regardless of p; the two arms then trained on differently shuffled epochs
+    and their losses differed by 0.3 - 1 % from epoch 2 on.)"""
     from poweflownet_b200 import _lib
     from poweflownet_b200.losses import Masked_L2_loss
     from poweflownet_b200.networks.MPN import MaskEmbdMultiMPN
@@ -134,8 +134,9 @@ def test_reference_training_loop_with_the_swapped_module_tracks_the_cpu_oracle(t
     assert _lib.lib().pfn_launch_count() - before > 100  # the steps really ran on libpfn_b200.so
     for key in ("train", "val"):
         for ep, (a, b) in enumerate(zip(ours[key], ref[key])):
-            assert abs(a - b) <= (1e-4 if ep == 0 else 5e-2) * abs(b), (key, ours[key], ref[key])
-    assert abs(ours["test"] - ref["test"]) <= 5e-2 * abs(ref["test"])
+            assert abs(a - b) <= (1e-4 if ep == 0 else 1e-3) * abs(b), (key, ours[key], ref[key])
+    print("dropin", loss_name, ours["train"], ref["train"], ours["val"], ref["val"], ours["test"], ref["test"])
+    assert abs(ours["test"] - ref["test"]) <= 1e-3 * abs(ref["test"])
     assert ours["train"][-1] < ours["train"][0]  # it learns
     # the checkpoint written by the B200 arm is a reference checkpoint: it loads into the oracle model and evaluates alike
     from torch_geometric.loader import DataLoader

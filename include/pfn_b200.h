@@ -97,7 +97,7 @@ PFN_API int pfn_graph_prep(const int64_t* edge_index, int64_t ei_row_stride, con
  * P = e_raw / n_tiles.  Fills the workspace with exactly the bytes pfn_graph_prep writes.  The layout is validated on
  * the device: a column whose endpoints leave its tile raises the same flag pfn_graph_tile_status reports (and the
  * graph-resident kernels then return NaN for that tile); call pfn_graph_prep instead for such batches.
- * pfn_graph_prep_tiled_supported: 1 when the shape qualifies (tile_rows <= 128, n_tiles divides e_raw, P <= 768);
+ * pfn_graph_prep_tiled_supported: 1 when the shape qualifies (tile_rows <= 128 divides n_nodes, n_tiles divides e_raw, P <= 768);
  * pfn_graph_prep_tiled returns PFN_E_UNSUPPORTED otherwise. */
 PFN_API int pfn_graph_prep_tiled_supported(int64_t n_nodes, int64_t e_raw, int64_t tile_rows);
 PFN_API int pfn_graph_prep_tiled(const int64_t* edge_index, int64_t ei_row_stride, const float* edge_attr,

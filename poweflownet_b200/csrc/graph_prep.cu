@@ -535,7 +535,7 @@ extern "C" int pfn_graph_prep_tiled(const int64_t* edge_index, int64_t ei_row_st
 extern "C" int pfn_graph_prep_tiled_supported(int64_t n_nodes, int64_t e_raw, int64_t tile_rows) {
   if (n_nodes <= 0 || e_raw <= 0 || tile_rows <= 0 || tile_rows > kTileRows) return 0;
   const int64_t n_tiles = ceil_div64(n_nodes, tile_rows);
-  if (e_raw % n_tiles != 0) return 0;
+  if (n_nodes % tile_rows != 0 || e_raw % n_tiles != 0) return 0;  // a short last tile holds fewer graphs, hence fewer columns
   return e_raw / n_tiles <= kTileEdgeCap ? 1 : 0;
 }
 

@@ -101,7 +101,7 @@ def _run(model, sets, device, train_loss, eval_loss, masked, epochs, tmp_path, t
 @pytest.mark.parametrize("loss_name", ["mse_loss", "masked_l2"])
 def test_reference_training_loop_with_the_swapped_module_tracks_the_cpu_oracle(tmp_path, loss_name):
     """Dropout off (the two arms draw different random streams otherwise): the B200 arm's per-epoch train / validation
-    losses track the CPU oracle's to 1e-4 relative in the first epoch (4 AdamW steps) and 1e-3 afterwards, and the saved
+    losses track the CPU oracle's to 2e-5 relative over all three epochs (measured: 1e-6), and the saved
     best-validation checkpoint loads into the ORACLE model (same state_dict keys and shapes) giving the same test loss.
     Both arms see the same shuffled batches: with dropout off the module draws nothing from torch's global generator
     (networks/MPN.py `_next_seed`), so the DataLoader's permutations are those of the reference run.  (An earlier
@@ -134,9 +134,8 @@ def test_reference_training_loop_with_the_swapped_module_tracks_the_cpu_oracle(t
     assert _lib.lib().pfn_launch_count() - before > 100  # the steps really ran on libpfn_b200.so
     for key in ("train", "val"):
         for ep, (a, b) in enumerate(zip(ours[key], ref[key])):
-            assert abs(a - b) <= (1e-4 if ep == 0 else 1e-3) * abs(b), (key, ours[key], ref[key])
-    print("dropin", loss_name, ours["train"], ref["train"], ours["val"], ref["val"], ours["test"], ref["test"])
-    assert abs(ours["test"] - ref["test"]) <= 1e-3 * abs(ref["test"])
+            assert abs(a - b) <= 2e-5 * abs(b), (key, ours[key], ref[key])
+    assert abs(ours["test"] - ref["test"]) <= 2e-5 * abs(ref["test"])
     assert ours["train"][-1] < ours["train"][0]  # it learns
     # the checkpoint written by the B200 arm is a reference checkpoint: it loads into the oracle model and evaluates alike
     from torch_geometric.loader import DataLoader

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       }
       const int s = p_it % S;
       const uint32_t ph = (p_it / S) & 1;
-      mbar_wait(empty_bar(s), ph ^ 1u);
+      mbar_wait_sleep(empty_bar(s), ph ^ 1u);
       mbar_arrive_expect_tx(full_bar(s), a_bytes + (item.presplit ? 2u : 1u) * b_bytes);
       const uint32_t st = base + uint32_t(s) * stage_bytes;
       tma_load_2d(st, &item.a, p_k0, m0, full_bar(s));
@@ -321,11 +321,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       for (int k0 = 0; k0 < K; k0 += kTcBK, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
-        mbar_wait(conv_bar(s), ph);
+        mbar_wait_sleep(conv_bar(s), ph);
         const int dt = args.drain_tiles;
         const int phase = it / dt, slot = phase % n_hi;  // DRAIN only
         const bool phase_first = it % dt == 0;
-        if (DRAIN && phase_first && phase >= n_hi) mbar_wait(drained_bar(slot), uint32_t(phase / n_hi - 1) & 1u);
+        if (DRAIN && phase_first && phase >= n_hi) mbar_wait_sleep(drained_bar(slot), uint32_t(phase / n_hi - 1) & 1u);
         tc_fence_after();
         const int nk = min(kTcBK / 8, (K - k0 + 7) / 8);  // 8 TF32 elements (32 bytes) per UMMA K step
         if (lane == 0 && it < 8) PFN_TSTAMP(18 + it);
@@ -365,11 +365,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     const int q = warp & 3, half = wk >> 2;  // TMEM lane quarter this warp may read / which 16-column chunks it drains
     const uint32_t lane_base = tmem_base + (uint32_t(32 * q) << 16);
     // DRAIN: this thread's share of the output tile (row 32 q + lane, columns 16 half + 32 i + [0, 16)) lives in registers
-    float racc[DRAIN ? kTcDrainChunks : 1][16];
+    // (kept as packed pairs: the flush below adds two values per instruction)
+    uint64_t racc2[DRAIN ? kTcDrainChunks : 1][8];
 #pragma unroll
     for (int i = 0; i < (DRAIN ? kTcDrainChunks : 1); ++i)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) racc[i][j] = 0.f;
+      for (int j = 0; j < 8; ++j) racc2[i][j] = 0ull;
     // racc += TMEM columns [col0, col0 + BN) of this thread's row.  `ulps` > 0 (the hi*hi slots): every value read is first
     // moved `ulps` units in the last place AWAY from zero.  A phase sum has been truncated towards zero once per
     // accumulating instruction (4 per K tile), i.e. it comes out ~1.5 ulp too small in magnitude on average (measured:
@@ -383,8 +384,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         if (c0 < BN) {  // warp-uniform
           uint32_t r[16];
           tmem_ld16(lane_base + col0 + uint32_t(c0), r);
+          // two instructions per PAIR of values (this loop is the mainloop's instruction budget: 64 values per thread and
+          // K tile): the integer add moves the magnitude `ulps` up -- a +-0 becomes a denormal, which the flush-to-zero
+          // add then drops again, so exact zeros stay exact -- and one packed add accumulates both
 #pragma unroll
-          for (int j = 0; j < 16; ++j) racc[i][j] += __uint_as_float((r[j] << 1) != 0u ? r[j] + ulps : r[j]);
+          for (int j = 0; j < 16; j += 2) {
+            uint64_t v;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(r[j] + ulps), "r"(r[j + 1] + ulps));
+            asm("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(racc2[i][j >> 1]) : "l"(v));
+          }
         }
       }
     };
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       for (int k0 = 0; k0 < K; k0 += kTcBK, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
-        mbar_wait(full_bar(s), ph);
+        mbar_wait_sleep(full_bar(s), ph);
         if (tid_c == 0 && it < 8) PFN_TSTAMP(2 + it);
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         split_tile(st, a_bytes, kTcBM * 8, tid_c);
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
           // every tile of phase p has been handed to the tensor core: read out phase p - 1 (issued a phase ago, so its
           // MMAs have normally completed) while phase p is being multiplied
           const int pd = (it + 1) / args.drain_tiles - 2, slot = pd % args.n_hi;
-          mbar_wait(ready_bar(slot), uint32_t(pd / args.n_hi) & 1u);
+          mbar_wait_sleep(ready_bar(slot), uint32_t(pd / args.n_hi) & 1u);
           tc_fence_after();
           drain_slot(uint32_t(slot * BN), uint32_t(args.debias_ulps));
           tc_fence_before();
@@ -418,7 +426,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         }
       }
     }
-    mbar_wait(accum_bar, 0);
+    mbar_wait_sleep(accum_bar, 0);
     tc_fence_after();
     // The staging tile written below overlays pipeline stage 0, last written by split_tile.  The mbarrier chain (conv_bar
     // arrivals of ALL converter warps -> MMA -> accum_bar) already orders the two; this named barrier restates the
@@ -443,8 +451,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         if (c0 < ncols) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + 4u * (c0 + j)), "f"(racc[DRAIN ? i : 0][j]),
-                         "f"(racc[DRAIN ? i : 0][j + 1]), "f"(racc[DRAIN ? i : 0][j + 2]), "f"(racc[DRAIN ? i : 0][j + 3]) : "memory");
+            asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(row_addr + 4u * (c0 + j)), "l"(racc2[DRAIN ? i : 0][j >> 1]),
+                         "l"(racc2[DRAIN ? i : 0][(j >> 1) + 1]) : "memory");
         }
       }
     } else {
@@ -582,7 +590,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         const int k0 = k_beg + it * kTcBK;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_wait_sleep(empty_bar(s), ph ^ 1u);
         mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes);
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         for (int b = 0; b < mt * 4; ++b) tma_load_2d(st + uint32_t(b) * 4096u, &item.a, row0 + 32 * b, k0, full_bar(s));
@@ -596,7 +604,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
     for (int it = 0; it < n_tiles; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
-      mbar_wait(conv_bar(s), ph);
+      mbar_wait_sleep(conv_bar(s), ph);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t st = base + uint32_t(s) * stage_bytes;
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
       const int k0 = k_beg + it * kTcBK;
-      mbar_wait(full_bar(s), ph);
+      mbar_wait_sleep(full_bar(s), ph);
       const uint32_t st = base + uint32_t(s) * stage_bytes;
       if (args.extra_col != 0) {
         // virtual column N of X := 1 (or extra_vec[node]) -> its dot products with dY are the bias gradient
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
     float* __restrict__ const part = args.partial + size_t(split * args.count + prob) * size_t(Mo) * n_eff;
     const uint32_t tile_ld = uint32_t(BN) + 4u;
     if (n_tiles > 0) {
-      mbar_wait(accum_bar, 0);
+      mbar_wait_sleep(accum_bar, 0);
       tc_fence_after();
     }
     asm volatile("bar.sync 2, %0;" ::"n"(kTcWorkers) : "memory");  // (see k_gemm_tc: orders split_tile's stores before the staging tile's)

@@ -75,6 +75,7 @@ class PreparedGraph:
             workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         self.ws = workspace
         stride = int(self.edge_index.stride(0)) if e_raw > 0 else 0
+        self.tile_rows = int(tile_rows)  # the caller's closed-tile promise (0: none), whichever preparation runs
         self.tiled = tile_rows > 0 and bool(lib().pfn_graph_prep_tiled_supported(self.n_nodes, e_raw, int(tile_rows)))
         if self.tiled:
             check(lib().pfn_graph_prep_tiled(_ptr(self.edge_index), max(stride, e_raw), _ptr(self.edge_attr), self.n_nodes,
@@ -159,6 +160,11 @@ def linear_wgrad(dy, x, n_in, n_out, dw, lddw, *, dbias=None, rowscale=None, dw_
 
 
 def ea_fwd(hi, hj, graph: PreparedGraph, w1, fin, h, s):
+    if graph.tile_rows > 0:  # the batch is promised to be laid out tile by tile: tile-resident kernel
+        check(lib().pfn_ea_fwd_tiled(hi.data_ptr(), hj.data_ptr(), _ld(hi), graph.ws.data_ptr(), graph.n_nodes, graph.e_raw,
+                                     w1.data_ptr() + 4 * 2 * fin, 2 * fin + 2, s.data_ptr(), _ld(s), h, graph.tile_rows,
+                                     _stream()), "pfn_ea_fwd_tiled")
+        return s
     check(lib().pfn_ea_fwd(hi.data_ptr(), hj.data_ptr(), _ld(hi), graph.ws.data_ptr(), graph.n_nodes, graph.e_raw,
                            w1.data_ptr() + 4 * 2 * fin, 2 * fin + 2, s.data_ptr(), _ld(s), h, _stream()), "pfn_ea_fwd")
     return s

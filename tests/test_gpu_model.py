@@ -236,6 +236,10 @@ def test_masked_l2_loss_through_autograd():
 
 def test_standalone_layers_match_oracle_layers():
     from poweflownet_b200.networks.MPN import EdgeAggregation, TAGConv
+    # the layers below draw their initial weights from torch's global generator: pin it, so that the case does not depend
+    # on how many random numbers earlier tests consumed (an unlucky draw puts a ReLU pre-activation at rounding level,
+    # where the mask -- hence dx -- legitimately differs between two summation orders; see FULL_SIZE_CASES)
+    torch.manual_seed(20240229)
     batch = common.make_batch("mixed")
     ei, ea = O.undirect_graph(batch.edge_index, batch.edge_attr)
     n = batch.num_nodes

@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
 
   if (warp == 0) {
     // ===== TMA producer: the weight K-tiles of every tensor-core GEMM, in program order =====
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       auto load_weight = [&](int w_row, int w_rows) {
         for (int kt = 0; kt < KT; ++kt, ++it) {
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         mbar_wait(bfull(s), ph);
         tc_fence_after();
         const int nk = min(4, (hm - kt * 32 + 7) / 8);
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = BS + uint32_t(s) * kBStageBytes;
           const uint64_t a_hi = umma_desc_k128(R0 + uint32_t(kt) * kKTileBytes), a_lo = umma_desc_k128(R1 + uint32_t(kt) * kKTileBytes);
           const uint64_t b_hi = umma_desc_k128(st), b_lo = umma_desc_k128(st + kKTileBytes);
@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           wait_a();
           int kk = 0;
           gemm(0u, 1, 128u, kk);
-          if (lane == 0) umma_commit(acc_done);
+          if (elect_one()) umma_commit(acc_done);
           __syncwarp();
         }
         if (L.type == kFusedEaTc) {  // d cur = dHj Wj + dHi Wi: two segments into the same accumulators
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           for (int seg = 0; seg < 2; ++seg) {
             wait_a();
             gemm(256u, 1, 384u, kk);
-            if (lane == 0) umma_commit(acc_done);
+            if (elect_one()) umma_commit(acc_done);
             __syncwarp();
           }
         }
@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
         for (int k = 0; k <= args.K; ++k) {
           wait_a();
           gemm(0u, 3, 384u, kk);
-          if (lane == 0) umma_commit(acc_done);
+          if (elect_one()) umma_commit(acc_done);
           __syncwarp();
         }
       } else {
@@ -814,14 +814,14 @@ __global__ void __launch_bounds__(kFThreads, 1) k_mpn_fused_fwd(const __grid_con
           gemm(0u, 1, 128u, kk);
           kk = 0;
           gemm(256u, 1, 384u, kk);
-          if (lane == 0) umma_commit(acc_done);
+          if (elect_one()) umma_commit(acc_done);
           __syncwarp();
         }
         if (!L.last) {
           wait_a();
           int kk = 0;
           gemm(0u, 1, 128u, kk);
-          if (lane == 0) umma_commit(acc_done);
+          if (elect_one()) umma_commit(acc_done);
           __syncwarp();
         }
       }

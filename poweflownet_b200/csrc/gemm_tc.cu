@@ -54,7 +54,7 @@ struct TcArgs {
   TcItem it[kGemmMaxItems];
   float* C[kGemmMaxItems];
   const float* bias[kGemmMaxItems];
-  int n_items, batched, M, N, BN, ldc, stages, tmem_cols, n_hi, drain_tiles, debias_ulps, pad1_;
+  int n_items, batched, M, N, BN, ldc, stages, tmem_cols, n_hi, drain_tiles, debias_ulps, n_lo;
   const float* rowscale;
   const float* addend;
   const float* ymask;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       ++p_it;
     }
   };
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {  // (warp-uniform first operand: all of warp 0 reaches the election)
     for (int seg = seg_begin; seg < seg_end; ++seg) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.it[seg].a)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&args.it[seg].b)) : "memory");
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
 
   if (warp == 0) {
     // ===== TMA producer: remaining tiles =====
-    if (lane == 0) produce(1 << 30);
+    if (elect_one()) produce(1 << 30);
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
@@ -314,14 +314,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     // accumulating instructions.  The hi*hi products therefore rotate over n_hi accumulators and the (2^-11 smaller)
     // lo terms go to their own accumulator; the epilogue adds them in round-to-nearest fp32.
     const int n_hi = args.n_hi;
+    // (DRAIN, n_lo == 2: the two lo products of a K step go to SEPARATE accumulators, so that no instruction accumulates
+    // into the tile its predecessor is still writing)
     const uint32_t d_lo = tmem_base + uint32_t(n_hi * BN);
+    const uint32_t d_lo2 = (DRAIN && args.n_lo == 2) ? d_lo + uint32_t(BN) : d_lo;
     int it = 0, kk = 0;
     for (int seg = seg_begin; seg < seg_end; ++seg) {
       const int K = args.it[seg].K;
       for (int k0 = 0; k0 < K; k0 += kTcBK, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
+        if (lane == 0 && it == 5) PFN_TSTAMP(61);
         mbar_wait_sleep(conv_bar(s), ph);
+        if (lane == 0 && it == 5) PFN_TSTAMP(62);
         const int dt = args.drain_tiles;
         const int phase = it / dt, slot = phase % n_hi;  // DRAIN only
         const bool phase_first = it % dt == 0;
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         tc_fence_after();
         const int nk = min(kTcBK / 8, (K - k0 + 7) / 8);  // 8 TF32 elements (32 bytes) per UMMA K step
         if (lane == 0 && it < 8) PFN_TSTAMP(18 + it);
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = base + uint32_t(s) * stage_bytes;
           const uint64_t a_hi = umma_desc_k128(st), a_lo = umma_desc_k128(st + a_bytes);
           const uint64_t b_hi = umma_desc_k128(st + 2u * a_bytes), b_lo = umma_desc_k128(st + 2u * a_bytes + b_bytes);
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
               acc_hi = k_idx >= n_hi ? 1u : 0u;
             }
             umma_tf32(d_lo, a_lo + adv, b_hi + adv, idesc, k_idx > 0 ? 1u : 0u);
-            umma_tf32(d_lo, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_tf32(d_lo2, a_hi + adv, b_lo + adv, idesc, (d_lo2 != d_lo && k_idx == 0) ? 0u : 1u);
             umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, acc_hi);
           }
           umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         __syncwarp();
       }
     }
-    if (lane == 0) umma_commit(accum_bar);
+    if (elect_one()) umma_commit(accum_bar);
     if (lane == 0) PFN_TSTAMP(26);
     __syncwarp();
   } else {
@@ -403,7 +408,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       for (int k0 = 0; k0 < K; k0 += kTcBK, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
+        if (tid_c == 0 && it == 5) PFN_TSTAMP(56);
         mbar_wait_sleep(full_bar(s), ph);
+        if (tid_c == 0 && it == 5) PFN_TSTAMP(57);
         if (tid_c == 0 && it < 8) PFN_TSTAMP(2 + it);
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         split_tile(st, a_bytes, kTcBM * 8, tid_c);
@@ -412,16 +419,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         if (tid_c == 0 && it < 8) PFN_TSTAMP(10 + it);
         __syncwarp();
         if (lane == 0) mbar_arrive(conv_bar(s));
+        if (tid_c == 0 && it == 5) PFN_TSTAMP(58);
         if (DRAIN && (it + 1) % args.drain_tiles == 0 && it + 1 >= 2 * args.drain_tiles) {
           // every tile of phase p has been handed to the tensor core: read out phase p - 1 (issued a phase ago, so its
           // MMAs have normally completed) while phase p is being multiplied
           const int pd = (it + 1) / args.drain_tiles - 2, slot = pd % args.n_hi;
           mbar_wait_sleep(ready_bar(slot), uint32_t(pd / args.n_hi) & 1u);
+          if (tid_c == 0 && it == 5) PFN_TSTAMP(59);
           tc_fence_after();
           drain_slot(uint32_t(slot * BN), uint32_t(args.debias_ulps));
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(drained_bar(slot));
+          if (tid_c == 0 && it == 5) PFN_TSTAMP(60);
           next_drain = pd + 1;
         }
       }
@@ -444,6 +454,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       const int n_phases = (n_tiles_total + args.drain_tiles - 1) / args.drain_tiles;
       for (int pd = next_drain; pd < n_phases; ++pd) drain_slot(uint32_t((pd % args.n_hi) * BN), uint32_t(args.debias_ulps));
       drain_slot(uint32_t(args.n_hi * BN), 0u);  // the (2^-11 smaller) lo terms: no correction
+      if (args.n_lo == 2) drain_slot(uint32_t((args.n_hi + 1) * BN), 0u);
       const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
 #pragma unroll
       for (int i = 0; i < kTcDrainChunks; ++i) {
@@ -585,7 +596,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -606,7 +617,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
       const uint32_t ph = (it / S) & 1;
       mbar_wait_sleep(conv_bar(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         const uint32_t b_hi = st + 2u * a_bytes, b_lo = b_hi + b_bytes;
         for (int j = 0; j < kTcBK / 8; ++j) {  // 8 nodes per UMMA K step = one 1024-byte K group
@@ -626,7 +637,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_tc(const __grid_constan
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(accum_bar);
+    if (elect_one()) umma_commit(accum_bar);
     __syncwarp();
   } else {
     const int tid_c = threadIdx.x - 64;
@@ -808,7 +819,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
   if (threadIdx.x == 0) WSTAMP(1);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < n_tiles; ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -833,7 +844,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       mbar_wait(conv_bar(s), ph);
       tc_fence_after();
       if (lane == 0 && it < 12) WSTAMP(30 + it);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         const uint32_t b_hi = st + 2u * a_bytes, b_lo = b_hi + b_bytes;
         for (int j = 0; j < kTcBK / 8; ++j) {  // 8 nodes per UMMA K step = one 1024-byte K group
@@ -858,7 +869,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(accum_bar);
+    if (elect_one()) umma_commit(accum_bar);
     if (lane == 0) WSTAMP(44);
     __syncwarp();
   } else {
@@ -1201,8 +1212,17 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   a.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 2048u) / stage_bytes));
   if (a.stages < 1) return 1;
   a.n_hi = std::max(1, std::min(3, 512 / bn - 1));
+  a.n_lo = 1;
+  static const int lo2_env = [] {
+    const char* e = std::getenv("PFN_TC_LO2");  // experiment: separate accumulators for the two lo products
+    return e != nullptr && e[0] == '1' ? 1 : 0;
+  }();
+  if (lo2_env && 512 / bn - 2 >= 2) {
+    a.n_lo = 2;
+    a.n_hi = std::min(3, 512 / bn - 2);
+  }
   int cols = 32;
-  while (cols < (a.n_hi + 1) * bn) cols <<= 1;
+  while (cols < (a.n_hi + a.n_lo) * bn) cols <<= 1;
   a.tmem_cols = cols;
   for (int i = 0; i < g.n_items; ++i) {
     const GemmItem& it = g.it[i];
@@ -1256,6 +1276,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   }();
   a.debias_ulps = a.drain_tiles == 1 ? debias_env : 2 * debias_env;
   const bool drain = a.n_hi >= 2 && bn <= 32 * kTcDrainChunks && (drain_env >= 0 ? drain_env == 1 : max_tiles >= kTcDrainMinTiles);
+  if (!drain) a.n_lo = 1;  // (the plain kernel's epilogue reads one lo accumulator; the spare columns stay unused)
   static SmemAttrOnce attr_once;
   PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] {
     const cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
@@ -1279,6 +1300,8 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
             g.act, t[1] - t[0]);
     for (int i = 0; i < 8 && t[2 + i]; ++i)
       fprintf(stderr, " tile%d: full@%lld conv@%lld mma@%lld |", i, t[2 + i] - t[0], t[10 + i] - t[0], t[18 + i] - t[0]);
+    fprintf(stderr, " worker it5: top@%lld full@%lld conv@%lld ready@%lld drained@%lld | issuer it5: top@%lld conv@%lld n_hi=%d S=%d |", t[56] - t[0], t[57] - t[0], t[58] - t[0],
+            t[59] - t[0], t[60] - t[0], t[61] - t[0], t[62] - t[0], a.n_hi, a.stages);
     fprintf(stderr, " mma_done@%lld accum@%lld epi1@%lld bar@%lld end@%lld || epi: entry@%lld bias@%lld b0@%lld b1@%lld b2@%lld b3@%lld vec@%lld tail@%lld\n",
             t[26] - t[0], t[27] - t[0], t[28] - t[0], t[29] - t[0], t[30] - t[0], t[32] - t[0], t[33] - t[0], t[34] - t[0], t[35] - t[0],
             t[36] - t[0], t[37] - t[0], t[38] - t[0], t[39] - t[0]);

@@ -54,7 +54,7 @@ struct TcArgs {
   TcItem it[kGemmMaxItems];
   float* C[kGemmMaxItems];
   const float* bias[kGemmMaxItems];
-  int n_items, batched, M, N, BN, ldc, stages, tmem_cols, n_hi, drain_tiles, debias_ulps, n_lo;
+  int n_items, batched, M, N, BN, ldc, stages, tmem_cols, n_hi, drain_tiles, debias_ulps, a_tmem;  // a_tmem: first TMEM column of the two A-operand stages (ATMEM kernels)
   const float* rowscale;
   const float* addend;
   const float* ymask;
@@ -222,14 +222,22 @@ constexpr int kTcDrainTilesDefault = 1;  // measured (case6470rte x 2, hidden 51
 constexpr int kTcDrainMinTiles = 2;
 constexpr int kTcDrainChunks = 5;  // 16-column chunks per worker thread: ceil(160 / 32)
 
-template <bool DRAIN>
+// ATMEM = true: the A operand of every MMA lives in TENSOR MEMORY.  Measured (ncu + cycle stamps at case6470rte x 32,
+// hidden 512): the mainloop is bound by the shared-memory pipe -- per K tile the tensor core reads 96 KB of operands, the
+// converters read 16 KB and write 32 KB, TMA writes 48 KB: ~1.5 k wavefronts against 768 cycles of MMA work -- and the MMAs
+// execute at ~170 cycles each instead of the 64 they take alone (scripts/probes/tmem_a_probe.cu).  With ATMEM a worker thread
+// reads its row's share of the TMA-landed fp32 tile, splits it and writes (hi, lo) with tcgen05.st into one of two TMEM
+// operand stages (lane = row, column = k); the MMAs take A from there (no A descriptor reads, no hi/lo planes in shared
+// memory, a stage shrinks from 64 to 48 KB -> four stages in flight).  B is unchanged (weights pre-split by k_pack_weights).
+template <bool DRAIN, bool ATMEM>
 __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant__ TcArgs args) {
   extern __shared__ uint8_t smem_dyn[];
   if (threadIdx.x == 0) PFN_TSTAMP(0);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
   const int BN = args.BN, S = args.stages;
   const uint32_t a_bytes = kTcBM * 128u, b_bytes = uint32_t(BN) * 128u;
-  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes);  // A_hi | A_lo | B_hi | B_lo
+  const uint32_t b_off = ATMEM ? a_bytes : 2u * a_bytes;          // ATMEM: A (fp32 as landed) | B_hi | B_lo
+  const uint32_t stage_bytes = b_off + 2u * b_bytes;              // else:  A_hi | A_lo | B_hi | B_lo
   const uint32_t bar_base = base + uint32_t(S) * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto conv_bar = [&](int s) { return bar_base + 8u * (kTcMaxStages + s); };
@@ -259,12 +267,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       }
       const int s = p_it % S;
       const uint32_t ph = (p_it / S) & 1;
-      mbar_wait_sleep(empty_bar(s), ph ^ 1u);
+      mbar_wait(empty_bar(s), ph ^ 1u);
       mbar_arrive_expect_tx(full_bar(s), a_bytes + (item.presplit ? 2u : 1u) * b_bytes);
       const uint32_t st = base + uint32_t(s) * stage_bytes;
       tma_load_2d(st, &item.a, p_k0, m0, full_bar(s));
-      tma_load_2d(st + 2u * a_bytes, &item.b, p_k0, n0, full_bar(s));
-      if (item.presplit) tma_load_2d(st + 2u * a_bytes + b_bytes, &item.b_lo, p_k0, n0, full_bar(s));
+      tma_load_2d(st + b_off, &item.b, p_k0, n0, full_bar(s));
+      if (item.presplit) tma_load_2d(st + b_off + b_bytes, &item.b_lo, p_k0, n0, full_bar(s));
       p_k0 += kTcBK;
       ++p_it;
     }
@@ -314,10 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
     // accumulating instructions.  The hi*hi products therefore rotate over n_hi accumulators and the (2^-11 smaller)
     // lo terms go to their own accumulator; the epilogue adds them in round-to-nearest fp32.
     const int n_hi = args.n_hi;
-    // (DRAIN, n_lo == 2: the two lo products of a K step go to SEPARATE accumulators, so that no instruction accumulates
-    // into the tile its predecessor is still writing)
     const uint32_t d_lo = tmem_base + uint32_t(n_hi * BN);
-    const uint32_t d_lo2 = (DRAIN && args.n_lo == 2) ? d_lo + uint32_t(BN) : d_lo;
     int it = 0, kk = 0;
     for (int seg = seg_begin; seg < seg_end; ++seg) {
       const int K = args.it[seg].K;
@@ -325,19 +330,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         if (lane == 0 && it == 5) PFN_TSTAMP(61);
-        mbar_wait_sleep(conv_bar(s), ph);
+        mbar_wait(conv_bar(s), ph);
         if (lane == 0 && it == 5) PFN_TSTAMP(62);
         const int dt = args.drain_tiles;
         const int phase = it / dt, slot = phase % n_hi;  // DRAIN only
         const bool phase_first = it % dt == 0;
-        if (DRAIN && phase_first && phase >= n_hi) mbar_wait_sleep(drained_bar(slot), uint32_t(phase / n_hi - 1) & 1u);
+        if (DRAIN && phase_first && phase >= n_hi) mbar_wait(drained_bar(slot), uint32_t(phase / n_hi - 1) & 1u);
         tc_fence_after();
         const int nk = min(kTcBK / 8, (K - k0 + 7) / 8);  // 8 TF32 elements (32 bytes) per UMMA K step
         if (lane == 0 && it < 8) PFN_TSTAMP(18 + it);
         if (elect_one()) {
           const uint32_t st = base + uint32_t(s) * stage_bytes;
           const uint64_t a_hi = umma_desc_k128(st), a_lo = umma_desc_k128(st + a_bytes);
-          const uint64_t b_hi = umma_desc_k128(st + 2u * a_bytes), b_lo = umma_desc_k128(st + 2u * a_bytes + b_bytes);
+          const uint64_t b_hi = umma_desc_k128(st + b_off), b_lo = umma_desc_k128(st + b_off + b_bytes);
+          const uint32_t at_hi = tmem_base + uint32_t(args.a_tmem + 64 * (it & 1)), at_lo = at_hi + 32u;  // ATMEM: this tile's operand stage
+          if (DRAIN && nk == kTcBK / 8) {
+            // the common case straight-line: four K steps with constant offsets and constant accumulate flags (only the
+            // first step of a phase / of the whole reduction starts from zero).  The issuing thread's instruction stream
+            // is the pipeline's pace-maker: ~100 cycles of descriptor arithmetic per MMA in the general loop below
+            const uint32_t d_hi = tmem_base + uint32_t(slot * BN);
+            const uint32_t acc_hi0 = phase_first ? 0u : 1u, acc_lo0 = kk > 0 ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < kTcBK / 8; ++j) {
+              const uint64_t adv = uint64_t(j * 2);
+              if (ATMEM) {
+                umma_tf32_ts(d_lo, at_lo + uint32_t(8 * j), b_hi + adv, idesc, j == 0 ? acc_lo0 : 1u);
+                umma_tf32_ts(d_lo, at_hi + uint32_t(8 * j), b_lo + adv, idesc, 1u);
+                umma_tf32_ts(d_hi, at_hi + uint32_t(8 * j), b_hi + adv, idesc, j == 0 ? acc_hi0 : 1u);
+              } else {
+                umma_tf32(d_lo, a_lo + adv, b_hi + adv, idesc, j == 0 ? acc_lo0 : 1u);
+                umma_tf32(d_lo, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, j == 0 ? acc_hi0 : 1u);
+              }
+            }
+          } else
           for (int j = 0; j < nk; ++j) {
             const uint64_t adv = uint64_t(j * 2);  // +32 bytes in the 16-byte-granular start-address field
             const int k_idx = kk + j;
@@ -349,9 +375,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
               d_hi = tmem_base + uint32_t((k_idx % n_hi) * BN);
               acc_hi = k_idx >= n_hi ? 1u : 0u;
             }
-            umma_tf32(d_lo, a_lo + adv, b_hi + adv, idesc, k_idx > 0 ? 1u : 0u);
-            umma_tf32(d_lo2, a_hi + adv, b_lo + adv, idesc, (d_lo2 != d_lo && k_idx == 0) ? 0u : 1u);
-            umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, acc_hi);
+            if (ATMEM) {
+              umma_tf32_ts(d_lo, at_lo + uint32_t(8 * j), b_hi + adv, idesc, k_idx > 0 ? 1u : 0u);
+              umma_tf32_ts(d_lo, at_hi + uint32_t(8 * j), b_lo + adv, idesc, 1u);
+              umma_tf32_ts(d_hi, at_hi + uint32_t(8 * j), b_hi + adv, idesc, acc_hi);
+            } else {
+              umma_tf32(d_lo, a_lo + adv, b_hi + adv, idesc, k_idx > 0 ? 1u : 0u);
+              umma_tf32(d_lo, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_tf32(d_hi, a_hi + adv, b_hi + adv, idesc, acc_hi);
+            }
           }
           umma_commit(empty_bar(s));  // implies tcgen05.fence::before_thread_sync
           if (DRAIN && (it % dt == dt - 1 || it == n_tiles_total - 1)) umma_commit(ready_bar(slot));
@@ -409,13 +441,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         if (tid_c == 0 && it == 5) PFN_TSTAMP(56);
-        mbar_wait_sleep(full_bar(s), ph);
+        mbar_wait(full_bar(s), ph);
         if (tid_c == 0 && it == 5) PFN_TSTAMP(57);
         if (tid_c == 0 && it < 8) PFN_TSTAMP(2 + it);
         const uint32_t st = base + uint32_t(s) * stage_bytes;
-        split_tile(st, a_bytes, kTcBM * 8, tid_c);
-        if (!args.it[seg].presplit) split_tile(st + 2u * a_bytes, b_bytes, BN * 8, tid_c);  // weights arrive pre-split
-        proxy_fence_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        if (ATMEM) {
+          // this thread: row 32 q + lane of the tile, K elements [16 half, 16 half + 16) -- four 16-byte chunks of the
+          // 128-byte swizzled row (chunk c of row r sits at position c ^ (r mod 8))
+          const int row = 32 * q + lane;
+          const uint32_t row_addr = st + uint32_t(row) * 128u;
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t pos = uint32_t((4 * half + c) ^ (row & 7));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3]) : "r"(row_addr + 16u * pos));
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float h = tf32_rn(v[i]);
+            hi[i] = __float_as_uint(h);
+            lo[i] = __float_as_uint(tf32_rn(v[i] - h));
+          }
+          // the operand stage was last read by the MMAs of tile it - 2: their completion is what frees that tile's
+          // shared-memory stage (empty_bar)
+          if (it >= 2) {
+            mbar_wait(empty_bar((it - 2) % S), uint32_t((it - 2) / S) & 1u);
+            tc_fence_after();
+          }
+          const uint32_t at = lane_base + uint32_t(args.a_tmem + 64 * (it & 1) + 16 * half);
+          tmem_st16(at, hi);
+          tmem_st16(at + 32u, lo);
+          tmem_st_wait();
+          if (!args.it[seg].presplit) {
+            split_tile(st + b_off, b_bytes, BN * 8, tid_c);
+            proxy_fence_async();
+          }
+          tc_fence_before();  // the MMA issuer orders the tcgen05.st above through conv_bar + fence::after_thread_sync
+        } else {
+          split_tile(st, a_bytes, kTcBM * 8, tid_c);
+          if (!args.it[seg].presplit) split_tile(st + 2u * a_bytes, b_bytes, BN * 8, tid_c);  // weights arrive pre-split
+          proxy_fence_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        }
         if (tid_c == 0 && it < 8) PFN_TSTAMP(10 + it);
         __syncwarp();
         if (lane == 0) mbar_arrive(conv_bar(s));
@@ -424,7 +491,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
           // every tile of phase p has been handed to the tensor core: read out phase p - 1 (issued a phase ago, so its
           // MMAs have normally completed) while phase p is being multiplied
           const int pd = (it + 1) / args.drain_tiles - 2, slot = pd % args.n_hi;
-          mbar_wait_sleep(ready_bar(slot), uint32_t(pd / args.n_hi) & 1u);
+          mbar_wait(ready_bar(slot), uint32_t(pd / args.n_hi) & 1u);
           if (tid_c == 0 && it == 5) PFN_TSTAMP(59);
           tc_fence_after();
           drain_slot(uint32_t(slot * BN), uint32_t(args.debias_ulps));
@@ -436,7 +503,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
         }
       }
     }
-    mbar_wait_sleep(accum_bar, 0);
+    mbar_wait(accum_bar, 0);
     tc_fence_after();
     // The staging tile written below overlays pipeline stage 0, last written by split_tile.  The mbarrier chain (conv_bar
     // arrivals of ALL converter warps -> MMA -> accum_bar) already orders the two; this named barrier restates the
@@ -454,7 +521,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_tc(const __grid_constant
       const int n_phases = (n_tiles_total + args.drain_tiles - 1) / args.drain_tiles;
       for (int pd = next_drain; pd < n_phases; ++pd) drain_slot(uint32_t((pd % args.n_hi) * BN), uint32_t(args.debias_ulps));
       drain_slot(uint32_t(args.n_hi * BN), 0u);  // the (2^-11 smaller) lo terms: no correction
-      if (args.n_lo == 2) drain_slot(uint32_t((args.n_hi + 1) * BN), 0u);
       const uint32_t row_addr = base + (uint32_t(32 * q + lane) * tile_ld) * 4u;
 #pragma unroll
       for (int i = 0; i < kTcDrainChunks; ++i) {
@@ -1208,21 +1274,21 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   a.batched = g.batched;
   a.M = g.M;
   a.N = g.N;
-  const uint32_t stage_bytes = 2u * (kTcBM + bn) * 128u;
+  // A operand in tensor memory (default; PFN_TC_ATMEM=0 keeps the hi / lo planes in shared memory): two operand stages of
+  // 64 columns behind the accumulators, which leaves (512 - 128) / BN accumulators
+  static const bool atmem_env = [] {
+    const char* e = std::getenv("PFN_TC_ATMEM");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool atmem = atmem_env && (512 - 128) / bn >= 3;  // (at least two rotating hi*hi accumulators + lo must remain)
+  const uint32_t stage_bytes = (atmem ? (kTcBM + 2u * bn) : 2u * (kTcBM + bn)) * 128u;
   a.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 2048u) / stage_bytes));
   if (a.stages < 1) return 1;
-  a.n_hi = std::max(1, std::min(3, 512 / bn - 1));
-  a.n_lo = 1;
-  static const int lo2_env = [] {
-    const char* e = std::getenv("PFN_TC_LO2");  // experiment: separate accumulators for the two lo products
-    return e != nullptr && e[0] == '1' ? 1 : 0;
-  }();
-  if (lo2_env && 512 / bn - 2 >= 2) {
-    a.n_lo = 2;
-    a.n_hi = std::min(3, 512 / bn - 2);
-  }
+  if (uint32_t(a.stages) * stage_bytes < kTcBM * uint32_t(bn + 4) * 4u) return 1;  // (the epilogue's staging tile overlays the stages)
+  a.n_hi = std::max(1, std::min(3, (atmem ? 384 : 512) / bn - 1));
+  a.a_tmem = (a.n_hi + 1) * bn;
   int cols = 32;
-  while (cols < (a.n_hi + a.n_lo) * bn) cols <<= 1;
+  while (cols < (a.n_hi + 1) * bn + (atmem ? 128 : 0)) cols <<= 1;
   a.tmem_cols = cols;
   for (int i = 0; i < g.n_items; ++i) {
     const GemmItem& it = g.it[i];
@@ -1276,11 +1342,13 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   }();
   a.debias_ulps = a.drain_tiles == 1 ? debias_env : 2 * debias_env;
   const bool drain = a.n_hi >= 2 && bn <= 32 * kTcDrainChunks && (drain_env >= 0 ? drain_env == 1 : max_tiles >= kTcDrainMinTiles);
-  if (!drain) a.n_lo = 1;  // (the plain kernel's epilogue reads one lo accumulator; the spare columns stay unused)
   static SmemAttrOnce attr_once;
   PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] {
-    const cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
-    return e != cudaSuccess ? e : cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
+    return e;
   }));
   dim3 grid(static_cast<unsigned>(ceil_div64(g.M, kTcBM)), static_cast<unsigned>(ceil_div64(g.N, bn)), static_cast<unsigned>(count));
   static const bool timing_on = std::getenv("PFN_TC_TIMING") != nullptr;  // debug aid: phase timestamps of CTA 0
@@ -1290,7 +1358,8 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     cudaMemsetAsync(timing_dev, 0, 64 * sizeof(long long), stream);
     a.timing = timing_dev;
   }
-  PFN_CUDA_OK(launch_kernel(drain ? k_gemm_tc<true> : k_gemm_tc<false>, grid, dim3(kTcThreads), smem, stream, a));
+  auto kernel = drain ? (atmem ? k_gemm_tc<true, true> : k_gemm_tc<true, false>) : (atmem ? k_gemm_tc<false, true> : k_gemm_tc<false, false>);
+  PFN_CUDA_OK(launch_kernel(kernel, grid, dim3(kTcThreads), smem, stream, a));
   PFN_LAUNCHED();
   if (timing_on) {
     long long t[64];

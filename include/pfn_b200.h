@@ -115,15 +115,6 @@ PFN_API int pfn_graph_export(const int64_t* edge_index, int64_t ei_row_stride, c
  *      the second Linear is applied after the sum by pfn_linear (sum aggregation is linear). ------- */
 PFN_API int pfn_ea_fwd(const float* Hi, const float* Hj, int64_t ldh, const void* graph_ws, int64_t n_nodes,
                int64_t e_raw, const float* We, int64_t ldwe, float* S, int64_t lds, int64_t h, void* stream);
-/* The same sum for batches of small graphs laid out tile by tile: the caller promises that rows [t*tile_rows,
- * (t+1)*tile_rows), tile_rows <= 128, are closed under the graph's edges (the promise of pfn_mpn_forward_tiled; true for a
- * PyG batch of equal-sized graphs with tile_rows = a whole number of graphs).  One CTA then keeps a tile's Hj rows in
- * shared memory (bulk copies) and no gather leaves the SM.  The promise is not trusted: a neighbour outside its tile is
- * read from global memory (same result, slower).  Results are bit-identical to pfn_ea_fwd; shapes whose tile does not fit
- * in shared memory (or Hi/Hj with padded rows, ldh != round_up(h, 4)) run pfn_ea_fwd's kernels. */
-PFN_API int pfn_ea_fwd_tiled(const float* Hi, const float* Hj, int64_t ldh, const void* graph_ws, int64_t n_nodes,
-               int64_t e_raw, const float* We, int64_t ldwe, float* S, int64_t lds, int64_t h, int64_t tile_rows,
-               void* stream);
 /* backward of the above: dHi, dHj [N, ldd]; dWe [h, 2] written with row stride lddwe (it is a column
  * block of the gradient of edge_aggr.0.weight).  scratch: at least pfn_ea_bwd_scratch_bytes(h). */
 PFN_API size_t pfn_ea_bwd_scratch_bytes(int64_t h);

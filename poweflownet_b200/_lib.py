@@ -50,8 +50,6 @@ SIGNATURES = {
     "pfn_graph_export": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pfn_ea_fwd": (C.c_int, [c_f32p, c_f32p, c_i64, C.c_void_p, c_i64, c_i64, c_f32p, c_i64, c_f32p, c_i64, c_i64,
                              C.c_void_p]),
-    "pfn_ea_fwd_tiled": (C.c_int, [c_f32p, c_f32p, c_i64, C.c_void_p, c_i64, c_i64, c_f32p, c_i64, c_f32p, c_i64, c_i64,
-                                   c_i64, C.c_void_p]),
     "pfn_ea_bwd_scratch_bytes": (c_sz, [c_i64]),
     "pfn_ea_bwd": (C.c_int, [c_f32p, c_i64, c_f32p, c_f32p, c_i64, C.c_void_p, c_i64, c_i64, c_f32p, c_i64, c_f32p,
                              c_f32p, c_i64, c_f32p, c_i64, C.c_void_p, c_i64, C.c_void_p]),

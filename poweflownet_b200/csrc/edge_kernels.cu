@@ -757,166 +757,6 @@ k_hop(const float* __restrict__ X, int64_t ldx, const int* __restrict__ rowptr, 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_ea_fwd_tile: the message + aggregate for batches of SMALL graphs laid out tile by tile (the closed-tile promise of
-// the graph-resident kernels: rows [t T, (t+1) T) are closed under the edges, T <= 128 -- a PyG batch of case14 / case118
-// graphs).  The gather then never leaves the tile, so the dependent chain "row pointers -> neighbour ids -> rows" that
-// bounds k_ea_fwd_tma at this size (10 us for 24 MB, every CTA sees ~2 batches) disappears: at its FIRST instruction a
-// CTA knows everything it will read --
-//   * Hj rows [t T, (t+1) T): ONE contiguous range -> a handful of bulk copies (cp.async.bulk, SASS UBLKCP) into shared
-//     memory, completion counted in bytes on one mbarrier;
-//   * its own Hi rows: independent 16-byte loads into registers, issued before anything is waited for;
-//   * the tile's CSR slice (row pointers, then neighbour ids + edge_attr): two coalesced round trips that overlap the copy;
-// and every byte of Hi, Hj and S crosses the SM boundary exactly once (no halo, no re-gather through L2).
-// Thread (x, y) owns 16-byte column chunk x and rows y, y + lanes, ... of the tile; neighbours come from shared memory
-// in ascending edge id with the packed arithmetic of k_ea_fwd_tma: results are BIT-IDENTICAL to k_ea_fwd.
-// The promise is NOT trusted: a neighbour outside the tile is read from global memory instead (same sum, slower), and
-// edges beyond the staged window of a tile are read from the CSR arrays directly.
-constexpr int kTileMaxRows = 128;
-constexpr int kTileEdges = 1536;     // staged neighbour ids / edge_attr of one tile (more: read from global memory)
-constexpr int kTileThreads = 1024;
-constexpr int kTileHiPieces = 4;     // the tile's Hi rows land in this many separately awaited pieces
-
-struct TileArgs {
-  const float* Hi;
-  const float* Hj;
-  const int* rowptr;
-  const int* nbr;
-  const float2* ea;
-  const float* We;
-  float* S;
-  long long ldh, lds, ldwe;
-  int n_nodes, h, c4, tile_rows, lanes;
-  unsigned long long* stamps;  // debug (PFN_EA_TILE_TIMING=1): thread 0 of CTAs 0 and 100 leaves clock / %globaltimer stamps
-};
-
-__global__ void __launch_bounds__(kTileThreads, 1) k_ea_fwd_tile(const __grid_constant__ TileArgs a) {
-  extern __shared__ __align__(128) uint8_t tile_smem[];  // Hj rows of the tile | Hi rows of the tile
-  __shared__ int s_rp[kTileMaxRows + 1];
-  __shared__ int s_nbr[kTileEdges];
-  __shared__ float2 s_ea[kTileEdges];
-  __shared__ __align__(8) uint64_t s_bar[1 + kTileHiPieces];
-  const int tid = threadIdx.x, nthr = blockDim.x;
-#define TSTAMP(slot)                                                                                     \
-  do {                                                                                                   \
-    if (a.stamps != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100)) {                       \
-      unsigned long long gt;                                                                             \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));                                             \
-      a.stamps[(blockIdx.x == 0 ? 0 : 16) + (slot)] = gt;                                                \
-    }                                                                                                    \
-  } while (0)
-  TSTAMP(0);
-  const int c4 = a.c4;
-  const uint32_t rowbytes = uint32_t(c4) * 16u;
-  const int t0 = blockIdx.x * a.tile_rows, nr = min(a.tile_rows, a.n_nodes - t0);
-  const uint32_t win = tma_smem_u32(tile_smem), hiw = win + uint32_t(a.tile_rows) * rowbytes;
-  const uint32_t bar_hj = tma_smem_u32(&s_bar[0]);
-  auto bar_hi = [&](int p) { return tma_smem_u32(&s_bar[1 + p]); };
-  const int piece_rows = (nr + kTileHiPieces - 1) / kTileHiPieces;  // Hi arrives in pieces: a row waits for its piece only
-  const int x = tid % c4, y = tid / c4;
-  const bool active = y < a.lanes;
-  if (tid == 0) {
-    for (int p = 0; p <= kTileHiPieces; ++p) tma_mbar_init(tma_smem_u32(&s_bar[p]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  pdl_wait();
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next launch cannot share the SM anyway: let it queue up
-  TSTAMP(1);
-  // the latency chain first (row pointers -> neighbour ids), before the bulk data fills the memory queues
-  int rp_val = 0;
-  const bool rp_reg = nthr > nr;  // (always, except single-chunk rows with 128-row tiles)
-  if (rp_reg && tid <= nr) rp_val = a.rowptr[t0 + tid];
-  if (tid == 0) {
-    // Hj rows of the tile: one contiguous range, a few copies in flight; then the Hi rows piece by piece
-    const uint32_t total = uint32_t(nr) * rowbytes;
-    tma_mbar_expect_tx(bar_hj, total);
-    const uint32_t piece = ((total / 4u) + 15u) & ~15u;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.Hj + size_t(t0) * a.ldh);
-    for (uint32_t off = 0; off < total; off += piece) bulk_g2s(win + off, src + off, min(piece, total - off), bar_hj);
-    const uint8_t* srci = reinterpret_cast<const uint8_t*>(a.Hi + size_t(t0) * a.ldh);
-    for (int p = 0; p < kTileHiPieces; ++p) {
-      const int r_lo = min(nr, p * piece_rows), r_hi = min(nr, r_lo + piece_rows);
-      const uint32_t bytes = uint32_t(r_hi - r_lo) * rowbytes;
-      if (bytes == 0) {
-        tma_mbar_arrive(bar_hi(p));
-        continue;
-      }
-      tma_mbar_expect_tx(bar_hi(p), bytes);
-      bulk_g2s(hiw + uint32_t(r_lo) * rowbytes, srci + size_t(r_lo) * rowbytes, bytes, bar_hi(p));
-    }
-  }
-  float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-  if (active) load_we(a.We, a.ldwe, x, a.h, w0, w1);
-  TSTAMP(2);
-  if (rp_reg) {
-    if (tid <= nr) s_rp[tid] = rp_val;
-  } else {
-    for (int i = tid; i <= nr; i += nthr) s_rp[i] = a.rowptr[t0 + i];
-  }
-  __syncthreads();  // (also publishes the mbarrier initialisation)
-  TSTAMP(3);
-  const int e0 = s_rp[0], ne = s_rp[nr] - e0;
-  for (int i = tid; i < min(ne, kTileEdges); i += nthr) {
-    s_nbr[i] = a.nbr[e0 + i];
-    s_ea[i] = a.ea[e0 + i];
-  }
-  __syncthreads();
-  TSTAMP(4);
-  if (!active) return;
-  tma_mbar_wait(bar_hj, 0);
-  TSTAMP(5);
-  const Pair4 w0p = pair4(w0), w1p = pair4(w1);
-  const uint32_t xoff = uint32_t(x) * 16u;
-  auto row_of = [&](int e, float2& av) -> float4 {  // slot e of the tile: the neighbour's Hj chunk and the edge's attributes
-    int j;
-    if (e < kTileEdges) {
-      j = s_nbr[e];
-      av = s_ea[e];
-    } else {
-      j = a.nbr[e0 + e];
-      av = a.ea[e0 + e];
-    }
-    const unsigned loc = unsigned(j - t0);
-    return loc < unsigned(nr) ? lds4(win + loc * rowbytes + xoff) : ldg4(a.Hj + size_t(j) * a.ldh + 4 * x);
-  };
-  int waited = -1;
-  for (int r = y; r < nr; r += a.lanes) {
-    const int beg = s_rp[r] - e0, fin = s_rp[r + 1] - e0;
-    const int piece = r / piece_rows;
-    while (waited < piece) tma_mbar_wait(bar_hi(++waited), 0);  // rows ascend: pieces are awaited in order
-    const Pair4 hi = pair4(lds4(hiw + uint32_t(r) * rowbytes + xoff));
-    Pair4 acc{pack2(0.f, 0.f), pack2(0.f, 0.f)};
-    int e = beg;
-    for (; e + 3 < fin; e += 4) {  // four shared-memory row reads in flight per thread
-      float2 a0, a1, a2, a3;
-      const float4 h0 = row_of(e, a0), h1 = row_of(e + 1, a1), h2 = row_of(e + 2, a2), h3 = row_of(e + 3, a3);
-      add_relu_preact2(acc, hi, h0, a0, w0p, w1p);
-      add_relu_preact2(acc, hi, h1, a1, w0p, w1p);
-      add_relu_preact2(acc, hi, h2, a2, w0p, w1p);
-      add_relu_preact2(acc, hi, h3, a3, w0p, w1p);
-    }
-    if (e + 1 < fin) {
-      float2 a0, a1;
-      const float4 h0 = row_of(e, a0), h1 = row_of(e + 1, a1);
-      add_relu_preact2(acc, hi, h0, a0, w0p, w1p);
-      add_relu_preact2(acc, hi, h1, a1, w0p, w1p);
-      e += 2;
-    }
-    if (e < fin) {
-      float2 a0;
-      const float4 h0 = row_of(e, a0);
-      add_relu_preact2(acc, hi, h0, a0, w0p, w1p);
-    }
-    float4 o;
-    unpack2(acc.lo, o.x, o.y);
-    unpack2(acc.hi, o.z, o.w);
-    st4(a.S + size_t(t0 + r) * a.lds + 4 * x, o);
-    if (r == y) TSTAMP(6);
-  }
-  TSTAMP(7);
-#undef TSTAMP
-}
-
 // ---- host side of k_ea_fwd_tma ----------------------------------------------------------------------------------------
 // PFN_EA_FWD=cta forces the CTA-slab kernel (k_ea_fwd); unset / anything else takes the bulk-copy kernel whenever the
 // width fits.  Read per call so that tests can compare the two.  Tuning knobs (experiments): PFN_EA_STAGES (2..4),
@@ -1005,49 +845,6 @@ int ea_fwd_tma_launch(const float* Hi, const float* Hj, int64_t ldh, const Graph
   static SmemAttrOnce attr_once;
   PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] { return cudaFuncSetAttribute(k_ea_fwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTmaSmemLimit)); }));
   PFN_CUDA_OK(launch_kernel(k_ea_fwd_tma, dim3(grid), dim3(32 * (a.cons_warps + a.prod_warps)), smem, stream, a));
-  PFN_LAUNCHED();
-  return 0;
-}
-
-unsigned long long* tile_debug_stamps() {
-  static unsigned long long* buf = [] {
-    unsigned long long* p = nullptr;
-    const char* e = std::getenv("PFN_EA_TILE_TIMING");
-    if (e != nullptr && e[0] == '1' && cudaMalloc(&p, 32 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(p, 0, 32 * sizeof(unsigned long long));
-    return p;
-  }();
-  return buf;
-}
-
-// 0 = launched, 1 = shape outside the tile kernel (caller uses the general kernels)
-int ea_fwd_tile_launch(const float* Hi, const float* Hj, int64_t ldh, const GraphView& g, int64_t n_nodes, const float* We,
-                       int64_t ldwe, float* S, int64_t lds, int64_t h, int64_t tile_rows, cudaStream_t stream) {
-  const int c4 = static_cast<int>((h + 3) / 4);
-  const uint32_t rowbytes = uint32_t(c4) * 16u;
-  if (tile_rows <= 0 || tile_rows > kTileMaxRows || ldh * 4 != int64_t(rowbytes) || c4 > kTileThreads || n_nodes >= (int64_t(1) << 31) - 256) return 1;
-  const uint32_t smem = 2u * uint32_t(tile_rows) * rowbytes;  // Hj rows | Hi rows
-  if (smem > 200u * 1024u) return 1;
-  TileArgs a{};
-  a.lanes = std::max(1, std::min<int>(static_cast<int>(tile_rows), kTileThreads / c4));
-  a.Hi = Hi;
-  a.Hj = Hj;
-  a.rowptr = g.rowptr_t;
-  a.nbr = g.nbr_t;
-  a.ea = reinterpret_cast<const float2*>(g.ea_t);
-  a.We = We;
-  a.S = S;
-  a.ldh = ldh;
-  a.lds = lds;
-  a.ldwe = ldwe;
-  a.n_nodes = static_cast<int>(n_nodes);
-  a.h = static_cast<int>(h);
-  a.c4 = c4;
-  a.tile_rows = static_cast<int>(tile_rows);
-  a.stamps = tile_debug_stamps();
-  const int threads = (a.lanes * c4 + 31) / 32 * 32;
-  static SmemAttrOnce attr_once;
-  PFN_CUDA_OK(ensure_dynamic_smem(attr_once, [] { return cudaFuncSetAttribute(k_ea_fwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
-  PFN_CUDA_OK(launch_kernel(k_ea_fwd_tile, dim3(static_cast<unsigned>(ceil_div64(n_nodes, tile_rows))), dim3(threads), smem, stream, a));
   PFN_LAUNCHED();
   return 0;
 }
@@ -1173,32 +970,6 @@ extern "C" int pfn_ea_fwd(const float* Hi, const float* Hj, int64_t ldh, const v
   PFN_REQUIRE(graph_ws != nullptr, PFN_E_INVALID, "pfn_ea_fwd: null graph workspace");
   return ea_fwd_launch(Hi, Hj, ldh, graph_view(graph_ws, n_nodes, e_raw), n_nodes, We, ldwe, S, lds, h,
                        static_cast<cudaStream_t>(stream));
-}
-
-// debug only (not part of include/pfn_b200.h): the stamps of the last k_ea_fwd_tile launch under PFN_EA_TILE_TIMING=1
-extern "C" PFN_API int pfn_debug_ea_tile_stamps(unsigned long long* host32) {
-  unsigned long long* d = tile_debug_stamps();
-  if (d == nullptr || host32 == nullptr) return PFN_E_INVALID;
-  return static_cast<int>(cudaMemcpy(host32, d, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-}
-
-extern "C" int pfn_ea_fwd_tiled(const float* Hi, const float* Hj, int64_t ldh, const void* graph_ws, int64_t n_nodes,
-                                int64_t e_raw, const float* We, int64_t ldwe, float* S, int64_t lds, int64_t h,
-                                int64_t tile_rows, void* stream_) {
-  PFN_REQUIRE(graph_ws != nullptr, PFN_E_INVALID, "pfn_ea_fwd_tiled: null graph workspace");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const GraphView g = graph_view(graph_ws, n_nodes, e_raw);
-  PFN_REQUIRE(rows_ok(Hi, ldh) && rows_ok(Hj, ldh) && rows_ok(S, lds) && We != nullptr, PFN_E_INVALID,
-              "ea_fwd: node matrices must be 16-byte aligned with ld %% 4 == 0");
-  PFN_REQUIRE(h > 0 && ldh >= round_up64(h, 4) && lds >= round_up64(h, 4), PFN_E_INVALID, "ea_fwd: ld < round_up(h,4)");
-  if (n_nodes == 0) return 0;
-  const char* env = std::getenv("PFN_EA_FWD");  // "cta" / "tma" force the general kernels (comparisons)
-  if (env == nullptr || env[0] == '\0' || env[0] == 'w') {
-    ProfScope prof(PFN_PROF_EA_FWD, stream);
-    const int rc = ea_fwd_tile_launch(Hi, Hj, ldh, g, n_nodes, We, ldwe, S, lds, h, tile_rows, stream);
-    if (rc != 1) return rc;
-  }
-  return ea_fwd_launch(Hi, Hj, ldh, g, n_nodes, We, ldwe, S, lds, h, stream);
 }
 
 extern "C" size_t pfn_ea_bwd_scratch_bytes(int64_t h) {

@@ -160,11 +160,6 @@ def linear_wgrad(dy, x, n_in, n_out, dw, lddw, *, dbias=None, rowscale=None, dw_
 
 
 def ea_fwd(hi, hj, graph: PreparedGraph, w1, fin, h, s):
-    if graph.tile_rows > 0:  # the batch is promised to be laid out tile by tile: tile-resident kernel
-        check(lib().pfn_ea_fwd_tiled(hi.data_ptr(), hj.data_ptr(), _ld(hi), graph.ws.data_ptr(), graph.n_nodes, graph.e_raw,
-                                     w1.data_ptr() + 4 * 2 * fin, 2 * fin + 2, s.data_ptr(), _ld(s), h, graph.tile_rows,
-                                     _stream()), "pfn_ea_fwd_tiled")
-        return s
     check(lib().pfn_ea_fwd(hi.data_ptr(), hj.data_ptr(), _ld(hi), graph.ws.data_ptr(), graph.n_nodes, graph.e_raw,
                            w1.data_ptr() + 4 * 2 * fin, 2 * fin + 2, s.data_ptr(), _ld(s), h, _stream()), "pfn_ea_fwd")
     return s

@@ -22,7 +22,7 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 lib = _lib.lib()
 peak = bench.load_peaks()["hbm_gbs"]
-KNOBS = ("AB_TILE_ROWS", "PFN_EA_FWD", "PFN_EA_STAGES", "PFN_EA_THREADS", "PFN_EA_PREFETCH", "PFN_EA_PRODUCERS", "PFN_EA_BULK", "PFN_EA_CHUNK", "PFN_EDGE_CYCLIC", "PFN_EA_ROUND", "PFN_EA_BULK8", "PFN_EA_CTAS_PER_SM")
+KNOBS = ("PFN_EA_FWD", "PFN_EA_STAGES", "PFN_EA_THREADS", "PFN_EA_PREFETCH", "PFN_EA_PRODUCERS", "PFN_EA_BULK", "PFN_EA_CHUNK", "PFN_EDGE_CYCLIC", "PFN_EA_ROUND", "PFN_EA_BULK8", "PFN_EA_CTAS_PER_SM")
 
 
 def run(case, b, h, variants, iters, n_sets):
@@ -37,11 +37,6 @@ def run(case, b, h, variants, iters, n_sets):
 
     def launch(i, stream):
         hi, hj, s = sets[i % n_sets]
-        tile = int(os.environ.get("AB_TILE_ROWS", "0"))
-        if tile > 0:  # the tile-resident kernel under the closed-tile promise (one case118 graph per tile)
-            _lib.check(lib.pfn_ea_fwd_tiled(hi.data_ptr(), hj.data_ptr(), ld, g.ws.data_ptr(), n, g.e_raw, we.data_ptr(), 2,
-                                            s.data_ptr(), ld, h, tile, stream), "pfn_ea_fwd_tiled")
-            return
         _lib.check(lib.pfn_ea_fwd(hi.data_ptr(), hj.data_ptr(), ld, g.ws.data_ptr(), n, g.e_raw, we.data_ptr(), 2,
                                   s.data_ptr(), ld, h, stream), "pfn_ea_fwd")
 
@@ -120,7 +115,7 @@ def run(case, b, h, variants, iters, n_sets):
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None  # optional: comma-separated variant names
 P = {"PFN_EA_FWD": "tma"}
-small = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tile", {"AB_TILE_ROWS": "118"}), ("tma_1sm", {**P, "PFN_EA_CTAS_PER_SM": "1"}), ("tma_2sm_t128", {**P, "PFN_EA_THREADS": "128"}),
+small = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_1sm", {**P, "PFN_EA_CTAS_PER_SM": "1"}), ("tma_2sm_t128", {**P, "PFN_EA_THREADS": "128"}),
          ("tma_2sm_t384_p4", {**P, "PFN_EA_THREADS": "384"}), ("tma_2sm_p2", {**P, "PFN_EA_PRODUCERS": "2"}), ("tma_2sm_p6", {**P, "PFN_EA_PRODUCERS": "6"}),
          ("tma_2sm_s1", {**P, "PFN_EA_STAGES": "1"}), ("tma_2sm_s3", {**P, "PFN_EA_STAGES": "3"}), ("tma_2sm_prefetch", {**P, "PFN_EA_PREFETCH": "1"})]
 large = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_2sm", {**P, "PFN_EA_CTAS_PER_SM": "2"})]

@@ -251,65 +251,3 @@ def test_ea_forward_bulk_copy_full_size_and_strided(monkeypatch):
             outs[which] = s
         assert torch.equal(outs["cta"], outs["tma"]) and float(outs["tma"][:, :ld].abs().max()) == 0.0
 
-
-# ---- tile-resident message + aggregate (pfn_ea_fwd_tiled, k_ea_fwd_tile) ---------------------------------------------
-def _tile_vs_cta(batch, h, tile_rows, monkeypatch, seed=21, expect_launch=True):
-    """S from the tile-resident kernel under the promise `tile_rows`, bit for bit against the CTA-slab kernel on the same
-    prepared graph (and both against the double-precision sum)."""
-    from poweflownet_b200 import _lib, ops
-    n, ei, ea, hi, hj, ds, w1, fin, graph = _edge_case(batch, h, seed=seed)
-    src, tgt = ei[0], ei[1]
-    pre = hi.double()[tgt] + hj.double()[src] + ea.double() @ w1[:, 2 * fin:].double().T
-    s_ref = seg_sum(torch.relu(pre), tgt, n)
-    monkeypatch.setenv("PFN_EA_FWD", "cta")
-    want = ops.new_rows(n, h, DEV)
-    ops.ea_fwd(_rows(hi), _rows(hj), graph, w1.to(DEV), fin, h, want)
-    monkeypatch.delenv("PFN_EA_FWD")
-    graph.tile_rows = tile_rows
-    got = ops.new_rows(n, h, DEV)
-    got.fill_(float("nan"))
-    ops.ea_fwd(_rows(hi), _rows(hj), graph, w1.to(DEV), fin, h, got)
-    _assert_close(got[:, :h], s_ref, what="S (tile-resident)")
-    assert torch.equal(got[:, :h], want[:, :h])
-    return got
-
-
-@pytest.mark.parametrize("h", [8, 33, 64, 129, 132, 256, 384])
-@pytest.mark.parametrize("case,b,tile_rows", [("118v2", 16, 118), ("14", 27, 126), ("14", 20, 126), ("14", 3, 14), ((128, 700), 2, 128)])
-def test_ea_forward_tile_resident_kernel_equals_cta_kernel(case, b, tile_rows, h, monkeypatch):
-    """Closed tiles of one case118 graph, nine case14 graphs (full and with a short last tile), one tiny graph, and 128-bus
-    graphs whose 1400 directed edges exceed the staged neighbour window -- hidden widths from 8 to 384."""
-    from poweflownet_b200.data import synthetic_batch
-    _tile_vs_cta(synthetic_batch(cases=[case] * b, seed=9), h, tile_rows, monkeypatch)
-
-
-@pytest.mark.parametrize("tile_rows", [64, 100, 118, 128])
-def test_ea_forward_tile_resident_kernel_survives_a_broken_promise(tile_rows, monkeypatch):
-    """The promise is a performance hint: tiles that cut graphs in two (64, 100, 128 rows on 118-bus graphs), or an edge
-    joining two tiles, give the same bits -- neighbours outside the tile are read from global memory."""
-    from poweflownet_b200.data import synthetic_batch
-    batch = synthetic_batch(cases=["118v2"] * 5, seed=4)
-    batch.edge_index[:, -1] = torch.tensor([3, 500])
-    _tile_vs_cta(batch, 129, tile_rows, monkeypatch)
-
-
-def test_ea_forward_tile_resident_shapes_outside_the_kernel_take_the_general_path(monkeypatch):
-    """Rows too wide for a 128-row tile in shared memory (hidden 512), or operands with padded rows: same call, same bits."""
-    from poweflownet_b200 import ops
-    from poweflownet_b200.data import synthetic_batch
-    _tile_vs_cta(synthetic_batch(cases=["118v2"] * 4, seed=3), 512, 118, monkeypatch)
-    n, ei, ea, hi, hj, ds, w1, fin, graph = _edge_case(synthetic_batch(cases=["14"] * 9, seed=3), 64, seed=2)
-    graph.tile_rows = 126
-    wide = torch.zeros(n, 3 * 64, device=DEV)
-    wide[:, :64].copy_(hi)
-    wide[:, 64:128].copy_(hj)
-    outs = []
-    for env in ("cta", None):
-        if env:
-            monkeypatch.setenv("PFN_EA_FWD", env)
-        else:
-            monkeypatch.delenv("PFN_EA_FWD")
-        s = ops.new_rows(n, 64, DEV)
-        ops.ea_fwd(wide[:, :64], wide[:, 64:128], graph, w1.to(DEV), fin, 64, s)
-        outs.append(s)
-    assert torch.equal(outs[0], outs[1])

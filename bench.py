@@ -447,12 +447,17 @@ def dp_parity(model, dev, cfg, world, rank, strong):
                 off_n += s.num_nodes
             whole = GraphBatch(**{f: torch.cat(v, dim=1 if f == "edge_index" else 0) for f, v in parts.items()})
             fused_mse_step(model, whole.to(dev), total)
-            ref = torch.cat([p.grad.reshape(-1) for p in model._engine_params()])
+            ref = torch.cat([p.grad.reshape(-1) for p in model._engine_params()]).clone()
+            # control: rank 0's own shard WITHOUT the reduction -- the reduced gradient must differ from it by O(1),
+            # otherwise the comparison above would say nothing about the exchange
+            fused_mse_step(model, shards[rank].to(dev), total)
+            local = torch.cat([p.grad.reshape(-1) for p in model._engine_params()])
         finally:
             model._grad_reducer = reducer
         d = (flat.double() - ref.double())
         return {"max_rel": float(d.abs().max() / ref.double().abs().max()), "fro_rel": float(d.norm() / ref.double().norm()),
-                "global_graphs": sum(s.num_graphs for s in shards), "global_nodes": off_n}
+                "global_graphs": sum(s.num_graphs for s in shards), "global_nodes": off_n,
+                "unreduced_rank0_vs_global_fro_rel": float((local.double() - ref.double()).norm() / ref.double().norm())}
     finally:
         model.dropout.p = p_keep
         dist.barrier()

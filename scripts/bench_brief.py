@@ -14,7 +14,7 @@ for e in d.get("roofline_step", []):
 for k in ("dp_parity", "strong_scaling", "cpu_baseline", "reference_gpu", "clocks"):
     if k in d:
         v = d[k]
-        print(" " + k, {kk: (round(vv, 6) if isinstance(vv, float) else (vv if not isinstance(vv, str) else vv[:60])) for kk, vv in v.items()} if isinstance(v, dict) else v)
+        print(" " + k, {kk: ((float(f"{vv:.4g}")) if isinstance(vv, float) else (vv if not isinstance(vv, str) else vv[:60])) for kk, vv in v.items()} if isinstance(v, dict) else v)
 if "configs3" in d:
     c = d["configs3"]
     print(" configs3", {k: (round(c[k], 3) if isinstance(c.get(k), float) else c.get(k)) for k in ("value", "ms_per_step", "error")}, "roofline frac", c.get("roofline", {}).get("frac"))

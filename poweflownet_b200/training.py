@@ -10,7 +10,7 @@ Any other loss goes through `model(data)` + torch autograd as in the reference.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Callable, Optional, Tuple
 
 import torch
 
@@ -267,6 +267,28 @@ class PipelinedMSESteps:
             self.copy_stream.wait_event(self.done[k])  # the replay that last read this buffer set has finished
             self.steps[k].load(batch)
             self.ready[k].record(self.copy_stream)
+
+    def step_async(self) -> "Callable[[], float]":
+        """`step()` whose loss travels to the host asynchronously: the 4-byte device->host copy is queued behind the replay
+        into a pinned slot of its own, and the returned callable waits for THAT copy only.  Reading the loss of step i
+        after step i + 1 has been queued keeps the GPU busy across the read-back (an asynchronous logger); the values are
+        the ones `step().item()` returns."""
+        loss = self.step()
+        if not hasattr(self, "_loss_host"):
+            self._loss_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+            self._loss_events = [torch.cuda.Event() for _ in range(8)]
+            self._loss_k = 0
+        k = self._loss_k
+        self._loss_k = (k + 1) % 8
+        slot = self._loss_host[k:k + 1]
+        slot.copy_(loss.reshape(1), non_blocking=True)
+        ev = self._loss_events[k]
+        ev.record(torch.cuda.current_stream(loss.device))
+
+        def read() -> float:
+            ev.synchronize()
+            return float(slot[0])
+        return read
 
     def step(self) -> torch.Tensor:
         if self._pending <= 0:

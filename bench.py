@@ -530,16 +530,25 @@ def run_ours(args, cfg):
     pipe = PipelinedMSESteps(model, dev_batches[0], total_count) if use_graphs else None
 
     def e2e_pipe(i):
-        # batch i was copied while step i-1 ran; this step issues the copy of batch i+1, computes batch i, reads its loss
+        # batch i was copied while step i-1 ran; this iteration queues the step of batch i FIRST (so that the GPU does not
+        # wait for the host to issue the next copies), then the copy of batch i+1, then reads the loss of batch i
+        loss = pipe.step()
         pipe.prefetch(host_batches[(i + 1) % n_rot])
-        return float(pipe.step().item())
+        return float(loss.item())
+
+    def step_pipe(i):
+        # resident batches through the same two-buffer pipeline: the device-to-device copy of batch i+1 into the captured
+        # step's input buffers runs on the copy stream while batch i computes (GraphedMSEStep alone queues its eight
+        # small copies in front of every replay)
+        pipe.step()
+        pipe.prefetch(dev_batches[(i + 1) % n_rot])
     pending_loss = []
 
     def e2e_pipe_async(i):
         # as e2e_pipe, but the loss of step i is read after step i + 1 has been queued (4-byte pinned D2H + event per step);
         # informational: shows how much of e2e_pipe is the host waiting on `.item()` rather than GPU work
-        pipe.prefetch(host_batches[(i + 1) % n_rot])
         pending_loss.append(pipe.step_async())
+        pipe.prefetch(host_batches[(i + 1) % n_rot])
         if len(pending_loss) > 1:
             pending_loss.pop(0)()
     for i in range(max(args.warmup, 3)):
@@ -566,8 +575,17 @@ def run_ours(args, cfg):
     ms_graph = None
     if graphed is not None:
         ms_graph, _, _ = timed(step_graph, args.steps)
-    use_graph = ms_graph is not None and ms_graph < ms_eager
-    ms_total_clean = ms_graph if use_graph else ms_eager
+    ms_pipe = None
+    if pipe is not None:
+        pipe.prefetch(dev_batches[0])
+        for i in range(3):
+            step_pipe(i)
+        ms_pipe = timed(lambda i: step_pipe(i + 3), args.steps)[0]
+        pipe.step()  # drain the batch prefetched by the last timed step
+    modes = {"eager": ms_eager, "graph": ms_graph, "pipelined": ms_pipe}
+    launch_mode = min((k for k, v in modes.items() if v is not None), key=lambda k: modes[k])
+    use_graph = launch_mode != "eager"
+    ms_total_clean = modes[launch_mode]
     t1b = time.time()
     clocks = sampler.stop(t0, t1b) if rank == 0 else None
     # ---- end to end from pinned host memory (same launch modes) ----
@@ -681,13 +699,15 @@ def run_ours(args, cfg):
                                     ", one NCCL all-reduce of the flat fp32 gradient buffer per step") if world > 1 else "single GPU",
                     "l2": f"steps rotate over {n_rot} resident batches; per-step activation+scratch working set > 126 MB L2 (no explicit flush)",
                     "timed_region": "graph prep + forward + fused MSE + backward (+ all-reduce); optimizer.step excluded (SURVEY 8 f4; see train_epoch)",
-                    "launch": "CUDA graph replay of the captured step (training.GraphedMSEStep)" if use_graph
-                              else "eager: stream-ordered launches with programmatic dependent launch (training.fused_mse_step)",
+                    "launch": {"graph": "CUDA graph replay of the captured step (training.GraphedMSEStep)",
+                               "pipelined": "CUDA graph replays of the captured step over two input-buffer sets, the device-to-device copy of "
+                                            "the next resident batch into the idle set on a side stream (training.PipelinedMSESteps)",
+                               "eager": "eager: stream-ordered launches with programmatic dependent launch (training.fused_mse_step)"}[launch_mode],
                     "route": "graph-resident kernels (pfn_mpn_forward_tiled / pfn_mpn_backward_tiled)" if fused_route else "layer-wise kernels"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": host_batches[0].nbytes(), "d2h_bytes_per_step": 4,
-                "api": {"pipelined": "poweflownet_b200.training.PipelinedMSESteps: prefetch(pinned batch i+1) on a copy stream, "
-                                     "step() of batch i (CUDA-graph replay), loss.item() -- one H2D, one step, one D2H per iteration",
+                "api": {"pipelined": "poweflownet_b200.training.PipelinedMSESteps: step() of batch i (CUDA-graph replay), prefetch(pinned "
+                                     "batch i+1) on a copy stream, loss.item() of batch i -- one H2D, one step, one D2H per iteration",
                         "graph": "poweflownet_b200.training.GraphedMSEStep(model, batch)(pinned_host_batch) + loss.item()",
                         "eager": "poweflownet_b200.training.fused_mse_step(model, pinned_host_batch.to(device, non_blocking=True)) + loss.item()"}[e2e_mode]},
         "gpu_launches": launches,
@@ -698,6 +718,7 @@ def run_ours(args, cfg):
         "ms_per_step_with_timing_hooks": step_ms_hooks,
         "ms_per_step_eager": ms_eager / args.steps,
         "ms_per_step_cuda_graph": None if ms_graph is None else ms_graph / args.steps,
+        "ms_per_step_pipelined": None if ms_pipe is None else ms_pipe / args.steps,
         "e2e_ms_per_step_eager": ms_e2e_eager / args.steps,
         "e2e_ms_per_step_cuda_graph": None if ms_e2e_graph is None else ms_e2e_graph / args.steps,
         "e2e_ms_per_step_pipelined": None if ms_e2e_pipe is None else ms_e2e_pipe / args.steps,

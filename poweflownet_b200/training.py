@@ -245,8 +245,9 @@ class PipelinedMSESteps:
 
         pipe.prefetch(batch_0)
         for i in range(n):
-            pipe.prefetch(batch_{i+1})        # asynchronous, overlaps the step below
-            loss = float(pipe.step().item())  # forward + MSE + backward of batch_i, then the device->host read
+            loss = pipe.step()                # queue forward + MSE + backward of batch_i (already on the device)
+            pipe.prefetch(batch_{i+1})        # asynchronous copy on the side stream, overlaps the step
+            value = float(loss.item())        # the device->host read of batch_i's loss
     """
 
     def __init__(self, model: MaskEmbdMultiMPN, example_batch, total_count: Optional[int] = None):

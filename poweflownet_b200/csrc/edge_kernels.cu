@@ -787,7 +787,10 @@ int ea_fwd_tma_launch(const float* Hi, const float* Hj, int64_t ldh, const Graph
   // (row pointers -> neighbour ids -> rows) overlap each other (PFN_EA_CTAS_PER_SM=2; measured at case118v2 x 128: 10.4 us
   // against 10.1 us -- no gain, it stays an experiment knob).
   const int per_sm = std::max(1, std::min(2, env_int("PFN_EA_CTAS_PER_SM", 1)));
-  a.prod_warps = std::max(1, std::min(8, env_int("PFN_EA_PRODUCERS", a.bulk_eighths >= 8 ? 1 : (per_sm == 2 ? 4 : 8))));
+  // producer warps: 8, or 12 for wide rows whose chunk count divides 12 warps' lanes (every lane then keeps ONE column chunk
+  // for the whole kernel, the cheap addressing path; measured at 2 KB rows: 8 -> 254 us, 12 -> 247 us, 10 / 14 -> 282 us)
+  const int prod_default = a.bulk_eighths >= 8 ? 1 : (per_sm == 2 ? 4 : ((c4 >= 128 && 384 % c4 == 0) ? 12 : 8));
+  a.prod_warps = std::max(1, std::min(16, env_int("PFN_EA_PRODUCERS", prod_default)));
   const int max_cons = (32 / per_sm - a.prod_warps) * 32;
   if (c4 > max_cons) return 1;
   const int want_threads = std::max(c4, std::min(max_cons, env_int("PFN_EA_THREADS", per_sm == 2 ? 256 : 512)));

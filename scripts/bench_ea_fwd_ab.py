@@ -115,10 +115,14 @@ def run(case, b, h, variants, iters, n_sets):
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 only = set(sys.argv[2].split(",")) if len(sys.argv) > 2 else None  # optional: comma-separated variant names
 P = {"PFN_EA_FWD": "tma"}
-small = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_1sm", {**P, "PFN_EA_CTAS_PER_SM": "1"}), ("tma_2sm_t128", {**P, "PFN_EA_THREADS": "128"}),
+small = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_p10", {**P, "PFN_EA_PRODUCERS": "10"}), ("tma_p12", {**P, "PFN_EA_PRODUCERS": "12"}), ("tma_p16", {**P, "PFN_EA_PRODUCERS": "16"}), ("tma_1sm", {**P, "PFN_EA_CTAS_PER_SM": "1"}), ("tma_2sm_t128", {**P, "PFN_EA_THREADS": "128"}),
          ("tma_2sm_t384_p4", {**P, "PFN_EA_THREADS": "384"}), ("tma_2sm_p2", {**P, "PFN_EA_PRODUCERS": "2"}), ("tma_2sm_p6", {**P, "PFN_EA_PRODUCERS": "6"}),
          ("tma_2sm_s1", {**P, "PFN_EA_STAGES": "1"}), ("tma_2sm_s3", {**P, "PFN_EA_STAGES": "3"}), ("tma_2sm_prefetch", {**P, "PFN_EA_PREFETCH": "1"})]
-large = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_2sm", {**P, "PFN_EA_CTAS_PER_SM": "2"})]
+large = [("cta", {"PFN_EA_FWD": "cta"}), ("tma", P), ("tma_c32", {**P, "PFN_EA_CHUNK": "32"}), ("tma_c64", {**P, "PFN_EA_CHUNK": "64"}), ("tma_c96", {**P, "PFN_EA_CHUNK": "96"}),
+         ("tma_c192", {**P, "PFN_EA_CHUNK": "192"}), ("tma_c256", {**P, "PFN_EA_CHUNK": "256"}), ("tma_c64_s3", {**P, "PFN_EA_CHUNK": "64", "PFN_EA_STAGES": "3"}),
+         ("tma_p6", {**P, "PFN_EA_PRODUCERS": "6"}), ("tma_t640", {**P, "PFN_EA_THREADS": "640"}),
+         ("tma_p10", {**P, "PFN_EA_PRODUCERS": "10"}), ("tma_p12", {**P, "PFN_EA_PRODUCERS": "12"}), ("tma_p14", {**P, "PFN_EA_PRODUCERS": "14"}), ("tma_p16", {**P, "PFN_EA_PRODUCERS": "16"}),
+         ("tma_p12_t384", {**P, "PFN_EA_PRODUCERS": "12", "PFN_EA_THREADS": "384"}), ("tma_p16_t256", {**P, "PFN_EA_PRODUCERS": "16", "PFN_EA_THREADS": "256"}), ("tma_2sm", {**P, "PFN_EA_CTAS_PER_SM": "2"})]
 if only is not None:
     small = [v for v in small if v[0] in only]
     large = [v for v in large if v[0] in only]

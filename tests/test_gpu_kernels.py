@@ -214,7 +214,7 @@ def test_ea_forward_bulk_copy_kernel_equals_cta_kernel(name, h, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"PFN_EA_STAGES": "2"}, {"PFN_EA_STAGES": "3", "PFN_EA_THREADS": "256"}, {"PFN_EA_THREADS": "992"},
-                                 {"PFN_EA_THREADS": "64", "PFN_EA_PRODUCERS": "1"}, {"PFN_EA_PRODUCERS": "7", "PFN_EA_THREADS": "800"},
+                                 {"PFN_EA_THREADS": "64", "PFN_EA_PRODUCERS": "1"}, {"PFN_EA_PRODUCERS": "7", "PFN_EA_THREADS": "800"}, {"PFN_EA_PRODUCERS": "12"}, {"PFN_EA_PRODUCERS": "16", "PFN_EA_THREADS": "256"},
                                  {"PFN_EA_BULK": "1"}, {"PFN_EA_BULK": "0", "PFN_EA_PRODUCERS": "2"}, {"PFN_EA_PREFETCH": "1"},
                                  {"PFN_EA_BULK8": "3"}, {"PFN_EA_BULK8": "5", "PFN_EA_STAGES": "4"}, {"PFN_EA_BULK8": "7", "PFN_EA_PRODUCERS": "3"},
                                  {"PFN_EA_CHUNK": "8", "PFN_EA_BULK8": "4"}, {"PFN_EA_ROUND": "1"}, {"PFN_EA_CTAS_PER_SM": "1"},

@@ -818,6 +818,7 @@ struct WgGroupProb {
   int acc_hi[2], acc_lo[2];
   int odd, oddn;
   int n_hi;  // mt == 1: hi*hi products rotate over n_hi accumulators at columns 0, BN, ... (lo terms at n_hi * BN)
+  int atmem, a_tmem;  // A operand in tensor memory: first column of its two 64-column stages
 };
 struct WgGroupArgs {
   WgGroupProb p[kWgMaxProb];
@@ -845,10 +846,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
   // P.oddn: Ni = 128 + 1 likewise: X column 128 and the virtual bias column are multiplied by the converter threads too
   // (thread m: sums over nodes of dY[node][m] X[node][128] and dY[node][m] e[node]), so the B operand is exactly four
   // 32-column boxes and a third pipeline stage fits in shared memory.
-  const uint32_t oddx_off = 2u * (a_bytes + b_bytes) + (P.odd ? 4096u : 0u);  // X columns 128..159 (P.oddn)
+  // P.atmem: the A operand (dY^T) lives in TENSOR MEMORY.  A converter thread owns one output feature m (= TMEM lane) and
+  // 16 of the tile's 32 nodes: it reads dY[node][m] from the TMA-landed tile (column reads: one wavefront per node and
+  // warp), splits and writes (hi, lo) with tcgen05.st into one of two 64-column operand stages -- a transposed copy for
+  // free.  No hi / lo planes of A in shared memory (a stage shrinks by 16 KB: a fourth stage fits at hidden 129), no
+  // in-place rewrite of the A tile and no A descriptor reads by the MMAs: ~640 of the ~2650 shared-memory wavefronts per
+  // tile that bound this kernel (profiles/r2_summary.md).  Costs one rotating accumulator (two instead of three).
+  const bool atmem = P.atmem != 0;
+  const uint32_t b_off = atmem ? a_bytes : 2u * a_bytes;                     // A (as landed) | B_hi | B_lo | odd boxes
+  const uint32_t oddy_off = b_off + 2u * b_bytes;                            // dY column 128..159 (P.odd)
+  const uint32_t oddx_off = oddy_off + (P.odd ? 4096u : 0u);                 // X columns 128..159 (P.oddn)
   const uint32_t odd_bytes = (P.odd ? 4096u : 0u) + (P.oddn ? 4096u : 0u);
   __shared__ float evec[kTcMaxStages][kTcBK];  // the bias column's entries (ones / extra_vec) of the tile in each stage
-  const uint32_t stage_bytes = 2u * (a_bytes + b_bytes) + odd_bytes;  // A_hi | A_lo | B_hi | B_lo | (odd dY box)
+  const uint32_t stage_bytes = oddy_off + odd_bytes;  // (A_hi | A_lo without atmem)
   const uint32_t bar_base = base + uint32_t(S) * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto conv_bar = [&](int s) { return bar_base + 8u * (kTcMaxStages + s); };
@@ -894,9 +904,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         mbar_arrive_expect_tx(full_bar(s), a_bytes + b_bytes + odd_bytes);
         const uint32_t st = base + uint32_t(s) * stage_bytes;
         for (int b = 0; b < mt * 4; ++b) tma_load_2d(st + uint32_t(b) * 4096u, &P.a, row0 + 32 * b, k0, full_bar(s));
-        if (P.odd) tma_load_2d(st + 2u * (a_bytes + b_bytes), &P.a, kTcBM, k0, full_bar(s));
+        if (P.odd) tma_load_2d(st + oddy_off, &P.a, kTcBM, k0, full_bar(s));
         if (P.oddn) tma_load_2d(st + oddx_off, &P.b, 128, k0, full_bar(s));
-        for (int b = 0; b < nb; ++b) tma_load_2d(st + 2u * a_bytes + uint32_t(b) * 4096u, &P.b, 32 * b, k0, full_bar(s));
+        for (int b = 0; b < nb; ++b) tma_load_2d(st + b_off + uint32_t(b) * 4096u, &P.b, 32 * b, k0, full_bar(s));
       }
     }
   } else if (warp == 1) {
@@ -912,11 +922,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       if (lane == 0 && it < 12) WSTAMP(30 + it);
       if (elect_one()) {
         const uint32_t st = base + uint32_t(s) * stage_bytes;
-        const uint32_t b_hi = st + 2u * a_bytes, b_lo = b_hi + b_bytes;
+        const uint32_t b_hi = st + b_off, b_lo = b_hi + b_bytes;
         for (int j = 0; j < kTcBK / 8; ++j) {  // 8 nodes per UMMA K step = one 1024-byte K group
           const uint32_t koff = uint32_t(j) * kstep;
           const uint64_t dbh = umma_desc_mn128(b_hi + koff, lbo, sbo), dbl = umma_desc_mn128(b_lo + koff, lbo, sbo);
           const int k_idx = it * (kTcBK / 8) + j;
+          if (atmem) {  // (mt == 1) A from the tile's operand stage in tensor memory: K-major there, so without the A-major bit
+            const uint32_t at_hi = tmem_base + uint32_t(P.a_tmem + 64 * (it & 1) + 8 * j), at_lo = at_hi + 32u;
+            const uint32_t idesc_ts = idesc & ~(1u << 15);
+            const uint32_t d_lo = tmem_base + uint32_t(P.acc_lo[0]), d_hi = tmem_base + uint32_t((k_idx % P.n_hi) * BN);
+            umma_tf32_ts(d_lo, at_lo, dbh, idesc_ts, k_idx > 0 ? 1u : 0u);
+            umma_tf32_ts(d_lo, at_hi, dbl, idesc_ts, 1u);
+            umma_tf32_ts(d_hi, at_hi, dbh, idesc_ts, k_idx >= P.n_hi ? 1u : 0u);
+            continue;
+          }
           for (int t = 0; t < mt; ++t) {
             const uint32_t a_hi = st + uint32_t(t) * 16384u, a_lo = a_hi + a_bytes;
             const uint64_t dah = umma_desc_mn128(a_hi + koff, lbo, sbo), dal = umma_desc_mn128(a_lo + koff, lbo, sbo);
@@ -963,7 +982,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         if (tid_c == 0 && it == 4) WSTAMP(50);
         asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");
         if (tid_c == 0 && it == 4) WSTAMP(51);
-        const uint32_t ycol = st + 2u * (a_bytes + b_bytes), xodd = st + oddx_off;
+        const uint32_t ycol = st + oddy_off, xodd = st + oddx_off;
         // all eight converter warps: thread -> (m = tid mod 128, rows [16 (tid / 128), +16)); the halves meet in the epilogue
         {
           // column 128 and the bias column of dW rows 0..127:  sum_r dY[r][m] * X[r][128],  sum_r dY[r][m] * e[r]
@@ -1004,7 +1023,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
           const int node = k0 + r;
           float v = 0.f;
           if (node < k_end) v = P.extra_col == 1 ? 1.f : P.extra_vec[node];
-          const uint32_t addr = st + 2u * a_bytes + uint32_t(bb) * 4096u + uint32_t(r) * 128u +
+          const uint32_t addr = st + b_off + uint32_t(bb) * 4096u + uint32_t(r) * 128u +
                                 (uint32_t((cc >> 3) ^ (r & 3)) << 5) + uint32_t(cc & 7) * 4u;
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
         }
@@ -1016,8 +1035,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
         const int rbeg = P.oddn ? (tid_c >> 7) * 16 : 0, rend = P.oddn ? rbeg + 16 : kTcBK;
         if (P.oddn || tid_c < P.n_eff) {
           const int bb = ncol >> 5, cc = ncol & 31;
-          const uint32_t xcol = st + 2u * a_bytes + uint32_t(bb) * 4096u + uint32_t(cc & 7) * 4u;
-          const uint32_t ycol = st + 2u * (a_bytes + b_bytes);
+          const uint32_t xcol = st + b_off + uint32_t(bb) * 4096u + uint32_t(cc & 7) * 4u;
+          const uint32_t ycol = st + oddy_off;
           for (int r8 = rbeg; r8 < rend; r8 += 8) {  // 128-byte rows, 32-byte chunks XOR-swizzled with (row mod 4)
             float x[8], y[8];
 #pragma unroll
@@ -1034,8 +1053,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_wgrad_group(const __grid_cons
       if (tid_c == 0 && it == 4) WSTAMP(52);
       if (P.odd || P.oddn) asm volatile("bar.sync 1, %0;" ::"n"(kTcWorkers) : "memory");  // the split below rewrites the tiles in place
       if (tid_c == 0 && it == 4) WSTAMP(53);
-      split_tile(st, a_bytes, int(a_bytes / 16u), tid_c);
-      split_tile(st + 2u * a_bytes, b_bytes, int(b_bytes / 16u), tid_c);
+      if (atmem) {
+        // feature m = 32 (warp mod 4) + lane (the TMEM lanes this warp may access), nodes [16 nh, 16 nh + 16) of the tile
+        const int m = 32 * (warp & 3) + lane, nh = (warp - 2) >> 2;
+        const uint32_t ym = st + uint32_t(m >> 5) * 4096u + uint32_t(m & 7) * 4u;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int r = 16 * nh + u;
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ym + uint32_t(r) * 128u + (uint32_t(((m & 31) >> 3) ^ (r & 3)) << 5)));
+          const float h = tf32_rn(v);
+          hi[u] = __float_as_uint(h);
+          lo[u] = __float_as_uint(tf32_rn(v - h));
+        }
+        if (it >= 2) {  // the operand stage was last read by the MMAs of tile it - 2
+          mbar_wait(empty_bar((it - 2) % S), uint32_t((it - 2) / S) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t at = tmem_base + (uint32_t(32 * (warp & 3)) << 16) + uint32_t(P.a_tmem + 64 * (it & 1) + 16 * nh);
+        tmem_st16(at, hi);
+        tmem_st16(at + 32u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        split_tile(st, a_bytes, int(a_bytes / 16u), tid_c);
+      }
+      split_tile(st + b_off, b_bytes, int(b_bytes / 16u), tid_c);
       if (tid_c == 0 && it == 4) WSTAMP(54);
       proxy_fence_async();
       if (tid_c == 0 && it < 12) WSTAMP(16 + it);
@@ -1512,9 +1556,16 @@ static int wgrad_batch_launch(const WgradProblem* probs, int n, int64_t nodes, f
     P.m_groups = static_cast<int>(ceil_div64(m_tiles, P.mt));
     int used;
     P.n_hi = 1;
+    static const bool atmem_env = [] {
+      const char* e = std::getenv("PFN_WG_ATMEM");
+      return !(e != nullptr && e[0] == '0');
+    }();
+    P.atmem = (atmem_env && P.mt == 1 && 384 / P.BN - 1 >= 2) ? 1 : 0;  // (two rotating accumulators + lo + 128 operand columns)
     if (P.mt == 1) {
-      P.n_hi = std::max(1, std::min(3, 512 / P.BN - 1));
+      P.n_hi = std::max(1, std::min(3, (P.atmem ? 384 : 512) / P.BN - 1));
       P.acc_hi[0] = 0; P.acc_lo[0] = P.n_hi * P.BN; used = (P.n_hi + 1) * P.BN;
+      P.a_tmem = used;
+      if (P.atmem) used += 128;
     } else if (3 * P.BN <= 512) {
       P.acc_hi[0] = 0; P.acc_lo[0] = P.BN; P.acc_hi[1] = P.acc_lo[1] = 2 * P.BN; used = 3 * P.BN;
     } else {
@@ -1523,7 +1574,7 @@ static int wgrad_batch_launch(const WgradProblem* probs, int n, int64_t nodes, f
     int cols = 32;
     while (cols < used) cols <<= 1;
     P.tmem_cols = cols;
-    const uint32_t stage_bytes = 2u * (uint32_t(P.mt) * 16384u + uint32_t(P.nb) * 4096u) + (P.odd ? 4096u : 0u) + (P.oddn ? 4096u : 0u);
+    const uint32_t stage_bytes = (P.atmem ? 1u : 2u) * uint32_t(P.mt) * 16384u + 2u * uint32_t(P.nb) * 4096u + (P.odd ? 4096u : 0u) + (P.oddn ? 4096u : 0u);
     P.stages = static_cast<int>(std::min<uint32_t>(kTcMaxStages, (kSmemLimit - 3072u) / stage_bytes));
     if (P.stages < 2) return 1;
     smem_max = std::max(smem_max, uint32_t(P.stages) * stage_bytes + 1024u + 8u * (3 * kTcMaxStages + 2));

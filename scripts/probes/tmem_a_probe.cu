@@ -10,6 +10,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 __device__ __forceinline__ uint64_t desc_k128(uint32_t saddr) {
   return uint64_t((saddr >> 4) & 0x3FFFu) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
+__device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {  // SWIZZLE_128B_BASE32B, MN-major TF32
+  return uint64_t((saddr >> 4) & 0x3FFFu) | (uint64_t((lbo >> 4) & 0x3FFFu) << 16) | (uint64_t((sbo >> 4) & 0x3FFFu) << 32) | (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -187,6 +190,43 @@ __global__ void __launch_bounds__(128, 1) probe(float* out_ss, float* out_ts, lo
     if (warp == 0 && t0 != 0) cycles[8 + which] = t0;
     __syncthreads();
   }
+  // MN-major operands (the weight-gradient kernels' layout: [node][feature] tiles, 32-column boxes of 4 KB, K step = 1024 B):
+  // which 0: A and B MN-major from shared memory; 1: A from tensor memory, B MN-major
+  for (int which = 0; which < 2; ++which) {
+    long long t0 = 0;
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint32_t idesc_mn = idesc | (1u << 16) | (which == 0 ? (1u << 15) : 0u);
+        t0 = clock64();
+        for (int i = 0; i < reps; ++i) {
+          const int j = i & 3;
+          const int stage = (i >> 2) % 3;
+          const uint32_t st = base + uint32_t(stage) * 65536u;
+          const uint32_t koff = uint32_t(j) * 1024u;
+          const uint64_t ah = desc_mn128(st + koff, 4096u, 512u), al = desc_mn128(st + 16384u + koff, 4096u, 512u);
+          const uint64_t bh = desc_mn128(st + 32768u + koff, 4096u, 512u), bl = desc_mn128(st + 49152u + koff, 4096u, 512u);
+          const uint32_t dlo = tmem + 2u * uint32_t(N), dhi = tmem + uint32_t(((i >> 2) & 1) * N);
+          if (which == 0) {
+            mma_ss(dlo, al, bh, idesc_mn, 1u);
+            mma_ss(dlo, ah, bl, idesc_mn, 1u);
+            mma_ss(dhi, ah, bh, idesc_mn, 1u);
+          } else {
+            const uint32_t at = tmem + 3u * uint32_t(N) + uint32_t((stage & 1) * 64);
+            mma_ts(dlo, at + 32u + uint32_t(8 * j), bh, idesc_mn, 1u);
+            mma_ts(dlo, at + uint32_t(8 * j), bl, idesc_mn, 1u);
+            mma_ts(dhi, at + uint32_t(8 * j), bh, idesc_mn, 1u);
+          }
+        }
+        commit(smem_u32(&bar));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bar), phase);
+    phase ^= 1;
+    if (tid == 0) cycles[17 + which] = clock64();
+    if (warp == 0 && t0 != 0) cycles[19 + which] = t0;
+    __syncthreads();
+  }
   // latency of one K tile: 12 MMAs (GEMM pattern, A in TMEM), commit, wait -- repeated; the wait is done by ANOTHER warp
   // (warp 1, as a worker would) which then releases the issuer through a second barrier
   {
@@ -256,9 +296,9 @@ void run(int reps) {
       bad_ss += hs[m * N + n] != ref;
       bad_ts += ht[m * N + n] != ref;
     }
-  printf("N=%3d: mismatches SS %d, TS %d of %d | cycles per MMA: same tiles SS %.1f TS %.1f | GEMM pattern SS %.1f TS %.1f | + shared-memory traffic SS %.1f TS %.1f | + tcgen05.ld traffic SS %.1f TS %.1f | one K tile (12 MMAs) issue -> commit seen by another warp -> issuer released: %lld cycles\n",
+  printf("N=%3d: mismatches SS %d, TS %d of %d | cycles per MMA: same tiles SS %.1f TS %.1f | GEMM pattern SS %.1f TS %.1f | + shared-memory traffic SS %.1f TS %.1f | + tcgen05.ld traffic SS %.1f TS %.1f | one K tile (12 MMAs) issue -> commit seen by another warp -> issuer released: %lld cycles | MN-major operands (weight-gradient layout): SS %.1f, A in TMEM %.1f cycles per MMA\n",
          N, bad_ss, bad_ts, 128 * N, double(hc[0] - hc[8]) / reps, double(hc[1] - hc[9]) / reps, double(hc[2] - hc[10]) / (3.0 * reps),
-         double(hc[3] - hc[11]) / (3.0 * reps), double(hc[4] - hc[12]) / (3.0 * reps), double(hc[5] - hc[13]) / (3.0 * reps), double(hc[6] - hc[14]) / (3.0 * reps), double(hc[7] - hc[15]) / (3.0 * reps), hc[16]);
+         double(hc[3] - hc[11]) / (3.0 * reps), double(hc[4] - hc[12]) / (3.0 * reps), double(hc[5] - hc[13]) / (3.0 * reps), double(hc[6] - hc[14]) / (3.0 * reps), double(hc[7] - hc[15]) / (3.0 * reps), hc[16], double(hc[17] - hc[19]) / (3.0 * reps), double(hc[18] - hc[20]) / (3.0 * reps));
 }
 
 int main() {

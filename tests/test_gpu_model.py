@@ -374,3 +374,22 @@ def test_loss_curve_matches_oracle_over_optimizer_steps():
     assert curve_o[-1] < curve_o[0]  # it trains
     for a, b in zip(curve_m, curve_o):
         assert abs(a - b) <= 1e-4 * abs(b), (curve_m, curve_o)
+
+
+@pytest.mark.parametrize("case,graphs,hidden,layers,repeats", [("118v2", 128, 129, 4, 30), ("6470rte", 1, 512, 3, 6)])
+def test_gradients_are_bitwise_reproducible(case, graphs, hidden, layers, repeats):
+    """No atomics anywhere on the path (fixed-order split-K sums in k_wgrad_group_reduce, segment sums in edge order): every
+    repeat of the step reproduces the first run's 35+ gradient tensors bit for bit, on the graph-resident route (bench
+    size; grouped weight gradients with dY^T in tensor memory) and on the layer-wise route (hidden 512)."""
+    from poweflownet_b200.data import synthetic_batch
+    from poweflownet_b200.training import fused_mse_step
+    kw = dict(common.MODEL_DIMS, hidden_dim=hidden, n_gnn_layers=layers, K=3, dropout_rate=0.0)
+    m = _model(kw).train()
+    batch = synthetic_batch(case, graphs).to(DEV)
+    first_loss = float(fused_mse_step(m, batch))
+    first = [p.grad.clone() for p in m.parameters()]
+    for _ in range(repeats):
+        loss = float(fused_mse_step(m, batch))
+        assert loss == first_loss
+        differing = [k for (k, p), g in zip(m.named_parameters(), first) if not torch.equal(p.grad, g)]
+        assert not differing, differing
